@@ -1,0 +1,147 @@
+"""Pins the oracle (oracle/restate.py) against (1) the reference's own known-answer demo values and
+(2) fixtures produced by the unmodified reference modules (oracle/make_golden.py). CPU only."""
+import numpy as np
+import pytest
+
+from oracle import restate as R
+
+
+def test_demo_miou_known_answer(golden):
+    d = golden("demo_fixtures")
+    # compute_mIoU.py:139-149 prints 0.9513888955116272 for both evaluators
+    assert float(d["compute_mIoU_value"]) == pytest.approx(0.9513888955116272, abs=0)
+    m = R.MIoU(4)
+    m(d["compute_mIoU_y_pred"], d["compute_mIoU_y_true"])
+    assert m.compute() == np.float32(0.9513888955116272)
+    vals = [R.img_miou(d["compute_mIoU_y_pred"][i:i + 1], d["compute_mIoU_y_true"][i]) for i in range(2)]
+    # img_mIoU is fed the whole batch at once in the demo (squeeze keeps N=2): restate that call
+    assert R.img_miou(d["compute_mIoU_y_pred"], d["compute_mIoU_y_true"]) == pytest.approx(
+        float(d["compute_mIoU_img_value"]), abs=1e-7)
+    assert len(vals) == 2
+
+
+def test_demo_seg_metrics_known_answer(golden):
+    d = golden("demo_fixtures")
+    tp, fp, fn = R.compute_basics(d["seg_metrics_y_pred"], d["seg_metrics_y_true"])
+    np.testing.assert_array_equal(tp, d["seg_metrics_tp"])
+    np.testing.assert_array_equal(fp, d["seg_metrics_fp"])
+    np.testing.assert_array_equal(fn, d["seg_metrics_fn"])
+    # printed digits in seg_metrics.py's demo: macro R/P/F1 0.8500/0.9667/0.8419
+    s = 1e-6
+    rec = ((tp + s) / (tp + fn + s)).mean(-1).mean()
+    pre = ((tp + s) / (tp + fp + s)).mean(-1).mean()
+    f1 = ((2 * tp + s) / (2 * tp + fn + fp + s)).mean(-1).mean()
+    assert round(float(rec), 4) == 0.8500 and round(float(pre), 4) == 0.9667 and round(float(f1), 4) == 0.8419
+    assert float(d["seg_metrics_recall_macro"]) == pytest.approx(rec, abs=1e-6)
+
+
+def test_metrics_vs_reference(golden):
+    d = golden("metrics")
+    tp, fp, fn = R.compute_basics(d["logits"], d["targets"])
+    np.testing.assert_array_equal(tp, d["tp"])
+    np.testing.assert_array_equal(fp, d["fp"])
+    np.testing.assert_array_equal(fn, d["fn"])
+    m = R.MIoU(21)
+    m(d["logits"], d["targets"])
+    m(d["logits"][::-1], d["targets"])
+    np.testing.assert_array_equal(m.acc, d["acc"])
+    assert m.compute() == d["miou"] or (np.isnan(m.compute()) and np.isnan(d["miou"]))
+    im = np.mean([R.img_miou(d["logits"][i:i + 1], d["targets"][i:i + 1]) for i in range(2)])
+    assert im == pytest.approx(float(d["img_miou"]), abs=1e-6)
+
+
+def test_entropy_vs_reference(golden):
+    d = golden("entropy")
+    assert R.img_norm_entropy(d["probs"], 21) == pytest.approx(float(d["ent"]), abs=2e-6)
+    for s in (2, 4, 5):
+        assert R.img_norm_entropy(d["probs"], 21, s=s) == pytest.approx(float(d[f"max_{s}"]), abs=2e-6)
+        assert R.img_norm_entropy(d["probs"], 21, pool_min=True, s=s) == pytest.approx(
+            float(d[f"min_{s}"]), abs=2e-6)
+    # from logits: softmax then entropy
+    assert R.img_norm_entropy(R.softmax_c(d["logits"], 0), 21) == pytest.approx(float(d["ent"]), abs=2e-6)
+
+
+CE_CASES = {
+    "sum": dict(ignore_index=21, b_reduction="sum", n_exits=3),
+    "mean": dict(ignore_index=21, b_reduction="mean", n_exits=3),
+    "none": dict(ignore_index=21, b_reduction="none", n_exits=3),
+    "wsum": dict(ignore_index=21, b_reduction="sum", n_exits=3, weights=[0.25, 0.5, 1.0]),
+    "two": dict(ignore_index=21, b_reduction="sum", n_exits=2),
+}
+
+
+@pytest.mark.parametrize("tag", list(CE_CASES))
+def test_ce_vs_reference(golden, tag):
+    d = golden("ce")
+    loss, grad, _ = R.br_xentropy(d["y_pred"], d["targets"], **CE_CASES[tag])
+    np.testing.assert_allclose(loss, d[f"{tag}_loss"], rtol=1e-5)
+    np.testing.assert_allclose(grad, d[f"{tag}_grad"], rtol=1e-4, atol=1e-9)
+
+
+def test_ce_single_and_noignore(golden):
+    d = golden("ce")
+    loss, grad, _ = R.br_xentropy(d["y_pred"][0], d["targets"], ignore_index=21)
+    np.testing.assert_allclose(loss, d["single_loss"], rtol=1e-5)
+    np.testing.assert_allclose(grad, d["single_grad"], rtol=1e-4, atol=1e-9)
+    loss, grad, _ = R.br_xentropy(d["y_pred"], np.minimum(d["targets"], 20), b_reduction="mean", n_exits=3)
+    np.testing.assert_allclose(loss, d["noign_loss"], rtol=1e-5)
+    np.testing.assert_allclose(grad, d["noign_grad"], rtol=1e-4, atol=1e-9)
+
+
+LOV_CASES = {
+    "present": dict(classes="present", ignore=19, n_branches=2),
+    "all": dict(classes="all", ignore=19, n_branches=2),
+    "per_image": dict(classes="present", per_image=True, ignore=19, n_branches=2),
+    "prev_out": dict(classes="present", ignore=19, n_branches=2, prev_out=True),
+    "noignore": dict(classes="present", ignore=None, n_branches=1),
+}
+
+
+@pytest.mark.parametrize("tag", list(LOV_CASES))
+def test_lovasz_vs_reference(golden, tag):
+    d = golden("lovasz")
+    loss, grad, _ = R.br_lovasz(d["y_pred"], d["targets"], **LOV_CASES[tag])
+    np.testing.assert_allclose(loss, d[f"{tag}_loss"], rtol=2e-5)
+    g_ref = d[f"{tag}_grad"]
+    np.testing.assert_allclose(grad[: g_ref.shape[0]], g_ref, rtol=1e-3, atol=1e-7)
+
+
+def test_lovasz_probas_vs_reference(golden):
+    d = golden("lovasz")
+    loss, grad = R.lovasz_softmax(d["probas"], d["targets"], classes="present", ignore=19)
+    np.testing.assert_allclose(loss, d["probas_loss"], rtol=2e-5)
+    np.testing.assert_allclose(grad, d["probas_grad"], rtol=1e-3, atol=1e-7)
+
+
+def test_upsample_vs_reference(golden):
+    d = golden("upsample")
+    np.testing.assert_allclose(R.bilinear_upsample(d["a"], (65, 49)), d["a_up"], atol=3e-6)
+    np.testing.assert_allclose(R.bilinear_upsample(d["b"], (513, 513))[..., ::7, ::5], d["b_up"], atol=2e-5)
+
+
+def test_br_evaluator_vs_reference(golden):
+    d = golden("br_eval")
+    y, tg = d["y"], d["targets"]
+    n_img, E = y.shape[:2]
+    C = y.shape[3]
+    for key in d["configs"]:
+        key = str(key)
+        tau = float(d[f"{key}/t"])
+        size = int(d[f"{key}/pool_size"])
+        mode = "ent" if "_ent" in key else ("max" if "_max" in key else "min")
+        acc = [R.MIoU(C) for _ in range(E + 1)]
+        cnt = [0] * (E + 1)
+        for k in range(n_img):
+            ents = [R.img_norm_entropy(R.softmax_c(y[k, i, 0], 0), C, pool_min=(mode == "min"),
+                                       s=size if mode != "ent" else 1) for i in range(E - 1)]
+            ex = R.first_confident_exit(ents, tau)
+            slot = ex if ex < E - 1 else E - 1  # accumulator[-2] is the final exit
+            acc[slot](y[k, ex], tg[k]); acc[-1](y[k, ex], tg[k])
+            cnt[slot] += 1; cnt[-1] += 1
+        for i in range(E - 1):
+            assert cnt[i] == int(d[f"{key}/b{i+1}_count"]), key
+            a, b = float(acc[i].compute()), float(d[f"{key}/b{i+1}_mIoU"])
+            assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, abs=1e-6), key
+        assert cnt[-2] == int(d[f"{key}/count_out"]) and cnt[-1] == int(d[f"{key}/out_gl"])
+        a, b = float(acc[-1].compute()), float(d[f"{key}/mIoU_gl"])
+        assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, abs=1e-6), key
