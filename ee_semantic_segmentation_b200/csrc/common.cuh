@@ -1,0 +1,84 @@
+// Shared helpers for libeeseg_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/eeseg.h"
+
+namespace eeseg {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs (grids are sized in multiples of this)
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return EESEG_ERR_CUDA;
+  }
+  return EESEG_OK;
+}
+
+#define EESEG_REQUIRE(cond, ...)      \
+  do {                                \
+    if (!(cond)) {                    \
+      ::eeseg::set_error(__VA_ARGS__); \
+      return EESEG_ERR_ARG;           \
+    }                                 \
+  } while (0)
+
+#define EESEG_CUDA(call)                                                       \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      ::eeseg::set_error("%s: %s", #call, cudaGetErrorString(e__));            \
+      return EESEG_ERR_CUDA;                                                   \
+    }                                                                          \
+  } while (0)
+
+// ---- typed scalar access ------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) {
+  return __bfloat162float(__ldg(p));
+}
+// streaming (read-once) variants: bypass L1 allocation
+__device__ __forceinline__ float ldf_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldf_stream(const __nv_bfloat16* p) {
+  unsigned short u;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+  return __uint_as_float(((unsigned)u) << 16);
+}
+__device__ __forceinline__ void stf(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) {
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  __stcs(reinterpret_cast<unsigned short*>(p), *reinterpret_cast<unsigned short*>(&b));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace eeseg

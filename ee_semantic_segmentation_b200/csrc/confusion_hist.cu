@@ -1,0 +1,192 @@
+// Confusion-matrix histogram: cm[n][t'][p] (int64) from logits (argmax in-kernel) or a class map.
+// Reference contract: SegMetric._compute_basics (seg_metrics.py:13-28) — see include/eeseg.h.
+//
+// HBM-bound integer work. Layout: logits are NCHW planes, lanes walk consecutive pixels of a plane
+// (coalesced 128 B / 64 B requests), targets are int64 (256 B per warp request). Counters are
+// privatised per warp in shared memory (32-bit), warp-aggregated with match.any so that the
+// blocky label maps of segmentation data do not serialise on one bank, then flushed once per block
+// with 64-bit global atomics.
+#include "common.cuh"
+
+namespace eeseg {
+
+__device__ __forceinline__ void hist_add(unsigned* h, int key) {
+  // key < 0: lane has no pixel. Lanes with equal keys elect one leader that adds the group size.
+  unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0) {
+    int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(h + key, (unsigned)__popc(peers));
+  }
+}
+
+__device__ __forceinline__ void hist_flush(const unsigned* hist, int copies, int bins,
+                                           unsigned long long* cm_n) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+    unsigned long long s = 0;
+    for (int k = 0; k < copies; ++k) s += hist[k * bins + i];
+    if (s) atomicAdd(cm_n + i, s);
+  }
+}
+
+template <typename T, int PIX>
+__global__ void __launch_bounds__(256) cm_from_logits_kernel(const T* __restrict__ logits,
+                                                              const int64_t* __restrict__ targets,
+                                                              int C, int64_t HW, int copies,
+                                                              unsigned long long* __restrict__ cm) {
+  extern __shared__ unsigned hist[];
+  const int bins = (C + 1) * C;
+  for (int i = threadIdx.x; i < copies * bins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  unsigned* h = hist + ((threadIdx.x >> 5) % copies) * bins;
+  const int n = blockIdx.y;
+  const T* base = logits + (int64_t)n * C * HW;
+  const int64_t* tg = targets + (int64_t)n * HW;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * PIX;
+  // all lanes of a warp iterate together (the loop bound is rounded to the warp) for match.any
+  for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x * PIX + (threadIdx.x & ~31); p0 < HW;
+       p0 += step) {
+    float best[PIX];
+    int arg[PIX];
+    int64_t pp[PIX];
+#pragma unroll
+    for (int j = 0; j < PIX; ++j) {
+      pp[j] = p0 + (threadIdx.x & 31) + (int64_t)j * blockDim.x;
+      best[j] = -INFINITY;
+      arg[j] = 0;
+    }
+    int64_t t[PIX];
+#pragma unroll
+    for (int j = 0; j < PIX; ++j) t[j] = pp[j] < HW ? __ldg(tg + pp[j]) : -1;
+#pragma unroll 7
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int j = 0; j < PIX; ++j) {
+        float v = pp[j] < HW ? ldf_stream(base + (int64_t)c * HW + pp[j]) : 0.f;
+        // torch.argmax: first maximal index, NaN counts as the maximum
+        bool take = (v > best[j]) || (v != v && best[j] == best[j]) || (c == 0);
+        if (take) { best[j] = v; arg[j] = c; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PIX; ++j) {
+      int tt = (t[j] >= 0 && t[j] < C) ? (int)t[j] : C;
+      hist_add(h, pp[j] < HW ? tt * C + arg[j] : -1);
+    }
+  }
+  hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
+}
+
+template <typename P, int PIX>
+__global__ void __launch_bounds__(256) cm_from_map_kernel(const P* __restrict__ pred,
+                                                           const int64_t* __restrict__ targets,
+                                                           int C, int64_t HW, int copies,
+                                                           unsigned long long* __restrict__ cm) {
+  extern __shared__ unsigned hist[];
+  const int bins = (C + 1) * C;
+  for (int i = threadIdx.x; i < copies * bins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  unsigned* h = hist + ((threadIdx.x >> 5) % copies) * bins;
+  const int n = blockIdx.y;
+  const P* pr = pred + (int64_t)n * HW;
+  const int64_t* tg = targets + (int64_t)n * HW;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * PIX;
+  for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x * PIX + (threadIdx.x & ~31); p0 < HW;
+       p0 += step) {
+    int64_t t[PIX];
+    int a[PIX];
+#pragma unroll
+    for (int j = 0; j < PIX; ++j) {
+      int64_t pp = p0 + (threadIdx.x & 31) + (int64_t)j * blockDim.x;
+      bool ok = pp < HW;
+      t[j] = ok ? __ldg(tg + pp) : -1;
+      a[j] = ok ? (int)__ldg(pr + pp) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < PIX; ++j) {
+      int key = -1;
+      if (a[j] >= 0 && a[j] < C) {  // a class map value outside [0,C) is not counted
+        int tt = (t[j] >= 0 && t[j] < C) ? (int)t[j] : C;
+        key = tt * C + a[j];
+      }
+      hist_add(h, key);
+    }
+  }
+  hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
+}
+
+// Fallback for very large C (histogram does not fit shared memory): global atomics.
+template <typename T>
+__global__ void cm_from_logits_global_kernel(const T* __restrict__ logits,
+                                             const int64_t* __restrict__ targets, int C,
+                                             int64_t HW, unsigned long long* __restrict__ cm) {
+  const int n = blockIdx.y;
+  const T* base = logits + (int64_t)n * C * HW;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    float best = ldf_stream(base + p);
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+      float v = ldf_stream(base + (int64_t)c * HW + p);
+      if ((v > best) || (v != v && best == best)) { best = v; arg = c; }
+    }
+    int64_t t = targets[(int64_t)n * HW + p];
+    int tt = (t >= 0 && t < C) ? (int)t : C;
+    atomicAdd(cm + ((int64_t)n * (C + 1) + tt) * C + arg, 1ull);
+  }
+}
+
+}  // namespace eeseg
+
+using namespace eeseg;
+
+extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype,
+                                    const int64_t* targets, int N, int C, int64_t HW, int64_t* cm,
+                                    int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EESEG_REQUIRE(pred && targets && cm, "confusion_hist: null pointer");
+  EESEG_REQUIRE(N >= 0 && C >= 1 && HW >= 0, "confusion_hist: bad sizes N=%d C=%d HW=%lld", N, C,
+                (long long)HW);
+  EESEG_REQUIRE(pred_kind >= 0 && pred_kind <= 2, "confusion_hist: pred_kind %d", pred_kind);
+  EESEG_REQUIRE(pred_kind != 1 || C <= 256, "confusion_hist: uint8 map needs C <= 256");
+  const int64_t bins = (int64_t)(C + 1) * C;
+  if (!accumulate) EESEG_CUDA(cudaMemsetAsync(cm, 0, sizeof(int64_t) * bins * (N > 0 ? N : 0), stream));
+  if (N == 0 || HW == 0) return EESEG_OK;
+  auto* cmu = reinterpret_cast<unsigned long long*>(cm);
+  constexpr int kThreads = 256, kPix = 2;
+  const size_t bytes1 = (size_t)bins * sizeof(unsigned);
+  int copies = (int)((48 * 1024) / bytes1);
+  if (copies > kThreads / 32) copies = kThreads / 32;
+  int64_t want = (HW + kThreads * kPix - 1) / (kThreads * kPix);
+  int64_t cap = (kNumSMs * 8 + N - 1) / N;
+  dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)N);
+  if (pred_kind == 0) {
+    EESEG_REQUIRE(dtype == EESEG_F32 || dtype == EESEG_BF16, "confusion_hist: dtype %d", dtype);
+    if (copies == 0) {
+      dim3 g2((unsigned)((HW + 255) / 256 < cap ? (HW + 255) / 256 : cap), (unsigned)N);
+      if (dtype == EESEG_F32)
+        cm_from_logits_global_kernel<float><<<g2, 256, 0, stream>>>((const float*)pred, targets, C, HW, cmu);
+      else
+        cm_from_logits_global_kernel<__nv_bfloat16><<<g2, 256, 0, stream>>>((const __nv_bfloat16*)pred, targets, C, HW, cmu);
+      return check_launch("cm_from_logits_global_kernel");
+    }
+    if (dtype == EESEG_F32)
+      cm_from_logits_kernel<float, kPix><<<grid, kThreads, copies * bytes1, stream>>>(
+          (const float*)pred, targets, C, HW, copies, cmu);
+    else
+      cm_from_logits_kernel<__nv_bfloat16, kPix><<<grid, kThreads, copies * bytes1, stream>>>(
+          (const __nv_bfloat16*)pred, targets, C, HW, copies, cmu);
+    return check_launch("cm_from_logits_kernel");
+  }
+  EESEG_REQUIRE(copies > 0, "confusion_hist: C=%d too large for the class-map path", C);
+  constexpr int kPixMap = 4;
+  want = (HW + kThreads * kPixMap - 1) / (kThreads * kPixMap);
+  grid.x = (unsigned)(want < cap ? want : cap);
+  if (pred_kind == 1)
+    cm_from_map_kernel<uint8_t, kPixMap><<<grid, kThreads, copies * bytes1, stream>>>(
+        (const uint8_t*)pred, targets, C, HW, copies, cmu);
+  else
+    cm_from_map_kernel<int64_t, kPixMap><<<grid, kThreads, copies * bytes1, stream>>>(
+        (const int64_t*)pred, targets, C, HW, copies, cmu);
+  return check_launch("cm_from_map_kernel");
+}

@@ -1,0 +1,478 @@
+// Implicit-GEMM convolution for the exit heads (DeepLabHead / ASPP): tcgen05.mma with the fp32
+// accumulator in TMEM, operands staged by TMA into 128B-swizzled shared memory, BatchNorm folded
+// into a per-channel scale/shift (+ReLU) epilogue. Reference contract: the dense contraction of
+// torchvision DeepLabHead/ASPP/ASPPConv called at from_deepv3_new.py:147,151 — see include/eeseg.h.
+//
+// GEMM view: D[M = output pixels][N = Cout] = sum over taps (r,s) and input channels of
+//            X[n, y + (r-R/2)*dil, x + (s-S/2)*dil, c] * W[co, r, s, c]
+// * A tile (128 x 64 bf16, K-major, SW128): ONE 4-D TMA box {64 ch, BW, BH, 1 image} of the NHWC
+//   activation tensor per (tap, channel block); the tap is a coordinate offset and TMA's
+//   out-of-bounds zero fill IS the padding — no im2col buffer, no halo copies. The tile is a BW x BH
+//   pixel rectangle chosen on the host to minimise the tile count (65x65 maps -> 11x11 = 121 rows).
+// * B tile (BN x 64 bf16, K-major, SW128): 2-D TMA box of the [Cout][R*S*Cin] weight matrix.
+// * Taps that fall entirely into the zero padding for a tile (common for dilation 24/36 on a 65x65
+//   map) are skipped: they contribute exactly 0.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+//   warps 2..5 = epilogue (tcgen05.ld 32x32b, each warp its TMEM lane quadrant; thread = output
+//   pixel, so every thread stores 32 consecutive channels of its NHWC pixel).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace eeseg {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct ConvParams {
+  int N, h, w, Cin, Cout, R, S, dil;
+  int BW, BH, tiles_x, tiles_y;
+  int BN;          // output-channel tile (multiple of 16, <= 256)
+  int stages;
+  int relu;
+  int out_f32;
+  int64_t ldo;     // output pixel stride (elements)
+  int64_t shift_sn;
+  const float* scale;
+  const float* shift;
+  void* out;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (sm_100 format:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) = 2)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__host__ __device__ inline uint32_t tmem_cols_for(int bn) {
+  return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u;
+}
+
+// Which taps touch at least one real pixel for the tile at (y0, x0)? bit (r*S+s).
+__device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x0) {
+  uint32_t m = 0;
+  const int y_hi = min(y0 + p.BH, p.h), x_hi = min(x0 + p.BW, p.w);
+  for (int r = 0; r < p.R; ++r) {
+    const int dy = (r - p.R / 2) * p.dil;
+    if (y_hi - 1 + dy < 0 || y0 + dy >= p.h) continue;
+    for (int s = 0; s < p.S; ++s) {
+      const int dx = (s - p.S / 2) * p.dil;
+      if (x_hi - 1 + dx < 0 || x0 + dx >= p.w) continue;
+      m |= 1u << (r * p.S + s);
+    }
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB][B BN*128 B] | barriers | tmem ptr | scale/shift
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = kBlockM * kBlockK * 2;
+  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_scale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* s_shift = s_scale + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  const int m_tile = blockIdx.x;
+  const int n_img = m_tile / (p.tiles_x * p.tiles_y);
+  const int trem = m_tile % (p.tiles_x * p.tiles_y);
+  const int y0 = (trem / p.tiles_x) * p.BH, x0 = (trem % p.tiles_x) * p.BW;
+  const int n0 = blockIdx.y * p.BN;
+  const uint32_t taps = live_taps(p, y0, x0);
+  const int cblocks = p.Cin / kBlockK;
+  const int num_kb = __popc(taps) * cblocks;
+  const uint32_t ncols = tmem_cols_for(p.BN);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int kb = 0;
+      for (int t = 0; t < p.R * p.S; ++t) {
+        if (!((taps >> t) & 1u)) continue;
+        const int dy = (t / p.S - p.R / 2) * p.dil, dx = (t % p.S - p.S / 2) * p.dil;
+        for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+          const int s = kb % p.stages;
+          const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+          mbar_wait(empty_bar + s, ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
+          tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 + dx, y0 + dy, n_img);
+          tma_load_2d(sb, &tmap_w, full_bar + s, t * p.Cin + cb * kBlockK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                           ((uint32_t)(kBlockM >> 4) << 24);
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(full_bar + s, ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + a_bytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // +32 B per K step inside the 128 B swizzle span (start-address field is in 16 B units)
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    for (int i = et; i < p.BN; i += 128) {
+      s_scale[i] = p.scale[n0 + i];
+      s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int m = q * 32 + lane;
+    const int yy = y0 + m / p.BW, xx = x0 + m % p.BW;
+    const bool live = m < p.BW * p.BH && yy < p.h && xx < p.w;
+    const int64_t pix = ((int64_t)n_img * p.h + yy) * p.w + xx;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (live) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+          f[j] = p.relu ? fmaxf(x, 0.f) : x;
+        }
+        if (p.out_f32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&b0);
+            u.y = *reinterpret_cast<uint32_t*>(&b1);
+            u.z = *reinterpret_cast<uint32_t*>(&b2);
+            u.w = *reinterpret_cast<uint32_t*>(&b3);
+            o[j] = u;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
+                 : "memory");
+  }
+}
+
+// ---- global average pool (ASPPPooling) -----------------------------------------------------------
+__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int64_t hw, int C,
+                                    float* __restrict__ out) {
+  // grid (C/64 chunks, N); block 256 = 8 pixel lanes x 32 channel pairs; coalesced 128 B rows
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  const int pl = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    const __nv_bfloat16* base = x + (int64_t)n * hw * C + c;
+    for (int64_t p = pl; p < hw; p += 8) {
+      __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + p * C);
+      a0 += __low2float(v);
+      a1 += __high2float(v);
+    }
+  }
+  __shared__ float s0[8][32], s1[8][32];
+  s0[pl][threadIdx.x & 31] = a0;
+  s1[pl][threadIdx.x & 31] = a1;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < 8; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
+    out[(int64_t)n * C + c] = t0 / (float)hw;
+    if (c + 1 < C) out[(int64_t)n * C + c + 1] = t1 / (float)hw;
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static void pick_tile(int h, int w, int& BW, int& BH) {
+  int best = 1 << 30;
+  BW = 1; BH = 1;
+  for (int bw = 1; bw <= (w < 128 ? w : 128); ++bw) {
+    int bh = 128 / bw;
+    if (bh > h) bh = h;
+    if (bh < 1) continue;
+    if (bh > 256) bh = 256;
+    const int tiles = ((w + bw - 1) / bw) * ((h + bh - 1) / bh);
+    // fewer tiles first; then wider boxes (longer contiguous TMA rows)
+    if (tiles < best || (tiles == best && bw > BW)) { best = tiles; BW = bw; BH = bh; }
+  }
+}
+
+}  // namespace eeseg
+
+using namespace eeseg;
+
+extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
+                                    const float* shift, int64_t shift_sn, int N, int h, int w, int Cin,
+                                    int Cout, int R, int S, int dilation, int relu, void* out,
+                                    int out_dtype, int64_t ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EESEG_REQUIRE(x && wt && scale && shift && out, "conv_igemm: null pointer");
+  EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_igemm: bad sizes");
+  EESEG_REQUIRE(Cin % kBlockK == 0, "conv_igemm: Cin=%d must be a multiple of 64", Cin);
+  EESEG_REQUIRE(Cout % 16 == 0, "conv_igemm: Cout=%d must be a multiple of 16", Cout);
+  EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32 && (R & 1) && (S & 1), "conv_igemm: odd kernel sizes up to 32 taps");
+  EESEG_REQUIRE(out_dtype == EESEG_BF16 || out_dtype == EESEG_F32, "conv_igemm: out_dtype %d", out_dtype);
+  EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                    (ldo % 8) == 0,
+                "conv_igemm: pointers must be 16-byte aligned and ldo a multiple of 8");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    set_error("conv_igemm: cuTensorMapEncodeTiled unavailable (driver too old?)");
+    return EESEG_ERR_CUDA;
+  }
+  ConvParams p;
+  p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
+  pick_tile(h, w, p.BW, p.BH);
+  p.tiles_x = (w + p.BW - 1) / p.BW;
+  p.tiles_y = (h + p.BH - 1) / p.BH;
+  // output-channel tile: largest multiple of 16 <= 256 dividing Cout
+  int BN = Cout < 256 ? Cout : 256;
+  while (Cout % BN) BN -= 16;
+  p.BN = BN;
+  p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.ldo = ldo; p.shift_sn = shift_sn;
+  p.scale = scale; p.shift = shift; p.out = out;
+  const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
+  const size_t tail_bytes = (2 * kMaxStages + 1) * 8 + 8 + 2 * 256 * 4;
+  int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
+  p.stages = stages;
+  const size_t smem_bytes = 1024 + stages * stage_bytes + tail_bytes;
+
+  CUtensorMap tmx, tmw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)w * Cin * 2, (cuuint64_t)h * w * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
+                        es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_igemm: cuTensorMapEncodeTiled(x) failed: %d", (int)r); return EESEG_ERR_CUDA; }
+  }
+  {
+    const cuuint64_t Kt = (cuuint64_t)R * S * Cin;
+    cuuint64_t dims[2] = {Kt, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {Kt * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tmw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wt), dims, strides, box,
+                        es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_igemm: cuTensorMapEncodeTiled(w) failed: %d", (int)r); return EESEG_ERR_CUDA; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    EESEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(N * p.tiles_x * p.tiles_y), (unsigned)(Cout / BN));
+  conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
+  return check_launch("conv_igemm_kernel");
+}
+
+extern "C" int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out,
+                                         void* stream_) {
+  EESEG_REQUIRE(x && out, "global_avgpool: null pointer");
+  EESEG_REQUIRE(C % 2 == 0, "global_avgpool: C must be even");
+  if (N == 0) return EESEG_OK;
+  dim3 grid((C + 63) / 64, N);
+  avgpool_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, hw, C, out);
+  return check_launch("avgpool_nhwc_kernel");
+}

@@ -1,0 +1,332 @@
+// Exit gate: fused bilinear up-sample + per-pixel softmax + normalised entropy + argmax + threshold,
+// with ordered per-block partial sums for the per-image score, and the per-image exit decision +
+// active-image compaction. Reference contract: from_deepv3_new.py:149-152 (interpolate),
+// eval_br_ent.py:19-36 (img_norm_entropy), eval_br_ent.py:57-64 / ee_dnn_op_ne.py:80-87 (gate).
+//
+// Mapping: one thread per output column X (lanes = consecutive X, so every plane store is a
+// coalesced 128 B / 64 B request), each thread walks a strip of kRowsPerStrip output rows keeping
+// the horizontally interpolated low-res rows (top / bottom) in registers: the four-tap lerp costs
+// 2*C cached loads per low-res row step instead of 4*C per pixel. Low-res logits (<= 1 MB per
+// image) stay L1/L2 resident; HBM traffic is the optional full-res output planes.
+#include "common.cuh"
+
+namespace eeseg {
+
+constexpr int kGateThreads = 128;
+constexpr int kRowsPerStrip = 8;
+
+struct GateParams {
+  const void* in;
+  int64_t in_sn, in_sc, in_sy, in_sx;
+  int N, C, h, w, H, W;
+  int in_kind;  // 0 logits, 1 probabilities
+  float tau;
+  float scale_y, scale_x;
+  void* up;
+  int64_t up_sn;
+  float* ent;
+  uint8_t* amax;
+  uint8_t* mask;
+  double* part_sum;
+  int32_t* part_cnt;
+  int stats;  // any of ent/amax/mask/part_* requested
+};
+
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1,
+                                          float& l0, float& l1) {
+  // ATen area_pixel_compute_source_index(align_corners=False): max(scale*(dst+0.5)-0.5, 0)
+  float src = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)src, in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <typename TI, typename TO, int CMAX, bool INTERP>
+__global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) {
+  const int X = blockIdx.x * kGateThreads + threadIdx.x;
+  const int n = blockIdx.z;
+  const int Y0 = blockIdx.y * kRowsPerStrip;
+  const int Y1 = min(Y0 + kRowsPerStrip, p.H);
+  const bool live = X < p.W;
+  const int C = p.C;
+  const TI* in = reinterpret_cast<const TI*>(p.in) + (int64_t)n * p.in_sn;
+  TO* up = p.up ? reinterpret_cast<TO*>(p.up) + (int64_t)n * p.up_sn : nullptr;
+  const int64_t HW = (int64_t)p.H * p.W;
+  const float inv_lnC = C > 1 ? 1.f / logf((float)C) : 0.f;
+
+  double acc_ent = 0.0;
+  int acc_cnt = 0;
+
+  float top[CMAX], bot[CMAX];
+  int x0 = 0, x1 = 0, cur_y0 = -1, cur_y1 = -1;
+  float lx0 = 1.f, lx1 = 0.f;
+  if (INTERP && live) src_index(X, p.scale_x, p.w, x0, x1, lx0, lx1);
+
+  if (live) {
+    for (int Y = Y0; Y < Y1; ++Y) {
+      float v[CMAX];
+      if (INTERP) {
+        int y0, y1;
+        float ly0, ly1;
+        src_index(Y, p.scale_y, p.h, y0, y1, ly0, ly1);
+        if (y0 != cur_y0 || y1 != cur_y1) {
+          if (y0 == cur_y1 && cur_y1 >= 0) {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) top[c] = bot[c];
+          } else {
+            const TI* r = in + (int64_t)y0 * p.in_sy;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+              if (c < C)
+                top[c] = lx0 * ldf(r + x0 * p.in_sx + c * p.in_sc) +
+                         lx1 * ldf(r + x1 * p.in_sx + c * p.in_sc);
+          }
+          if (y1 == y0) {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) bot[c] = top[c];
+          } else {
+            const TI* r = in + (int64_t)y1 * p.in_sy;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+              if (c < C)
+                bot[c] = lx0 * ldf(r + x0 * p.in_sx + c * p.in_sc) +
+                         lx1 * ldf(r + x1 * p.in_sx + c * p.in_sc);
+          }
+          cur_y0 = y0;
+          cur_y1 = y1;
+        }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) v[c] = ly0 * top[c] + ly1 * bot[c];
+      } else {
+        const TI* r = in + (int64_t)Y * p.in_sy + (int64_t)X * p.in_sx;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) v[c] = ldf_stream(r + c * p.in_sc);
+      }
+      const int64_t pix = (int64_t)Y * p.W + X;
+      if (up) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) stf(up + c * HW + pix, v[c]);
+      }
+      if (p.stats) {
+        float m = v[0];
+        int am = 0;
+#pragma unroll
+        for (int c = 1; c < CMAX; ++c)
+          if (c < C && ((v[c] > m) || (v[c] != v[c] && m == m))) { m = v[c]; am = c; }
+        float hn;
+        if (p.in_kind == 0) {
+          float S = 0.f, T = 0.f;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+              float z = v[c] - m;
+              float e = exp2f(z * 1.4426950408889634f);
+              S += e;
+              T = fmaf(e, z, T);  // e == 0 -> contributes 0 (entr(0) = 0)
+            }
+          hn = (__logf(S) - T / S) * inv_lnC;
+        } else {
+          float S = 0.f;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) S += v[c];
+          float invS = 1.f / S, T = 0.f;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+              float q = v[c] * invS;
+              T -= q > 0.f ? q * __logf(q) : 0.f;
+            }
+          hn = T * inv_lnC;
+        }
+        hn = fmaxf(hn, 0.f) + 0.f * hn;  // clamp tiny negatives, keep NaN
+        if (p.ent) __stcs(p.ent + (int64_t)n * HW + pix, hn);
+        if (p.amax) p.amax[(int64_t)n * HW + pix] = (uint8_t)am;
+        const bool below = hn < p.tau;
+        if (p.mask) p.mask[(int64_t)n * HW + pix] = below ? 1 : 0;
+        acc_ent += (double)hn;
+        acc_cnt += below ? 1 : 0;
+      }
+    }
+  }
+
+  if (p.part_sum || p.part_cnt) {
+    __shared__ double s_sum[kGateThreads / 32];
+    __shared__ int s_cnt[kGateThreads / 32];
+    double ws = warp_sum(acc_ent);
+    int wc = warp_sum(acc_cnt);
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = ws; s_cnt[threadIdx.x >> 5] = wc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      int k = 0;
+      for (int i = 0; i < kGateThreads / 32; ++i) { t += s_sum[i]; k += s_cnt[i]; }
+      const int64_t slot = (int64_t)n * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x;
+      if (p.part_sum) p.part_sum[slot] = t;
+      if (p.part_cnt) p.part_cnt[slot] = k;
+    }
+  }
+}
+
+__global__ void pool_mean_kernel(const float* __restrict__ ent, int H, int W, int s, int mode,
+                                 float* __restrict__ score) {
+  const int n = blockIdx.x;
+  const float* e = ent + (int64_t)n * H * W;
+  const int bh = (H + s - 1) / s, bw = (W + s - 1) / s;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < bh * bw; b += blockDim.x) {
+    const int by = b / bw, bx = b % bw;
+    // skimage pads the end with 0: ragged blocks see zeros (matters for min; entropies are >= 0)
+    const bool ragged = (by + 1) * s > H || (bx + 1) * s > W;
+    float r = mode == 0 ? 0.f : (ragged ? 0.f : INFINITY);
+    bool nan = false;
+    for (int yy = by * s; yy < min((by + 1) * s, H); ++yy)
+      for (int xx = bx * s; xx < min((bx + 1) * s, W); ++xx) {
+        float v = e[(int64_t)yy * W + xx];
+        nan |= (v != v);
+        r = mode == 0 ? fmaxf(r, v) : fminf(r, v);
+      }
+    acc += nan ? (double)NAN : (double)r;
+  }
+  __shared__ double sm[32];
+  double ws = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ws;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+    score[n] = (float)(t / (double)((int64_t)bh * bw));
+  }
+}
+
+__global__ void decide_kernel(const double* __restrict__ part_sum,
+                              const int32_t* __restrict__ part_cnt, int num_partials,
+                              const float* __restrict__ score_in, int N, int64_t HW, float tau,
+                              int less_than, int exit_id, int32_t* __restrict__ exit_idx,
+                              float* __restrict__ score_out, int64_t* __restrict__ exited_px,
+                              int32_t* __restrict__ active_list,
+                              int32_t* __restrict__ active_count) {
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float sc;
+    if (part_sum) {
+      double t = 0.0;
+      for (int k = 0; k < num_partials; ++k) t += part_sum[(int64_t)n * num_partials + k];
+      sc = (float)(t / (double)HW);
+    } else {
+      sc = score_in[n];
+    }
+    if (score_out) score_out[n] = sc;
+    if (exited_px) {
+      int64_t k = 0;
+      if (part_cnt)
+        for (int i = 0; i < num_partials; ++i) k += part_cnt[(int64_t)n * num_partials + i];
+      exited_px[n] = k;
+    }
+    if (exit_idx) {
+      const bool conf = less_than ? (sc < tau) : (sc > tau);
+      if (exit_idx[n] < 0 && conf) exit_idx[n] = exit_id;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && active_list && active_count && exit_idx) {
+    int k = 0;
+    for (int n = 0; n < N; ++n)
+      if (exit_idx[n] < 0) active_list[k++] = n;
+    *active_count = k;
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_gate(const GateParams& p, bool interp, cudaStream_t stream) {
+  dim3 grid((p.W + kGateThreads - 1) / kGateThreads, (p.H + kRowsPerStrip - 1) / kRowsPerStrip, p.N);
+#define EESEG_GATE_CASE(CM)                                                                  \
+  if (p.C <= CM) {                                                                            \
+    if (interp) gate_kernel<TI, TO, CM, true><<<grid, kGateThreads, 0, stream>>>(p);          \
+    else gate_kernel<TI, TO, CM, false><<<grid, kGateThreads, 0, stream>>>(p);                \
+    return check_launch("gate_kernel");                                                       \
+  }
+  EESEG_GATE_CASE(24)
+  EESEG_GATE_CASE(32)
+  EESEG_GATE_CASE(64)
+#undef EESEG_GATE_CASE
+  set_error("exit_gate: C=%d > 64 classes is not supported by this build", p.C);
+  return EESEG_ERR_UNSUPPORTED;
+}
+
+static int dispatch_gate(const GateParams& p, int in_dtype, int up_dtype, cudaStream_t stream) {
+  const bool interp = !(p.h == p.H && p.w == p.W);
+  EESEG_REQUIRE(in_dtype == EESEG_F32 || in_dtype == EESEG_BF16, "exit_gate: in_dtype %d", in_dtype);
+  EESEG_REQUIRE(!p.up || up_dtype == EESEG_F32 || up_dtype == EESEG_BF16, "exit_gate: up_dtype %d", up_dtype);
+  if (in_dtype == EESEG_F32) {
+    if (up_dtype == EESEG_BF16 && p.up) return launch_gate<float, __nv_bfloat16>(p, interp, stream);
+    return launch_gate<float, float>(p, interp, stream);
+  }
+  if (up_dtype == EESEG_BF16 || !p.up) return launch_gate<__nv_bfloat16, __nv_bfloat16>(p, interp, stream);
+  return launch_gate<__nv_bfloat16, float>(p, interp, stream);
+}
+
+}  // namespace eeseg
+
+using namespace eeseg;
+
+extern "C" int eeseg_exit_gate_num_partials(int H, int W) {
+  return ((W + kGateThreads - 1) / kGateThreads) * ((H + kRowsPerStrip - 1) / kRowsPerStrip);
+}
+
+extern "C" int eeseg_exit_gate_pixels(const void* in, int in_dtype, int in_kind, int64_t in_sn,
+                                      int64_t in_sc, int64_t in_sy, int64_t in_sx, int N, int C,
+                                      int h, int w, int H, int W, float tau, void* up_logits,
+                                      int up_dtype, int64_t up_sn, float* ent, uint8_t* amax,
+                                      uint8_t* mask, double* part_sum, int32_t* part_cnt,
+                                      void* stream) {
+  EESEG_REQUIRE(in, "exit_gate: null input");
+  EESEG_REQUIRE(N >= 0 && C >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "exit_gate: bad sizes");
+  EESEG_REQUIRE(N <= 65535, "exit_gate: N=%d > 65535", N);
+  EESEG_REQUIRE(in_kind == 0 || in_kind == 1, "exit_gate: in_kind %d", in_kind);
+  EESEG_REQUIRE(!amax || C <= 256, "exit_gate: uint8 argmax needs C <= 256");
+  if (N == 0) return EESEG_OK;
+  GateParams p;
+  p.in = in; p.in_sn = in_sn; p.in_sc = in_sc; p.in_sy = in_sy; p.in_sx = in_sx;
+  p.N = N; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W; p.in_kind = in_kind; p.tau = tau;
+  p.scale_y = (float)h / (float)H; p.scale_x = (float)w / (float)W;
+  p.up = up_logits; p.up_sn = up_sn; p.ent = ent; p.amax = amax; p.mask = mask;
+  p.part_sum = part_sum; p.part_cnt = part_cnt;
+  p.stats = (ent || amax || mask || part_sum || part_cnt) ? 1 : 0;
+  return dispatch_gate(p, in_dtype, up_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int eeseg_upsample_bilinear(const void* in, int in_dtype, int64_t in_sn, int64_t in_sc,
+                                       int64_t in_sy, int64_t in_sx, int N, int C, int h, int w,
+                                       int H, int W, void* out, int out_dtype, int64_t out_sn,
+                                       void* stream) {
+  EESEG_REQUIRE(out, "upsample: null output");
+  return eeseg_exit_gate_pixels(in, in_dtype, 0, in_sn, in_sc, in_sy, in_sx, N, C, h, w, H, W, 0.f,
+                                out, out_dtype, out_sn, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                stream);
+}
+
+extern "C" int eeseg_entropy_pool_mean(const float* ent, int N, int H, int W, int s, int mode,
+                                       float* score, void* stream) {
+  EESEG_REQUIRE(ent && score, "entropy_pool_mean: null pointer");
+  EESEG_REQUIRE(s >= 1 && (mode == 0 || mode == 1), "entropy_pool_mean: s=%d mode=%d", s, mode);
+  if (N == 0) return EESEG_OK;
+  pool_mean_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(ent, H, W, s, mode, score);
+  return check_launch("pool_mean_kernel");
+}
+
+extern "C" int eeseg_exit_gate_decide(const double* part_sum, const int32_t* part_cnt,
+                                      int num_partials, const float* score_in, int N, int64_t HW,
+                                      float tau, int less_than, int exit_id, int32_t* exit_idx,
+                                      float* score_out, int64_t* exited_px, int32_t* active_list,
+                                      int32_t* active_count, void* stream) {
+  EESEG_REQUIRE(part_sum || score_in, "exit_gate_decide: need part_sum or score_in");
+  if (N == 0) return EESEG_OK;
+  decide_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(part_sum, part_cnt, num_partials, score_in, N,
+                                                      HW, tau, less_than, exit_id, exit_idx,
+                                                      score_out, exited_px, active_list,
+                                                      active_count);
+  return check_launch("decide_kernel");
+}

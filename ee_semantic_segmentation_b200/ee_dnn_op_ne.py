@@ -1,0 +1,137 @@
+"""Drop-in for the reference's ee_dnn_op_ne.py: the entropy early-exit operator
+`eval_ee_deeplabv3` (:40-108) and its small numpy `mIoU` helper (:20-38).
+
+Same constructor / call signature and result keys ('exit', 'n', 'last', 'exit_flops', 'edge_flops',
+'last_flops'). Differences in how the work runs:
+* the gate (softmax -> entropy -> mean -> threshold) is the fused kernel on low-res logits; only the
+  uint8 argmax map is copied to the host;
+* FLOP tables are computed once per input shape on meta tensors and cached, instead of a pthflops
+  trace per section per image (:64-78);
+* `compute_last=False` skips the tail the reference always executes (:91-101) when the image left
+  early — the reference behaviour (`last` always present) stays the default."""
+import numpy as np
+import torch as tch
+
+from . import ops
+from .eval_flops import check_flops
+
+
+class mIoU:
+    def __init__(self, n_classes):
+        self.n_classes = n_classes
+        self.accumulator = np.zeros((2, n_classes), dtype=np.int64)
+
+    def __call__(self, Img, Gt):
+        # inter_i = |gt==i & img==i|, union_i = |gt==i | img==i|  (ee_dnn_op_ne.py:25-33)
+        Img = tch.as_tensor(Img).reshape(1, -1).to(tch.int64)
+        Gt = tch.as_tensor(Gt).reshape(1, -1).to(tch.int64)
+        C = self.n_classes
+        if Img.is_cuda:
+            cm = ops.confusion_hist(Img.clamp(0, C - 1), Gt.to(Img.device), C)[0].cpu().numpy()
+        else:
+            g = np.where((Gt.numpy() >= 0) & (Gt.numpy() < C), Gt.numpy(), C)[0]
+            p = Img.numpy()[0]
+            ok = (p >= 0) & (p < C)
+            cm = np.bincount(g[ok] * C + p[ok], minlength=(C + 1) * C).reshape(C + 1, C)
+        inter = np.diagonal(cm[:C])
+        union = cm[:C].sum(axis=1) + cm.sum(axis=0) - inter
+        self.accumulator[0] += inter
+        self.accumulator[1] += union
+
+    def compute(self):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            cIoU = self.accumulator[0, :] / self.accumulator[1, :]
+        return np.sum(cIoU) / self.n_classes
+
+
+class eval_ee_deeplabv3():
+    def __init__(self, ee_model, metric, th, less_than=True, ignore=[], device=tch.device('cpu'),
+                 compute_last=True):
+        self.model = ee_model
+        self.n = self.model.n_branches
+        self.ignore = ignore
+        self.metric = metric
+        self.less_than = less_than
+        self.threshold = th
+        self.device = device
+        self.last_br = max([i for i in range(self.n) if i not in ignore])
+        self.compute_last = compute_last
+        self._flops = {}
+
+    def _flop_table(self, shape):
+        """(main_flops per section, branch_flops per head incl. classifier) for an input shape."""
+        key = tuple(shape)
+        if key not in self._flops:
+            main, heads = [], []
+            x = tch.empty(1, *shape, device='meta')
+            for i in range(self.n + 1):
+                main.append(check_flops(self.model.base_model[i], x.shape[-2:], x.shape[1], 'meta'))
+                with tch.no_grad():
+                    x = _meta_copy(self.model.base_model[i])(x)
+                head = self.model.branches[i] if i < self.n else self.model.classifier
+                heads.append(check_flops(head, x.shape[-2:], x.shape[1], 'meta'))
+            self._flops[key] = (main, heads)
+        return self._flops[key]
+
+    def _score(self, low, out_hw):
+        l = self.metric
+        if hasattr(l, 'scores'):
+            sc, res = l.scores(low, kind='logits', out_hw=out_hw, layout='NHWC', want_amax=True)
+            return float(sc.item()), res.amax
+        # arbitrary callable on probabilities [C,H,W] (reference protocol)
+        up = ops.upsample_bilinear(low, out_hw, out_dtype=tch.float32, layout='NHWC',
+                                   n_classes=self.model.num_classes)
+        probs = tch.softmax(up, 1).squeeze(0)
+        am = ops.exit_gate(up, None, want_score=False).amax
+        return float(self.metric(probs)), am
+
+    def __call__(self, X):
+        output = dict()
+        inp_shape = X.shape[-2:]
+        main_all, head_all = self._flop_table(X.shape)
+        main_flops, branch_flops = [], []
+        left = False
+        model = self.model
+        X = X.unsqueeze(0)
+        if not X.is_cuda:
+            raise RuntimeError('eval_ee_deeplabv3 needs a CUDA input (no CPU fallback)')
+        with tch.no_grad(), tch.autocast('cuda', dtype=tch.bfloat16):
+            X = X.contiguous(memory_format=tch.channels_last)
+            for i in range(self.n):
+                if left and not self.compute_last:
+                    break
+                main_flops.append(main_all[i])
+                X = model.base_model[i](X)
+                if i not in self.ignore and not left:
+                    low = model._plan(i).run(X)
+                    branch_flops.append(head_all[i])
+                    t, am = self._score(low, inp_shape)
+                    if (t < self.threshold) if self.less_than else (t > self.threshold):
+                        output['exit'] = am.squeeze(0).to(tch.int64).cpu()
+                        output['exit_flops'] = sum(branch_flops) + sum(main_flops)
+                        output['edge_flops'] = output['exit_flops']
+                        output['n'] = i + 1
+                        left = True
+                if not left and i == self.last_br:
+                    output['edge_flops'] = sum(branch_flops) + sum(main_flops)
+            if left and not self.compute_last:
+                return output
+            main_flops.append(main_all[self.n])
+            X = model.base_model[-1](X)
+            main_flops.append(head_all[self.n])
+            low = model._plan(self.n).run(X)
+            am = ops.exit_gate(low, inp_shape, layout='NHWC', n_classes=model.num_classes,
+                               want_score=False).amax
+        Y = am.squeeze(0).to(tch.int64).cpu()
+        output['last'] = Y
+        output['last_flops'] = sum(branch_flops) + sum(main_flops)
+        if not left:
+            output['exit'] = Y
+            output['exit_flops'] = output['last_flops']
+            output['n'] = self.n + 1
+        return output
+
+
+def _meta_copy(module):
+    import copy
+    return copy.deepcopy(module).to('meta').eval()

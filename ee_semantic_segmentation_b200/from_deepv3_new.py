@@ -1,0 +1,259 @@
+"""Drop-in for the reference's from_deepv3_new.py (and, through from_deepv3.py, its v1 twin):
+`my_branch` (:15-39), `get_base_model` (:41-54) and `branchyDeepv3` (:56-155).
+
+Same constructor arguments, attribute names (`base_model`, `branches`, `classifier`, `n_branches`,
+`count_branches`) and state-dict layout as the reference, so its checkpoints load. What differs is
+how the work runs on a B200:
+
+* `forward(X)` in eval mode on CUDA returns the same `[E,N,C,H,W]` fp32 tensor, but each exit's head
+  runs on the eeseg implicit-GEMM kernels (bf16 NHWC, BatchNorm folded; csrc/conv_igemm.cu) and the
+  bilinear up-sampling kernel writes straight into the stacked output (no `unsqueeze`+`cat` copy,
+  from_deepv3_new.py:150-155).
+* `forward_lowres(X)` stops before the up-sampling and feeds the fused exit gate
+  (`ee_semantic_segmentation_b200.ops.exit_gate`), which never materialises full-resolution logits.
+* training mode keeps the PyTorch modules (autograd through cuDNN) and only the loss runs on eeseg
+  kernels; conv dgrad/wgrad kernels are future work.
+
+Branch placement follows from_deepv3_new.py:75-89 literally; FLOPs are counted with
+torch.utils.flop_counter on meta tensors (the reference's `pthflops` is not installed anywhere and
+is unpinned, so placement parity is "unpinned" — pass `sections=[...]` to copy a reference split).
+"""
+import copy
+import os
+import re
+import warnings
+
+import torch as tch
+import torchvision
+from torch import nn
+from torch.nn import functional as F
+from torch.utils.flop_counter import FlopCounterMode
+from torchvision.models.segmentation.deeplabv3 import ASPP, DeepLabHead
+
+from . import ops
+from .head_plan import HeadPlan
+
+
+class my_branch(nn.Sequential):
+    def __init__(self, nin_channels, num_classes, atrous_rates, nout_channels, bottleneck=None, **kwargs):
+        if bottleneck:
+            super().__init__(
+                nn.Conv2d(nin_channels, bottleneck, 1),
+                ASPP(bottleneck, atrous_rates, nout_channels),
+                nn.Conv2d(nout_channels, nout_channels, 3, padding=1, bias=False),
+                nn.BatchNorm2d(nout_channels),
+                nn.ReLU(),
+                nn.Conv2d(nout_channels, num_classes, 1),
+            )
+        else:
+            super().__init__(
+                ASPP(nin_channels, atrous_rates, nout_channels),
+                nn.Conv2d(nout_channels, nout_channels, 3, padding=1, bias=False),
+                nn.BatchNorm2d(nout_channels),
+                nn.ReLU(),
+                nn.Conv2d(nout_channels, num_classes, 1),
+            )
+
+
+def get_base_model(name, model='deeplabv3_resnet101', pretrained=True):
+    """from_deepv3_new.py:41-54: load the pickled whole module at `name`, else build the torchvision
+    model and save it there. Without network access pretrained weights cannot be fetched; the
+    model is then random-initialised (with a warning) instead of failing."""
+    trained_model = None
+    if name is not None and os.path.exists(name):
+        try:
+            trained_model = tch.load(name, weights_only=False)
+        except Exception:
+            trained_model = None
+    if trained_model is None:
+        if not re.search('deeplabv3', model):
+            raise ValueError(f'unsupported base model {model}')
+        ctor = (torchvision.models.segmentation.deeplabv3_resnet50 if re.search('resnet50', model)
+                else torchvision.models.segmentation.deeplabv3_resnet101)
+        if pretrained:
+            try:
+                trained_model = ctor(weights='DEFAULT')
+            except Exception as err:  # no egress in this environment
+                warnings.warn(f'pretrained weights unavailable ({type(err).__name__}); using random init')
+        if trained_model is None:
+            trained_model = ctor(weights=None, weights_backbone=None, num_classes=21, aux_loss=True)
+        if name is not None and not os.path.exists(name):
+            tch.save(trained_model, name)
+    return trained_model
+
+
+def _meta_flops(module, x):
+    was = module.training
+    module.eval()
+    try:
+        with tch.no_grad(), FlopCounterMode(display=False) as fc:
+            y = module(x)
+    finally:
+        module.train(was)
+    return fc.get_total_flops(), y
+
+
+class branchyDeepv3(nn.Module):
+    def __init__(self, base_name, base_type, n, img_dim, count_branches=True, skip=0,
+                 branch_params=None, *, num_classes=21, sections=None, pretrained=True):
+        super().__init__()
+        aux_model = get_base_model(base_name, base_type, pretrained)
+        self.classifier = copy.deepcopy(aux_model.classifier)
+        self.count_branches = count_branches
+        self.num_classes = num_classes
+        if num_classes != self.classifier[-1].out_channels:
+            # the reference hard-codes 21 classes (from_deepv3_new.py:86,131); other label sets get a
+            # fresh final 1x1 classifier
+            self.classifier[-1] = nn.Conv2d(self.classifier[-1].in_channels, num_classes, 1)
+        self._branch_params = branch_params
+
+        modules = self._backbone_units(aux_model.backbone)
+        if sections is None:
+            sections = self._place(aux_model.backbone, n, img_dim, count_branches, skip, branch_params)
+        assert sum(sections) == len(modules), (sections, len(modules))
+        base, branches, pos = [], [], 0
+        for k, ln in enumerate(sections):
+            sec = modules[pos:pos + ln]
+            pos += ln
+            base.append(nn.Sequential(*sec))
+            if k < len(sections) - 1:
+                branches.append(self._gen_branch(self._out_channels(sec), num_classes, branch_params))
+        self.base_model = nn.ModuleList(base)
+        self.branches = nn.ModuleList(branches)
+        self.n_branches = len(self.branches)
+        # __init_branches (from_deepv3_new.py:133-140) is a no-op in the reference (get_layers always
+        # returns []), so the branches keep PyTorch's default initialisation.
+        self._plans = {}
+        self.fast_inference = True
+
+    # ---- construction helpers ---------------------------------------------------------------------
+    @staticmethod
+    def _backbone_units(backbone):
+        """Stem modules (deep-copied like :77-78) followed by every Bottleneck `layerX.Y` (:80-82)."""
+        units, input_layers = [], True
+        for name, mod in list(backbone.named_modules())[1:]:
+            if input_layers and not re.match(r'layer', name):
+                units.append(copy.deepcopy(mod))
+            elif re.match(r'layer[0-9]+.[0-9]+$', name):
+                units.append(mod)
+            else:
+                input_layers = False
+        return units
+
+    @staticmethod
+    def _out_channels(section):
+        for m in reversed(list(nn.Sequential(*section).modules())):
+            if isinstance(m, nn.Conv2d):
+                # last conv of a Bottleneck is conv3 unless a downsample conv follows it in module
+                # order; both have the same out_channels
+                return m.out_channels
+        raise ValueError('section has no convolution')
+
+    @staticmethod
+    def _gen_branch(nin_channels, nout_channels=21, branch_params=None):
+        if isinstance(branch_params, dict) and all(k in branch_params for k in ('nout_channels', 'atrous_rates')):
+            return my_branch(nin_channels=nin_channels, num_classes=nout_channels, **branch_params)
+        return DeepLabHead(nin_channels, nout_channels)
+
+    @classmethod
+    def _place(cls, backbone, n, img_dim, count_branches, skip, branch_params):
+        """The FLOP-quantile walk of from_deepv3_new.py:66-91 on a meta-device copy of the backbone."""
+        meta = copy.deepcopy(backbone).to('meta')
+        units = cls._backbone_units(meta)
+        x0 = tch.empty(1, 3, img_dim, img_dim, device='meta')
+        tot_flops, _ = _meta_flops(meta, x0)
+        flop_pos = tot_flops / (n + 1)
+        sections, meta_sections, meta_branches, cur = [], [], [], []
+        # stem modules never trigger a placement check in the reference (only Bottlenecks do)
+        stem_len = 0
+        for name, _ in list(meta.named_modules())[1:]:
+            if re.match(r'layer', name):
+                break
+            stem_len += 1
+
+        def check_flops(upto):
+            fl, _ = _meta_flops(nn.Sequential(*units[:upto]), x0)
+            if meta_branches and count_branches:
+                t = x0
+                for sec, br in zip(meta_sections, meta_branches):
+                    with tch.no_grad():
+                        t = sec.eval()(t)
+                    bf, _ = _meta_flops(br, t)
+                    fl += bf
+            return fl
+
+        for idx in range(len(units)):
+            cur.append(units[idx])
+            if idx < stem_len:
+                continue
+            nb = len(meta_branches)
+            if n > nb:
+                fl = check_flops(idx + 1)
+                if tot_flops > fl > flop_pos * (nb + (1 + skip)):
+                    sections.append(len(cur))
+                    meta_sections.append(nn.Sequential(*cur))
+                    br = cls._gen_branch(cls._out_channels(cur), 21, branch_params).to('meta')
+                    meta_branches.append(br)
+                    cur = []
+        sections.append(len(cur))
+        return sections
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def _plan(self, i):
+        """Folded-BN kernel plan of head i (i == n_branches -> classifier); rebuilt when parameters
+        change (tracked through their version counters)."""
+        head = self.classifier if i == self.n_branches else self.branches[i]
+        key = tuple((p.data_ptr(), p._version) for p in head.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in head.buffers())
+        ent = self._plans.get(i)
+        if ent is None or ent[0] != key:
+            ent = (key, HeadPlan(head))
+            self._plans[i] = ent
+        return ent[1]
+
+    def _section(self, i, X):
+        return self.base_model[i](X)
+
+    def _forward_torch(self, X):
+        """The reference data flow on PyTorch modules (used for training / autograd)."""
+        outputs = []
+        inp_shape = X.shape[-2:]
+        for i in range(self.n_branches):
+            X = self.base_model[i](X)
+            br = self.branches[i](X)
+            outputs.append(F.interpolate(br, size=inp_shape, mode='bilinear', align_corners=False).unsqueeze(0))
+        y = self.classifier(self.base_model[-1](X))
+        outputs.append(F.interpolate(y, size=inp_shape, mode='bilinear', align_corners=False).unsqueeze(0))
+        return tch.cat(outputs)
+
+    def _use_fast(self, X):
+        return self.fast_inference and X.is_cuda and not self.training and not tch.is_grad_enabled()
+
+    def forward_lowres(self, X, active=None):
+        """Low-resolution logits of every exit: list of E tensors [N,h,w,Cp] (fp32, NHWC, Cp >= C
+        padded to the kernel's column multiple). Inference only."""
+        if not X.is_cuda:
+            raise RuntimeError('branchyDeepv3 fast path needs CUDA tensors (no CPU fallback)')
+        outs = []
+        with tch.no_grad(), tch.autocast('cuda', dtype=tch.bfloat16):
+            X = X.contiguous(memory_format=tch.channels_last)
+            for i in range(self.n_branches):
+                X = self.base_model[i](X)
+                outs.append(self._plan(i).run(X))
+            X = self.base_model[-1](X)
+            outs.append(self._plan(self.n_branches).run(X))
+        return outs
+
+    def forward(self, X):
+        if not self._use_fast(X):
+            if not X.is_cuda:
+                raise RuntimeError('branchyDeepv3 runs on CUDA tensors only (no CPU fallback); '
+                                   'the CPU oracle lives under oracle/')
+            return self._forward_torch(X)
+        H, W = X.shape[-2:]
+        lows = self.forward_lowres(X)
+        N = X.shape[0]
+        out = tch.empty((len(lows), N, self.num_classes, H, W), dtype=tch.float32, device=X.device)
+        for e, lo in enumerate(lows):
+            ops.upsample_bilinear(lo, (H, W), out=out[e], layout='NHWC', n_classes=self.num_classes)
+        return out

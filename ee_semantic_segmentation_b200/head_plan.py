@@ -1,0 +1,124 @@
+"""Inference plan of one DeepLabHead / my_branch exit head on the eeseg kernels.
+
+Takes the torchvision module (parameter container, reference layout `branches.{i}.0.convs.*`),
+folds every BatchNorm into a per-channel scale/shift, converts weights once to bf16 [Cout][R][S][Cin]
+and runs the head as implicit-GEMM launches (csrc/conv_igemm.cu) on NHWC bf16 activations:
+
+    ASPP 1x1 + three atrous 3x3 -> written side by side into one [N,h,w,4*256] buffer (no concat),
+    pooled branch -> global-avg-pool kernel + tiny matvec, folded into the projection as a
+    per-image shift (the broadcast "bilinear" up-sampling of a 1x1 map is a constant),
+    projection 1x1 (K = 4*256) -> 3x3 -> final 1x1 (+bias) to fp32 logits [N,h,w,Cp].
+
+Mirrors torchvision.models.segmentation.deeplabv3.{DeepLabHead,ASPP,ASPPConv,ASPPPooling} as called
+from from_deepv3_new.py:34,131,147,151. Dropout(0.5) in ASPP.project is the identity in eval mode.
+"""
+import os
+
+import torch
+from torch import nn
+from torchvision.models.segmentation.deeplabv3 import ASPP
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _fold_bn(bn):
+    """y = gamma*(x-mean)/sqrt(var+eps)+beta  ->  scale, shift (fp32)."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+def _krsc(conv):
+    """[Cout,Cin,R,S] -> bf16 [Cout,R,S,Cin] contiguous."""
+    return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0):
+    """x bf16 NHWC [N,h,w,Cin]; wt bf16 [Cout,R,S,Cin]; out: tensor view whose data_ptr is the first
+    output channel and whose pixel stride is ldo elements."""
+    N, h, w, Cin = x.shape
+    Cout, R, S, _ = wt.shape
+    with torch.cuda.device(x.device):
+        check(lib().eeseg_conv_igemm_fwd(
+            x.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), shift_sn, N, h, w, Cin,
+            Cout, R, S, dilation, 1 if relu else 0, out.data_ptr(), out_dtype_code, ldo,
+            torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_fwd")
+
+
+class HeadPlan:
+    def __init__(self, head):
+        mods = list(head.children())
+        self.pre = None
+        if isinstance(mods[0], nn.Conv2d):      # my_branch bottleneck 1x1 (+bias, no BN/ReLU)
+            self.pre = mods[0]
+            mods = mods[1:]
+        aspp, conv3, bn3, _relu, last = mods
+        assert isinstance(aspp, ASPP)
+        dev = last.weight.device
+        self.dev = dev
+        self.n_classes = last.out_channels
+        self.mid = aspp.project[0].out_channels
+        self.branches = []
+        for br in list(aspp.convs)[:-1]:
+            conv, bn = br[0], br[1]
+            s, b = _fold_bn(bn)
+            self.branches.append((_krsc(conv), s.contiguous(), b.contiguous(), conv.dilation[0]))
+        pool = aspp.convs[-1]
+        self.pool_w = pool[1].weight.detach().float().flatten(1)           # [mid, Cin]
+        self.pool_s, self.pool_b = _fold_bn(pool[2])
+        nb = len(self.branches)
+        proj = aspp.project[0].weight.detach().float().flatten(1)          # [mid, (nb+1)*mid]
+        self.proj_w = proj[:, :nb * self.mid].contiguous().view(self.mid, 1, 1, nb * self.mid).to(torch.bfloat16)
+        self.proj_pool_w = proj[:, nb * self.mid:].contiguous()             # [mid, mid] fp32
+        self.proj_s, self.proj_b = _fold_bn(aspp.project[1])
+        self.c3_w = _krsc(conv3)
+        self.c3_s, self.c3_b = _fold_bn(bn3)
+        # final classifier: pad Cout to a multiple of 16 for the MMA N dimension
+        C = self.n_classes
+        Cp = (C + 15) // 16 * 16
+        self.Cp = Cp
+        lw = torch.zeros((Cp, 1, 1, last.in_channels), dtype=torch.bfloat16, device=dev)
+        lw[:C] = _krsc(last)
+        self.last_w = lw
+        self.last_s = torch.ones(Cp, dtype=torch.float32, device=dev)
+        lb = torch.zeros(Cp, dtype=torch.float32, device=dev)
+        if last.bias is not None:
+            lb[:C] = last.bias.detach().float()
+        self.last_b = lb
+        if self.pre is not None:
+            self.pre_w = _krsc(self.pre)
+            self.pre_s = torch.ones(self.pre.out_channels, dtype=torch.float32, device=dev)
+            self.pre_b = (self.pre.bias.detach().float() if self.pre.bias is not None
+                          else torch.zeros(self.pre.out_channels, dtype=torch.float32, device=dev))
+
+    def run(self, x):
+        """x: [N,Cin,h,w] (any memory format / float dtype). Returns fp32 NHWC [N,h,w,Cp]."""
+        N, Cin, h, w = x.shape
+        dev = x.device
+        xh = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()       # NHWC bf16 (a view when channels_last)
+        BF, F32 = _lib.BF16, _lib.F32
+        if self.pre is not None:
+            t = torch.empty((N, h, w, self.pre_w.shape[0]), dtype=torch.bfloat16, device=dev)
+            conv_igemm(xh, self.pre_w, self.pre_s, self.pre_b, 1, False, t, BF, t.shape[-1])
+            xh = t
+        nb, mid = len(self.branches), self.mid
+        cat = torch.empty((N, h, w, nb * mid), dtype=torch.bfloat16, device=dev)
+        for k, (wt, s, b, dil) in enumerate(self.branches):
+            conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)
+        # pooled branch: avg-pool -> 1x1 -> BN -> ReLU, then its share of the projection, per image
+        pooled = torch.empty((N, xh.shape[-1]), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().eeseg_global_avgpool_nhwc(xh.data_ptr(), N, h * w, xh.shape[-1], pooled.data_ptr(),
+                                                  torch.cuda.current_stream(dev).cuda_stream),
+                  "eeseg_global_avgpool_nhwc")
+        pv = torch.relu(pooled @ self.pool_w.t() * self.pool_s + self.pool_b)   # [N, mid] (tiny GEMV)
+        pshift = (pv @ self.proj_pool_w.t()) * self.proj_s + self.proj_b         # [N, mid]
+        pshift = pshift.contiguous()
+        y = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
+        conv_igemm(cat, self.proj_w, self.proj_s, pshift, 1, True, y, BF, mid, shift_sn=mid)
+        z = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
+        conv_igemm(y, self.c3_w, self.c3_s, self.c3_b, 1, True, z, BF, mid)
+        out = torch.empty((N, h, w, self.Cp), dtype=torch.float32, device=dev)
+        conv_igemm(z, self.last_w, self.last_s, self.last_b, 1, False, out, F32, self.Cp)
+        return out

@@ -1,0 +1,313 @@
+"""Tensor-level wrappers over the C ABI (include/eeseg.h): argument checks, output allocation and
+autograd glue. torch is used for device memory and streams only; every op here raises on CPU
+tensors — there is no fallback path."""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, check, lib
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"eeseg kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the eeseg kernels have no CPU fallback")
+    return t
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------------------
+# confusion histogram
+# --------------------------------------------------------------------------------------------------
+def confusion_hist(pred, targets, n_classes, out=None, accumulate=False):
+    """pred: logits [N,C,...] (f32/bf16) or class map [N,...] (uint8/int64). targets: anything
+    viewable to [N,-1] (cast to int64 like seg_metrics.py:18). Returns int64 [N, C+1, C]."""
+    _cuda(pred, "pred")
+    C = int(n_classes)
+    N = pred.shape[0]
+    with torch.cuda.device(pred.device):
+        if pred.dtype in (torch.uint8, torch.int64):
+            kind = 1 if pred.dtype == torch.uint8 else 2
+            pr = pred.reshape(N, -1).contiguous()
+            HW = pr.shape[1]
+            dt = 0
+        else:
+            if pred.shape[1] != C:
+                raise ValueError(f"logits have {pred.shape[1]} channels, expected {C}")
+            kind = 0
+            pr = pred.reshape(N, C, -1).contiguous()
+            HW = pr.shape[2]
+            dt = _dt(pr)
+        tg = _cuda(targets, "targets").reshape(N, -1)
+        if tg.dtype != torch.int64:
+            tg = tg.to(torch.int64)
+        tg = tg.contiguous()
+        if tg.shape[1] != HW:
+            raise ValueError(f"targets have {tg.shape[1]} pixels per image, predictions {HW}")
+        if out is None:
+            out = torch.empty((N, C + 1, C), dtype=torch.int64, device=pred.device)
+            accumulate = False
+        check(lib().eeseg_confusion_hist(pr.data_ptr(), kind, dt, tg.data_ptr(), N, C, HW,
+                                         out.data_ptr(), 1 if accumulate else 0, _stream(pred)),
+              "eeseg_confusion_hist")
+    return out
+
+
+def basics_from_cm(cm):
+    """TP/FP/FN [..., C] int64 from cm [..., C+1, C] (void row counts as FP, seg_metrics.py:25-27)."""
+    C = cm.shape[-1]
+    tp = torch.diagonal(cm[..., :C, :], dim1=-2, dim2=-1)
+    fp = cm.sum(dim=-2) - tp
+    fn = cm[..., :C, :].sum(dim=-1) - tp
+    return tp, fp, fn
+
+
+# --------------------------------------------------------------------------------------------------
+# exit gate
+# --------------------------------------------------------------------------------------------------
+class GateResult:
+    __slots__ = ("ent", "amax", "mask", "score", "exited_px", "up_logits", "part_sum", "part_cnt")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def exit_gate(x, out_hw=None, *, layout="NCHW", kind="logits", tau=0.0, n_classes=None,
+              want_ent=False, want_amax=True, want_mask=False, want_score=True,
+              up_out=None, up_dtype=None):
+    """Fused (bilinear up-sample ->) softmax -> normalised entropy -> argmax -> threshold.
+
+    x: [N,C,h,w] (layout 'NCHW') or [N,h,w,Cp] with Cp >= C (layout 'NHWC', pass n_classes).
+    out_hw: (H,W) to interpolate to (align_corners=False); None = same size.
+    up_out: optional preallocated [N,C,H,W] tensor (contiguous C,H,W planes) receiving the
+            up-sampled logits; or up_dtype to allocate one.
+    Returns GateResult; score = per-image mean normalised entropy (img_norm_entropy, s == 1)."""
+    _cuda(x, "x")
+    if layout == "NCHW":
+        N, C, h, w = x.shape
+        sn, sc, sy, sx = x.stride()
+    elif layout == "NHWC":
+        N, h, w, Cp = x.shape
+        C = int(n_classes) if n_classes is not None else Cp
+        sn, sy, sx, sc = x.stride()
+    else:
+        raise ValueError(layout)
+    H, W = (h, w) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    res = GateResult()
+    dev = x.device
+    with torch.cuda.device(dev):
+        npart = lib().eeseg_exit_gate_num_partials(H, W)
+        if up_out is None and up_dtype is not None:
+            up_out = torch.empty((N, C, H, W), dtype=up_dtype, device=dev)
+        up_sn = 0
+        if up_out is not None:
+            if tuple(up_out.shape) != (N, C, H, W) or up_out.stride()[1:] != (H * W, W, 1):
+                raise ValueError("up_out must be [N,C,H,W] with contiguous (C,H,W) planes")
+            up_sn = up_out.stride(0)
+            res.up_logits = up_out
+        if want_ent:
+            res.ent = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+        if want_amax:
+            res.amax = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+        if want_mask:
+            res.mask = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+        if want_score:
+            res.part_sum = torch.empty((N, npart), dtype=torch.float64, device=dev)
+            res.part_cnt = torch.empty((N, npart), dtype=torch.int32, device=dev)
+        check(lib().eeseg_exit_gate_pixels(
+            x.data_ptr(), _dt(x), 0 if kind == "logits" else 1, sn, sc, sy, sx, N, C, h, w, H, W,
+            float(tau), _p(up_out), _dt(up_out) if up_out is not None else 0, up_sn,
+            _p(res.ent), _p(res.amax), _p(res.mask), _p(res.part_sum), _p(res.part_cnt),
+            _stream(x)), "eeseg_exit_gate_pixels")
+        if want_score:
+            res.score = torch.empty((N,), dtype=torch.float32, device=dev)
+            res.exited_px = torch.empty((N,), dtype=torch.int64, device=dev)
+            check(lib().eeseg_exit_gate_decide(
+                res.part_sum.data_ptr(), res.part_cnt.data_ptr(), npart, None, N, H * W, float(tau),
+                1, 0, None, res.score.data_ptr(), res.exited_px.data_ptr(), None, None, _stream(x)),
+                "eeseg_exit_gate_decide")
+    return res
+
+
+def entropy_pool_mean(ent, s, pool_min=False):
+    """ent f32 [N,H,W] -> f32 [N]: mean of the s x s block max (or min) with zero end-padding."""
+    _cuda(ent, "ent")
+    ent = ent.contiguous()
+    N, H, W = ent.shape
+    out = torch.empty((N,), dtype=torch.float32, device=ent.device)
+    with torch.cuda.device(ent.device):
+        check(lib().eeseg_entropy_pool_mean(ent.data_ptr(), N, H, W, int(s), 1 if pool_min else 0,
+                                            out.data_ptr(), _stream(ent)), "eeseg_entropy_pool_mean")
+    return out
+
+
+def gate_decide(score, tau, exit_id, exit_idx, less_than=True, want_active=True):
+    """Per-image decision + compaction on the device. score f32 [N]; exit_idx int32 [N] in/out
+    (-1 = active). Returns (active_list int32 [N], active_count int32 [1]) or (None, None)."""
+    _cuda(score, "score")
+    N = score.shape[0]
+    dev = score.device
+    al = ac = None
+    with torch.cuda.device(dev):
+        if want_active:
+            al = torch.empty((N,), dtype=torch.int32, device=dev)
+            ac = torch.empty((1,), dtype=torch.int32, device=dev)
+        check(lib().eeseg_exit_gate_decide(None, None, 0, score.data_ptr(), N, 1, float(tau),
+                                           1 if less_than else 0, int(exit_id), exit_idx.data_ptr(),
+                                           None, None, _p(al), _p(ac), _stream(score)),
+              "eeseg_exit_gate_decide")
+    return al, ac
+
+
+def upsample_bilinear(x, out_hw, out=None, out_dtype=None, layout="NCHW", n_classes=None):
+    """F.interpolate(x, size=out_hw, mode='bilinear', align_corners=False) into planes [N,C,H,W]."""
+    r = exit_gate(x, out_hw, layout=layout, n_classes=n_classes, want_amax=False, want_score=False,
+                  up_out=out, up_dtype=(out_dtype or (x.dtype if out is None else None)))
+    return r.up_logits
+
+
+# --------------------------------------------------------------------------------------------------
+# multi-exit cross-entropy
+# --------------------------------------------------------------------------------------------------
+class _MultiExitCE(torch.autograd.Function):
+    """per_exit[e] = mean over valid pixels of -log softmax(y[e])[t]. When y needs a gradient the
+    forward kernel also writes d per_exit/dy scaled by `coef` (the d total/d per_exit the caller is
+    about to apply); backward rescales only if the incoming gradient differs (decided on device)."""
+
+    @staticmethod
+    def forward(ctx, y, targets, ignore_index, coef):
+        E, N, C = y.shape[:3]
+        HW = y[0, 0, 0].numel()
+        dev = y.device
+        need_grad = y.requires_grad
+        with torch.cuda.device(dev):
+            per_exit = torch.empty((E,), dtype=torch.float32, device=dev)
+            valid = torch.empty((1,), dtype=torch.int64, device=dev)
+            ws = torch.empty((lib().eeseg_multi_exit_ce_workspace_bytes(E, N, HW),), dtype=torch.uint8, device=dev)
+            dy = torch.empty_like(y) if need_grad else None
+            check(lib().eeseg_multi_exit_ce_fwd(
+                y.data_ptr(), _dt(y), y.stride(0), targets.data_ptr(), E, N, C, HW, int(ignore_index),
+                coef.data_ptr(), per_exit.data_ptr(), valid.data_ptr(), _p(dy), ws.data_ptr(),
+                _stream(y)), "eeseg_multi_exit_ce_fwd")
+        ctx.dy = dy
+        ctx.save_for_backward(coef)
+        ctx.mark_non_differentiable(valid)
+        return per_exit, valid
+
+    @staticmethod
+    def backward(ctx, g, _gv):
+        dy = ctx.dy
+        (coef,) = ctx.saved_tensors
+        if dy is None:
+            return None, None, None, None
+        g = g.contiguous().float()
+        with torch.cuda.device(dy.device):
+            check(lib().eeseg_scale_exits(dy.data_ptr(), _dt(dy), dy.stride(0), dy.shape[0],
+                                          dy[0].numel(), g.data_ptr(), coef.data_ptr(), _stream(dy)),
+                  "eeseg_scale_exits")
+        ctx.dy = None
+        return dy, None, None, None
+
+
+def multi_exit_ce(y, targets, ignore_index=-100, coef=None):
+    """y [E,N,C,*spatial] f32/bf16 CUDA; targets [N,*spatial] int64. Returns (per_exit f32 [E],
+    valid_count int64 [1]). coef f32 [E]: expected upstream gradient per exit (default ones)."""
+    _cuda(y, "y_pred")
+    _cuda(targets, "targets")
+    if y.dim() < 4:
+        raise ValueError("y_pred must be [E,N,C,...]")
+    if not y.is_contiguous():
+        y = y.contiguous()
+    E, N = y.shape[:2]
+    tg = targets.reshape(N, -1)
+    if tg.dtype != torch.int64:
+        tg = tg.to(torch.int64)
+    tg = tg.contiguous()
+    if tg.shape[1] != y[0, 0, 0].numel():
+        raise ValueError(f"targets {tuple(targets.shape)} do not match logits {tuple(y.shape)}")
+    if coef is None:
+        coef = torch.ones((E,), dtype=torch.float32, device=y.device)
+    coef = coef.detach().to(device=y.device, dtype=torch.float32).contiguous()
+    return _MultiExitCE.apply(y, tg, ignore_index, coef)
+
+
+def multi_exit_ce_backward_unfused(y, targets, ignore_index, g, valid):
+    """Second-pass gradient (reads logits again): g[e]/valid * (softmax - onehot)."""
+    E, N, C = y.shape[:3]
+    HW = y[0, 0, 0].numel()
+    dy = torch.empty_like(y)
+    tg = targets.reshape(N, -1).to(torch.int64).contiguous()
+    with torch.cuda.device(y.device):
+        check(lib().eeseg_multi_exit_ce_bwd(y.data_ptr(), _dt(y), y.stride(0), tg.data_ptr(), E, N, C,
+                                            HW, int(ignore_index), g.float().contiguous().data_ptr(),
+                                            valid.data_ptr(), dy.data_ptr(), _stream(y)),
+              "eeseg_multi_exit_ce_bwd")
+    return dy
+
+
+# --------------------------------------------------------------------------------------------------
+# Lovasz-softmax
+# --------------------------------------------------------------------------------------------------
+class _Lovasz(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, labels, has_ignore, ignore, classes_mode, per_image):
+        E, N, C = y.shape[:3]
+        HW = y[0, 0, 0].numel()
+        dev = y.device
+        need_grad = y.requires_grad
+        with torch.cuda.device(dev):
+            per_exit = torch.empty((E,), dtype=torch.float32, device=dev)
+            nbytes = lib().eeseg_lovasz_workspace_bytes(E, N, C, HW)
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            dy = torch.empty_like(y) if need_grad else None
+            check(lib().eeseg_lovasz_fwd_bwd(
+                y.data_ptr(), _dt(y), y.stride(0), labels.data_ptr(), E, N, C, HW, int(has_ignore),
+                int(ignore), int(classes_mode), int(per_image), per_exit.data_ptr(), _p(dy),
+                ws.data_ptr(), nbytes, _stream(y)), "eeseg_lovasz_fwd_bwd")
+        ctx.dy = dy
+        return per_exit
+
+    @staticmethod
+    def backward(ctx, g):
+        dy = ctx.dy
+        if dy is None:
+            return (None,) * 6
+        ctx.dy = None
+        E = dy.shape[0]
+        return dy * g.to(dy.dtype).view(E, *([1] * (dy.dim() - 1))), None, None, None, None, None
+
+
+def lovasz_multi_exit(y, labels, classes="present", per_image=False, ignore=None):
+    """y [E,N,C,H,W] ('probas' — raw logits on the reference path), labels [N,(1,)H,W].
+    Returns per-exit losses f32 [E] (differentiable w.r.t. y)."""
+    _cuda(y, "probas")
+    _cuda(labels, "labels")
+    if classes not in ("present", "all"):
+        raise NotImplementedError("eeseg Lovasz kernel supports classes='present' or 'all'")
+    if not y.is_contiguous():
+        y = y.contiguous()
+    N = y.shape[1]
+    lab = labels.reshape(N, -1)
+    if lab.dtype != torch.int64:
+        lab = lab.to(torch.int64)
+    lab = lab.contiguous()
+    if lab.shape[1] != y[0, 0, 0].numel():
+        raise ValueError(f"labels {tuple(labels.shape)} do not match probas {tuple(y.shape)}")
+    return _Lovasz.apply(y, lab, ignore is not None, 0 if ignore is None else int(ignore),
+                         0 if classes == "present" else 1, bool(per_image))

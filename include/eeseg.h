@@ -1,0 +1,171 @@
+/*
+ * eeseg.h — C ABI of libeeseg_b200.so: the sm_100a kernels behind the early-exit segmentation
+ * hot path of MateusGilbert/ee_semantic_segmentation (BranchyDeepLabV3).
+ *
+ * The reference is 100 % Python/PyTorch and has no FFI of its own; the entry
+ * points below are what a binding for this path would call. Each one names the reference
+ * interface (file:line under /root/reference) whose inner work it replaces. The Python mirror of
+ * the reference API that calls them lives in ee_semantic_segmentation_b200/ (ctypes; see
+ * INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; no allocation inside;
+ *   - all launchers are asynchronous on `stream` (a cudaStream_t passed as void*) and re-entrant;
+ *   - return value: 0 = ok, non-zero = error (EESEG_ERR_*); eeseg_last_error() gives the text for
+ *     the calling thread;
+ *   - logits/probabilities are NCHW planes ("[N][C][HW]") unless a stride is passed explicitly;
+ *     dtype codes: EESEG_F32 / EESEG_BF16;
+ *   - class targets are int64, any value outside [0,C) is "void" (get_seg_datasets.py:79-86 maps
+ *     255 -> C).
+ */
+#ifndef EESEG_H_
+#define EESEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EESEG_ABI_VERSION 1
+
+enum { EESEG_F32 = 0, EESEG_BF16 = 1 };
+enum { EESEG_OK = 0, EESEG_ERR_ARG = 1, EESEG_ERR_CUDA = 2, EESEG_ERR_UNSUPPORTED = 3 };
+
+int eeseg_abi_version(void);
+const char* eeseg_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's
+ * gpu_launches claim) */
+int64_t eeseg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Confusion-matrix histogram.
+ * Replaces SegMetric._compute_basics (seg_metrics.py:13-28) as used by mIoU.forward
+ * (compute_mIoU.py:16-27): cm[n][t'][p] += 1 with p = argmax_c logits (first index on ties),
+ * t' = t if 0 <= t < C else C (void row). TP/FP/FN follow from cm (void rows count as FP).
+ *   pred_kind 0: `pred` = logits [N][C][HW] of `dtype`         (argmax taken in the kernel)
+ *   pred_kind 1: `pred` = uint8  class map [N][HW]
+ *   pred_kind 2: `pred` = int64  class map [N][HW]
+ * cm: int64 [N][C+1][C]; accumulate != 0 adds to the existing content, else cm is overwritten.
+ * ---------------------------------------------------------------------------------------------- */
+int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype, const int64_t* targets,
+                         int N, int C, int64_t HW, int64_t* cm, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exit gate, stage 1 (per pixel).
+ * Replaces, fused: F.interpolate(bilinear, align_corners=False) (from_deepv3_new.py:149,152),
+ * F.softmax(.,1) (eval_br_ent.py:58, ee_dnn_op_ne.py:80), scipy entropy base C
+ * (eval_br_ent.py:29), argmax (ee_dnn_op_ne.py:82,100), and the per-pixel threshold.
+ *
+ *   in:  logits of `in_dtype`, element strides (in_sn, in_sc, in_sy, in_sx), spatial size h x w.
+ *        When (h,w) == (H,W) no interpolation is done (standalone gate on full-res tensors).
+ *   in_kind 0 = logits (softmax inside), 1 = probabilities (re-normalised p/sum p like scipy).
+ *   out (each optional, NULL to skip):
+ *        up_logits  [N][C][H][W] of up_dtype with image stride up_sn elements (C planes of H*W)
+ *        ent        f32 [N][H][W]   normalised entropy  -sum p ln p / ln C
+ *        amax       u8  [N][H][W]   argmax class (first index on ties)
+ *        mask       u8  [N][H][W]   1 where ent < tau
+ *        part_sum   f64 [N][eeseg_exit_gate_num_partials(H,W)]  per-block entropy sums (ordered)
+ *        part_cnt   i32 [N][same]   per-block count of pixels with ent < tau
+ * ---------------------------------------------------------------------------------------------- */
+int eeseg_exit_gate_num_partials(int H, int W);
+int eeseg_exit_gate_pixels(const void* in, int in_dtype, int in_kind,
+                           int64_t in_sn, int64_t in_sc, int64_t in_sy, int64_t in_sx,
+                           int N, int C, int h, int w, int H, int W, float tau,
+                           void* up_logits, int up_dtype, int64_t up_sn,
+                           float* ent, uint8_t* amax, uint8_t* mask,
+                           double* part_sum, int32_t* part_cnt, void* stream);
+
+/* Block max/min pooling of an entropy map followed by the mean: img_norm_entropy with s != 1
+ * (eval_br_ent.py:33-35; skimage block_reduce pads the END of each axis with 0).
+ * ent f32 [N][H][W] -> score f32 [N]. mode 0 = max, 1 = min. */
+int eeseg_entropy_pool_mean(const float* ent, int N, int H, int W, int s, int mode,
+                            float* score, void* stream);
+
+/* Exit gate, stage 2 (per image): the decision rule of br_evaluator (eval_br_ent.py:57-64) and
+ * eval_ee_deeplabv3.__call__ (ee_dnn_op_ne.py:80-87).
+ *   score[n] = sum(part_sum[n][:]) / (H*W)       (or taken from score_in when part_sum == NULL)
+ *   image n leaves at exit `exit_id` iff exit_idx[n] < 0 (still active) and
+ *       less_than ? score < tau : score > tau
+ *   exit_idx  i32 [N]  in/out (-1 = still active)       score_out f32 [N] (optional)
+ *   exited_px i64 [N]  out, sum(part_cnt) (optional)
+ *   active_list i32 [N] + active_count i32 [1]: compacted ascending list of images still active
+ *   after this exit (optional) — the batch the next backbone section has to run. */
+int eeseg_exit_gate_decide(const double* part_sum, const int32_t* part_cnt, int num_partials,
+                           const float* score_in, int N, int64_t HW, float tau, int less_than,
+                           int exit_id, int32_t* exit_idx, float* score_out, int64_t* exited_px,
+                           int32_t* active_list, int32_t* active_count, void* stream);
+
+/* Plain bilinear up-sampling of E stacked low-res logit tensors into [.. ][C][H][W] planes
+ * (the reference's forward return value, from_deepv3_new.py:149-155, without the cat copy). */
+int eeseg_upsample_bilinear(const void* in, int in_dtype,
+                            int64_t in_sn, int64_t in_sc, int64_t in_sy, int64_t in_sx,
+                            int N, int C, int h, int w, int H, int W,
+                            void* out, int out_dtype, int64_t out_sn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-exit pixelwise cross-entropy.
+ * Replaces BrXEntropyLoss.forward / _cross_entropy._compute_loss (my_pixelwise_xentropy.py:11-14,
+ * 30-46): per exit e, L_e = mean over valid pixels of -log softmax(y_e)[t].
+ *   logits [E][N][C][HW] (exit stride exit_stride elements), targets int64 [N][HW]
+ *   coef   f32 [E] (optional): d(total)/dL_e the caller will apply; used only for dlogits
+ *   per_exit f32 [E] out; valid_count i64 [1] out
+ *   dlogits (optional, same dtype/layout as logits): coef[e]/valid * (softmax - onehot), 0 at void
+ *   workspace: eeseg_multi_exit_ce_workspace_bytes(E,N,HW) bytes of scratch
+ * ---------------------------------------------------------------------------------------------- */
+size_t eeseg_multi_exit_ce_workspace_bytes(int E, int N, int64_t HW);
+int eeseg_multi_exit_ce_fwd(const void* logits, int dtype, int64_t exit_stride,
+                            const int64_t* targets, int E, int N, int C, int64_t HW,
+                            int64_t ignore_index, const float* coef, float* per_exit,
+                            int64_t* valid_count, void* dlogits, void* workspace, void* stream);
+/* Unfused backward (reads logits again): dlogits = g[e]/valid * (softmax - onehot). */
+int eeseg_multi_exit_ce_bwd(const void* logits, int dtype, int64_t exit_stride,
+                            const int64_t* targets, int E, int N, int C, int64_t HW,
+                            int64_t ignore_index, const float* g, const int64_t* valid_count,
+                            void* dlogits, void* stream);
+/* dlogits[e] *= g[e]/coef[e], skipped on the device when every ratio is exactly 1. */
+int eeseg_scale_exits(void* dlogits, int dtype, int64_t exit_stride, int E, int64_t per_exit_elems,
+                      const float* g, const float* coef, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lovasz-softmax (multi-exit).
+ * Replaces lovasz_softmax / lovasz_softmax_flat / flatten_probas / lovasz_grad
+ * (lovaszsoftmax.py:154-219, 19-31) as looped by BSL.LovaszSoftmax.forward
+ * (branchy_seg_losses.py:151-159).
+ *   probas [E][N][C][HW] (raw logits on the reference path), labels int64 [N][HW]
+ *   ignore: label value to drop (has_ignore != 0), classes_mode 0 = 'present', 1 = 'all'
+ *   per_image != 0: loss per image then mean over images
+ *   per_exit f32 [E] out
+ *   dprobas (optional): d per_exit[e] / d probas[e]  (caller scales by its weights)
+ * ---------------------------------------------------------------------------------------------- */
+size_t eeseg_lovasz_workspace_bytes(int E, int N, int C, int64_t HW);
+int eeseg_lovasz_fwd_bwd(const void* probas, int dtype, int64_t exit_stride, const int64_t* labels,
+                         int E, int N, int C, int64_t HW, int has_ignore, int64_t ignore,
+                         int classes_mode, int per_image, float* per_exit, void* dprobas,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution (tcgen05 / TMEM / TMA), inference form with folded BatchNorm.
+ * Replaces the dense contraction of torchvision DeepLabHead / ASPP / ASPPConv as called from
+ * from_deepv3_new.py:34,131,147,151 (branches[i](X), classifier(X)).
+ *   x   bf16 NHWC [N][h][w][Cin]           (Cin % 64 == 0)
+ *   wt  bf16 [Cout][R][S][Cin]             (Cout % 16 == 0, <= 256 per launch column block)
+ *   y = act( scale[co] * conv(x, wt; dilation, padding = dilation*(R-1)/2) + shift[n?][co] )
+ *   shift_sn: image stride of `shift` in elements (0 = shared by all images)
+ *   out NHWC with pixel stride ldo elements, written at channel offset already applied to `out`
+ *   out_dtype EESEG_BF16 or EESEG_F32; relu != 0 applies max(.,0)
+ * ---------------------------------------------------------------------------------------------- */
+int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, const float* shift,
+                         int64_t shift_sn, int N, int h, int w, int Cin, int Cout, int R, int S,
+                         int dilation, int relu, void* out, int out_dtype, int64_t ldo,
+                         void* stream);
+
+/* Global average pool of an NHWC bf16 tensor: [N][h][w][C] -> f32 [N][C] (ASPPPooling's
+ * AdaptiveAvgPool2d(1), torchvision deeplabv3.py:70-83). */
+int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EESEG_H_ */

