@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the early-exit segmentation hot path (BASELINE.json metric: early-exit images/sec at
+513x513).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl eeseg|reference]
+
+Workload (config.workload): BranchyDeepLabV3 ResNet-50, 3 exits (heads on 1024/2048/2048 channels),
+entropy-threshold early-exit inference in bf16 on synthetic VOC-shaped 513x513 images, 4 images per
+GPU (global batch 32 on 8 GPUs -> weak scaling). A step = one batch through
+EarlyExitEngine.evaluate: backbone sections, tcgen05 exit heads, fused up-sample/softmax/entropy/
+argmax gate, per-image exit decision, confusion histogram of the exit taken.
+
+One JSON line on stdout (rank 0): value = images/s with inputs resident in HBM; e2e = the same step
+from pinned HOST buffers with H2D of images+targets and D2H of the per-image results inside the
+timed region; roofline = the implicit-GEMM conv kernel (dominant) against the measured bf16 peak;
+cpu_baseline = the oracle port of the reference's CPU path on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SECTIONS = [16, 3, 1]      # SURVEY.md §3.1 probe: n=2 -> heads on Cin = 1024, 2048
+N_CLASSES = 21
+IMG = 513
+PER_GPU_BATCH = 4
+TAU = 0.5
+
+
+def synth_batch(rank, n, img=IMG, n_classes=N_CLASSES):
+    """seed 1234+rank, randn images, blocky labels at 1/16 resolution, 5 % void."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1234 + rank)
+    X = torch.randn(n, 3, img, img, generator=g)
+    low = torch.randint(0, n_classes, (n, 1, (img + 15) // 16, (img + 15) // 16), generator=g)
+    y = F.interpolate(low.float(), size=(img, img), mode="nearest").long()
+    void = torch.rand(n, 1, img, img, generator=g) < 0.05
+    y = torch.where(void, torch.full_like(y, n_classes), y)
+    return X, y
+
+
+def head_flops(h, w, n, cins, n_classes=N_CLASSES):
+    """Nominal dense FLOPs (2*M*N*K, no discount for taps in the zero padding) of the implicit-GEMM
+    launches of one step: per head 1x1 + 3 atrous 3x3 (Cin->256), projection (4*256->256, the pooled
+    branch enters as a shift), 3x3 256->256, final 1x1 256->Cpad."""
+    M = n * h * w
+    cp = (n_classes + 15) // 16 * 16
+    tot = 0
+    for cin in cins:
+        tot += 2 * M * 256 * cin * (1 + 3 * 9)
+        tot += 2 * M * 256 * (4 * 256)
+        tot += 2 * M * 256 * (9 * 256)
+        tot += 2 * M * cp * 256
+    return tot
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="eeseg_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_images=2):
+    """The reference's CPU path (oracle port: torchvision fp32 model + numpy/scipy-style entropy gate
+    + confusion matrix), all host threads, on `sample_images` images per step."""
+    import torch
+    from oracle import model_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = model_port.build_port(SECTIONS, seed=0).eval()
+    X, y = synth_batch(0, sample_images)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        model_port.evaluate_batch_cpu(net, X, y, N_CLASSES, TAU)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return {"value": sample_images / mean, "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port", "ms_per_step": mean * 1e3,
+            "sample": f"{sample_images} images of 513x513 per step x {steps} steps (+{warmup} warm-up), "
+                      f"fp32, 3 exits, oracle/model_port.evaluate_batch_cpu"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    cb = cpu_reference_run(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "early_exit_images_per_sec_513", "value": cb["value"], "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "BranchyDeepLabV3 ResNet-50, 3 exits (sections 16/3/1, heads Cin 1024/2048/2048), "
+                        "entropy-threshold early-exit inference, synthetic VOC 21-class 513x513",
+            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "tau": TAU,
+            "parallelism": f"dp{n_gpus}", "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="eeseg", choices=["eeseg", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ee_semantic_segmentation_b200 import _lib, head_plan
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the eeseg kernels have no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    steps = args.steps
+
+    torch.manual_seed(0)
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, IMG, sections=SECTIONS, pretrained=False).to(dev).eval()
+    eng = EarlyExitEngine(net, N_CLASSES, TAU)
+    Xh, yh = synth_batch(rank, PER_GPU_BATCH)
+    Xh, yh = Xh.pin_memory(), yh.pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """k steps, each bracketed by CUDA events on the launching (current) stream, L2 flushed
+        between steps; returns (sum of step ms, wall ms incl. flushes)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        if world > 1:
+            eng.all_reduce()           # the sweep's one integer collective (once, not per step)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return sum(a.elapsed_time(b) for a, b in ev), wall
+
+    def step_device():
+        eng.evaluate(Xd, yd)
+
+    def step_e2e():
+        X = Xh.to(dev, non_blocking=True)
+        y = yh.to(dev, non_blocking=True)
+        out = eng.evaluate(X, y)
+        return out["exit"].cpu(), out["scores"].cpu()    # D2H of the per-image results (syncs)
+
+    for _ in range(warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    dev_ms, wall_ms = timed(step_device, steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, steps)
+
+    # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
+    prof = []
+    head_plan.PROFILE = prof
+    barrier()
+    for _ in range(steps):
+        flush.fill_(1)
+        step_device()
+    torch.cuda.synchronize()
+    head_plan.PROFILE = None
+    conv_ms = sum(a.elapsed_time(b) for a, b in prof)
+    n_conv = len(prof)
+
+    t = torch.tensor([dev_ms, e2e_ms, conv_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, conv_ms = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        imgs = PER_GPU_BATCH * world * steps
+        h = (IMG - 1) // 8 + 1
+        fl = head_flops(h, h, PER_GPU_BATCH, [1024, 2048, 2048]) * steps
+        achieved = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        res = eng.results()
+        line = {
+            "metric": "early_exit_images_per_sec_513", "value": imgs / (dev_ms * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 8,
+                    "d2h_bytes_per_step": PER_GPU_BATCH * 4 + 2 * PER_GPU_BATCH * 4, "ms_per_step": e2e_ms / steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, 21 launches/step)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "launches_timed": n_conv, "conv_ms_per_step": conv_ms / steps,
+                         "conv_share_of_step": conv_ms / dev_ms if dev_ms else None,
+                         "flops_per_step": fl / steps},
+            "clocks": clocks,
+            "wall_ms_timed_region": wall_ms,
+            "exit_stats": {k: res[k] for k in ("b1_count", "b2_count", "count_out", "out_gl")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_reference_run(steps=3, warmup=1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -38,9 +38,11 @@ class mIoU(SegMetric):
         self.cm = cm.clone() if self.cm is None else self.cm + cm.to(self.cm.device)
 
     def compute(self):
+        # the [3,C] float32 accumulator is brought to the host first so the few-element reduction
+        # is the same arithmetic, in the same order, as the reference's CPU run
+        self.accumulator = self.accumulator.cpu()
         den = self.accumulator.sum(dim=0)
         cIoU = tch.div(self.accumulator[0], den)
-        self.accumulator = self.accumulator.cpu()
         cIoU[cIoU == float('nan')] = 1.   # never matches (compute_mIoU.py:35): absent class -> NaN
         return (cIoU.sum() / self.C).cpu()
 

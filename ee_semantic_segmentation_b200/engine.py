@@ -1,0 +1,136 @@
+"""Batched early-exit inference / evaluation engine — the public entry point the benchmark times.
+
+It performs, for a whole batch on the device, what the reference does one image at a time in
+`br_evaluator` (eval_br_ent.py:51-70) and `eval_ee_deeplabv3.__call__` (ee_dnn_op_ne.py:51-108):
+
+    sections -> exit head -> (fused up-sample + softmax + entropy + argmax) -> per-image decision
+
+with the per-image rule of the reference (first early exit i >= skip whose mean normalised entropy
+is < tau, else the final exit), plus the integer confusion matrices of the exit taken. Nothing but
+the small per-image results ever leaves the device, and full-resolution logits are never written.
+
+`skip_compute=True` adds what the reference only accounts for (it always runs the tail,
+ee_dnn_op_ne.py:91-101): after each gate the still-active images are compacted (device-side list
+from `eeseg_exit_gate_decide`) and only they run through the next backbone section.
+"""
+import torch
+
+from . import ops
+
+
+class EarlyExitEngine:
+    def __init__(self, net, n_classes, tau, metric='ent', size=1, skip=0, skip_compute=False):
+        self.net = net
+        self.C = n_classes
+        self.tau = float(tau)
+        self.metric = metric.lower()
+        assert self.metric in ('ent', 'max', 'min')
+        self.size = size if self.metric != 'ent' else 1
+        self.skip = skip
+        self.skip_compute = skip_compute
+        self.E = net.n_branches + 1
+        dev = next(net.parameters()).device
+        self.device = dev
+        # [E+1, C+1, C]: one matrix per exit, last = global (exit actually taken)
+        self.cm = torch.zeros((self.E + 1, n_classes + 1, n_classes), dtype=torch.int64, device=dev)
+        self.counts = torch.zeros((self.E + 1,), dtype=torch.int64, device=dev)
+        self.exited_px = torch.zeros((self.E,), dtype=torch.int64, device=dev)
+
+    def reset(self):
+        self.cm.zero_(); self.counts.zero_(); self.exited_px.zero_()
+
+    # ------------------------------------------------------------------------------------------
+    def _gate(self, low, out_hw, want_score):
+        pool = self.metric != 'ent'
+        res = ops.exit_gate(low, out_hw, layout='NHWC', n_classes=self.C, tau=self.tau,
+                            want_ent=pool and want_score, want_amax=True,
+                            want_score=want_score and not pool)
+        if pool and want_score:
+            res.score = ops.entropy_pool_mean(res.ent, self.size, self.metric == 'min')
+        return res
+
+    @torch.no_grad()
+    def infer(self, X):
+        """X [N,3,H,W] on the device. Returns dict: 'exit' int32 [N] (0-based exit taken),
+        'pred' uint8 [N,H,W] (argmax map of that exit), 'scores' f32 [E-1,N]."""
+        net = self.net
+        N, _, H, W = X.shape
+        dev = X.device
+        exit_idx = torch.full((N,), -1, dtype=torch.int32, device=dev)
+        pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+        scores = torch.full((max(self.E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)
+        active = None   # index tensor of images still in flight (skip_compute only)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            Xc = X.contiguous(memory_format=torch.channels_last)
+            for i in range(self.E):
+                Xc = net.base_model[i](Xc)
+                low = net._plan(i).run(Xc)
+                last = i == self.E - 1
+                res = self._gate(low, (H, W), want_score=not last and i >= self.skip)
+                idx = active if active is not None else slice(None)
+                if last:
+                    still = exit_idx[idx] < 0
+                    sel = still.view(-1, 1, 1)
+                    pred[idx] = torch.where(sel, res.amax, pred[idx])
+                    exit_idx[idx] = torch.where(still, torch.full_like(exit_idx[idx], i), exit_idx[idx])
+                    break
+                if i >= self.skip:
+                    scores[i, idx] = res.score
+                    sub = exit_idx[idx].contiguous()
+                    before = sub < 0
+                    al, ac = ops.gate_decide(res.score, self.tau, i, sub, want_active=self.skip_compute)
+                    took = before & (sub == i)
+                    pred[idx] = torch.where(took.view(-1, 1, 1), res.amax, pred[idx])
+                    exit_idx[idx] = sub
+                    self.exited_px[i] += res.exited_px.sum() if res.exited_px is not None else 0
+                    if self.skip_compute:
+                        k = int(ac.item())              # one 4-byte D2H per exit
+                        if k == 0:
+                            break
+                        if k < Xc.shape[0]:
+                            keep = al[:k].long()
+                            Xc = Xc[keep]
+                            active = keep if active is None else active[keep]
+        return {'exit': exit_idx, 'pred': pred, 'scores': scores}
+
+    @torch.no_grad()
+    def evaluate(self, X, y):
+        """infer + integer confusion matrices of the exit taken: accumulates self.cm[e] for the exit
+        each image left at and self.cm[-1] globally (the accumulators of eval_br_ent.py:39,61-69)."""
+        out = self.infer(X)
+        cm = ops.confusion_hist(out['pred'], y, self.C)                  # [N, C+1, C]
+        ex = out['exit'].long()
+        self.cm.index_add_(0, ex, cm)
+        self.cm[-1] += cm.sum(dim=0)
+        self.counts.index_add_(0, ex, torch.ones_like(ex))
+        self.counts[-1] += ex.numel()
+        return out
+
+    def all_reduce(self):
+        """Sum the integer accumulators over ranks (NCCL): exact, order-independent."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.cm)
+            dist.all_reduce(self.counts)
+            dist.all_reduce(self.exited_px)
+
+    def results(self):
+        """Result dict with the reference's keys (eval_br_ent.py:72-84); mIoU from exact counts."""
+        cm = self.cm.cpu()
+        counts = self.counts.cpu()
+
+        def miou(m):
+            tp, fp, fn = ops.basics_from_cm(m)
+            return float(((tp.double() / (tp + fp + fn).double()).sum() / self.C))
+        res = {}
+        for i in range(self.E - 1):
+            res[f'b{i+1}_mIoU'] = miou(cm[i])
+            res[f'b{i+1}_count'] = int(counts[i])
+        res['mIoU_out'] = miou(cm[self.E - 1])
+        res['count_out'] = int(counts[self.E - 1])
+        res['mIoU_gl'] = miou(cm[-1])
+        res['out_gl'] = int(counts[-1])
+        res['t'] = self.tau
+        res['pool'] = self.metric
+        res['pool_size'] = self.size
+        return res

@@ -34,16 +34,25 @@ def _krsc(conv):
     return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
 
 
+PROFILE = None   # bench.py sets this to a list to collect (start, end) CUDA events per conv launch
+
+
 def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0):
     """x bf16 NHWC [N,h,w,Cin]; wt bf16 [Cout,R,S,Cin]; out: tensor view whose data_ptr is the first
     output channel and whose pixel stride is ldo elements."""
     N, h, w, Cin = x.shape
     Cout, R, S, _ = wt.shape
     with torch.cuda.device(x.device):
+        if PROFILE is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         check(lib().eeseg_conv_igemm_fwd(
             x.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), shift_sn, N, h, w, Cin,
             Cout, R, S, dilation, 1 if relu else 0, out.data_ptr(), out_dtype_code, ldo,
             torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_fwd")
+        if PROFILE is not None:
+            b.record()
+            PROFILE.append((a, b))
 
 
 class HeadPlan:

@@ -27,7 +27,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from oracle import ref_import
+from oracle import model_port, ref_import
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -196,8 +196,8 @@ def main():
     x = torch.randn(2, 3, 65, 65, generator=g)
     md["x"] = x.numpy()
     for n in (1, 2):
-        torch.manual_seed(100 + n)  # branch init comes from the global RNG inside the ctor
         net = fd_new.branchyDeepv3(base_path, "deeplabv3_resnet50", n, 513)
+        model_port.reinit_branches(net.branches, 100 + n)  # see model_port.reinit_branches
         net.eval()
         with torch.no_grad():
             y = net(x)

@@ -1,0 +1,143 @@
+"""End-to-end parity on the GPU: the product model / evaluators / engine against the CPU oracle port
+(oracle/model_port.py, itself pinned to the reference by tests/golden/model.npz) and against the
+reference's br_evaluator fixture (tests/golden/br_eval.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_port
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def nets():
+    sections = [16, 3, 1]
+    port = model_port.build_port(sections, seed=0, branch_seed=7).eval()
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=sections, pretrained=False)
+    net.load_state_dict(port.state_dict())
+    return port, net.to(dev()).eval()
+
+
+def test_forward_logits_vs_oracle_port(nets):
+    port, net = nets
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 129, 129, generator=g)
+    with torch.no_grad():
+        ref = port(x)                       # fp32 CPU, reference data flow
+        got = net(x.to(dev()))
+    assert got.shape == ref.shape == (3, 2, 21, 129, 129) and got.dtype == torch.float32
+    for e in range(3):
+        rel = (got[e].cpu() - ref[e]).abs().max().item() / ref[e].abs().max().item()
+        assert rel < 3e-2, (e, rel)         # bf16 end to end (53 conv layers): ~1e-2 of the logit range
+    # fp32 PyTorch-module path of the same model object (training path) agrees to fp32 accuracy
+    net.fast_inference = False
+    with torch.no_grad():
+        got32 = net(x.to(dev()))
+    net.fast_inference = True
+    assert (got32.cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_golden_forward_slice(golden):
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    d = golden("model")
+    sections = [int(s) for s in d["n2_sections"]]
+    port = model_port.build_port(sections, seed=0, branch_seed=102)
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=sections, pretrained=False)
+    net.load_state_dict(port.state_dict())
+    net = net.to(dev()).eval()
+    with torch.no_grad():
+        y = net(torch.tensor(d["x"]).to(dev()))
+    ref = d["n2_out_slice"]
+    got = y[..., ::8, ::8].cpu().numpy()
+    for e in range(ref.shape[0]):
+        assert np.abs(got[e] - ref[e]).max() < 3e-2 * np.abs(ref[e]).max()
+
+
+def test_engine_decisions_and_confusion_vs_oracle(nets):
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine
+    port, net = nets
+    g = torch.Generator().manual_seed(22)
+    N = 3
+    x = torch.randn(N, 3, 97, 113, generator=g)
+    y = torch.randint(0, 22, (N, 1, 97, 113), generator=g)
+    with torch.no_grad():
+        logits = port(x)
+    ents = np.array([[R.img_norm_entropy(R.softmax_c(logits[i, k].numpy(), 0), 21) for k in range(N)] for i in range(2)])
+    tau = float(np.median(ents))            # some images leave early, some do not
+    for skip_compute in (False, True):
+        eng = EarlyExitEngine(net, 21, tau, skip_compute=skip_compute)
+        out = eng.evaluate(x.to(dev()), y.to(dev()))
+        sc = out["scores"].cpu().numpy()
+        exits = out["exit"].cpu().numpy()
+        for k in range(N):
+            # decisions identical except within 1e-4 of the threshold; bf16 logits move the mean
+            # entropy by O(1e-3), so the comparison uses the engine's own scores for the rule and the
+            # oracle's for the value
+            rule = R.first_confident_exit([sc[0, k], sc[1, k]] if not skip_compute else
+                                          [s for s in (sc[0, k], sc[1, k])], tau)
+            assert exits[k] == rule
+            assert abs(sc[0, k] - ents[0, k]) < 5e-3
+        # confusion matrix of the exit taken == oracle confusion of the engine's own prediction map
+        pred = out["pred"].cpu().numpy().reshape(N, -1)
+        cm_ref = R.confusion_matrix(pred, y.numpy().reshape(N, -1), 21)
+        np.testing.assert_array_equal(eng.cm[-1].cpu().numpy(), cm_ref.sum(0))
+        assert int(eng.counts[-1]) == N and int(eng.counts[:3].sum()) == N
+        r = eng.results()
+        assert r["out_gl"] == N and set(r) >= {"b1_mIoU", "b1_count", "b2_mIoU", "mIoU_out", "mIoU_gl", "t", "pool", "pool_size"}
+
+
+def test_br_evaluator_golden(golden):
+    """The reference's br_evaluator result dicts (fake 3-exit net, several tau / pool modes)."""
+    from ee_semantic_segmentation_b200.eval_br_ent import br_evaluator
+    d = golden("br_eval")
+    ys, tg = torch.tensor(d["y"]), torch.tensor(d["targets"])
+    n_img, E, _, C, H, W = ys.shape
+
+    class FakeNet:
+        def __init__(self): self.k = 0
+        def __call__(self, X):
+            out = ys[self.k].to(dev()); self.k += 1
+            return out
+    loader = [(torch.zeros(1, 3, H, W), tg[k]) for k in range(n_img)]
+    for key in d["configs"]:
+        key = str(key)
+        tau, size = float(d[f"{key}/t"]), int(d[f"{key}/pool_size"])
+        metric = "ent" if "_ent" in key else ("max" if "_max" in key else "min")
+        res = br_evaluator(FakeNet(), E, C, loader, dev(), tau, metric=metric, size=size)
+        for k, v in res.items():
+            if k == "pool":
+                continue
+            ref = float(d[f"{key}/{k}"])
+            assert (np.isnan(v) and np.isnan(ref)) or v == pytest.approx(ref, abs=1e-6), (key, k, v, ref)
+
+
+def test_mIoU_evaluator_and_operator(nets):
+    from ee_semantic_segmentation_b200.ee_dnn_op_ne import eval_ee_deeplabv3
+    from ee_semantic_segmentation_b200.eval_br_ent import img_norm_entropy
+    from ee_semantic_segmentation_b200.eval_mIoU import mIoU_evaluator
+    port, net = nets
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(2, 3, 65, 81, generator=g)
+    y = torch.randint(0, 22, (2, 1, 65, 81), generator=g)
+    res = mIoU_evaluator(net, 3, 21, [(x, y)], dev())
+    assert set(res) == {"b1_mIoU", "b2_mIoU", "mIoU"}
+    # exact integer path == oracle on the model's own argmax
+    with torch.no_grad():
+        logits = net(x.to(dev()))
+    mo = R.MIoU(21); mo(logits[-1].cpu().numpy(), y.numpy())
+    a, b = res["mIoU"], float(mo.compute())
+    assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 5e-3
+    op = eval_ee_deeplabv3(net, img_norm_entropy(21), 2.0, device=dev())     # tau=2: leaves at exit 1
+    out = op(x[0].to(dev()))
+    assert out["n"] == 1 and out["exit"].shape == (65, 81) and out["exit"].dtype == torch.int64
+    assert out["exit_flops"] < out["last_flops"] and out["edge_flops"] == out["exit_flops"]
+    op = eval_ee_deeplabv3(net, img_norm_entropy(21), -1.0, device=dev())    # never confident
+    out = op(x[0].to(dev()))
+    assert out["n"] == 3 and torch.equal(out["exit"], out["last"])

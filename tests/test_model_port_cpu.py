@@ -1,0 +1,36 @@
+"""Pins oracle/model_port.py (the CPU port used as model oracle and CPU baseline) against outputs of
+the unmodified reference model captured in tests/golden/model.npz, and checks the product model's
+host logic (placement, state-dict layout) on CPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_port
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_port_matches_reference_forward(golden, n):
+    d = golden("model")
+    sections = [int(s) for s in d[f"n{n}_sections"]]
+    # make_golden.py: base under manual_seed(0); ctor (branches) under manual_seed(100+n)
+    net = model_port.build_port(sections, seed=0, branch_seed=100 + n).eval()
+    assert [b[0].convs[0][0].in_channels for b in net.branches] == [int(c) for c in d[f"n{n}_cin"]]
+    with torch.no_grad():
+        y = net(torch.tensor(d["x"]))
+    assert list(y.shape) == [int(s) for s in d[f"n{n}_out_shape"]]
+    np.testing.assert_allclose(y[..., ::8, ::8].numpy(), d[f"n{n}_out_slice"], rtol=1e-4, atol=1e-5)
+
+
+def test_product_model_placement_and_state_dict(golden):
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    d = golden("model")
+    for n in (1, 2):
+        net = branchyDeepv3(None, "deeplabv3_resnet50", n, 513, pretrained=False)
+        # same FLOP-quantile split as the reference run with the FlopCounterMode stand-in
+        assert [len(s) for s in net.base_model] == [int(s) for s in d[f"n{n}_sections"]]
+        port = model_port.build_port([len(s) for s in net.base_model])
+        assert set(net.state_dict().keys()) == set(port.state_dict().keys())
+        net.load_state_dict(port.state_dict())
+    assert net.n_branches == 2 and net.count_branches is True
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.eval()(torch.zeros(1, 3, 33, 33))
