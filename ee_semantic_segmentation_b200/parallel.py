@@ -1,0 +1,55 @@
+"""Data-parallel plumbing for the early-exit path: one process per GPU, images
+sharded across ranks with no data-path collective; the only exchanges are (1) one integer all-reduce
+of the stacked confusion matrices / exit counters at the end of an evaluation sweep and (2) the
+gradient all-reduce of training (torch DDP over NCCL). The reference has no distributed code at all.
+Works with the `gloo` backend on CPU tensors (used by the CPU tests) and `nccl` on the GPU box."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, **kw)
+    return rank, world, local
+
+
+def shard_range(n_items, rank, world):
+    """Image indices rank `rank` evaluates: r, r+world, r+2*world, ...."""
+    return range(rank, n_items, world)
+
+
+def all_reduce_counts(*tensors):
+    """In-place SUM all-reduce of integer accumulators; exact and independent of the rank order."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in tensors:
+            assert not t.dtype.is_floating_point, "only integer accumulators are reduced across ranks"
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return tensors
+
+
+def miou_from_cm(cm):
+    """cm int64 [..., C+1, C] -> float64 mIoU per leading index (NaN when a class never occurs)."""
+    C = cm.shape[-1]
+    tp = torch.diagonal(cm[..., :C, :], dim1=-2, dim2=-1).double()
+    fp = cm.sum(dim=-2).double() - tp
+    fn = cm[..., :C, :].sum(dim=-1).double() - tp
+    return (tp / (tp + fp + fn)).sum(dim=-1) / C
+
+
+def wrap_ddp(net, local_rank):
+    """Training: torch DDP (bucketed gradient all-reduce over NCCL, overlapped with backward).
+    BatchNorm stays per rank, as in a single-GPU reference run at the per-GPU batch."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    return DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True)
