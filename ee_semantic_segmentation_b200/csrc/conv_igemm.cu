@@ -28,7 +28,10 @@ constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
 
 struct ConvParams {
-  int N, h, w, Cin, Cout, R, S, dil;
+  int N, h, w, Cin, Cout, R, S, dil;   // h, w: OUTPUT spatial size
+  int hin, win, stride;                // input spatial size and convolution stride
+  const __nv_bfloat16* res;            // optional residual (NHWC bf16, pixel stride ldr), added before ReLU
+  int64_t ldr;
   int BW, BH, tiles_x, tiles_y;
   int BN;          // output-channel tile (multiple of 16, <= 256)
   int stages;
@@ -172,10 +175,10 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x
   const int y_hi = min(y0 + p.BH, p.h), x_hi = min(x0 + p.BW, p.w);
   for (int r = 0; r < p.R; ++r) {
     const int dy = (r - p.R / 2) * p.dil;
-    if (y_hi - 1 + dy < 0 || y0 + dy >= p.h) continue;
+    if ((y_hi - 1) * p.stride + dy < 0 || y0 * p.stride + dy >= p.hin) continue;
     for (int s = 0; s < p.S; ++s) {
       const int dx = (s - p.S / 2) * p.dil;
-      if (x_hi - 1 + dx < 0 || x0 + dx >= p.w) continue;
+      if ((x_hi - 1) * p.stride + dx < 0 || x0 * p.stride + dx >= p.win) continue;
       m |= 1u << (r * p.S + s);
     }
   }
@@ -246,7 +249,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
-          tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 + dx, y0 + dy, n_img);
+          tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
           tma_load_2d(sb, &tmap_w, full_bar + s, t * p.Cin + cb * kBlockK, n0);
         }
       }
@@ -297,9 +300,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (live) {
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
-          f[j] = p.relu ? fmaxf(x, 0.f) : x;
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+        if (p.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.ldr + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 u = __ldg(rp + j);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f[8 * j + 2 * k] += __uint_as_float(w4[k] << 16);
+              f[8 * j + 2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (p.out_f32) {
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n0 + c0);
@@ -334,16 +351,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 }
 
 // ---- global average pool (ASPPPooling) -----------------------------------------------------------
-__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int64_t hw, int C,
-                                    float* __restrict__ out) {
-  // grid (C/64 chunks, N); block 256 = 8 pixel lanes x 32 channel pairs; coalesced 128 B rows
-  const int n = blockIdx.y;
+constexpr int kPoolSplits = 32;
+
+__global__ void avgpool_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t hw, int C,
+                                       float* __restrict__ part) {
+  // grid (C/64 chunks, splits, N); block 256 = 8 pixel lanes x 32 channel pairs (128 B rows)
+  const int n = blockIdx.z, sp = blockIdx.y;
   const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
   const int pl = threadIdx.x >> 5;
+  const int64_t per = (hw + kPoolSplits - 1) / kPoolSplits;
+  const int64_t p0 = (int64_t)sp * per, p1 = min(p0 + per, hw);
   float a0 = 0.f, a1 = 0.f;
   if (c < C) {
     const __nv_bfloat16* base = x + (int64_t)n * hw * C + c;
-    for (int64_t p = pl; p < hw; p += 8) {
+#pragma unroll 4
+    for (int64_t p = p0 + pl; p < p1; p += 8) {
       __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + p * C);
       a0 += __low2float(v);
       a1 += __high2float(v);
@@ -356,9 +378,20 @@ __global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int64_t
   if (pl == 0 && c < C) {
     float t0 = 0.f, t1 = 0.f;
     for (int i = 0; i < 8; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
-    out[(int64_t)n * C + c] = t0 / (float)hw;
-    if (c + 1 < C) out[(int64_t)n * C + c + 1] = t1 / (float)hw;
+    float* o = part + ((int64_t)n * kPoolSplits + sp) * C + c;
+    o[0] = t0;
+    if (c + 1 < C) o[1] = t1;
   }
+}
+
+__global__ void avgpool_final_kernel(const float* __restrict__ part, int64_t hw, int C,
+                                     float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int sp = 0; sp < kPoolSplits; ++sp) t += part[((int64_t)n * kPoolSplits + sp) * C + c];  // fixed order
+  out[(int64_t)n * C + c] = t / (float)hw;
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -398,12 +431,18 @@ static void pick_tile(int h, int w, int& BW, int& BH) {
 using namespace eeseg;
 
 extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
-                                    const float* shift, int64_t shift_sn, int N, int h, int w, int Cin,
-                                    int Cout, int R, int S, int dilation, int relu, void* out,
+                                    const float* shift, int64_t shift_sn, int N, int hin, int win,
+                                    int Cin, int Cout, int R, int S, int dilation, int stride,
+                                    int relu, const void* residual, int64_t ldr, void* out,
                                     int out_dtype, int64_t ldo, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EESEG_REQUIRE(x && wt && scale && shift && out, "conv_igemm: null pointer");
-  EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_igemm: bad sizes");
+  EESEG_REQUIRE(N >= 1 && hin >= 1 && win >= 1, "conv_igemm: bad sizes");
+  EESEG_REQUIRE(stride == 1 || stride == 2, "conv_igemm: stride %d (1 or 2)", stride);
+  EESEG_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && (ldr % 8) == 0),
+                "conv_igemm: residual must be 16-byte aligned with ldr a multiple of 8");
+  // 'same' padding = dilation*(R/2): output size (in-1)/stride+1
+  const int h = (hin - 1) / stride + 1, w = (win - 1) / stride + 1;
   EESEG_REQUIRE(Cin % kBlockK == 0, "conv_igemm: Cin=%d must be a multiple of 64", Cin);
   EESEG_REQUIRE(Cout % 16 == 0, "conv_igemm: Cout=%d must be a multiple of 16", Cout);
   EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32 && (R & 1) && (S & 1), "conv_igemm: odd kernel sizes up to 32 taps");
@@ -418,6 +457,8 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   }
   ConvParams p;
   p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
+  p.hin = hin; p.win = win; p.stride = stride;
+  p.res = (const __nv_bfloat16*)residual; p.ldr = ldr;
   pick_tile(h, w, p.BW, p.BH);
   p.tiles_x = (w + p.BW - 1) / p.BW;
   p.tiles_y = (h + p.BH - 1) / p.BH;
@@ -437,10 +478,11 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
 
   CUtensorMap tmx, tmw;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)w * Cin * 2, (cuuint64_t)h * w * Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)win * Cin * 2, (cuuint64_t)hin * win * Cin * 2};
+    // with an element stride s TMA loads ceil(box/s) elements: box = tile*s fetches tile pixels
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -467,12 +509,20 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   return check_launch("conv_igemm_kernel");
 }
 
+extern "C" size_t eeseg_global_avgpool_workspace_bytes(int N, int C) {
+  return (size_t)(N > 0 ? N : 0) * kPoolSplits * (size_t)(C > 0 ? C : 0) * sizeof(float) + 256;
+}
+
 extern "C" int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out,
-                                         void* stream_) {
-  EESEG_REQUIRE(x && out, "global_avgpool: null pointer");
+                                         void* workspace, void* stream_) {
+  EESEG_REQUIRE(x && out && workspace, "global_avgpool: null pointer");
   EESEG_REQUIRE(C % 2 == 0, "global_avgpool: C must be even");
   if (N == 0) return EESEG_OK;
-  dim3 grid((C + 63) / 64, N);
-  avgpool_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, hw, C, out);
-  return check_launch("avgpool_nhwc_kernel");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* part = reinterpret_cast<float*>(workspace);
+  avgpool_partial_kernel<<<dim3((C + 63) / 64, kPoolSplits, N), 256, 0, stream>>>((const __nv_bfloat16*)x, hw, C, part);
+  int rc = check_launch("avgpool_partial_kernel");
+  if (rc) return rc;
+  avgpool_final_kernel<<<dim3((C + 255) / 256, N), 256, 0, stream>>>(part, hw, C, out);
+  return check_launch("avgpool_final_kernel");
 }

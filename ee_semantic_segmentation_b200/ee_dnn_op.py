@@ -21,11 +21,10 @@ class eval_ee_deeplabv3(_EntropyOp):
         if not X.is_cuda:
             raise RuntimeError('eval_ee_deeplabv3 needs a CUDA input (no CPU fallback)')
         X = X.unsqueeze(0)
-        with tch.no_grad(), tch.autocast('cuda', dtype=tch.bfloat16):
-            X = X.contiguous(memory_format=tch.channels_last)
+        with tch.no_grad():
             for i in range(self.n):
                 main_flops.append(main_all[i])
-                X = model.base_model[i](X)
+                X = model.run_section(i, X)
                 if i not in self.ignore and not left:
                     low = model._plan(i).run(X)
                     branch_flops.append(head_all[i])
@@ -43,7 +42,7 @@ class eval_ee_deeplabv3(_EntropyOp):
                 if not left and i == self.last_br:
                     output['edge_flops'] = sum(branch_flops) + sum(main_flops)
             main_flops.append(main_all[self.n])
-            X = model.base_model[-1](X)
+            X = model.run_section(self.n, X)
             main_flops.append(head_all[self.n])
             low = model._plan(self.n).run(X)
             Y = ops.exit_gate(low, inp_shape, layout='NHWC', n_classes=model.num_classes,

@@ -95,13 +95,12 @@ class eval_ee_deeplabv3():
         X = X.unsqueeze(0)
         if not X.is_cuda:
             raise RuntimeError('eval_ee_deeplabv3 needs a CUDA input (no CPU fallback)')
-        with tch.no_grad(), tch.autocast('cuda', dtype=tch.bfloat16):
-            X = X.contiguous(memory_format=tch.channels_last)
+        with tch.no_grad():
             for i in range(self.n):
                 if left and not self.compute_last:
                     break
                 main_flops.append(main_all[i])
-                X = model.base_model[i](X)
+                X = model.run_section(i, X)
                 if i not in self.ignore and not left:
                     low = model._plan(i).run(X)
                     branch_flops.append(head_all[i])
@@ -117,7 +116,7 @@ class eval_ee_deeplabv3():
             if left and not self.compute_last:
                 return output
             main_flops.append(main_all[self.n])
-            X = model.base_model[-1](X)
+            X = model.run_section(self.n, X)
             main_flops.append(head_all[self.n])
             low = model._plan(self.n).run(X)
             am = ops.exit_gate(low, inp_shape, layout='NHWC', n_classes=model.num_classes,

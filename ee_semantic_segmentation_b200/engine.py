@@ -19,7 +19,15 @@ from . import ops
 
 
 class EarlyExitEngine:
-    def __init__(self, net, n_classes, tau, metric='ent', size=1, skip=0, skip_compute=False):
+    def __init__(self, net, n_classes, tau, metric='ent', size=1, skip=0, skip_compute=False,
+                 use_graph=False):
+        """use_graph: capture the whole (static) step — backbone sections, heads, gates, decision,
+        histogram — into one CUDA graph per input shape and replay it; removes the per-launch host
+        overhead of the ~700 launches of a step. Not available with skip_compute (the compaction
+        reads the active count on the host)."""
+        assert not (use_graph and skip_compute), "CUDA-graph replay needs a static step"
+        self.use_graph = use_graph
+        self._graphs = {}
         self.net = net
         self.C = n_classes
         self.tau = float(tau)
@@ -49,10 +57,56 @@ class EarlyExitEngine:
             res.score = ops.entropy_pool_mean(res.ent, self.size, self.metric == 'min')
         return res
 
+    def static_inputs(self, shape, with_targets=True):
+        """Graph mode: the device buffers the captured step reads. Fill them (e.g. H2D copies
+        straight from pinned memory) and call replay() to avoid an extra device copy."""
+        g = self._capture(tuple(shape), with_targets)
+        return g['X'], g['y']
+
+    def _capture(self, shape, with_targets):
+        key = (shape, with_targets)
+        if key in self._graphs:
+            return self._graphs[key]
+        N, _, H, W = shape
+        dev = self.device
+        Xs = torch.zeros(shape, dtype=torch.float32, device=dev)
+        ys = torch.full((N, 1, H, W), self.C, dtype=torch.int64, device=dev) if with_targets else None
+        fn = (lambda: self._evaluate(Xs, ys)) if with_targets else (lambda: self._infer(Xs))
+        saved = (self.cm.clone(), self.counts.clone(), self.exited_px.clone())
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):          # warm-up: lazy inits, plan cache, allocator
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn()
+        # the warm-up / capture runs must not count
+        self.cm.copy_(saved[0]); self.counts.copy_(saved[1]); self.exited_px.copy_(saved[2])
+        g = {'graph': graph, 'X': Xs, 'y': ys, 'out': out}
+        self._graphs[key] = g
+        return g
+
+    def replay(self, shape, with_targets=True):
+        g = self._capture(tuple(shape), with_targets)
+        g['graph'].replay()
+        return g['out']
+
     @torch.no_grad()
     def infer(self, X):
         """X [N,3,H,W] on the device. Returns dict: 'exit' int32 [N] (0-based exit taken),
-        'pred' uint8 [N,H,W] (argmax map of that exit), 'scores' f32 [E-1,N]."""
+        'pred' uint8 [N,H,W] (argmax map of that exit), 'scores' f32 [E-1,N]. In graph mode the
+        returned tensors are the graph's static outputs (overwritten by the next call)."""
+        if self.use_graph:
+            g = self._capture(tuple(X.shape), False)
+            g['X'].copy_(X, non_blocking=True)
+            g['graph'].replay()
+            return g['out']
+        return self._infer(X)
+
+    @torch.no_grad()
+    def _infer(self, X):
         net = self.net
         N, _, H, W = X.shape
         dev = X.device
@@ -60,10 +114,10 @@ class EarlyExitEngine:
         pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
         scores = torch.full((max(self.E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)
         active = None   # index tensor of images still in flight (skip_compute only)
-        with torch.autocast('cuda', dtype=torch.bfloat16):
-            Xc = X.contiguous(memory_format=torch.channels_last)
+        if True:
+            Xc = X
             for i in range(self.E):
-                Xc = net.base_model[i](Xc)
+                Xc = net.run_section(i, Xc)
                 low = net._plan(i).run(Xc)
                 last = i == self.E - 1
                 res = self._gate(low, (H, W), want_score=not last and i >= self.skip)
@@ -97,7 +151,17 @@ class EarlyExitEngine:
     def evaluate(self, X, y):
         """infer + integer confusion matrices of the exit taken: accumulates self.cm[e] for the exit
         each image left at and self.cm[-1] globally (the accumulators of eval_br_ent.py:39,61-69)."""
-        out = self.infer(X)
+        if self.use_graph:
+            g = self._capture(tuple(X.shape), True)
+            g['X'].copy_(X, non_blocking=True)
+            g['y'].copy_(y.view_as(g['y']), non_blocking=True)
+            g['graph'].replay()
+            return g['out']
+        return self._evaluate(X, y)
+
+    @torch.no_grad()
+    def _evaluate(self, X, y):
+        out = self._infer(X)
         cm = ops.confusion_hist(out['pred'], y, self.C)                  # [N, C+1, C]
         ex = out['exit'].long()
         self.cm.index_add_(0, ex, cm)

@@ -31,6 +31,7 @@ from torch.utils.flop_counter import FlopCounterMode
 from torchvision.models.segmentation.deeplabv3 import ASPP, DeepLabHead
 
 from . import ops
+from .backbone_plan import SectionPlan, supported as _section_supported
 from .head_plan import HeadPlan
 
 
@@ -124,7 +125,9 @@ class branchyDeepv3(nn.Module):
         # __init_branches (from_deepv3_new.py:133-140) is a no-op in the reference (get_layers always
         # returns []), so the branches keep PyTorch's default initialisation.
         self._plans = {}
-        self.fast_inference = True
+        self._section_plans = {}
+        self.fast_inference = True     # eval-mode CUDA forward on the eeseg kernels
+        self.fast_backbone = True      # ... including the ResNet bottlenecks of the sections
 
     # ---- construction helpers ---------------------------------------------------------------------
     @staticmethod
@@ -203,16 +206,31 @@ class branchyDeepv3(nn.Module):
         """Folded-BN kernel plan of head i (i == n_branches -> classifier); rebuilt when parameters
         change (tracked through their version counters)."""
         head = self.classifier if i == self.n_branches else self.branches[i]
-        key = tuple((p.data_ptr(), p._version) for p in head.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in head.buffers())
+        key = self._state_key(head)
         ent = self._plans.get(i)
         if ent is None or ent[0] != key:
             ent = (key, HeadPlan(head))
             self._plans[i] = ent
         return ent[1]
 
-    def _section(self, i, X):
-        return self.base_model[i](X)
+    @staticmethod
+    def _state_key(mod):
+        return tuple((p.data_ptr(), p._version) for p in mod.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in mod.buffers())
+
+    def run_section(self, i, X):
+        """Inference forward of base_model[i]: Bottlenecks on the eeseg conv kernel (BN/ReLU/residual
+        fused) when fast_backbone is set, else the PyTorch modules under bf16 autocast."""
+        sec = self.base_model[i]
+        if self.fast_backbone and _section_supported(sec):
+            key = self._state_key(sec)
+            ent = self._section_plans.get(i)
+            if ent is None or ent[0] != key:
+                ent = (key, SectionPlan(sec))
+                self._section_plans[i] = ent
+            return ent[1].run(X)
+        with tch.autocast('cuda', dtype=tch.bfloat16):
+            return sec(X.contiguous(memory_format=tch.channels_last))
 
     def _forward_torch(self, X):
         """The reference data flow on PyTorch modules (used for training / autograd)."""
@@ -235,13 +253,10 @@ class branchyDeepv3(nn.Module):
         if not X.is_cuda:
             raise RuntimeError('branchyDeepv3 fast path needs CUDA tensors (no CPU fallback)')
         outs = []
-        with tch.no_grad(), tch.autocast('cuda', dtype=tch.bfloat16):
-            X = X.contiguous(memory_format=tch.channels_last)
-            for i in range(self.n_branches):
-                X = self.base_model[i](X)
+        with tch.no_grad():
+            for i in range(self.n_branches + 1):
+                X = self.run_section(i, X)
                 outs.append(self._plan(i).run(X))
-            X = self.base_model[-1](X)
-            outs.append(self._plan(self.n_branches).run(X))
         return outs
 
     def forward(self, X):

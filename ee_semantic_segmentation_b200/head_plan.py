@@ -37,9 +37,11 @@ def _krsc(conv):
 PROFILE = None   # bench.py sets this to a list to collect (start, end) CUDA events per conv launch
 
 
-def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0):
+def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0, stride=1,
+               residual=None):
     """x bf16 NHWC [N,h,w,Cin]; wt bf16 [Cout,R,S,Cin]; out: tensor view whose data_ptr is the first
-    output channel and whose pixel stride is ldo elements."""
+    output channel and whose pixel stride is ldo elements; residual: optional bf16 NHWC tensor of
+    the output shape (added before the ReLU)."""
     N, h, w, Cin = x.shape
     Cout, R, S, _ = wt.shape
     with torch.cuda.device(x.device):
@@ -48,11 +50,26 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
             a.record()
         check(lib().eeseg_conv_igemm_fwd(
             x.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), shift_sn, N, h, w, Cin,
-            Cout, R, S, dilation, 1 if relu else 0, out.data_ptr(), out_dtype_code, ldo,
+            Cout, R, S, dilation, stride, 1 if relu else 0,
+            None if residual is None else residual.data_ptr(),
+            0 if residual is None else residual.stride(2), out.data_ptr(), out_dtype_code, ldo,
             torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_fwd")
         if PROFILE is not None:
             b.record()
             PROFILE.append((a, b))
+
+
+def global_avgpool_nhwc(xh):
+    """bf16 NHWC [N,h,w,C] -> f32 [N,C] (AdaptiveAvgPool2d(1))."""
+    N, h, w, C = xh.shape
+    dev = xh.device
+    pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty((lib().eeseg_global_avgpool_workspace_bytes(N, C),), dtype=torch.uint8, device=dev)
+        check(lib().eeseg_global_avgpool_nhwc(xh.data_ptr(), N, h * w, C, pooled.data_ptr(), ws.data_ptr(),
+                                              torch.cuda.current_stream(dev).cuda_stream),
+              "eeseg_global_avgpool_nhwc")
+    return pooled
 
 
 class HeadPlan:
@@ -116,11 +133,7 @@ class HeadPlan:
         for k, (wt, s, b, dil) in enumerate(self.branches):
             conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)
         # pooled branch: avg-pool -> 1x1 -> BN -> ReLU, then its share of the projection, per image
-        pooled = torch.empty((N, xh.shape[-1]), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            check(lib().eeseg_global_avgpool_nhwc(xh.data_ptr(), N, h * w, xh.shape[-1], pooled.data_ptr(),
-                                                  torch.cuda.current_stream(dev).cuda_stream),
-                  "eeseg_global_avgpool_nhwc")
+        pooled = global_avgpool_nhwc(xh)
         pv = torch.relu(pooled @ self.pool_w.t() * self.pool_s + self.pool_b)   # [N, mid] (tiny GEMV)
         pshift = (pv @ self.proj_pool_w.t()) * self.proj_s + self.proj_b         # [N, mid]
         pshift = pshift.contiguous()

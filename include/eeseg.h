@@ -149,21 +149,28 @@ int eeseg_lovasz_fwd_bwd(const void* probas, int dtype, int64_t exit_stride, con
  * Implicit-GEMM convolution (tcgen05 / TMEM / TMA), inference form with folded BatchNorm.
  * Replaces the dense contraction of torchvision DeepLabHead / ASPP / ASPPConv as called from
  * from_deepv3_new.py:34,131,147,151 (branches[i](X), classifier(X)).
- *   x   bf16 NHWC [N][h][w][Cin]           (Cin % 64 == 0)
- *   wt  bf16 [Cout][R][S][Cin]             (Cout % 16 == 0, <= 256 per launch column block)
- *   y = act( scale[co] * conv(x, wt; dilation, padding = dilation*(R-1)/2) + shift[n?][co] )
+ * The same kernel runs the ResNet Bottleneck convolutions of the backbone sections
+ * (base_model[i], from_deepv3_new.py:146,151) with the residual add fused.
+ *   x   bf16 NHWC [N][hin][win][Cin]       (Cin % 64 == 0)
+ *   wt  bf16 [Cout][R][S][Cin]             (Cout % 16 == 0; tiled by <= 256 output channels)
+ *   y = act( scale[co] * conv(x, wt; dilation, stride, padding = dilation*(R/2)) + shift[n?][co]
+ *            + residual )            output spatial size (hin-1)/stride+1 x (win-1)/stride+1
  *   shift_sn: image stride of `shift` in elements (0 = shared by all images)
+ *   residual: optional bf16 NHWC tensor of the OUTPUT shape (pixel stride ldr), or NULL
  *   out NHWC with pixel stride ldo elements, written at channel offset already applied to `out`
- *   out_dtype EESEG_BF16 or EESEG_F32; relu != 0 applies max(.,0)
+ *   out_dtype EESEG_BF16 or EESEG_F32; relu != 0 applies max(.,0) last
  * ---------------------------------------------------------------------------------------------- */
 int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, const float* shift,
-                         int64_t shift_sn, int N, int h, int w, int Cin, int Cout, int R, int S,
-                         int dilation, int relu, void* out, int out_dtype, int64_t ldo,
-                         void* stream);
+                         int64_t shift_sn, int N, int hin, int win, int Cin, int Cout, int R, int S,
+                         int dilation, int stride, int relu, const void* residual, int64_t ldr,
+                         void* out, int out_dtype, int64_t ldo, void* stream);
 
 /* Global average pool of an NHWC bf16 tensor: [N][h][w][C] -> f32 [N][C] (ASPPPooling's
- * AdaptiveAvgPool2d(1), torchvision deeplabv3.py:70-83). */
-int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out, void* stream);
+ * AdaptiveAvgPool2d(1), torchvision deeplabv3.py:70-83). Two ordered stages (deterministic);
+ * workspace: eeseg_global_avgpool_workspace_bytes(N, C) bytes of scratch. */
+size_t eeseg_global_avgpool_workspace_bytes(int N, int C);
+int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out, void* workspace,
+                              void* stream);
 
 #ifdef __cplusplus
 }

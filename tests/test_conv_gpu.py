@@ -59,12 +59,12 @@ def test_conv_igemm_full_head_shapes():
 
 
 def test_avgpool():
-    from ee_semantic_segmentation_b200 import _lib
-    x = torch.randn(3, 65 * 65, 192).to(torch.bfloat16).to(dev())
-    out = torch.empty(3, 192, device=dev())
-    _lib.check(_lib.lib().eeseg_global_avgpool_nhwc(x.data_ptr(), 3, 65 * 65, 192, out.data_ptr(),
-                                                     torch.cuda.current_stream().cuda_stream), "avgpool")
-    np.testing.assert_allclose(out.cpu().numpy(), x.float().mean(1).cpu().numpy(), atol=1e-5)
+    from ee_semantic_segmentation_b200.head_plan import global_avgpool_nhwc
+    x = torch.randn(3, 65, 65, 192).to(torch.bfloat16).to(dev())
+    out = global_avgpool_nhwc(x)
+    np.testing.assert_allclose(out.cpu().numpy(), x.float().mean((1, 2)).cpu().numpy(), atol=1e-5)
+    x = torch.randn(1, 3, 5, 64).to(torch.bfloat16).to(dev())          # fewer pixels than splits
+    np.testing.assert_allclose(global_avgpool_nhwc(x).cpu().numpy(), x.float().mean((1, 2)).cpu().numpy(), atol=1e-5)
 
 
 @pytest.mark.parametrize("cin", [1024, 2048])
@@ -86,3 +86,57 @@ def test_head_plan_vs_torchvision(cin):
     got = low[..., :21].permute(0, 3, 1, 2).float().cpu()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-2, err      # five bf16 layers deep; logits within 1e-2 relative of fp32 typical
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=2, hin=129, win=129, Cin=128, Cout=128, R=3, stride=2),     # layer2.0.conv2
+    dict(N=1, hin=129, win=129, Cin=256, Cout=512, R=1, stride=2),     # layer2.0.downsample
+    dict(N=1, hin=34, win=50, Cin=64, Cout=64, R=3, stride=2),         # even sizes
+    dict(N=2, hin=65, win=65, Cin=256, Cout=1024, R=1, stride=1),      # conv3 + residual
+])
+def test_conv_stride_and_residual(cfg):
+    from ee_semantic_segmentation_b200 import _lib
+    from ee_semantic_segmentation_b200.head_plan import conv_igemm
+    N, hin, win, Cin, Cout, R, stride = (cfg[k] for k in ("N", "hin", "win", "Cin", "Cout", "R", "stride"))
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(N, hin, win, Cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(Cout, R, R, Cin, generator=g) / np.sqrt(R * R * Cin)).to(torch.bfloat16)
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    ho, wo = (hin - 1) // stride + 1, (win - 1) // stride + 1
+    res = torch.randn(N, ho, wo, Cout, generator=g).to(torch.bfloat16)
+    out = torch.empty(N, ho, wo, Cout, dtype=torch.bfloat16, device=dev())
+    conv_igemm(x.to(dev()), wt.to(dev()), scale.to(dev()), shift.to(dev()), 1, True, out, _lib.BF16, Cout,
+               stride=stride, residual=res.to(dev()))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), padding=R // 2, stride=stride)
+    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float().permute(0, 3, 1, 2)).relu()
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
+
+
+def test_section_plan_vs_torchvision():
+    """ResNet-50 sections (stem + bottlenecks incl. the stride-2 and dilated blocks) on the eeseg conv
+    kernel vs the PyTorch modules in fp32."""
+    import torchvision
+    from ee_semantic_segmentation_b200.backbone_plan import SectionPlan
+    from oracle.model_port import backbone_units
+    torch.manual_seed(1)
+    base = torchvision.models.segmentation.deeplabv3_resnet50(weights=None, weights_backbone=None, num_classes=21)
+    for m in base.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
+    units = backbone_units(base.backbone)
+    sec_a = torch.nn.Sequential(*units[:9]).eval()        # stem + layer1 + layer2.0/2.1 (stride 2 inside)
+    sec_b = torch.nn.Sequential(*units[9:]).eval()        # rest of layer2, layer3 (d=2), layer4 (d=4)
+    x = torch.randn(2, 3, 97, 113)
+    with torch.no_grad():
+        ra = sec_a(x)
+        rb = sec_b(ra)
+    ga = SectionPlan(sec_a.to(dev())).run(x.to(dev()))
+    assert ga.shape == ra.shape and ga.dtype == torch.bfloat16
+    assert (ga.float().cpu() - ra).abs().max().item() < 2e-2 * ra.abs().max().item()
+    gb = SectionPlan(sec_b.to(dev())).run(ga)
+    assert gb.shape == rb.shape
+    assert (gb.float().cpu() - rb).abs().max().item() < 3e-2 * rb.abs().max().item()
