@@ -10,7 +10,7 @@ import torch
 from torch import nn
 from torchvision.models.resnet import Bottleneck
 
-from . import _lib
+from . import _lib, head_plan
 from .head_plan import _fold_bn, _krsc, conv_igemm
 
 
@@ -65,6 +65,13 @@ class SectionPlan:
         """x: [N,C,h,w] tensor (any float dtype / memory format). Returns a bf16 [N,C',h',w'] tensor
         in channels_last memory format (an NHWC buffer viewed as NCHW)."""
         nhwc = None
+        head_plan.PROFILE_TAG = "backbone"
+        try:
+            return self._run(x, nhwc)
+        finally:
+            head_plan.PROFILE_TAG = "head"
+
+    def _run(self, x, nhwc):
         for op in self.ops:
             if isinstance(op, BottleneckPlan):
                 if nhwc is None:

@@ -473,6 +473,16 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
+  // Shallow-K layers (ResNet 1x1 / 64-channel 3x3) are prologue/epilogue-bound: give them only the
+  // stages they can use so several CTAs share an SM (shared memory and TMEM columns permitting) and
+  // one CTA's epilogue overlaps another's main loop. Deep-K layers keep the full ring.
+  const int kb_total = R * S * (Cin / kBlockK);
+  if (BN <= 128 || kb_total <= 16) {
+    const int fit_half = (int)((110 * 1024 - 1024 - tail_bytes) / stage_bytes);  // >= two CTAs per SM
+    const int want = kb_total < 6 ? kb_total : 6;
+    stages = fit_half < 2 ? 2 : (fit_half < want ? fit_half : want);
+    if (stages > kb_total) stages = kb_total;
+  }
   p.stages = stages;
   const size_t smem_bytes = 1024 + stages * stage_bytes + tail_bytes;
 

@@ -42,8 +42,40 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
   l0 = 1.f - l1;
 }
 
-template <typename TI, typename TO, int CMAX, bool INTERP>
-__global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Horizontal lerp of one low-res row into registers: out[c] = lx0*L[x0][c] + lx1*L[x1][c].
+// NHWC_VEC: channels contiguous and 16 B aligned (the conv kernel's [N,h,w,Cp] fp32 output):
+// 128-bit loads; otherwise scalar loads with a runtime channel stride.
+template <typename TI, int CMAX, bool NHWC_VEC>
+__device__ __forceinline__ void lerp_row(const TI* __restrict__ row, int off0, int off1, int sc, int C,
+                                         float lx0, float lx1, float (&out)[CMAX]) {
+  if constexpr (NHWC_VEC) {
+    const float4* a = reinterpret_cast<const float4*>(row + off0);
+    const float4* b = reinterpret_cast<const float4*>(row + off1);
+#pragma unroll
+    for (int q = 0; q < CMAX / 4; ++q) {
+      if (q * 4 < C) {
+        const float4 u = __ldg(a + q), v = __ldg(b + q);
+        out[4 * q + 0] = lx0 * u.x + lx1 * v.x;
+        out[4 * q + 1] = lx0 * u.y + lx1 * v.y;
+        out[4 * q + 2] = lx0 * u.z + lx1 * v.z;
+        out[4 * q + 3] = lx0 * u.w + lx1 * v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) out[c] = lx0 * ldf(row + off0 + c * sc) + lx1 * ldf(row + off1 + c * sc);
+  }
+}
+
+template <typename TI, typename TO, int CMAX, bool INTERP, bool NHWC_VEC>
+__global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 3 : 1))) gate_kernel(const GateParams p) {
   const int X = blockIdx.x * kGateThreads + threadIdx.x;
   const int n = blockIdx.z;
   const int Y0 = blockIdx.y * kRowsPerStrip;
@@ -54,6 +86,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
   TO* up = p.up ? reinterpret_cast<TO*>(p.up) + (int64_t)n * p.up_sn : nullptr;
   const int64_t HW = (int64_t)p.H * p.W;
   const float inv_lnC = C > 1 ? 1.f / logf((float)C) : 0.f;
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
   double acc_ent = 0.0;
   int acc_cnt = 0;
@@ -62,6 +95,9 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
   int x0 = 0, x1 = 0, cur_y0 = -1, cur_y1 = -1;
   float lx0 = 1.f, lx1 = 0.f;
   if (INTERP && live) src_index(X, p.scale_x, p.w, x0, x1, lx0, lx1);
+  // the low-res tensor of one image is far below 2^31 elements (checked on the host)
+  const int sx = (int)p.in_sx, sy = (int)p.in_sy, sc = (int)p.in_sc;
+  const int off0 = x0 * sx, off1 = x1 * sx;
 
   if (live) {
     for (int Y = Y0; Y < Y1; ++Y) {
@@ -75,23 +111,13 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) top[c] = bot[c];
           } else {
-            const TI* r = in + (int64_t)y0 * p.in_sy;
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-              if (c < C)
-                top[c] = lx0 * ldf(r + x0 * p.in_sx + c * p.in_sc) +
-                         lx1 * ldf(r + x1 * p.in_sx + c * p.in_sc);
+            lerp_row<TI, CMAX, NHWC_VEC>(in + y0 * sy, off0, off1, sc, C, lx0, lx1, top);
           }
           if (y1 == y0) {
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) bot[c] = top[c];
           } else {
-            const TI* r = in + (int64_t)y1 * p.in_sy;
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-              if (c < C)
-                bot[c] = lx0 * ldf(r + x0 * p.in_sx + c * p.in_sc) +
-                         lx1 * ldf(r + x1 * p.in_sx + c * p.in_sc);
+            lerp_row<TI, CMAX, NHWC_VEC>(in + y1 * sy, off0, off1, sc, C, lx0, lx1, bot);
           }
           cur_y0 = y0;
           cur_y1 = y1;
@@ -102,7 +128,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
         const TI* r = in + (int64_t)Y * p.in_sy + (int64_t)X * p.in_sx;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) v[c] = ldf_stream(r + c * p.in_sc);
+          if (c < C) v[c] = ldf_stream(r + (int64_t)c * p.in_sc);
       }
       const int64_t pix = (int64_t)Y * p.W + X;
       if (up) {
@@ -115,19 +141,21 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
         int am = 0;
 #pragma unroll
         for (int c = 1; c < CMAX; ++c)
-          if (c < C && ((v[c] > m) || (v[c] != v[c] && m == m))) { m = v[c]; am = c; }
+          if (c < C && v[c] > m) { m = v[c]; am = c; }   // first maximal index
         float hn;
         if (p.in_kind == 0) {
+          // H = ln S - sum e_c z_c / S with z = v - max, e = exp(z); computed in base 2
+          const float m2 = m * kLog2e;
           float S = 0.f, T = 0.f;
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
             if (c < C) {
-              float z = v[c] - m;
-              float e = exp2f(z * 1.4426950408889634f);
+              const float z2 = fmaf(v[c], kLog2e, -m2);   // (v - m) * log2(e) <= 0
+              const float e = ex2_approx(z2);
               S += e;
-              T = fmaf(e, z, T);  // e == 0 -> contributes 0 (entr(0) = 0)
+              T = fmaf(e, z2, T);                          // e == 0 contributes 0 (entr(0) = 0)
             }
-          hn = (__logf(S) - T / S) * inv_lnC;
+          hn = (__log2f(S) - __fdividef(T, S)) * (kLn2 * inv_lnC);
         } else {
           float S = 0.f;
 #pragma unroll
@@ -138,9 +166,9 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
           for (int c = 0; c < CMAX; ++c)
             if (c < C) {
               float q = v[c] * invS;
-              T -= q > 0.f ? q * __logf(q) : 0.f;
+              T -= q > 0.f ? q * __log2f(q) : 0.f;
             }
-          hn = T * inv_lnC;
+          hn = T * (kLn2 * inv_lnC);
         }
         hn = fmaxf(hn, 0.f) + 0.f * hn;  // clamp tiny negatives, keep NaN
         if (p.ent) __stcs(p.ent + (int64_t)n * HW + pix, hn);
@@ -202,30 +230,40 @@ __global__ void pool_mean_kernel(const float* __restrict__ ent, int H, int W, in
   }
 }
 
-__global__ void decide_kernel(const double* __restrict__ part_sum,
-                              const int32_t* __restrict__ part_cnt, int num_partials,
-                              const float* __restrict__ score_in, int N, int64_t HW, float tau,
-                              int less_than, int exit_id, int32_t* __restrict__ exit_idx,
-                              float* __restrict__ score_out, int64_t* __restrict__ exited_px,
-                              int32_t* __restrict__ active_list,
-                              int32_t* __restrict__ active_count) {
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float sc;
-    if (part_sum) {
-      double t = 0.0;
-      for (int k = 0; k < num_partials; ++k) t += part_sum[(int64_t)n * num_partials + k];
-      sc = (float)(t / (double)HW);
-    } else {
-      sc = score_in[n];
-    }
-    if (score_out) score_out[n] = sc;
-    if (exited_px) {
-      int64_t k = 0;
-      if (part_cnt)
-        for (int i = 0; i < num_partials; ++i) k += part_cnt[(int64_t)n * num_partials + i];
-      exited_px[n] = k;
-    }
-    if (exit_idx) {
+// Stage 2a: per-image score = ordered sum of the block partials / HW (one block per image; every
+// thread adds a fixed strided subset in order, then a fixed tree -> bit-reproducible).
+__global__ void score_kernel(const double* __restrict__ part_sum, const int32_t* __restrict__ part_cnt,
+                             int num_partials, int64_t HW, float* __restrict__ score,
+                             int64_t* __restrict__ exited_px) {
+  const int n = blockIdx.x;
+  double t = 0.0;
+  long long k = 0;
+  for (int i = threadIdx.x; i < num_partials; i += blockDim.x) {
+    if (part_sum) t += part_sum[(int64_t)n * num_partials + i];
+    if (part_cnt) k += part_cnt[(int64_t)n * num_partials + i];
+  }
+  __shared__ double st[128];
+  __shared__ long long sk[128];
+  st[threadIdx.x] = t;
+  sk[threadIdx.x] = k;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { st[threadIdx.x] += st[threadIdx.x + o]; sk[threadIdx.x] += sk[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (score) score[n] = (float)(st[0] / (double)HW);
+    if (exited_px) exited_px[n] = sk[0];
+  }
+}
+
+// Stage 2b: decision rule + compaction of the still-active images.
+__global__ void decide_kernel(const float* __restrict__ score, int N, float tau, int less_than,
+                              int exit_id, int32_t* __restrict__ exit_idx,
+                              int32_t* __restrict__ active_list, int32_t* __restrict__ active_count) {
+  if (exit_idx) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float sc = score[n];
       const bool conf = less_than ? (sc < tau) : (sc > tau);
       if (exit_idx[n] < 0 && conf) exit_idx[n] = exit_id;
     }
@@ -240,13 +278,14 @@ __global__ void decide_kernel(const double* __restrict__ part_sum,
 }
 
 template <typename TI, typename TO>
-static int launch_gate(const GateParams& p, bool interp, cudaStream_t stream) {
+static int launch_gate(const GateParams& p, bool interp, bool vec, cudaStream_t stream) {
   dim3 grid((p.W + kGateThreads - 1) / kGateThreads, (p.H + kRowsPerStrip - 1) / kRowsPerStrip, p.N);
-#define EESEG_GATE_CASE(CM)                                                                  \
-  if (p.C <= CM) {                                                                            \
-    if (interp) gate_kernel<TI, TO, CM, true><<<grid, kGateThreads, 0, stream>>>(p);          \
-    else gate_kernel<TI, TO, CM, false><<<grid, kGateThreads, 0, stream>>>(p);                \
-    return check_launch("gate_kernel");                                                       \
+#define EESEG_GATE_CASE(CM)                                                                        \
+  if (p.C <= CM) {                                                                                  \
+    if (interp && vec) gate_kernel<TI, TO, CM, true, true><<<grid, kGateThreads, 0, stream>>>(p);   \
+    else if (interp) gate_kernel<TI, TO, CM, true, false><<<grid, kGateThreads, 0, stream>>>(p);    \
+    else gate_kernel<TI, TO, CM, false, false><<<grid, kGateThreads, 0, stream>>>(p);               \
+    return check_launch("gate_kernel");                                                             \
   }
   EESEG_GATE_CASE(24)
   EESEG_GATE_CASE(32)
@@ -261,11 +300,15 @@ static int dispatch_gate(const GateParams& p, int in_dtype, int up_dtype, cudaSt
   EESEG_REQUIRE(in_dtype == EESEG_F32 || in_dtype == EESEG_BF16, "exit_gate: in_dtype %d", in_dtype);
   EESEG_REQUIRE(!p.up || up_dtype == EESEG_F32 || up_dtype == EESEG_BF16, "exit_gate: up_dtype %d", up_dtype);
   if (in_dtype == EESEG_F32) {
-    if (up_dtype == EESEG_BF16 && p.up) return launch_gate<float, __nv_bfloat16>(p, interp, stream);
-    return launch_gate<float, float>(p, interp, stream);
+    // 128-bit path: fp32 channels contiguous, every pixel 16 B aligned and padded to a multiple of 4
+    const int cpad = (p.C + 3) / 4 * 4;
+    const bool vec = interp && p.in_sc == 1 && p.in_sx >= cpad && (p.in_sx % 4) == 0 && (p.in_sy % 4) == 0 &&
+                     (p.in_sn % 4) == 0 && ((uintptr_t)p.in % 16) == 0;
+    if (up_dtype == EESEG_BF16 && p.up) return launch_gate<float, __nv_bfloat16>(p, interp, vec, stream);
+    return launch_gate<float, float>(p, interp, vec, stream);
   }
-  if (up_dtype == EESEG_BF16 || !p.up) return launch_gate<__nv_bfloat16, __nv_bfloat16>(p, interp, stream);
-  return launch_gate<__nv_bfloat16, float>(p, interp, stream);
+  if (up_dtype == EESEG_BF16 || !p.up) return launch_gate<__nv_bfloat16, __nv_bfloat16>(p, interp, false, stream);
+  return launch_gate<__nv_bfloat16, float>(p, interp, false, stream);
 }
 
 }  // namespace eeseg
@@ -287,6 +330,8 @@ extern "C" int eeseg_exit_gate_pixels(const void* in, int in_dtype, int in_kind,
   EESEG_REQUIRE(N <= 65535, "exit_gate: N=%d > 65535", N);
   EESEG_REQUIRE(in_kind == 0 || in_kind == 1, "exit_gate: in_kind %d", in_kind);
   EESEG_REQUIRE(!amax || C <= 256, "exit_gate: uint8 argmax needs C <= 256");
+  EESEG_REQUIRE((int64_t)h * in_sy < (1ll << 31) && (int64_t)w * in_sx < (1ll << 31) && (int64_t)C * in_sc < (1ll << 31),
+                "exit_gate: one low-res image must span fewer than 2^31 elements");
   if (N == 0) return EESEG_OK;
   GateParams p;
   p.in = in; p.in_sn = in_sn; p.in_sc = in_sc; p.in_sy = in_sy; p.in_sx = in_sx;
@@ -321,12 +366,21 @@ extern "C" int eeseg_exit_gate_decide(const double* part_sum, const int32_t* par
                                       int num_partials, const float* score_in, int N, int64_t HW,
                                       float tau, int less_than, int exit_id, int32_t* exit_idx,
                                       float* score_out, int64_t* exited_px, int32_t* active_list,
-                                      int32_t* active_count, void* stream) {
+                                      int32_t* active_count, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   EESEG_REQUIRE(part_sum || score_in, "exit_gate_decide: need part_sum or score_in");
+  EESEG_REQUIRE(!part_sum || score_out || !exit_idx, "exit_gate_decide: score_out is required with part_sum when deciding");
   if (N == 0) return EESEG_OK;
-  decide_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(part_sum, part_cnt, num_partials, score_in, N,
-                                                      HW, tau, less_than, exit_id, exit_idx,
-                                                      score_out, exited_px, active_list,
-                                                      active_count);
-  return check_launch("decide_kernel");
+  const float* score = score_in;
+  if (part_sum) {
+    score_kernel<<<N, 128, 0, stream>>>(part_sum, part_cnt, num_partials, HW, score_out, exited_px);
+    int rc = check_launch("score_kernel");
+    if (rc) return rc;
+    score = score_out;
+  }
+  if (exit_idx) {
+    decide_kernel<<<1, 256, 0, stream>>>(score, N, tau, less_than, exit_id, exit_idx, active_list, active_count);
+    return check_launch("decide_kernel");
+  }
+  return EESEG_OK;
 }

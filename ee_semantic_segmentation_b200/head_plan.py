@@ -34,7 +34,8 @@ def _krsc(conv):
     return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
 
 
-PROFILE = None   # bench.py sets this to a list to collect (start, end) CUDA events per conv launch
+PROFILE = None   # bench.py sets this to a list: (start event, end event, nominal FLOPs, tag) per conv launch
+PROFILE_TAG = "head"
 
 
 def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0, stride=1,
@@ -56,7 +57,8 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
             torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_fwd")
         if PROFILE is not None:
             b.record()
-            PROFILE.append((a, b))
+            ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+            PROFILE.append((a, b, 2 * N * ho * wo * Cout * R * S * Cin, PROFILE_TAG))
 
 
 def global_avgpool_nhwc(xh):
