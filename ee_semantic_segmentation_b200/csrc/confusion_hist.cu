@@ -7,6 +7,7 @@
 // blocky label maps of segmentation data do not serialise on one bank, then flushed once per block
 // with 64-bit global atomics.
 #include "common.cuh"
+#include "plane_stream.cuh"
 
 namespace eeseg {
 
@@ -73,6 +74,77 @@ __global__ void __launch_bounds__(256) cm_from_logits_kernel(const T* __restrict
       int tt = (t[j] >= 0 && t[j] < C) ? (int)t[j] : C;
       hist_add(h, pp[j] < HW ? tt * C + arg[j] : -1);
     }
+  }
+  hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
+}
+
+// Streaming variant (the default for logits): class planes staged through shared memory with
+// bulk-TMA copies (plane_stream.cuh), one persistent CTA per SM, several tiles in flight.
+template <typename T, int TILE>
+__global__ void __launch_bounds__(TILE, 1) cm_from_logits_stream_kernel(
+    const T* __restrict__ logits, const int64_t* __restrict__ targets, int C, int64_t HW, int copies,
+    unsigned long long* __restrict__ cm, const uint8_t* __restrict__ limit_logits,
+    const uint8_t* __restrict__ limit_targets, int stages) {
+  extern __shared__ __align__(128) uint8_t hs_smem[];
+  constexpr int ES = (int)sizeof(T);
+  constexpr int rb = ps::row_bytes(TILE, ES), rbt = ps::row_bytes(TILE, 8);
+  const int stage_bytes = C * rb + rbt;
+  uint64_t* full = reinterpret_cast<uint64_t*>(hs_smem + (size_t)stages * stage_bytes);
+  unsigned* hist = reinterpret_cast<unsigned*>(full + 8);
+  const int bins = (C + 1) * C;
+  for (int i = threadIdx.x; i < copies * bins; i += TILE) hist[i] = 0;
+  unsigned* h = hist + ((threadIdx.x >> 5) % copies) * bins;
+
+  const int n = blockIdx.y;
+  const uint8_t* base_b = reinterpret_cast<const uint8_t*>(logits + (int64_t)n * C * HW);
+  const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(targets + (int64_t)n * HW);
+  const int num_tiles = (int)((HW + TILE - 1) / TILE);
+  const int my_count = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto issue = [&](int k) {
+    const int s = k % stages;
+    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+    const int count = (int)min((int64_t)TILE, HW - p0);
+    uint8_t* st = hs_smem + (size_t)s * stage_bytes;
+    ps::issue_tile<ES>(st, rb, full + s, base_b, HW, C, p0, count, limit_logits);
+    ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) ps::mbar_init(full + s, 2);
+    ps::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < stages && k < my_count; ++k) issue(k);
+  const uint32_t delta = (uint32_t)(((uint64_t)HW * ES) & 15);
+  for (int k = 0; k < my_count; ++k) {
+    const int s = k % stages;
+    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+    const int64_t p = p0 + threadIdx.x;
+    const uint8_t* st = hs_smem + (size_t)s * stage_bytes;
+    ps::mbar_wait(full + s, (uint32_t)(k / stages) & 1u);
+    const uint32_t a0 = (uint32_t)((uintptr_t)(base_b + p0 * ES) & 15);
+    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15) / 8;
+    int key = -1;
+    if (p < HW) {
+      const int64_t t = reinterpret_cast<const int64_t*>(st + (size_t)C * rb)[t0 + threadIdx.x];
+      float best = 0.f;
+      int arg = 0;
+#pragma unroll 7
+      for (int c = 0; c < C; ++c) {
+        const uint32_t sh = ((a0 + (uint32_t)c * delta) & 15u) / ES;
+        float v;
+        if constexpr (ES == 4) v = reinterpret_cast<const float*>(st + (size_t)c * rb)[sh + threadIdx.x];
+        else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(st + (size_t)c * rb)[sh + threadIdx.x]);
+        // torch.argmax: first maximal index, NaN counts as the maximum
+        const bool take = (c == 0) || (v > best) || (v != v && best == best);
+        if (take) { best = v; arg = c; }
+      }
+      const int tt = (t >= 0 && t < C) ? (int)t : C;
+      key = tt * C + arg;
+    }
+    hist_add(h, key);
+    __syncthreads();
+    if (threadIdx.x == 0 && k + stages < my_count) issue(k + stages);
   }
   hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
 }
@@ -169,6 +241,37 @@ extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype,
       else
         cm_from_logits_global_kernel<__nv_bfloat16><<<g2, 256, 0, stream>>>((const __nv_bfloat16*)pred, targets, C, HW, cmu);
       return check_launch("cm_from_logits_global_kernel");
+    }
+    {
+      // streaming path: one persistent CTA per SM, bulk-TMA staged planes
+      constexpr int kTile = 512;
+      const int es = dtype == EESEG_F32 ? 4 : 2;
+      const size_t stage_bytes = (size_t)C * ps::row_bytes(kTile, es) + ps::row_bytes(kTile, 8);
+      int hcopies = copies < 4 ? copies : 4;
+      const size_t fixed = 8 * sizeof(uint64_t) + (size_t)hcopies * bytes1;
+      int stages = (int)((220 * 1024 - fixed) / stage_bytes);
+      if (stages > 6) stages = 6;
+      if (stages >= 2) {
+        const size_t smem = stages * stage_bytes + fixed;
+        int64_t per_img = kNumSMs / N;
+        if (per_img < 1) per_img = 1;
+        const int64_t tiles = (HW + kTile - 1) / kTile;
+        dim3 sgrid((unsigned)(per_img < tiles ? per_img : tiles), (unsigned)N);
+        const uintptr_t end_l = ((uintptr_t)pred + (size_t)N * C * HW * es + 15) & ~(uintptr_t)15;
+        const uintptr_t end_t = ((uintptr_t)(targets + (int64_t)N * HW) + 15) & ~(uintptr_t)15;
+        if (dtype == EESEG_F32) {
+          auto kern = cm_from_logits_stream_kernel<float, kTile>;
+          EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<sgrid, kTile, smem, stream>>>((const float*)pred, targets, C, HW, hcopies, cmu,
+                                               (const uint8_t*)end_l, (const uint8_t*)end_t, stages);
+        } else {
+          auto kern = cm_from_logits_stream_kernel<__nv_bfloat16, kTile>;
+          EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<sgrid, kTile, smem, stream>>>((const __nv_bfloat16*)pred, targets, C, HW, hcopies, cmu,
+                                               (const uint8_t*)end_l, (const uint8_t*)end_t, stages);
+        }
+        return check_launch("cm_from_logits_stream_kernel");
+      }
     }
     if (dtype == EESEG_F32)
       cm_from_logits_kernel<float, kPix><<<grid, kThreads, copies * bytes1, stream>>>(

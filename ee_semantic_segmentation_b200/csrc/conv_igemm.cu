@@ -14,7 +14,9 @@
 //   map) are skipped: they contribute exactly 0.
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
 //   warps 2..5 = epilogue (tcgen05.ld 32x32b, each warp its TMEM lane quadrant; thread = output
-//   pixel, so every thread stores 32 consecutive channels of its NHWC pixel).
+//   pixel): scale/shift (+ residual, prefetched by TMA into shared memory at kernel start) (+ ReLU),
+//   packed into a 128B-swizzled shared-memory tile and written with ONE TMA tensor store per
+//   64-channel block — full 128 B lines to L2, image-edge rows clipped by the tensor map.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,18 +32,17 @@ constexpr int kMaxStages = 8;
 struct ConvParams {
   int N, h, w, Cin, Cout, R, S, dil;   // h, w: OUTPUT spatial size
   int hin, win, stride;                // input spatial size and convolution stride
-  const __nv_bfloat16* res;            // optional residual (NHWC bf16, pixel stride ldr), added before ReLU
-  int64_t ldr;
+  int has_res;                         // residual tile (bf16, output shape) is TMA-prefetched and added before ReLU
+  int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
+  int main_bytes;                      // shared memory of the operand ring (the output staging overlays it)
   int BW, BH, tiles_x, tiles_y;
   int BN;          // output-channel tile (multiple of 16, <= 256)
   int stages;
   int relu;
   int out_f32;
-  int64_t ldo;     // output pixel stride (elements)
   int64_t shift_sn;
   const float* scale;
   const float* shift;
-  void* out;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -111,6 +112,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, 
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+      "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -187,18 +197,24 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A 16 KB][B BN*128 B] | barriers | tmem ptr | scale/shift
+  // carve: operand ring [stages][A 16 KB][B BN*128 B] (overlaid by the output staging tile after the
+  // last MMA) | residual tile | barriers | tmem ptr | scale/shift
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = kBlockM * kBlockK * 2;
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
+  const uint32_t res_blk_bytes = kBlockM * 128;               // 64 bf16 channels per pixel row
+  const int nblk_res = p.has_res ? p.BN / 64 : 0;
+  uint8_t* res_smem = smem + p.main_bytes;
+  uint8_t* tail = res_smem + (size_t)nblk_res * res_blk_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 1);
   float* s_scale = reinterpret_cast<float*>(tmem_ptr + 2);
   float* s_shift = s_scale + 256;
 
@@ -217,11 +233,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_out);
+    if (p.has_res) prefetch_tmap(&tmap_res);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -238,6 +257,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
+      if (p.has_res) {  // residual tile: lands while the main loop runs
+        mbar_expect_tx(res_bar, (uint32_t)nblk_res * (uint32_t)(p.BW * p.BH * 128));
+        for (int j = 0; j < nblk_res; ++j)
+          tma_load_4d(res_smem + (size_t)j * res_blk_bytes, &tmap_res, res_bar, n0 + j * 64, x0, y0, n_img);
+      }
       int kb = 0;
       for (int t = 0; t < p.R * p.S; ++t) {
         if (!((taps >> t) & 1u)) continue;
@@ -274,7 +298,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         umma_commit(empty_bar + s);  // frees the smem stage when these MMAs retire
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      umma_commit(tmem_full_bar);    // accumulator complete (and every operand stage consumed)
     }
     __syncwarp();
   } else {
@@ -288,24 +312,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-    const int m = q * 32 + lane;
-    const int yy = y0 + m / p.BW, xx = x0 + m % p.BW;
-    const bool live = m < p.BW * p.BH && yy < p.h && xx < p.w;
-    const int64_t pix = ((int64_t)n_img * p.h + yy) * p.w + xx;
+    if (p.has_res) mbar_wait(res_bar, 0);
+    const int m = q * 32 + lane;                       // tile row = output pixel (y0 + m / BW, x0 + m % BW)
+    const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(trow + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (live) {
+    const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
+    const int chunks16 = p.out_f32 ? 4 : 2;            // 16 B chunks produced per 16 columns
+    for (int blk = 0; blk < p.nblk; ++blk) {
+      uint8_t* orow = smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
+      for (int c16 = 0; c16 < p.blk_cols / 16; ++c16) {
+        const int col = blk * p.blk_cols + c16 * 16;
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)col, v);
+        tmem_ld_wait();
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
-        if (p.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.ldr + n0 + c0);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[col + j] + s_shift[col + j];
+        if (p.has_res) {
+          const uint8_t* rrow = res_smem + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
+          const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint4 u = __ldg(rp + j);
+            const uint4 u = *reinterpret_cast<const uint4*>(rrow + (((rk + j) ^ (uint32_t)(m & 7)) << 4));
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -318,12 +346,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        const uint32_t k0 = (uint32_t)(c16 * chunks16);
         if (p.out_f32) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n0 + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(orow + (((k0 + j) ^ sw) << 4)) =
+                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         } else {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + n0 + c0);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
@@ -335,11 +364,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             u.y = *reinterpret_cast<uint32_t*>(&b1);
             u.z = *reinterpret_cast<uint32_t*>(&b2);
             u.w = *reinterpret_cast<uint32_t*>(&b3);
-            o[j] = u;
+            *reinterpret_cast<uint4*>(orow + (((k0 + j) ^ sw) << 4)) = u;
           }
         }
       }
+      // generic-proxy writes -> visible to the async proxy, then one thread stores the block
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        tma_store_4d(&tmap_out, smem + (size_t)blk * blk_bytes, n0 + blk * p.blk_cols, x0, y0, n_img);
+        bulk_commit();
+      }
     }
+    if (et == 0) bulk_wait_read0();   // shared memory must outlive the stores' reads
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -430,6 +467,24 @@ static void pick_tile(int h, int w, int& BW, int& BH) {
 
 using namespace eeseg;
 
+static int encode_act_map(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt,
+                          int esize, int64_t C, int w, int h, int N, int64_t ld, int box_c, int box_w,
+                          int box_h, int stride, bool swizzle, const char* what) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * esize, (cuuint64_t)w * ld * esize, (cuuint64_t)h * w * ld * esize};
+  // with an element stride s TMA loads ceil(box/s) elements: box = tile*s fetches `tile` pixels
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = encode(tm, dt, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_igemm: cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+    return EESEG_ERR_CUDA;
+  }
+  return EESEG_OK;
+}
+
 extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
                                     const float* shift, int64_t shift_sn, int N, int hin, int win,
                                     int Cin, int Cout, int R, int S, int dilation, int stride,
@@ -439,64 +494,84 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   EESEG_REQUIRE(x && wt && scale && shift && out, "conv_igemm: null pointer");
   EESEG_REQUIRE(N >= 1 && hin >= 1 && win >= 1, "conv_igemm: bad sizes");
   EESEG_REQUIRE(stride == 1 || stride == 2, "conv_igemm: stride %d (1 or 2)", stride);
-  EESEG_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && (ldr % 8) == 0),
-                "conv_igemm: residual must be 16-byte aligned with ldr a multiple of 8");
-  // 'same' padding = dilation*(R/2): output size (in-1)/stride+1
-  const int h = (hin - 1) / stride + 1, w = (win - 1) / stride + 1;
   EESEG_REQUIRE(Cin % kBlockK == 0, "conv_igemm: Cin=%d must be a multiple of 64", Cin);
   EESEG_REQUIRE(Cout % 16 == 0, "conv_igemm: Cout=%d must be a multiple of 16", Cout);
   EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32 && (R & 1) && (S & 1), "conv_igemm: odd kernel sizes up to 32 taps");
   EESEG_REQUIRE(out_dtype == EESEG_BF16 || out_dtype == EESEG_F32, "conv_igemm: out_dtype %d", out_dtype);
+  const int oes = out_dtype == EESEG_F32 ? 4 : 2;
   EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
-                    (ldo % 8) == 0,
-                "conv_igemm: pointers must be 16-byte aligned and ldo a multiple of 8");
+                    (ldo * oes) % 16 == 0,
+                "conv_igemm: pointers and the output pixel stride must be 16-byte aligned");
+  EESEG_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && (ldr % 8) == 0 && out_dtype == EESEG_BF16 &&
+                              Cout % 64 == 0),
+                "conv_igemm: residual needs bf16 output, Cout %% 64 == 0, 16-byte alignment");
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     set_error("conv_igemm: cuTensorMapEncodeTiled unavailable (driver too old?)");
     return EESEG_ERR_CUDA;
   }
+  // 'same' padding = dilation*(R/2): output size (in-1)/stride+1
+  const int h = (hin - 1) / stride + 1, w = (win - 1) / stride + 1;
   ConvParams p;
   p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
   p.hin = hin; p.win = win; p.stride = stride;
-  p.res = (const __nv_bfloat16*)residual; p.ldr = ldr;
+  p.has_res = residual ? 1 : 0;
   pick_tile(h, w, p.BW, p.BH);
   p.tiles_x = (w + p.BW - 1) / p.BW;
   p.tiles_y = (h + p.BH - 1) / p.BH;
-  // output-channel tile: largest multiple of 16 <= 256 dividing Cout
-  int BN = Cout < 256 ? Cout : 256;
-  while (Cout % BN) BN -= 16;
+  const int kb_total = R * S * (Cin / kBlockK);
+  // output-channel tile: a power of two (16..256) dividing Cout; shallow-K wide-N layers (ResNet
+  // conv3 / projection shortcuts) are epilogue-bound: 128 columns let several CTAs share an SM
+  int BN = 256;
+  if (kb_total <= 8 && Cout >= 256) BN = 128;
+  while (BN > 16 && (Cout % BN)) BN >>= 1;
+  if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
-  p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.ldo = ldo; p.shift_sn = shift_sn;
-  p.scale = scale; p.shift = shift; p.out = out;
+  p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
+  p.scale = scale; p.shift = shift;
+  // epilogue blocks: 128 B of output per pixel row (64 bf16 / 32 fp32 channels), swizzled; narrower
+  // tiles use one dense block
+  const int full_cols = 128 / oes;
+  p.blk_cols = BN < full_cols ? BN : full_cols;
+  p.nblk = BN / p.blk_cols;
+  p.row_bytes = p.blk_cols * oes;
+  p.swz = p.row_bytes == 128 ? 1 : 0;
+  const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
+  const size_t res_bytes = residual ? (size_t)(BN / 64) * kBlockM * 128 : 0;
   const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
-  const size_t tail_bytes = (2 * kMaxStages + 1) * 8 + 8 + 2 * 256 * 4;
-  int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
+  const size_t tail_bytes = (2 * kMaxStages + 2) * 8 + 8 + 2 * 256 * 4;
+  const size_t budget = 227 * 1024 - 1024 - tail_bytes - res_bytes;
+  int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
+  if (stages < 1 || staging_bytes > budget) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
   // Shallow-K layers (ResNet 1x1 / 64-channel 3x3) are prologue/epilogue-bound: give them only the
   // stages they can use so several CTAs share an SM (shared memory and TMEM columns permitting) and
   // one CTA's epilogue overlaps another's main loop. Deep-K layers keep the full ring.
-  const int kb_total = R * S * (Cin / kBlockK);
   if (BN <= 128 || kb_total <= 16) {
-    const int fit_half = (int)((110 * 1024 - 1024 - tail_bytes) / stage_bytes);  // >= two CTAs per SM
+    const int fit_half = (int)((110 * 1024 - 1024 - tail_bytes - res_bytes) / stage_bytes);  // >= two CTAs per SM
     const int want = kb_total < 6 ? kb_total : 6;
-    stages = fit_half < 2 ? 2 : (fit_half < want ? fit_half : want);
-    if (stages > kb_total) stages = kb_total;
+    int st = fit_half < 2 ? 2 : (fit_half < want ? fit_half : want);
+    if (st < stages) stages = st;
   }
+  if (stages > kb_total) stages = kb_total;
   p.stages = stages;
-  const size_t smem_bytes = 1024 + stages * stage_bytes + tail_bytes;
+  const size_t ring = stages * stage_bytes;
+  p.main_bytes = (int)(((ring > staging_bytes ? ring : staging_bytes) + 1023) & ~(size_t)1023);
+  const size_t smem_bytes = 1024 + p.main_bytes + res_bytes + tail_bytes;
 
-  CUtensorMap tmx, tmw;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)win * Cin * 2, (cuuint64_t)hin * win * Cin * 2};
-    // with an element stride s TMA loads ceil(box/s) elements: box = tile*s fetches tile pixels
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), 1};
-    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
-                        es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv_igemm: cuTensorMapEncodeTiled(x) failed: %d", (int)r); return EESEG_ERR_CUDA; }
+  CUtensorMap tmx, tmw, tmo, tmr;
+  int rc = encode_act_map(encode, &tmx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cin, win, hin, N, Cin, kBlockK,
+                          p.BW, p.BH, stride, true, "x");
+  if (rc) return rc;
+  rc = encode_act_map(encode, &tmo, out, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      oes, Cout, w, h, N, ldo, p.blk_cols, p.BW, p.BH, 1, p.swz != 0, "out");
+  if (rc) return rc;
+  if (residual) {
+    rc = encode_act_map(encode, &tmr, residual, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, w, h, N, ldr, 64, p.BW,
+                        p.BH, 1, true, "residual");
+    if (rc) return rc;
+  } else {
+    tmr = tmo;
   }
   {
     const cuuint64_t Kt = (cuuint64_t)R * S * Cin;
@@ -515,7 +590,7 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
     attr_set = true;
   }
   dim3 grid((unsigned)(N * p.tiles_x * p.tiles_y), (unsigned)(Cout / BN));
-  conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
+  conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, tmo, tmr, p);
   return check_launch("conv_igemm_kernel");
 }
 

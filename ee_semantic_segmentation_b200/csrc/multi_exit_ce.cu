@@ -7,18 +7,23 @@
 // One thread per pixel (lanes = consecutive pixels of a class plane -> coalesced requests), the C
 // class values live in registers, per-block loss partials are written to a scratch array and
 // reduced in a fixed order (bit-reproducible loss).
+//
+// v2: the class planes are staged through shared memory with bulk-TMA copies (plane_stream.cuh),
+// 3-4 tiles in flight per CTA, one persistent CTA per SM; a thread still owns one pixel and keeps the
+// C values in registers while computing, and writes its gradient with coalesced plane stores.
 #include "common.cuh"
+#include "plane_stream.cuh"
 
 namespace eeseg {
 
-constexpr int kCeThreads = 256;
-constexpr int kCePix = 2;
+constexpr int kCeMaxStages = 4;
 
+// one persistent CTA per SM, split evenly over the E*N (exit, image) pairs
 static inline int ce_grid_x(int E, int N, int64_t HW) {
-  int64_t want = (HW + kCeThreads * kCePix - 1) / (kCeThreads * kCePix);
-  int64_t cap = (kNumSMs * 8 + (int64_t)E * N - 1) / ((int64_t)E * N);
-  if (cap < 1) cap = 1;
-  return (int)(want < cap ? want : cap);
+  int64_t per_pair = kNumSMs / ((int64_t)E * N);
+  if (per_pair < 1) per_pair = 1;
+  int64_t tiles = (HW + 255) / 256;
+  return (int)(per_pair < tiles ? per_pair : tiles);
 }
 
 __global__ void count_valid_kernel(const int64_t* __restrict__ targets, int64_t total, int C,
@@ -40,82 +45,115 @@ __global__ void count_valid_kernel(const int64_t* __restrict__ targets, int64_t 
   }
 }
 
-template <typename T, int CMAX>
-__global__ void __launch_bounds__(kCeThreads) ce_kernel(
+template <typename T, int CMAX, int TILE>
+__global__ void __launch_bounds__(TILE, 1) ce_kernel(
     const T* __restrict__ logits, int64_t exit_stride, const int64_t* __restrict__ targets, int N,
     int C, int64_t HW, int64_t ignore, const float* __restrict__ coef,
-    const int64_t* __restrict__ valid_count, T* __restrict__ dlogits, double* __restrict__ part) {
+    const int64_t* __restrict__ valid_count, T* __restrict__ dlogits, double* __restrict__ part,
+    const uint8_t* __restrict__ limit_logits, const uint8_t* __restrict__ limit_targets, int stages) {
+  extern __shared__ __align__(128) uint8_t ce_smem[];
+  constexpr int ES = (int)sizeof(T);
+  constexpr int rb = ps::row_bytes(TILE, ES), rbt = ps::row_bytes(TILE, 8);
+  const int stage_bytes = C * rb + rbt;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ce_smem + (size_t)stages * stage_bytes);
+
   const int e = blockIdx.y / N, n = blockIdx.y % N;
   const T* base = logits + (int64_t)e * exit_stride + (int64_t)n * C * HW;
   T* gbase = dlogits ? dlogits + (int64_t)e * exit_stride + (int64_t)n * C * HW : nullptr;
   const int64_t* tg = targets + (int64_t)n * HW;
-  float gscale = 0.f;
-  if (gbase) {
-    const float valid = (float)(*valid_count);
-    gscale = (coef ? coef[e] : 1.f) / valid;  // valid == 0 -> inf/NaN like torch's 0/0
+  const uint8_t* base_b = reinterpret_cast<const uint8_t*>(base);
+  const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(tg);
+
+  const int num_tiles = (int)((HW + TILE - 1) / TILE);
+  const int my_count = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  auto issue = [&](int k) {  // thread 0 only
+    const int s = k % stages;
+    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+    const int count = (int)min((int64_t)TILE, HW - p0);
+    uint8_t* st = ce_smem + (size_t)s * stage_bytes;
+    ps::issue_tile<ES>(st, rb, full + s, base_b, HW, C, p0, count, limit_logits);
+    ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) ps::mbar_init(full + s, 2);  // two arming arrivals per phase
+    ps::fence_barrier_init();
   }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < stages && k < my_count; ++k) issue(k);
+
+  float gscale = 0.f;
+  if (gbase) gscale = (coef ? coef[e] : 1.f) / (float)(*valid_count);  // valid == 0 -> NaN like torch
+  // misalignment (in elements) of plane c at a tile start: (a0 + c*delta) & 15, both mod 16 bytes
+  const uint32_t delta = (uint32_t)(((uint64_t)HW * ES) & 15);
   float loss_acc = 0.f;
-  const int64_t step = (int64_t)gridDim.x * kCeThreads * kCePix;
-  for (int64_t p0 = (int64_t)blockIdx.x * kCeThreads * kCePix + threadIdx.x; p0 < HW; p0 += step) {
-    float v[kCePix][CMAX];
-    int t[kCePix];
-    bool ok[kCePix];
+
+  for (int k = 0; k < my_count; ++k) {
+    const int s = k % stages;
+    const uint32_t ph = (uint32_t)(k / stages) & 1u;
+    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+    const int64_t p = p0 + threadIdx.x;
+    const uint8_t* st = ce_smem + (size_t)s * stage_bytes;
+    ps::mbar_wait(full + s, ph);
+    const uint32_t a0 = (uint32_t)((uintptr_t)(base_b + p0 * ES) & 15);
+    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15) / 8;
+    float v[CMAX];
+    int64_t tt = ignore;
+    if (p < HW) {
+      tt = reinterpret_cast<const int64_t*>(st + (size_t)C * rb)[t0 + threadIdx.x];
 #pragma unroll
-    for (int j = 0; j < kCePix; ++j) {
-      const int64_t p = p0 + (int64_t)j * kCeThreads;
-      int64_t tt = p < HW ? __ldg(tg + p) : ignore;
-      ok[j] = p < HW && tt != ignore && tt >= 0 && tt < C;
-      t[j] = (int)tt;
-    }
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-#pragma unroll
-      for (int j = 0; j < kCePix; ++j)
-        if (c < C && ok[j]) v[j][c] = ldf_stream(base + (int64_t)c * HW + p0 + (int64_t)j * kCeThreads);
-#pragma unroll
-    for (int j = 0; j < kCePix; ++j) {
-      const int64_t p = p0 + (int64_t)j * kCeThreads;
-      if (ok[j]) {
-        float m = v[j][0];
-#pragma unroll
-        for (int c = 1; c < CMAX; ++c)
-          if (c < C) m = fmaxf(m, v[j][c]);
-        float S = 0.f, picked = 0.f;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < C) {
-            float z = v[j][c] - m;
-            v[j][c] = z;
-            S += exp2f(z * 1.4426950408889634f);
-            picked = (c == t[j]) ? z : picked;
-          }
-        const float lse = logf(S);
-        loss_acc += lse - picked;
-        if (gbase) {
-#pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < C) {
-              float sm = exp2f((v[j][c] - lse) * 1.4426950408889634f);
-              stf(gbase + (int64_t)c * HW + p, gscale * (sm - (c == t[j] ? 1.f : 0.f)));
-            }
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          const uint32_t sh = ((a0 + (uint32_t)c * delta) & 15u) / ES;
+          const T* row = reinterpret_cast<const T*>(st + (size_t)c * rb);
+          if constexpr (ES == 4) v[c] = reinterpret_cast<const float*>(row)[sh + threadIdx.x];
+          else v[c] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[sh + threadIdx.x]);
         }
-      } else if (gbase && p < HW) {
+    }
+    __syncthreads();                       // everyone holds its pixel in registers: stage s is free
+    if (threadIdx.x == 0 && k + stages < my_count) issue(k + stages);
+
+    const bool ok = p < HW && tt != ignore && tt >= 0 && tt < C;
+    if (ok) {
+      const int t = (int)tt;
+      float m = v[0];
+#pragma unroll
+      for (int c = 1; c < CMAX; ++c)
+        if (c < C) m = fmaxf(m, v[c]);
+      float S = 0.f, picked = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          const float z = v[c] - m;
+          const float ez = exp2f(z * 1.4426950408889634f);
+          v[c] = ez;                      // keep exp(z) for the gradient: one exp per class
+          S += ez;
+          picked = (c == t) ? z : picked;
+        }
+      loss_acc += logf(S) - picked;
+      if (gbase) {
+        const float inv = gscale / S;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) stf(gbase + (int64_t)c * HW + p, 0.f);
+          if (c < C) stf(gbase + (int64_t)c * HW + p, v[c] * inv - (c == t ? gscale : 0.f));
       }
+    } else if (gbase && p < HW) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) stf(gbase + (int64_t)c * HW + p, 0.f);
     }
   }
   if (part) {
-    __shared__ double s[kCeThreads / 32];
+    __shared__ double sred[32];
     double ws = warp_sum((double)loss_acc);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ws;
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ws;
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.0;
-      for (int i = 0; i < kCeThreads / 32; ++i) t += s[i];
-      // slot order: [e][n][blockIdx.x]
-      part[((int64_t)e * N + n) * gridDim.x + blockIdx.x] = t;
+      for (int i = 0; i < TILE / 32; ++i) t += sred[i];
+      part[((int64_t)e * N + n) * gridDim.x + blockIdx.x] = t;  // slot order: [e][n][blockIdx.x]
     }
   }
 }
@@ -150,21 +188,34 @@ __global__ void scale_exits_kernel(T* __restrict__ d, int64_t exit_stride, int64
     stf(p + i, ldf(p + i) * r);
 }
 
+template <typename T, int CMAX, int TILE>
+static int launch_ce_cfg(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
+                         int C, int64_t HW, int64_t ignore, const float* coef,
+                         const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
+  const int rb = ps::row_bytes(TILE, (int)sizeof(T)), rbt = ps::row_bytes(TILE, 8);
+  const size_t stage_bytes = (size_t)C * rb + rbt;
+  int stages = (int)((220 * 1024 - 64) / stage_bytes);
+  if (stages > kCeMaxStages) stages = kCeMaxStages;
+  if (stages < 1) { set_error("multi_exit_ce: C=%d does not fit the staging buffers", C); return EESEG_ERR_UNSUPPORTED; }
+  const size_t smem = stages * stage_bytes + kCeMaxStages * sizeof(uint64_t);
+  auto kern = ce_kernel<T, CMAX, TILE>;
+  EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uintptr_t end_l = (uintptr_t)(logits + (int64_t)(E - 1) * exit_stride + (int64_t)N * C * HW);
+  const uintptr_t end_t = (uintptr_t)(targets + (int64_t)N * HW);
+  dim3 grid(ce_grid_x(E, N, HW), E * N);
+  kern<<<grid, TILE, smem, stream>>>(logits, exit_stride, targets, N, C, HW, ignore, coef, valid_count,
+                                     dlogits, part, (const uint8_t*)((end_l + 15) & ~(uintptr_t)15),
+                                     (const uint8_t*)((end_t + 15) & ~(uintptr_t)15), stages);
+  return check_launch("ce_kernel");
+}
+
 template <typename T>
 static int launch_ce(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                      int C, int64_t HW, int64_t ignore, const float* coef,
                      const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
-  dim3 grid(ce_grid_x(E, N, HW), E * N);
-#define EESEG_CE_CASE(CM)                                                                    \
-  if (C <= CM) {                                                                              \
-    ce_kernel<T, CM><<<grid, kCeThreads, 0, stream>>>(logits, exit_stride, targets, N, C, HW, \
-                                                      ignore, coef, valid_count, dlogits, part); \
-    return check_launch("ce_kernel");                                                         \
-  }
-  EESEG_CE_CASE(24)
-  EESEG_CE_CASE(32)
-  EESEG_CE_CASE(64)
-#undef EESEG_CE_CASE
+  if (C <= 24) return launch_ce_cfg<T, 24, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C <= 32) return launch_ce_cfg<T, 32, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C <= 64) return launch_ce_cfg<T, 64, 256>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
   set_error("multi_exit_ce: C=%d > 64 classes is not supported by this build", C);
   return EESEG_ERR_UNSUPPORTED;
 }
