@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) cm_from_logits_kernel(const T* __restrict
 // Streaming variant (the default for logits): class planes staged through shared memory with
 // bulk-TMA copies (plane_stream.cuh), one persistent CTA per SM, several tiles in flight.
 template <typename T, int TILE>
-__global__ void __launch_bounds__(TILE, 1) cm_from_logits_stream_kernel(
+__global__ void __launch_bounds__(TILE, 2) cm_from_logits_stream_kernel(
     const T* __restrict__ logits, const int64_t* __restrict__ targets, int C, int64_t HW, int copies,
     unsigned long long* __restrict__ cm, const uint8_t* __restrict__ limit_logits,
     const uint8_t* __restrict__ limit_targets, int stages) {
@@ -100,21 +100,22 @@ __global__ void __launch_bounds__(TILE, 1) cm_from_logits_stream_kernel(
   const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(targets + (int64_t)n * HW);
   const int num_tiles = (int)((HW + TILE - 1) / TILE);
   const int my_count = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto issue = [&](int k) {
+  auto issue = [&](int k) {   // thread r issues row r (r < C: class plane, r == C: targets)
+    const int r = threadIdx.x;
+    if (r > C) return;
     const int s = k % stages;
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
     const int count = (int)min((int64_t)TILE, HW - p0);
     uint8_t* st = hs_smem + (size_t)s * stage_bytes;
-    ps::issue_tile<ES>(st, rb, full + s, base_b, HW, C, p0, count, limit_logits);
-    ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
+    if (r < C) ps::issue_tile<ES>(st + (size_t)r * rb, rb, full + s, base_b + (int64_t)r * HW * ES, 0, 1, p0, count, limit_logits);
+    else ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
   };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) ps::mbar_init(full + s, 2);
+    for (int s = 0; s < stages; ++s) ps::mbar_init(full + s, C + 1);
     ps::fence_barrier_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0)
-    for (int k = 0; k < stages && k < my_count; ++k) issue(k);
+  for (int k = 0; k < stages && k < my_count; ++k) issue(k);
   const uint32_t delta = (uint32_t)(((uint64_t)HW * ES) & 15);
   for (int k = 0; k < my_count; ++k) {
     const int s = k % stages;
@@ -123,28 +124,43 @@ __global__ void __launch_bounds__(TILE, 1) cm_from_logits_stream_kernel(
     const uint8_t* st = hs_smem + (size_t)s * stage_bytes;
     ps::mbar_wait(full + s, (uint32_t)(k / stages) & 1u);
     const uint32_t a0 = (uint32_t)((uintptr_t)(base_b + p0 * ES) & 15);
-    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15) / 8;
+    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15);
+    const uint32_t stu = ps::smem_u32(st);
+    constexpr int P = 16 / ES;   // the plane misalignment pattern repeats every P classes
+    uint32_t rowbase[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) rowbase[r] = stu + ((a0 + (uint32_t)r * delta) & 15u) + threadIdx.x * ES;
     int key = -1;
     if (p < HW) {
-      const int64_t t = reinterpret_cast<const int64_t*>(st + (size_t)C * rb)[t0 + threadIdx.x];
-      float best = 0.f;
+      int64_t t;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t) : "r"(stu + (uint32_t)C * rb + t0 + threadIdx.x * 8));
+      float best = -INFINITY;
       int arg = 0;
-#pragma unroll 7
-      for (int c = 0; c < C; ++c) {
-        const uint32_t sh = ((a0 + (uint32_t)c * delta) & 15u) / ES;
-        float v;
-        if constexpr (ES == 4) v = reinterpret_cast<const float*>(st + (size_t)c * rb)[sh + threadIdx.x];
-        else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(st + (size_t)c * rb)[sh + threadIdx.x]);
-        // torch.argmax: first maximal index, NaN counts as the maximum
-        const bool take = (c == 0) || (v > best) || (v != v && best == best);
-        if (take) { best = v; arg = c; }
+      for (int c0 = 0; c0 < C; c0 += P) {
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+          const int c = c0 + r;
+          if (c < C) {
+            float v;
+            if constexpr (ES == 4) {
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(rowbase[r] + (uint32_t)c * rb));
+            } else {
+              unsigned short u;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(rowbase[r] + (uint32_t)c * rb));
+              v = __uint_as_float(((uint32_t)u) << 16);
+            }
+            // torch.argmax: first maximal index, NaN counts as the maximum
+            const bool take = (v > best) || (v != v && best == best) || (c == 0);
+            if (take) { best = v; arg = c; }
+          }
+        }
       }
       const int tt = (t >= 0 && t < C) ? (int)t : C;
       key = tt * C + arg;
     }
+    __syncthreads();            // every thread has read its pixel: the stage can be refilled
+    if (k + stages < my_count) issue(k + stages);
     hist_add(h, key);
-    __syncthreads();
-    if (threadIdx.x == 0 && k + stages < my_count) issue(k + stages);
   }
   hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
 }
@@ -249,11 +265,11 @@ extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype,
       const size_t stage_bytes = (size_t)C * ps::row_bytes(kTile, es) + ps::row_bytes(kTile, 8);
       int hcopies = copies < 4 ? copies : 4;
       const size_t fixed = 8 * sizeof(uint64_t) + (size_t)hcopies * bytes1;
-      int stages = (int)((220 * 1024 - fixed) / stage_bytes);
-      if (stages > 6) stages = 6;
-      if (stages >= 2) {
+      int stages = (int)((112 * 1024 - fixed) / stage_bytes);   // two CTAs per SM
+      if (stages > 3) stages = 3;
+      if (stages >= 2 && C + 1 <= kTile) {
         const size_t smem = stages * stage_bytes + fixed;
-        int64_t per_img = kNumSMs / N;
+        int64_t per_img = 2 * kNumSMs / N;
         if (per_img < 1) per_img = 1;
         const int64_t tiles = (HW + kTile - 1) / kTile;
         dim3 sgrid((unsigned)(per_img < tiles ? per_img : tiles), (unsigned)N);

@@ -42,6 +42,11 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
   l0 = 1.f - l1;
 }
 
+// CMAX values 24/32/64 are register-array capacities with a runtime class count (guards in the
+// unrolled loops); any other CMAX (19 = Cityscapes, 21 = VOC) is the exact class count, so every
+// guard folds away at compile time.
+__host__ __device__ constexpr bool cmax_is_exact(int cmax) { return cmax != 24 && cmax != 32 && cmax != 64; }
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -58,13 +63,13 @@ __device__ __forceinline__ void lerp_row(const TI* __restrict__ row, int off0, i
     const float4* a = reinterpret_cast<const float4*>(row + off0);
     const float4* b = reinterpret_cast<const float4*>(row + off1);
 #pragma unroll
-    for (int q = 0; q < CMAX / 4; ++q) {
+    for (int q = 0; q < (CMAX + 3) / 4; ++q) {
       if (q * 4 < C) {
         const float4 u = __ldg(a + q), v = __ldg(b + q);
-        out[4 * q + 0] = lx0 * u.x + lx1 * v.x;
-        out[4 * q + 1] = lx0 * u.y + lx1 * v.y;
-        out[4 * q + 2] = lx0 * u.z + lx1 * v.z;
-        out[4 * q + 3] = lx0 * u.w + lx1 * v.w;
+        if (4 * q + 0 < CMAX) out[4 * q + 0] = lx0 * u.x + lx1 * v.x;
+        if (4 * q + 1 < CMAX) out[4 * q + 1] = lx0 * u.y + lx1 * v.y;
+        if (4 * q + 2 < CMAX) out[4 * q + 2] = lx0 * u.z + lx1 * v.z;
+        if (4 * q + 3 < CMAX) out[4 * q + 3] = lx0 * u.w + lx1 * v.w;
       }
     }
   } else {
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 
   const int Y0 = blockIdx.y * kRowsPerStrip;
   const int Y1 = min(Y0 + kRowsPerStrip, p.H);
   const bool live = X < p.W;
-  const int C = p.C;
+  const int C = cmax_is_exact(CMAX) ? CMAX : p.C;
   const TI* in = reinterpret_cast<const TI*>(p.in) + (int64_t)n * p.in_sn;
   TO* up = p.up ? reinterpret_cast<TO*>(p.up) + (int64_t)n * p.up_sn : nullptr;
   const int64_t HW = (int64_t)p.H * p.W;
@@ -287,6 +292,8 @@ static int launch_gate(const GateParams& p, bool interp, bool vec, cudaStream_t 
     else gate_kernel<TI, TO, CM, false, false><<<grid, kGateThreads, 0, stream>>>(p);               \
     return check_launch("gate_kernel");                                                             \
   }
+  if (p.C == 21) { EESEG_GATE_CASE(21) }
+  if (p.C == 19) { EESEG_GATE_CASE(19) }
   EESEG_GATE_CASE(24)
   EESEG_GATE_CASE(32)
   EESEG_GATE_CASE(64)

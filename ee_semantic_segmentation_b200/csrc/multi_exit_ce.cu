@@ -16,11 +16,10 @@
 
 namespace eeseg {
 
-constexpr int kCeMaxStages = 4;
 
-// one persistent CTA per SM, split evenly over the E*N (exit, image) pairs
+// two persistent CTAs per SM, split evenly over the E*N (exit, image) pairs
 static inline int ce_grid_x(int E, int N, int64_t HW) {
-  int64_t per_pair = kNumSMs / ((int64_t)E * N);
+  int64_t per_pair = 2 * kNumSMs / ((int64_t)E * N);
   if (per_pair < 1) per_pair = 1;
   int64_t tiles = (HW + 255) / 256;
   return (int)(per_pair < tiles ? per_pair : tiles);
@@ -45,75 +44,110 @@ __global__ void count_valid_kernel(const int64_t* __restrict__ targets, int64_t 
   }
 }
 
-template <typename T, int CMAX, int TILE>
-__global__ void __launch_bounds__(TILE, 1) ce_kernel(
+__device__ __forceinline__ float ce_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ce_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T>
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+  if constexpr (sizeof(T) == 4) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+  } else {
+    unsigned short u;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
+    return __uint_as_float(((uint32_t)u) << 16);
+  }
+}
+
+// The kernel is instruction-issue bound before it is HBM bound (ncu on v1: 836 thread instructions
+// per pixel-exit, issue slots 50 % busy at 36 % of DRAM peak), so the per-class work is kept to
+// ~10 instructions: one LDS with a compile-time offset (plane misalignments repeat with period
+// 16/sizeof(T), so only that many row bases are computed per tile), one exp2 (kept for the
+// gradient), base-2 log-sum-exp, the target logit fetched by one dynamic LDS.
+template <typename T, int CMAX, int TILE, int STAGES>
+__global__ void __launch_bounds__(TILE, 2) ce_kernel(
     const T* __restrict__ logits, int64_t exit_stride, const int64_t* __restrict__ targets, int N,
     int C, int64_t HW, int64_t ignore, const float* __restrict__ coef,
     const int64_t* __restrict__ valid_count, T* __restrict__ dlogits, double* __restrict__ part,
-    const uint8_t* __restrict__ limit_logits, const uint8_t* __restrict__ limit_targets, int stages) {
+    const uint8_t* __restrict__ limit_logits, const uint8_t* __restrict__ limit_targets) {
+  // CMAX 32/64 = register capacity with a runtime class count; any other CMAX is the exact count
+  // (19 Cityscapes, 21 VOC) and the per-class guards fold away
+  if (CMAX != 32 && CMAX != 64) C = CMAX;
   extern __shared__ __align__(128) uint8_t ce_smem[];
   constexpr int ES = (int)sizeof(T);
+  constexpr int P = 16 / ES;                       // period of the plane misalignment pattern
   constexpr int rb = ps::row_bytes(TILE, ES), rbt = ps::row_bytes(TILE, 8);
   const int stage_bytes = C * rb + rbt;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ce_smem + (size_t)stages * stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ce_smem + (size_t)STAGES * stage_bytes);
 
   const int e = blockIdx.y / N, n = blockIdx.y % N;
   const T* base = logits + (int64_t)e * exit_stride + (int64_t)n * C * HW;
   T* gbase = dlogits ? dlogits + (int64_t)e * exit_stride + (int64_t)n * C * HW : nullptr;
-  const int64_t* tg = targets + (int64_t)n * HW;
   const uint8_t* base_b = reinterpret_cast<const uint8_t*>(base);
-  const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(tg);
+  const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(targets + (int64_t)n * HW);
 
   const int num_tiles = (int)((HW + TILE - 1) / TILE);
-  const int my_count = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_count = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  auto issue = [&](int k) {  // thread 0 only
-    const int s = k % stages;
+  // row r of tile k is issued by thread r (r < C: class plane r, r == C: the int64 targets)
+  auto issue = [&](int k) {
+    const int r = threadIdx.x;
+    if (r > C) return;
+    const int s = k % STAGES;
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
     const int count = (int)min((int64_t)TILE, HW - p0);
     uint8_t* st = ce_smem + (size_t)s * stage_bytes;
-    ps::issue_tile<ES>(st, rb, full + s, base_b, HW, C, p0, count, limit_logits);
-    ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
+    if (r < C) ps::issue_tile<ES>(st + (size_t)r * rb, rb, full + s, base_b + (int64_t)r * HW * ES, 0, 1, p0, count, limit_logits);
+    else ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) ps::mbar_init(full + s, 2);  // two arming arrivals per phase
+    for (int s = 0; s < STAGES; ++s) ps::mbar_init(full + s, C + 1);  // one arming arrival per row
     ps::fence_barrier_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0)
-    for (int k = 0; k < stages && k < my_count; ++k) issue(k);
+  for (int k = 0; k < STAGES && k < my_count; ++k) issue(k);
 
   float gscale = 0.f;
   if (gbase) gscale = (coef ? coef[e] : 1.f) / (float)(*valid_count);  // valid == 0 -> NaN like torch
-  // misalignment (in elements) of plane c at a tile start: (a0 + c*delta) & 15, both mod 16 bytes
   const uint32_t delta = (uint32_t)(((uint64_t)HW * ES) & 15);
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   float loss_acc = 0.f;
 
   for (int k = 0; k < my_count; ++k) {
-    const int s = k % stages;
-    const uint32_t ph = (uint32_t)(k / stages) & 1u;
+    const int s = k % STAGES;
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
     const int64_t p = p0 + threadIdx.x;
-    const uint8_t* st = ce_smem + (size_t)s * stage_bytes;
-    ps::mbar_wait(full + s, ph);
+    const uint32_t st = ps::smem_u32(ce_smem + (size_t)s * stage_bytes);
+    ps::mbar_wait(full + s, (uint32_t)(k / STAGES) & 1u);
     const uint32_t a0 = (uint32_t)((uintptr_t)(base_b + p0 * ES) & 15);
-    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15) / 8;
+    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15);
+    uint32_t rowbase[P];                              // shared address of this thread's pixel in row c, minus c*rb
+#pragma unroll
+    for (int r = 0; r < P; ++r) rowbase[r] = st + ((a0 + (uint32_t)r * delta) & 15u) + threadIdx.x * ES;
     float v[CMAX];
     int64_t tt = ignore;
+    float vt = 0.f;
     if (p < HW) {
-      tt = reinterpret_cast<const int64_t*>(st + (size_t)C * rb)[t0 + threadIdx.x];
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(tt) : "r"(st + (uint32_t)C * rb + t0 + threadIdx.x * 8));
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
-        if (c < C) {
-          const uint32_t sh = ((a0 + (uint32_t)c * delta) & 15u) / ES;
-          const T* row = reinterpret_cast<const T*>(st + (size_t)c * rb);
-          if constexpr (ES == 4) v[c] = reinterpret_cast<const float*>(row)[sh + threadIdx.x];
-          else v[c] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[sh + threadIdx.x]);
-        }
+        if (c < C) v[c] = lds_f<T>(rowbase[c % P] + (uint32_t)c * rb);
+      if (tt >= 0 && tt < C) {
+        const uint32_t c = (uint32_t)tt;
+        vt = lds_f<T>(st + ((a0 + c * delta) & 15u) + threadIdx.x * ES + c * rb);   // target logit
+      }
     }
     __syncthreads();                       // everyone holds its pixel in registers: stage s is free
-    if (threadIdx.x == 0 && k + stages < my_count) issue(k + stages);
+    if (k + STAGES < my_count) issue(k + STAGES);
 
     const bool ok = p < HW && tt != ignore && tt >= 0 && tt < C;
     if (ok) {
@@ -122,27 +156,27 @@ __global__ void __launch_bounds__(TILE, 1) ce_kernel(
 #pragma unroll
       for (int c = 1; c < CMAX; ++c)
         if (c < C) m = fmaxf(m, v[c]);
-      float S = 0.f, picked = 0.f;
+      const float m2 = m * kLog2e;
+      float S = 0.f;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
         if (c < C) {
-          const float z = v[c] - m;
-          const float ez = exp2f(z * 1.4426950408889634f);
-          v[c] = ez;                      // keep exp(z) for the gradient: one exp per class
-          S += ez;
-          picked = (c == t) ? z : picked;
+          v[c] = ce_ex2(fmaf(v[c], kLog2e, -m2));   // exp(v - m), kept for the gradient
+          S += v[c];
         }
-      loss_acc += logf(S) - picked;
+      loss_acc += ce_lg2(S) * kLn2 - (vt - m);
       if (gbase) {
         const float inv = gscale / S;
+        T* gp = gbase + p;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) stf(gbase + (int64_t)c * HW + p, v[c] * inv - (c == t ? gscale : 0.f));
+          if (c < C) stf(gp + (int64_t)c * HW, fmaf(v[c], inv, c == t ? -gscale : 0.f));
       }
     } else if (gbase && p < HW) {
+      T* gp = gbase + p;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
-        if (c < C) stf(gbase + (int64_t)c * HW + p, 0.f);
+        if (c < C) stf(gp + (int64_t)c * HW, 0.f);
     }
   }
   if (part) {
@@ -192,20 +226,19 @@ template <typename T, int CMAX, int TILE>
 static int launch_ce_cfg(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                          int C, int64_t HW, int64_t ignore, const float* coef,
                          const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
+  constexpr int kStages = 2;   // two CTAs per SM x two tiles each in flight
   const int rb = ps::row_bytes(TILE, (int)sizeof(T)), rbt = ps::row_bytes(TILE, 8);
   const size_t stage_bytes = (size_t)C * rb + rbt;
-  int stages = (int)((220 * 1024 - 64) / stage_bytes);
-  if (stages > kCeMaxStages) stages = kCeMaxStages;
-  if (stages < 1) { set_error("multi_exit_ce: C=%d does not fit the staging buffers", C); return EESEG_ERR_UNSUPPORTED; }
-  const size_t smem = stages * stage_bytes + kCeMaxStages * sizeof(uint64_t);
-  auto kern = ce_kernel<T, CMAX, TILE>;
+  const size_t smem = kStages * stage_bytes + kStages * sizeof(uint64_t);
+  if (smem > 113 * 1024) { set_error("multi_exit_ce: C=%d does not fit the staging buffers", C); return EESEG_ERR_UNSUPPORTED; }
+  auto kern = ce_kernel<T, CMAX, TILE, kStages>;
   EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uintptr_t end_l = (uintptr_t)(logits + (int64_t)(E - 1) * exit_stride + (int64_t)N * C * HW);
   const uintptr_t end_t = (uintptr_t)(targets + (int64_t)N * HW);
   dim3 grid(ce_grid_x(E, N, HW), E * N);
   kern<<<grid, TILE, smem, stream>>>(logits, exit_stride, targets, N, C, HW, ignore, coef, valid_count,
                                      dlogits, part, (const uint8_t*)((end_l + 15) & ~(uintptr_t)15),
-                                     (const uint8_t*)((end_t + 15) & ~(uintptr_t)15), stages);
+                                     (const uint8_t*)((end_t + 15) & ~(uintptr_t)15));
   return check_launch("ce_kernel");
 }
 
@@ -213,9 +246,10 @@ template <typename T>
 static int launch_ce(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                      int C, int64_t HW, int64_t ignore, const float* coef,
                      const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
-  if (C <= 24) return launch_ce_cfg<T, 24, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C == 21) return launch_ce_cfg<T, 21, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C == 19) return launch_ce_cfg<T, 19, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
   if (C <= 32) return launch_ce_cfg<T, 32, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
-  if (C <= 64) return launch_ce_cfg<T, 64, 256>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C <= 64) return launch_ce_cfg<T, 64, 128>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
   set_error("multi_exit_ce: C=%d > 64 classes is not supported by this build", C);
   return EESEG_ERR_UNSUPPORTED;
 }
