@@ -55,6 +55,15 @@ __device__ __forceinline__ float ce_lg2(float x) {
   return y;
 }
 template <typename T>
+__device__ __forceinline__ void sts_f(uint32_t addr, float v) {
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+  } else {
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<unsigned short*>(&b)) : "memory");
+  }
+}
+template <typename T>
 __device__ __forceinline__ float lds_f(uint32_t addr) {
   if constexpr (sizeof(T) == 4) {
     float v;
@@ -146,9 +155,6 @@ __global__ void __launch_bounds__(TILE, 2) ce_kernel(
         vt = lds_f<T>(st + ((a0 + c * delta) & 15u) + threadIdx.x * ES + c * rb);   // target logit
       }
     }
-    __syncthreads();                       // everyone holds its pixel in registers: stage s is free
-    if (k + STAGES < my_count) issue(k + STAGES);
-
     const bool ok = p < HW && tt != ignore && tt >= 0 && tt < C;
     if (ok) {
       const int t = (int)tt;
@@ -166,19 +172,34 @@ __global__ void __launch_bounds__(TILE, 2) ce_kernel(
         }
       loss_acc += ce_lg2(S) * kLn2 - (vt - m);
       if (gbase) {
+        // gradient goes back IN PLACE into the staged rows (same misalignment as its destination
+        // plane), then leaves with one bulk store per row
         const float inv = gscale / S;
-        T* gp = gbase + p;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) stf(gp + (int64_t)c * HW, fmaf(v[c], inv, c == t ? -gscale : 0.f));
+          if (c < C) sts_f<T>(rowbase[c % P] + (uint32_t)c * rb, fmaf(v[c], inv, c == t ? -gscale : 0.f));
       }
     } else if (gbase && p < HW) {
-      T* gp = gbase + p;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
-        if (c < C) stf(gp + (int64_t)c * HW, 0.f);
+        if (c < C) sts_f<T>(rowbase[c % P] + (uint32_t)c * rb, 0.f);
+    }
+    if (gbase) ps::fence_proxy_async();      // generic-proxy smem writes -> visible to the bulk engine
+    __syncthreads();                         // inputs consumed (and gradients staged) by every thread
+    {
+      const int r = threadIdx.x;             // thread r owns row r: store it, then refill it
+      if (r <= C) {
+        if (gbase && r < C) {
+          const int count = (int)min((int64_t)TILE, HW - p0);
+          ps::store_row<T>(ce_smem + (size_t)s * stage_bytes + (size_t)r * rb, gbase + (int64_t)r * HW + p0, count);
+          ps::bulk_commit();
+          if (k + STAGES < my_count) ps::bulk_wait_read0();   // the row must be read out before it is refilled
+        }
+        if (k + STAGES < my_count) issue(k + STAGES);
+      }
     }
   }
+  if (gbase && threadIdx.x < C) ps::bulk_wait_read0();
   if (part) {
     __shared__ double sred[32];
     double ws = warp_sum((double)loss_acc);
@@ -226,11 +247,15 @@ template <typename T, int CMAX, int TILE>
 static int launch_ce_cfg(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                          int C, int64_t HW, int64_t ignore, const float* coef,
                          const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
-  constexpr int kStages = 2;   // two CTAs per SM x two tiles each in flight
+  constexpr int kStages = 3;   // two CTAs per SM x three tiles each in flight
   const int rb = ps::row_bytes(TILE, (int)sizeof(T)), rbt = ps::row_bytes(TILE, 8);
   const size_t stage_bytes = (size_t)C * rb + rbt;
   const size_t smem = kStages * stage_bytes + kStages * sizeof(uint64_t);
   if (smem > 113 * 1024) { set_error("multi_exit_ce: C=%d does not fit the staging buffers", C); return EESEG_ERR_UNSUPPORTED; }
+  if (dlogits && (((uintptr_t)dlogits ^ (uintptr_t)logits) & 15)) {
+    set_error("multi_exit_ce: logits and dlogits must have the same 16-byte misalignment");
+    return EESEG_ERR_ARG;
+  }
   auto kern = ce_kernel<T, CMAX, TILE, kStages>;
   EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uintptr_t end_l = (uintptr_t)(logits + (int64_t)(E - 1) * exit_stride + (int64_t)N * C * HW);
@@ -246,9 +271,9 @@ template <typename T>
 static int launch_ce(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                      int C, int64_t HW, int64_t ignore, const float* coef,
                      const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
-  if (C == 21) return launch_ce_cfg<T, 21, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
-  if (C == 19) return launch_ce_cfg<T, 19, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
-  if (C <= 32) return launch_ce_cfg<T, 32, 512>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C == 21) return launch_ce_cfg<T, 21, 256>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C == 19) return launch_ce_cfg<T, 19, 256>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+  if (C <= 32) return launch_ce_cfg<T, 32, 256>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
   if (C <= 64) return launch_ce_cfg<T, 64, 128>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
   set_error("multi_exit_ce: C=%d > 64 classes is not supported by this build", C);
   return EESEG_ERR_UNSUPPORTED;

@@ -80,6 +80,30 @@ __device__ __forceinline__ void issue_tile(uint8_t* smem, int rbytes, uint64_t* 
   }
 }
 
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Issued by ONE thread: writes `count` elements of one staged row (element i at row + (dst & 15) +
+// i*ESIZE, i.e. the same layout issue_tile produces) to global memory at dst: the 16 B-aligned
+// interior with one bulk store (full lines to L2), the < 16 B head and tail with scalar stores.
+template <typename T>
+__device__ __forceinline__ void store_row(const uint8_t* row, T* dst, int count) {
+  constexpr int ES = (int)sizeof(T);
+  const uintptr_t a = (uintptr_t)dst, b = a + (uintptr_t)count * ES;
+  uintptr_t a1 = (a + 15) & ~(uintptr_t)15, b1 = b & ~(uintptr_t)15;
+  const uint8_t* src = row + (a & 15);          // element 0
+  if (b1 <= a1) { a1 = b; b1 = b; }             // shorter than one aligned chunk: all scalar
+  for (uintptr_t q = a; q < a1; q += ES) *reinterpret_cast<T*>(q) = *reinterpret_cast<const T*>(src + (q - a));
+  for (uintptr_t q = b1; q < b; q += ES) *reinterpret_cast<T*>(q) = *reinterpret_cast<const T*>(src + (q - a));
+  if (b1 > a1) bulk_s2g(reinterpret_cast<void*>(a1), src + (a1 - a), (uint32_t)(b1 - a1));
+}
+
 // Element offset of pixel p0 inside the staged row of plane r.
 template <int ESIZE>
 __device__ __forceinline__ int row_shift(const uint8_t* base, int64_t plane_stride, int r, int64_t p0) {
