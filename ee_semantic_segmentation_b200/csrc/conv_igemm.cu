@@ -120,7 +120,19 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
       : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read(int pending) {
+  // wait until at most `pending` of this thread's bulk-store groups still have to read shared memory
+  switch (pending) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -176,7 +188,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 __host__ __device__ inline uint32_t tmem_cols_for(int bn) {
-  return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u;
+  return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : bn <= 256 ? 256u : 512u;
 }
 
 // Which taps touch at least one real pixel for the tile at (y0, x0)? bit (r*S+s).
@@ -195,40 +207,45 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x
   return m;
 }
 
+// Persistent, warp-specialised kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...
+// (n-tile fastest, so CTAs running at the same time share the A tile in L2). Three pipelines:
+//   operand ring   full[s]/empty[s]          TMA producer  <-> MMA issuer   (runs across tiles)
+//   accumulators   tmem_full[a]/tmem_empty[a] MMA issuer   <-> epilogue     (two TMEM buffers: the
+//                                             epilogue of tile i overlaps the main loop of tile i+1)
+//   residual tile  res_full[a]/res_empty[a]  TMA producer  <-> epilogue     (double buffered)
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: operand ring [stages][A 16 KB][B BN*128 B] (overlaid by the output staging tile after the
-  // last MMA) | residual tile | barriers | tmem ptr | scale/shift
+  // carve: operand ring [stages][A 16 KB][B BN*128 B] | output staging [nblk][128 rows] |
+  //        residual tiles [2][BN/64][128 x 128 B] | barriers | tmem ptr | scale/shift
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = kBlockM * kBlockK * 2;
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
   const uint32_t res_blk_bytes = kBlockM * 128;               // 64 bf16 channels per pixel row
   const int nblk_res = p.has_res ? p.BN / 64 : 0;
-  uint8_t* res_smem = smem + p.main_bytes;
-  uint8_t* tail = res_smem + (size_t)nblk_res * res_blk_bytes;
+  uint8_t* stg_smem = smem + p.main_bytes;
+  uint8_t* res_smem = stg_smem + (size_t)p.nblk * blk_bytes;
+  uint8_t* tail = res_smem + (size_t)2 * nblk_res * res_blk_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-  uint64_t* res_bar = tmem_full_bar + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;        // [2]
+  uint64_t* res_empty_bar = res_full_bar + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
   float* s_scale = reinterpret_cast<float*>(tmem_ptr + 2);
   float* s_shift = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates
-  const int m_tile = blockIdx.x;
-  const int n_img = m_tile / (p.tiles_x * p.tiles_y);
-  const int trem = m_tile % (p.tiles_x * p.tiles_y);
-  const int y0 = (trem / p.tiles_x) * p.BH, x0 = (trem % p.tiles_x) * p.BW;
-  const int n0 = blockIdx.y * p.BN;
-  const uint32_t taps = live_taps(p, y0, x0);
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int n_tiles = p.Cout / p.BN;
+  const int total_tiles = p.N * tiles_img * n_tiles;
   const int cblocks = p.Cin / kBlockK;
-  const int num_kb = __popc(taps) * cblocks;
-  const uint32_t ncols = tmem_cols_for(p.BN);
+  const uint32_t ncols = tmem_cols_for(2 * p.BN);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
@@ -239,8 +256,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(res_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + a, 1);
+      mbar_init(tmem_empty_bar + a, 4);   // one arrival per epilogue warp
+      mbar_init(res_full_bar + a, 1);
+      mbar_init(res_empty_bar + a, 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -254,27 +275,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // tile -> (image, y0, x0, n0); identical in every role
+  auto tile_coords = [&](int t, int& n_img, int& y0, int& x0, int& n0) {
+    const int nt = t % n_tiles, mt = t / n_tiles;
+    n_img = mt / tiles_img;
+    const int trem = mt % tiles_img;
+    y0 = (trem / p.tiles_x) * p.BH;
+    x0 = (trem % p.tiles_x) * p.BW;
+    n0 = nt * p.BN;
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      if (p.has_res) {  // residual tile: lands while the main loop runs
-        mbar_expect_tx(res_bar, (uint32_t)nblk_res * (uint32_t)(p.BW * p.BH * 128));
-        for (int j = 0; j < nblk_res; ++j)
-          tma_load_4d(res_smem + (size_t)j * res_blk_bytes, &tmap_res, res_bar, n0 + j * 64, x0, y0, n_img);
-      }
-      int kb = 0;
-      for (int t = 0; t < p.R * p.S; ++t) {
-        if (!((taps >> t) & 1u)) continue;
-        const int dy = (t / p.S - p.R / 2) * p.dil, dx = (t % p.S - p.S / 2) * p.dil;
-        for (int cb = 0; cb < cblocks; ++cb, ++kb) {
-          const int s = kb % p.stages;
-          const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-          mbar_wait(empty_bar + s, ph ^ 1u);
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
-          tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
-          tma_load_2d(sb, &tmap_w, full_bar + s, t * p.Cin + cb * kBlockK, n0);
+      uint32_t kbg = 0;   // k-block counter across tiles: stage = kbg % stages, phase = (kbg / stages) & 1
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int n_img, y0, x0, n0;
+        tile_coords(t, n_img, y0, x0, n0);
+        const uint32_t taps = live_taps(p, y0, x0);
+        if (p.has_res) {  // residual tile: lands while the main loop runs
+          const int a = it & 1;
+          mbar_wait(res_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(res_full_bar + a, (uint32_t)nblk_res * (uint32_t)(p.BW * p.BH * 128));
+          for (int j = 0; j < nblk_res; ++j)
+            tma_load_4d(res_smem + (size_t)(a * nblk_res + j) * res_blk_bytes, &tmap_res, res_full_bar + a,
+                        n0 + j * 64, x0, y0, n_img);
+        }
+        for (int tp = 0; tp < p.R * p.S; ++tp) {
+          if (!((taps >> tp) & 1u)) continue;
+          const int dy = (tp / p.S - p.R / 2) * p.dil, dx = (tp % p.S - p.S / 2) * p.dil;
+          for (int cb = 0; cb < cblocks; ++cb, ++kbg) {
+            const int s = (int)(kbg % (uint32_t)p.stages);
+            const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
+            mbar_wait(empty_bar + s, ph ^ 1u);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            uint8_t* sb = sa + a_bytes;
+            mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
+            tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
+            tma_load_2d(sb, &tmap_w, full_bar + s, tp * p.Cin + cb * kBlockK, n0);
+          }
         }
       }
     }
@@ -283,100 +323,130 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                            ((uint32_t)(kBlockM >> 4) << 24);
     if (elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-        mbar_wait(full_bar + s, ph);
+      uint32_t kbg = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int n_img, y0, x0, n0;
+        tile_coords(t, n_img, y0, x0, n0);
+        const int num_kb = __popc(live_taps(p, y0, x0)) * cblocks;
+        const int a = it & 1;
+        mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + a_bytes);
+        const uint32_t tacc = tmem_base + (uint32_t)(a * p.BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = (int)(kbg % (uint32_t)p.stages);
+          const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
+          mbar_wait(full_bar + s, ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + a_bytes);
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // +32 B per K step inside the 128 B swizzle span (start-address field is in 16 B units)
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 B per K step inside the 128 B swizzle span (start-address field is in 16 B units)
+            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);     // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar + s);  // frees the smem stage when these MMAs retire
+        umma_commit(tmem_full_bar + a);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete (and every operand stage consumed)
     }
     __syncwarp();
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
     const int q = warp & 3;
     const int et = threadIdx.x - 64;  // 0..127
-    for (int i = et; i < p.BN; i += 128) {
-      s_scale[i] = p.scale[n0 + i];
-      s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    if (p.has_res) mbar_wait(res_bar, 0);
-    const int m = q * 32 + lane;                       // tile row = output pixel (y0 + m / BW, x0 + m % BW)
+    const int m = q * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
-    const int chunks16 = p.out_f32 ? 4 : 2;            // 16 B chunks produced per 16 columns
-    for (int blk = 0; blk < p.nblk; ++blk) {
-      uint8_t* orow = smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
-      for (int c16 = 0; c16 < p.blk_cols / 16; ++c16) {
-        const int col = blk * p.blk_cols + c16 * 16;
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)col, v);
-        tmem_ld_wait();
-        float f[16];
+    const int chunks16 = p.out_f32 ? 4 : 2;             // 16 B chunks produced per 16 columns
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int n_img, y0, x0, n0;
+      tile_coords(t, n_img, y0, x0, n0);
+      const int a = it & 1;
+      const uint32_t aph = ((uint32_t)it >> 1) & 1u;
+      // every epilogue thread passed the last barrier of the previous tile: scale/shift can change
+      for (int i = et; i < p.BN; i += 128) {
+        s_scale[i] = p.scale[n0 + i];
+        s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
+      }
+      mbar_wait(tmem_full_bar + a, aph);
+      tcgen05_fence_after();
+      if (p.has_res) mbar_wait(res_full_bar + a, aph);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN);
+      const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        // staging block `blk` is reused every tile: its previous TMA store must have been read out
+        if (et == 0) bulk_wait_read(p.nblk - 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* orow = stg_smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
+        for (int c16 = 0; c16 < p.blk_cols / 16; ++c16) {
+          const int col = blk * p.blk_cols + c16 * 16;
+          uint32_t v[16];
+          tmem_ld16(trow + (uint32_t)col, v);
+          tmem_ld_wait();
+          float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[col + j] + s_shift[col + j];
-        if (p.has_res) {
-          const uint8_t* rrow = res_smem + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
-          const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[col + j] + s_shift[col + j];
+          if (p.has_res) {
+            const uint8_t* rrow = res_a + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
+            const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(rrow + (((rk + j) ^ (uint32_t)(m & 7)) << 4));
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            for (int j = 0; j < 2; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rrow + (((rk + j) ^ (uint32_t)(m & 7)) << 4));
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              f[8 * j + 2 * k] += __uint_as_float(w4[k] << 16);
-              f[8 * j + 2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+              for (int k = 0; k < 4; ++k) {
+                f[8 * j + 2 * k] += __uint_as_float(w4[k] << 16);
+                f[8 * j + 2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          const uint32_t k0 = (uint32_t)(c16 * chunks16);
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(orow + (((k0 + j) ^ sw) << 4)) =
+                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&b0);
+              u.y = *reinterpret_cast<uint32_t*>(&b1);
+              u.z = *reinterpret_cast<uint32_t*>(&b2);
+              u.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(orow + (((k0 + j) ^ sw) << 4)) = u;
             }
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        const uint32_t k0 = (uint32_t)(c16 * chunks16);
-        if (p.out_f32) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(orow + (((k0 + j) ^ sw) << 4)) =
-                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&b0);
-            u.y = *reinterpret_cast<uint32_t*>(&b1);
-            u.z = *reinterpret_cast<uint32_t*>(&b2);
-            u.w = *reinterpret_cast<uint32_t*>(&b3);
-            *reinterpret_cast<uint4*>(orow + (((k0 + j) ^ sw) << 4)) = u;
+        if (blk == p.nblk - 1) {
+          // all TMEM reads (and residual reads) of this tile are done: hand both buffers back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(tmem_empty_bar + a);
+            if (p.has_res) mbar_arrive(res_empty_bar + a);
           }
         }
-      }
-      // generic-proxy writes -> visible to the async proxy, then one thread stores the block
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        tma_store_4d(&tmap_out, smem + (size_t)blk * blk_bytes, n0 + blk * p.blk_cols, x0, y0, n_img);
-        bulk_commit();
+        // generic-proxy writes -> visible to the async proxy, then one thread stores the block
+        fence_proxy_async();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (et == 0) {
+          tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, n0 + blk * p.blk_cols, x0, y0, n_img);
+          bulk_commit();
+        }
       }
     }
-    if (et == 0) bulk_wait_read0();   // shared memory must outlive the stores' reads
+    if (et == 0) bulk_wait_read(0);   // shared memory must outlive the stores' reads
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -523,7 +593,7 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   // output-channel tile: a power of two (16..256) dividing Cout; shallow-K wide-N layers (ResNet
   // conv3 / projection shortcuts) are epilogue-bound: 128 columns let several CTAs share an SM
   int BN = 256;
-  if (kb_total <= 8 && Cout >= 256) BN = 128;
+  if ((kb_total <= 8 && Cout >= 256) || residual) BN = 128;
   while (BN > 16 && (Cout % BN)) BN >>= 1;
   if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
@@ -537,27 +607,16 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   p.row_bytes = p.blk_cols * oes;
   p.swz = p.row_bytes == 128 ? 1 : 0;
   const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
-  const size_t res_bytes = residual ? (size_t)(BN / 64) * kBlockM * 128 : 0;
+  const size_t res_bytes = residual ? (size_t)2 * (BN / 64) * kBlockM * 128 : 0;   // double buffered
   const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
-  const size_t tail_bytes = (2 * kMaxStages + 2) * 8 + 8 + 2 * 256 * 4;
-  const size_t budget = 227 * 1024 - 1024 - tail_bytes - res_bytes;
-  int stages = (int)(budget / stage_bytes);
+  const size_t tail_bytes = (2 * kMaxStages + 8) * 8 + 8 + 2 * 256 * 4;
+  const size_t fixed = 1024 + staging_bytes + res_bytes + tail_bytes;
+  if (fixed + stage_bytes > 227 * 1024) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 1 || staging_bytes > budget) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
-  // Shallow-K layers (ResNet 1x1 / 64-channel 3x3) are prologue/epilogue-bound: give them only the
-  // stages they can use so several CTAs share an SM (shared memory and TMEM columns permitting) and
-  // one CTA's epilogue overlaps another's main loop. Deep-K layers keep the full ring.
-  if (BN <= 128 || kb_total <= 16) {
-    const int fit_half = (int)((110 * 1024 - 1024 - tail_bytes - res_bytes) / stage_bytes);  // >= two CTAs per SM
-    const int want = kb_total < 6 ? kb_total : 6;
-    int st = fit_half < 2 ? 2 : (fit_half < want ? fit_half : want);
-    if (st < stages) stages = st;
-  }
-  if (stages > kb_total) stages = kb_total;
   p.stages = stages;
-  const size_t ring = stages * stage_bytes;
-  p.main_bytes = (int)(((ring > staging_bytes ? ring : staging_bytes) + 1023) & ~(size_t)1023);
-  const size_t smem_bytes = 1024 + p.main_bytes + res_bytes + tail_bytes;
+  p.main_bytes = (int)((stages * stage_bytes + 1023) & ~(size_t)1023);
+  const size_t smem_bytes = 1024 + p.main_bytes + staging_bytes + res_bytes + tail_bytes;
 
   CUtensorMap tmx, tmw, tmo, tmr;
   int rc = encode_act_map(encode, &tmx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cin, win, hin, N, Cin, kBlockK,
@@ -589,7 +648,8 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
     EESEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)(N * p.tiles_x * p.tiles_y), (unsigned)(Cout / BN));
+  const int total_tiles = N * p.tiles_x * p.tiles_y * (Cout / BN);
+  dim3 grid((unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs));   // persistent: one CTA per SM
   conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, tmo, tmr, p);
   return check_launch("conv_igemm_kernel");
 }
