@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(TILE, 2) cm_from_logits_stream_kernel(
   constexpr int rb = ps::row_bytes(TILE, ES), rbt = ps::row_bytes(TILE, 8);
   const int stage_bytes = C * rb + rbt;
   uint64_t* full = reinterpret_cast<uint64_t*>(hs_smem + (size_t)stages * stage_bytes);
+  uint64_t* done = full + 4;   // every thread has read its pixel out of a stage
   unsigned* hist = reinterpret_cast<unsigned*>(full + 8);
+  constexpr int NW = TILE / 32;   // row r is owned by warp r % NW, lane r / NW
+  const int my_row = (int)(threadIdx.x & 31) * NW + (int)(threadIdx.x >> 5);
   const int bins = (C + 1) * C;
   for (int i = threadIdx.x; i < copies * bins; i += TILE) hist[i] = 0;
   unsigned* h = hist + ((threadIdx.x >> 5) % copies) * bins;
@@ -100,8 +103,8 @@ __global__ void __launch_bounds__(TILE, 2) cm_from_logits_stream_kernel(
   const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(targets + (int64_t)n * HW);
   const int num_tiles = (int)((HW + TILE - 1) / TILE);
   const int my_count = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto issue = [&](int k) {   // thread r issues row r (r < C: class plane, r == C: targets)
-    const int r = threadIdx.x;
+  auto issue = [&](int k) {   // the owner of row r issues it (r < C: class plane, r == C: targets)
+    const int r = my_row;
     if (r > C) return;
     const int s = k % stages;
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
@@ -111,7 +114,10 @@ __global__ void __launch_bounds__(TILE, 2) cm_from_logits_stream_kernel(
     else ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
   };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) ps::mbar_init(full + s, C + 1);
+    for (int s = 0; s < stages; ++s) {
+      ps::mbar_init(full + s, C + 1);
+      ps::mbar_init(done + s, TILE);
+    }
     ps::fence_barrier_init();
   }
   __syncthreads();
@@ -158,8 +164,11 @@ __global__ void __launch_bounds__(TILE, 2) cm_from_logits_stream_kernel(
       const int tt = (t >= 0 && t < C) ? (int)t : C;
       key = tt * C + arg;
     }
-    __syncthreads();            // every thread has read its pixel: the stage can be refilled
-    if (k + stages < my_count) issue(k + stages);
+    ps::mbar_arrive(done + s);  // this thread has read its pixel
+    if (my_row <= C && k + stages < my_count) {   // only the row owners wait before refilling the stage
+      ps::mbar_wait(done + s, (uint32_t)(k / stages) & 1u);
+      issue(k + stages);
+    }
     hist_add(h, key);
   }
   hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
@@ -267,7 +276,7 @@ extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype,
       const size_t fixed = 8 * sizeof(uint64_t) + (size_t)hcopies * bytes1;
       int stages = (int)((112 * 1024 - fixed) / stage_bytes);   // two CTAs per SM
       if (stages > 3) stages = 3;
-      if (stages >= 2 && C + 1 <= kTile) {
+      if (stages >= 2 && C + 1 <= kTile && stages <= 4) {
         const size_t smem = stages * stage_bytes + fixed;
         int64_t per_img = 2 * kNumSMs / N;
         if (per_img < 1) per_img = 1;

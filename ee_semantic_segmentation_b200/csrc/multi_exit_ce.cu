@@ -96,6 +96,11 @@ __global__ void __launch_bounds__(TILE, 2) ce_kernel(
   constexpr int rb = ps::row_bytes(TILE, ES), rbt = ps::row_bytes(TILE, 8);
   const int stage_bytes = C * rb + rbt;
   uint64_t* full = reinterpret_cast<uint64_t*>(ce_smem + (size_t)STAGES * stage_bytes);
+  uint64_t* done = full + STAGES;   // all TILE threads have consumed (and re-filled with gradients) a stage
+  // row ownership is spread over the warps (row r -> warp r % NW, lane r / NW) so that no single warp
+  // carries all the bulk-copy bookkeeping
+  constexpr int NW = TILE / 32;
+  const int my_row = (int)(threadIdx.x & 31) * NW + (int)(threadIdx.x >> 5);
 
   const int e = blockIdx.y / N, n = blockIdx.y % N;
   const T* base = logits + (int64_t)e * exit_stride + (int64_t)n * C * HW;
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(TILE, 2) ce_kernel(
 
   // row r of tile k is issued by thread r (r < C: class plane r, r == C: the int64 targets)
   auto issue = [&](int k) {
-    const int r = threadIdx.x;
+    const int r = my_row;
     if (r > C) return;
     const int s = k % STAGES;
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
@@ -119,7 +124,10 @@ __global__ void __launch_bounds__(TILE, 2) ce_kernel(
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) ps::mbar_init(full + s, C + 1);  // one arming arrival per row
+    for (int s = 0; s < STAGES; ++s) {
+      ps::mbar_init(full + s, C + 1);  // one arming arrival per row
+      ps::mbar_init(done + s, TILE);
+    }
     ps::fence_barrier_init();
   }
   __syncthreads();
@@ -185,21 +193,20 @@ __global__ void __launch_bounds__(TILE, 2) ce_kernel(
         if (c < C) sts_f<T>(rowbase[c % P] + (uint32_t)c * rb, 0.f);
     }
     if (gbase) ps::fence_proxy_async();      // generic-proxy smem writes -> visible to the bulk engine
-    __syncthreads();                         // inputs consumed (and gradients staged) by every thread
-    {
-      const int r = threadIdx.x;             // thread r owns row r: store it, then refill it
-      if (r <= C) {
-        if (gbase && r < C) {
-          const int count = (int)min((int64_t)TILE, HW - p0);
-          ps::store_row<T>(ce_smem + (size_t)s * stage_bytes + (size_t)r * rb, gbase + (int64_t)r * HW + p0, count);
-          ps::bulk_commit();
-          if (k + STAGES < my_count) ps::bulk_wait_read0();   // the row must be read out before it is refilled
-        }
-        if (k + STAGES < my_count) issue(k + STAGES);
+    ps::mbar_arrive(done + s);               // this thread is finished with stage s
+    if (my_row <= C) {                       // the row's owner stores it and refills it; nobody else waits
+      const int r = my_row;
+      ps::mbar_wait(done + s, (uint32_t)(k / STAGES) & 1u);
+      if (gbase && r < C) {
+        const int count = (int)min((int64_t)TILE, HW - p0);
+        ps::store_row<T>(ce_smem + (size_t)s * stage_bytes + (size_t)r * rb, gbase + (int64_t)r * HW + p0, count);
+        ps::bulk_commit();
+        if (k + STAGES < my_count) ps::bulk_wait_read0();   // the row must be read out before it is refilled
       }
+      if (k + STAGES < my_count) issue(k + STAGES);
     }
   }
-  if (gbase && threadIdx.x < C) ps::bulk_wait_read0();
+  if (gbase && my_row < C) ps::bulk_wait_read0();
   if (part) {
     __shared__ double sred[32];
     double ws = warp_sum((double)loss_acc);
@@ -250,7 +257,7 @@ static int launch_ce_cfg(const T* logits, int64_t exit_stride, const int64_t* ta
   constexpr int kStages = 3;   // two CTAs per SM x three tiles each in flight
   const int rb = ps::row_bytes(TILE, (int)sizeof(T)), rbt = ps::row_bytes(TILE, 8);
   const size_t stage_bytes = (size_t)C * rb + rbt;
-  const size_t smem = kStages * stage_bytes + kStages * sizeof(uint64_t);
+  const size_t smem = kStages * stage_bytes + 2 * kStages * sizeof(uint64_t);
   if (smem > 113 * 1024) { set_error("multi_exit_ce: C=%d does not fit the staging buffers", C); return EESEG_ERR_UNSUPPORTED; }
   if (dlogits && (((uintptr_t)dlogits ^ (uintptr_t)logits) & 15)) {
     set_error("multi_exit_ce: logits and dlogits must have the same 16-byte misalignment");
