@@ -39,6 +39,7 @@ PROTOTYPES = {
                                    c_p, c_p, c_p, c_sz, c_p]),
     "eeseg_conv_igemm_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                    c_i, c_i, c_i, c_p, c_i64, c_p, c_i, c_i64, c_p]),
+    "eeseg_conv_debug_stats": (c_i, [c_p]),
     "eeseg_global_avgpool_workspace_bytes": (c_sz, [c_i, c_i]),
     "eeseg_global_avgpool_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_p, c_p, c_p]),
 }

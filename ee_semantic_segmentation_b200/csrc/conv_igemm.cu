@@ -43,6 +43,7 @@ struct ConvParams {
   int64_t shift_sn;
   const float* scale;
   const float* shift;
+  unsigned long long* dbg;   // optional [gridDim.x][16] cycle counters (eeseg_conv_debug_stats)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -187,6 +188,18 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// cycle accounting for tuning: DBG_T(slot, stmt) adds the cycles `stmt` takes to counter `slot`
+#define DBG_T(slot, stmt)                                   \
+  do {                                                      \
+    if (p.dbg) {                                            \
+      const long long t0__ = clock64();                     \
+      stmt;                                                 \
+      dbg_acc[slot] += (unsigned long long)(clock64() - t0__); \
+    } else {                                                \
+      stmt;                                                 \
+    }                                                       \
+  } while (0)
+
 __host__ __device__ inline uint32_t tmem_cols_for(int bn) {
   return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : bn <= 256 ? 256u : 512u;
 }
@@ -288,6 +301,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
+      unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+      const long long dbg_t0 = clock64();
       uint32_t kbg = 0;   // k-block counter across tiles: stage = kbg % stages, phase = (kbg / stages) & 1
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -296,7 +311,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const uint32_t taps = live_taps(p, y0, x0);
         if (p.has_res) {  // residual tile: lands while the main loop runs
           const int a = it & 1;
-          mbar_wait(res_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u);
+          DBG_T(0, mbar_wait(res_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));
           mbar_expect_tx(res_full_bar + a, (uint32_t)nblk_res * (uint32_t)(p.BW * p.BH * 128));
           for (int j = 0; j < nblk_res; ++j)
             tma_load_4d(res_smem + (size_t)(a * nblk_res + j) * res_blk_bytes, &tmap_res, res_full_bar + a,
@@ -308,7 +323,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int cb = 0; cb < cblocks; ++cb, ++kbg) {
             const int s = (int)(kbg % (uint32_t)p.stages);
             const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
-            mbar_wait(empty_bar + s, ph ^ 1u);
+            DBG_T(1, mbar_wait(empty_bar + s, ph ^ 1u));
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             uint8_t* sb = sa + a_bytes;
             mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
@@ -317,12 +332,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
+      if (p.dbg) {
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+        d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = (unsigned long long)(clock64() - dbg_t0); d[3] = (unsigned long long)it;
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                            ((uint32_t)(kBlockM >> 4) << 24);
     if (elect_one()) {
+      unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+      const long long dbg_t0 = clock64();
       uint32_t kbg = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -330,13 +351,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tile_coords(t, n_img, y0, x0, n0);
         const int num_kb = __popc(live_taps(p, y0, x0)) * cblocks;
         const int a = it & 1;
-        mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
+        DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue drained this buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * p.BN);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = (int)(kbg % (uint32_t)p.stages);
           const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
-          mbar_wait(full_bar + s, ph);
+          DBG_T(1, mbar_wait(full_bar + s, ph));
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + a_bytes);
@@ -350,6 +371,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         umma_commit(tmem_full_bar + a);   // accumulator complete
       }
+      if (p.dbg) {
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16 + 4;
+        d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = (unsigned long long)(clock64() - dbg_t0);
+      }
     }
     __syncwarp();
   } else {
@@ -359,6 +384,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int m = q * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
     const int chunks16 = p.out_f32 ? 4 : 2;             // 16 B chunks produced per 16 columns
+    unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+    const long long dbg_t0 = clock64();
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int n_img, y0, x0, n0;
@@ -370,15 +397,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         s_scale[i] = p.scale[n0 + i];
         s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
       }
-      mbar_wait(tmem_full_bar + a, aph);
+      DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
-      if (p.has_res) mbar_wait(res_full_bar + a, aph);
+      if (p.has_res) DBG_T(1, mbar_wait(res_full_bar + a, aph));
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN);
       const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
       for (int blk = 0; blk < p.nblk; ++blk) {
         // staging block `blk` is reused every tile: its previous TMA store must have been read out
-        if (et == 0) bulk_wait_read(p.nblk - 1);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) DBG_T(2, bulk_wait_read(p.nblk - 1));
+        DBG_T(3, asm volatile("bar.sync 1, 128;" ::: "memory"));
         uint8_t* orow = stg_smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
         for (int c16 = 0; c16 < p.blk_cols / 16; ++c16) {
           const int col = blk * p.blk_cols + c16 * 16;
@@ -447,6 +474,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     if (et == 0) bulk_wait_read(0);   // shared memory must outlive the stores' reads
+    if (p.dbg && et == 0) {
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16 + 8;
+      d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3];
+      d[4] = (unsigned long long)(clock64() - dbg_t0);
+    }
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -555,6 +587,14 @@ static int encode_act_map(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr
   return EESEG_OK;
 }
 
+static unsigned long long* g_conv_dbg = nullptr;
+// Tuning hook (not part of the product path): device buffer of [148][16] uint64 cycle counters that
+// the next conv launches fill (producer / MMA / epilogue wait times); NULL switches it off.
+extern "C" int eeseg_conv_debug_stats(void* device_buffer) {
+  g_conv_dbg = reinterpret_cast<unsigned long long*>(device_buffer);
+  return EESEG_OK;
+}
+
 extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
                                     const float* shift, int64_t shift_sn, int N, int hin, int win,
                                     int Cin, int Cout, int R, int S, int dilation, int stride,
@@ -598,7 +638,7 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
-  p.scale = scale; p.shift = shift;
+  p.scale = scale; p.shift = shift; p.dbg = g_conv_dbg;
   // epilogue blocks: 128 B of output per pixel row (64 bf16 / 32 fp32 channels), swizzled; narrower
   // tiles use one dense block
   const int full_cols = 128 / oes;

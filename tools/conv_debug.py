@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Per-role wait-time breakdown of the persistent conv kernel for a few layer shapes (tuning aid)."""
+import sys, os
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ee_semantic_segmentation_b200 import _lib
+from ee_semantic_segmentation_b200.head_plan import conv_igemm
+
+dev = torch.device("cuda:0")
+shapes = [  # name, N, h, w, Cin, Cout, R, dil, stride, residual
+    ("l1.c3 64>256+res", 4, 129, 129, 64, 256, 1, 1, 1, True),
+    ("l1.c1 256>64", 4, 129, 129, 256, 64, 1, 1, 1, False),
+    ("l1.c2 3x3 64", 4, 129, 129, 64, 64, 3, 1, 1, False),
+    ("l3.c3 256>1024+res", 4, 65, 65, 256, 1024, 1, 1, 1, True),
+    ("l3.c1 1024>256", 4, 65, 65, 1024, 256, 1, 1, 1, False),
+    ("l3.c2 3x3 256 d2", 4, 65, 65, 256, 256, 3, 2, 1, False),
+    ("l4.c3 512>2048+res", 4, 65, 65, 512, 2048, 1, 1, 1, True),
+    ("l4.c2 3x3 512 d4", 4, 65, 65, 512, 512, 3, 4, 1, False),
+    ("aspp 3x3 d12 2048", 4, 65, 65, 2048, 256, 3, 12, 1, False),
+]
+buf = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+for name, N, h, w, cin, cout, R, dil, stride, res in shapes:
+    x = torch.randn(N, h, w, cin, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, R, R, cin, device=dev) * 0.02).to(torch.bfloat16)
+    sc, sh = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+    out = torch.empty(N, h, w, cout, dtype=torch.bfloat16, device=dev)
+    r = torch.randn(N, h, w, cout, device=dev).to(torch.bfloat16) if res else None
+    run = lambda: conv_igemm(x, wt, sc, sh, dil, True, out, _lib.BF16, cout, stride=stride, residual=r)
+    for _ in range(3):
+        run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(10):
+        run()
+    b.record(); torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 100
+    buf.zero_()
+    _lib.lib().eeseg_conv_debug_stats(buf.data_ptr())
+    run(); torch.cuda.synchronize()
+    _lib.lib().eeseg_conv_debug_stats(None)
+    d = buf.cpu().double()
+    act = d[:, 3] > 0
+    m = d[act].mean(0)
+    tiles = m[3]
+    print(f"{name:22s} {us:6.1f}us tiles/CTA {tiles:4.1f} | PROD total {m[2]:8.0f} wait_res_empty {m[0]:7.0f} wait_empty {m[1]:7.0f} | "
+          f"MMA total {m[6]:8.0f} wait_tmem_empty {m[4]:7.0f} wait_full {m[5]:7.0f} | "
+          f"EPI total {m[12]:8.0f} wait_tmem_full {m[8]:7.0f} wait_res {m[9]:7.0f} wait_store_read {m[10]:7.0f} bar {m[11]:7.0f}", flush=True)
