@@ -26,7 +26,9 @@ namespace eeseg {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quadrant (column halves)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer
 constexpr int kMaxStages = 8;
 
 struct ConvParams {
@@ -34,7 +36,8 @@ struct ConvParams {
   int hin, win, stride;                // input spatial size and convolution stride
   int has_res;                         // residual tile (bf16, output shape) is TMA-prefetched and added before ReLU
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
-  int main_bytes;                      // shared memory of the operand ring (the output staging overlays it)
+  int main_bytes;                      // shared memory of the operand ring
+  int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
   int BW, BH, tiles_x, tiles_y;
   int BN;          // output-channel tile (multiple of 16, <= 256)
   int stages;
@@ -240,8 +243,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
   const uint32_t res_blk_bytes = kBlockM * 128;               // 64 bf16 channels per pixel row
   const int nblk_res = p.has_res ? p.BN / 64 : 0;
-  uint8_t* stg_smem = smem + p.main_bytes;
-  uint8_t* res_smem = stg_smem + (size_t)p.nblk * blk_bytes;
+  uint8_t* stg_smem = smem + (p.overlay ? 0 : p.main_bytes);   // overlay: <= 1 tile per CTA, ring is idle by then
+  uint8_t* res_smem = smem + p.main_bytes + (p.overlay ? 0 : (size_t)p.nblk * blk_bytes);
   uint8_t* tail = res_smem + (size_t)2 * nblk_res * res_blk_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -250,7 +253,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   uint64_t* res_full_bar = tmem_empty_bar + 2;        // [2]
   uint64_t* res_empty_bar = res_full_bar + 2;         // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
-  float* s_scale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* s_scale = reinterpret_cast<float*>(tail + 256);   // 16 B aligned (read as float4)
   float* s_shift = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,9 +274,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + a, 1);
-      mbar_init(tmem_empty_bar + a, 4);   // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar + a, kEpiWarps);   // one arrival per epilogue warp
       mbar_init(res_full_bar + a, 1);
-      mbar_init(res_empty_bar + a, 4);
+      mbar_init(res_empty_bar + a, kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -378,12 +381,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    // ===== epilogue: warps 2..9. TMEM lane quadrant = warp % 4 (hardware rule); warps 2-5 take the
+    // lower half of the tile's columns, warps 6-9 the upper half =====
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int hsel = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;                    // 0..255
     const int m = q * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
-    const int chunks16 = p.out_f32 ? 4 : 2;             // 16 B chunks produced per 16 columns
+    const int col_lo = hsel * (p.BN >> 1) , col_hi = p.BN < 32 ? (hsel ? 0 : p.BN) : col_lo + (p.BN >> 1);
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     const long long dbg_t0 = clock64();
     int it = 0;
@@ -393,84 +398,98 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int a = it & 1;
       const uint32_t aph = ((uint32_t)it >> 1) & 1u;
       // every epilogue thread passed the last barrier of the previous tile: scale/shift can change
-      for (int i = et; i < p.BN; i += 128) {
+      for (int i = et; i < p.BN; i += kEpiThreads) {
         s_scale[i] = p.scale[n0 + i];
         s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
       }
+      // the staging tile is reused every tile: the previous TMA stores must have read it out
+      if (et == 0) DBG_T(2, bulk_wait_read(0));
+      DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
       if (p.has_res) DBG_T(1, mbar_wait(res_full_bar + a, aph));
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN);
       const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
-      for (int blk = 0; blk < p.nblk; ++blk) {
-        // staging block `blk` is reused every tile: its previous TMA store must have been read out
-        if (et == 0) DBG_T(2, bulk_wait_read(p.nblk - 1));
-        DBG_T(3, asm volatile("bar.sync 1, 128;" ::: "memory"));
+      for (int col = col_lo; col < col_hi; col += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)col, v);
+        // scale/shift for these 16 columns while the TMEM load is in flight
+        float4 sc4[4], sh4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc4[j] = *reinterpret_cast<const float4*>(s_scale + col + 4 * j);
+          sh4[j] = *reinterpret_cast<const float4*>(s_shift + col + 4 * j);
+        }
+        uint4 r4[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (p.has_res) {
+          const uint8_t* rrow = res_a + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
+          const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
+          r4[0] = *reinterpret_cast<const uint4*>(rrow + (((rk + 0) ^ (uint32_t)(m & 7)) << 4));
+          r4[1] = *reinterpret_cast<const uint4*>(rrow + (((rk + 1) ^ (uint32_t)(m & 7)) << 4));
+        }
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc4[j].x, sh4[j].x);
+          f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc4[j].y, sh4[j].y);
+          f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc4[j].z, sh4[j].z);
+          f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc4[j].w, sh4[j].w);
+        }
+        if (p.has_res) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t w4[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f[8 * j + 2 * k] += __uint_as_float(w4[k] << 16);
+              f[8 * j + 2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        const int blk = col / p.blk_cols;
         uint8_t* orow = stg_smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
-        for (int c16 = 0; c16 < p.blk_cols / 16; ++c16) {
-          const int col = blk * p.blk_cols + c16 * 16;
-          uint32_t v[16];
-          tmem_ld16(trow + (uint32_t)col, v);
-          tmem_ld_wait();
-          float f[16];
+        if (p.out_f32) {
+          const uint32_t k0 = (uint32_t)((col - blk * p.blk_cols) >> 2);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[col + j] + s_shift[col + j];
-          if (p.has_res) {
-            const uint8_t* rrow = res_a + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
-            const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(orow + (((k0 + j) ^ sw) << 4)) =
+                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          const uint32_t k0 = (uint32_t)((col - blk * p.blk_cols) >> 3);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rrow + (((rk + j) ^ (uint32_t)(m & 7)) << 4));
-              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                f[8 * j + 2 * k] += __uint_as_float(w4[k] << 16);
-                f[8 * j + 2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          const uint32_t k0 = (uint32_t)(c16 * chunks16);
-          if (p.out_f32) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(orow + (((k0 + j) ^ sw) << 4)) =
-                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&b0);
-              u.y = *reinterpret_cast<uint32_t*>(&b1);
-              u.z = *reinterpret_cast<uint32_t*>(&b2);
-              u.w = *reinterpret_cast<uint32_t*>(&b3);
-              *reinterpret_cast<uint4*>(orow + (((k0 + j) ^ sw) << 4)) = u;
-            }
+          for (int j = 0; j < 2; ++j) {
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&b0);
+            u.y = *reinterpret_cast<uint32_t*>(&b1);
+            u.z = *reinterpret_cast<uint32_t*>(&b2);
+            u.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(orow + (((k0 + j) ^ sw) << 4)) = u;
           }
         }
-        if (blk == p.nblk - 1) {
-          // all TMEM reads (and residual reads) of this tile are done: hand both buffers back
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(tmem_empty_bar + a);
-            if (p.has_res) mbar_arrive(res_empty_bar + a);
-          }
-        }
-        // generic-proxy writes -> visible to the async proxy, then one thread stores the block
-        fence_proxy_async();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (et == 0) {
+      }
+      // all TMEM reads (and residual reads) of this tile are done: hand both buffers back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(tmem_empty_bar + a);
+        if (p.has_res) mbar_arrive(res_empty_bar + a);
+      }
+      // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
+      fence_proxy_async();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (et == 0) {
+        for (int blk = 0; blk < p.nblk; ++blk)
           tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, n0 + blk * p.blk_cols, x0, y0, n_img);
-          bulk_commit();
-        }
+        bulk_commit();
       }
     }
     if (et == 0) bulk_wait_read(0);   // shared memory must outlive the stores' reads
@@ -649,14 +668,20 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
   const size_t res_bytes = residual ? (size_t)2 * (BN / 64) * kBlockM * 128 : 0;   // double buffered
   const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
-  const size_t tail_bytes = (2 * kMaxStages + 8) * 8 + 8 + 2 * 256 * 4;
-  const size_t fixed = 1024 + staging_bytes + res_bytes + tail_bytes;
+  const size_t tail_bytes = 256 + 2 * 256 * 4;   // barriers + tmem pointer (< 256 B), scale, shift
+  const int total_tiles = N * p.tiles_x * p.tiles_y * (Cout / BN);
+  // with at most one tile per CTA the ring is idle when the epilogue runs: the staging tile overlays
+  // it and the ring gets the shared memory (deep-K ASPP convs: 4 stages instead of 3)
+  p.overlay = total_tiles <= kNumSMs ? 1 : 0;
+  const size_t fixed = 1024 + (p.overlay ? 0 : staging_bytes) + res_bytes + tail_bytes;
   if (fixed + stage_bytes > 227 * 1024) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  p.main_bytes = (int)((stages * stage_bytes + 1023) & ~(size_t)1023);
-  const size_t smem_bytes = 1024 + p.main_bytes + staging_bytes + res_bytes + tail_bytes;
+  size_t ring = stages * stage_bytes;
+  if (p.overlay && ring < staging_bytes) ring = staging_bytes;
+  p.main_bytes = (int)((ring + 1023) & ~(size_t)1023);
+  const size_t smem_bytes = 1024 + p.main_bytes + (p.overlay ? 0 : staging_bytes) + res_bytes + tail_bytes;
 
   CUtensorMap tmx, tmw, tmo, tmr;
   int rc = encode_act_map(encode, &tmx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cin, win, hin, N, Cin, kBlockK,
@@ -688,7 +713,6 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
     EESEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = N * p.tiles_x * p.tiles_y * (Cout / BN);
   dim3 grid((unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs));   // persistent: one CTA per SM
   conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, tmo, tmr, p);
   return check_launch("conv_igemm_kernel");
