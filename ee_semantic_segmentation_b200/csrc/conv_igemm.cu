@@ -46,7 +46,7 @@ struct ConvParams {
   int64_t shift_sn;
   const float* scale;
   const float* shift;
-  unsigned long long* dbg;   // optional [gridDim.x][16] cycle counters (eeseg_conv_debug_stats)
+  unsigned long long* dbg;   // optional [gridDim.x][32] cycle counters (eeseg_conv_debug_stats)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -257,6 +257,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* s_shift = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.dbg && threadIdx.x == 0) {   // kernel-entry wall clock (ns) of this CTA
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[(size_t)blockIdx.x * 32 + 16] = g;
+  }
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.Cout / p.BN;
   const int total_tiles = p.N * tiles_img * n_tiles;
@@ -336,7 +341,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
       }
       if (p.dbg) {
-        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32;
         d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = (unsigned long long)(clock64() - dbg_t0); d[3] = (unsigned long long)it;
       }
     }
@@ -375,7 +380,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         umma_commit(tmem_full_bar + a);   // accumulator complete
       }
       if (p.dbg) {
-        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16 + 4;
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32 + 4;
         d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = (unsigned long long)(clock64() - dbg_t0);
       }
     }
@@ -389,8 +394,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int m = q * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
     const int col_lo = hsel * (p.BN >> 1) , col_hi = p.BN < 32 ? (hsel ? 0 : p.BN) : col_lo + (p.BN >> 1);
-    unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+    unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long dbg_t0 = clock64();
+    unsigned long long dbg_g0 = 0;
+    if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+    long long dbg_t1 = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int n_img, y0, x0, n0;
@@ -398,10 +406,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int a = it & 1;
       const uint32_t aph = ((uint32_t)it >> 1) & 1u;
       // every epilogue thread passed the last barrier of the previous tile: scale/shift can change
+      if (p.dbg) dbg_t1 = clock64();
       for (int i = et; i < p.BN; i += kEpiThreads) {
         s_scale[i] = p.scale[n0 + i];
         s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
       }
+      if (p.dbg) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
       // the staging tile is reused every tile: the previous TMA stores must have read it out
       if (et == 0) DBG_T(2, bulk_wait_read(0));
       DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
@@ -410,6 +420,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (p.has_res) DBG_T(1, mbar_wait(res_full_bar + a, aph));
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN);
       const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
+      if (p.dbg) dbg_t1 = clock64();
       for (int col = col_lo; col < col_hi; col += 16) {
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)col, v);
@@ -476,6 +487,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
+      if (p.dbg) { dbg_acc[5] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
       // all TMEM reads (and residual reads) of this tile are done: hand both buffers back
       tcgen05_fence_before();
       __syncwarp();
@@ -486,17 +498,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
       fence_proxy_async();
       asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (p.dbg) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
       if (et == 0) {
         for (int blk = 0; blk < p.nblk; ++blk)
           tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, n0 + blk * p.blk_cols, x0, y0, n_img);
         bulk_commit();
       }
+      if (p.dbg) dbg_acc[7] += (unsigned long long)(clock64() - dbg_t1);
     }
     if (et == 0) bulk_wait_read(0);   // shared memory must outlive the stores' reads
     if (p.dbg && et == 0) {
-      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16 + 8;
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32 + 8;
       d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3];
       d[4] = (unsigned long long)(clock64() - dbg_t0);
+      d[5] = dbg_acc[4]; d[6] = dbg_acc[5];
+      unsigned long long g1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+      d[7] = g1 - dbg_g0;   // wall nanoseconds of the epilogue role (clock calibration)
     }
     tcgen05_fence_before();
   }
@@ -505,6 +523,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
                  : "memory");
+  }
+  if (p.dbg && threadIdx.x == 0) {   // kernel-exit wall clock (ns)
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[(size_t)blockIdx.x * 32 + 17] = g;
   }
 }
 
@@ -607,7 +630,7 @@ static int encode_act_map(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr
 }
 
 static unsigned long long* g_conv_dbg = nullptr;
-// Tuning hook (not part of the product path): device buffer of [148][16] uint64 cycle counters that
+// Tuning hook (not part of the product path): device buffer of [148][32] uint64 cycle counters that
 // the next conv launches fill (producer / MMA / epilogue wait times); NULL switches it off.
 extern "C" int eeseg_conv_debug_stats(void* device_buffer) {
   g_conv_dbg = reinterpret_cast<unsigned long long*>(device_buffer);

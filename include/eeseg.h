@@ -165,7 +165,7 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
                          int dilation, int stride, int relu, const void* residual, int64_t ldr,
                          void* out, int out_dtype, int64_t ldo, void* stream);
 
-/* Tuning hook: device buffer of [148][16] uint64 cycle counters (per-CTA wait times of the producer,
+/* Tuning hook: device buffer of [148][32] uint64 cycle counters (per-CTA wait times of the producer,
  * MMA and epilogue roles) filled by subsequent eeseg_conv_igemm_fwd launches; NULL switches it off. */
 int eeseg_conv_debug_stats(void* device_buffer);
 

@@ -18,7 +18,7 @@ shapes = [  # name, N, h, w, Cin, Cout, R, dil, stride, residual
     ("l4.c2 3x3 512 d4", 4, 65, 65, 512, 512, 3, 4, 1, False),
     ("aspp 3x3 d12 2048", 4, 65, 65, 2048, 256, 3, 12, 1, False),
 ]
-buf = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(148, 32, dtype=torch.int64, device=dev)
 for name, N, h, w, cin, cout, R, dil, stride, res in shapes:
     x = torch.randn(N, h, w, cin, device=dev).to(torch.bfloat16)
     wt = (torch.randn(cout, R, R, cin, device=dev) * 0.02).to(torch.bfloat16)
@@ -42,6 +42,9 @@ for name, N, h, w, cin, cout, R, dil, stride, res in shapes:
     act = d[:, 3] > 0
     m = d[act].mean(0)
     tiles = m[3]
-    print(f"{name:22s} {us:6.1f}us tiles/CTA {tiles:4.1f} | PROD total {m[2]:8.0f} wait_res_empty {m[0]:7.0f} wait_empty {m[1]:7.0f} | "
+    di = buf.cpu()
+    kern_us = (di[act][:, 17].max() - di[act][:, 16].min()).item() / 1e3
+    pro_us = ((di[act][:, 17] - di[act][:, 16]).double().mean().item() - m[15].item()) / 1e3
+    print(f"{name:22s} event {us:6.1f}us KERNEL {kern_us:6.1f}us (outside epilogue role {pro_us:4.1f}us) tiles/CTA {tiles:4.1f} | PROD total {m[2]:8.0f} wait_res_empty {m[0]:7.0f} wait_empty {m[1]:7.0f} | "
           f"MMA total {m[6]:8.0f} wait_tmem_empty {m[4]:7.0f} wait_full {m[5]:7.0f} | "
-          f"EPI total {m[12]:8.0f} wait_tmem_full {m[8]:7.0f} wait_res {m[9]:7.0f} wait_store_read {m[10]:7.0f} bar {m[11]:7.0f}", flush=True)
+          f"EPI total {m[12]:8.0f} wait_tmem_full {m[8]:7.0f} wait_res {m[9]:7.0f} wait_store_read {m[10]:7.0f} bar1 {m[11]:6.0f} ss_load {m[13]:6.0f} colloop {m[14]:7.0f} epi_ns {m[15]:7.0f} => {m[12]/max(m[15],1):.2f} GHz", flush=True)
