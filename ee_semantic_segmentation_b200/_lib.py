@@ -38,7 +38,9 @@ PROTOTYPES = {
     "eeseg_lovasz_fwd_bwd": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i64, c_i, c_i64, c_i, c_i,
                                    c_p, c_p, c_p, c_sz, c_p]),
     "eeseg_conv_igemm_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
-                                   c_i, c_i, c_i, c_p, c_i64, c_p, c_i, c_i64, c_p]),
+                                   c_i, c_i, c_i, c_i, c_p, c_i64, c_p, c_i, c_i64, c_p]),
+    "eeseg_stem_space_to_depth": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
+    "eeseg_maxpool3x3s2_nhwc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_conv_debug_stats": (c_i, [c_p]),
     "eeseg_global_avgpool_workspace_bytes": (c_sz, [c_i, c_i]),
     "eeseg_global_avgpool_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_p, c_p, c_p]),

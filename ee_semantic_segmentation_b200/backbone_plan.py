@@ -48,6 +48,67 @@ class BottleneckPlan:
         return self.c3(t, True, residual=idn)
 
 
+class StemPlan:
+    """conv1 7x7/s2/p3 (3->64) + bn1 + relu + maxpool 3x3/s2/p1 of torchvision's ResNet on the eeseg
+    kernels: the fp32 NCHW image is space-to-depth'ed (2x2 -> 12 channels, zero-padded to the 64-channel
+    MMA K block) so the stride-2 7x7 conv is a stride-1 4x4 implicit GEMM with the first tap at offset
+    -2 (input row 2y-3+r = 2(y+t-2)+a with r = 2t+a-1); BatchNorm and ReLU are the conv epilogue; the
+    max-pool is one streaming kernel. Replaces a cuDNN conv + 3 elementwise kernels on a 4x larger
+    intermediate."""
+
+    def __init__(self, conv, bn):
+        dev = conv.weight.device
+        W = conv.weight.detach().float()                         # [64, 3, 7, 7]
+        cout = W.shape[0]
+        w2 = torch.zeros((cout, 4, 4, 64), dtype=torch.float32, device=dev)
+        for t in range(4):
+            for a in range(2):
+                r = 2 * t + a - 1
+                if not 0 <= r <= 6:
+                    continue
+                for u in range(4):
+                    for b in range(2):
+                        q = 2 * u + b - 1
+                        if not 0 <= q <= 6:
+                            continue
+                        ch = (a * 2 + b) * 3
+                        w2[:, t, u, ch:ch + 3] = W[:, :, r, q]
+        self.w = w2.to(torch.bfloat16).contiguous()
+        s, b = _fold_bn(bn)
+        self.s, self.b = s.contiguous(), b.contiguous()
+        self.cout = cout
+
+    @staticmethod
+    def matches(mods):
+        if len(mods) < 4:
+            return False
+        c, b, r, m = mods[:4]
+        return (isinstance(c, nn.Conv2d) and c.in_channels == 3 and c.kernel_size == (7, 7) and c.stride == (2, 2)
+                and c.padding == (3, 3) and c.bias is None and c.out_channels % 16 == 0
+                and isinstance(b, nn.BatchNorm2d) and isinstance(r, nn.ReLU) and isinstance(m, nn.MaxPool2d)
+                and m.kernel_size in (3, (3, 3)) and m.stride in (2, (2, 2)) and m.padding in (1, (1, 1))
+                and m.dilation in (1, (1, 1)) and not m.ceil_mode)
+
+    def run(self, x):
+        """x fp32 NCHW [N,3,H,W] -> bf16 NHWC [N, H/4-ish, W/4-ish, 64]."""
+        N, _, H, W = x.shape
+        dev = x.device
+        x = x.float().contiguous()
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            s2d = torch.empty((N, H2, W2, 64), dtype=torch.bfloat16, device=dev)
+            _lib.check(_lib.lib().eeseg_stem_space_to_depth(x.data_ptr(), N, H, W, s2d.data_ptr(), stream),
+                       "eeseg_stem_space_to_depth")
+            y = torch.empty((N, H2, W2, self.cout), dtype=torch.bfloat16, device=dev)
+            conv_igemm(s2d, self.w, self.s, self.b, 1, True, y, _lib.BF16, self.cout, pad=2)
+            ho, wo = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
+            out = torch.empty((N, ho, wo, self.cout), dtype=torch.bfloat16, device=dev)
+            _lib.check(_lib.lib().eeseg_maxpool3x3s2_nhwc(y.data_ptr(), N, H2, W2, self.cout, out.data_ptr(), stream),
+                       "eeseg_maxpool3x3s2_nhwc")
+        return out
+
+
 def supported(section):
     for m in section:
         if isinstance(m, Bottleneck):
@@ -59,7 +120,12 @@ def supported(section):
 
 class SectionPlan:
     def __init__(self, section):
-        self.ops = [BottleneckPlan(m) if isinstance(m, Bottleneck) else m for m in section]
+        mods = list(section)
+        self.ops = []
+        if StemPlan.matches(mods):
+            self.ops.append(StemPlan(mods[0], mods[1]))
+            mods = mods[4:]
+        self.ops += [BottleneckPlan(m) if isinstance(m, Bottleneck) else m for m in mods]
 
     def run(self, x):
         """x: [N,C,h,w] tensor (any float dtype / memory format). Returns a bf16 [N,C',h',w'] tensor
@@ -73,7 +139,9 @@ class SectionPlan:
 
     def _run(self, x, nhwc):
         for op in self.ops:
-            if isinstance(op, BottleneckPlan):
+            if isinstance(op, StemPlan):
+                nhwc = op.run(x)
+            elif isinstance(op, BottleneckPlan):
                 if nhwc is None:
                     nhwc = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
                 nhwc = op.run(nhwc)

@@ -33,7 +33,7 @@ constexpr int kMaxStages = 8;
 
 struct ConvParams {
   int N, h, w, Cin, Cout, R, S, dil;   // h, w: OUTPUT spatial size
-  int hin, win, stride;                // input spatial size and convolution stride
+  int hin, win, stride, pad;           // input spatial size, stride, offset of the first tap (tap r reads in = out*stride + r*dil - pad)
   int has_res;                         // residual tile (bf16, output shape) is TMA-prefetched and added before ReLU
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
   int main_bytes;                      // shared memory of the operand ring
@@ -212,10 +212,10 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x
   uint32_t m = 0;
   const int y_hi = min(y0 + p.BH, p.h), x_hi = min(x0 + p.BW, p.w);
   for (int r = 0; r < p.R; ++r) {
-    const int dy = (r - p.R / 2) * p.dil;
+    const int dy = r * p.dil - p.pad;
     if ((y_hi - 1) * p.stride + dy < 0 || y0 * p.stride + dy >= p.hin) continue;
     for (int s = 0; s < p.S; ++s) {
-      const int dx = (s - p.S / 2) * p.dil;
+      const int dx = s * p.dil - p.pad;
       if ((x_hi - 1) * p.stride + dx < 0 || x0 * p.stride + dx >= p.win) continue;
       m |= 1u << (r * p.S + s);
     }
@@ -327,7 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         for (int tp = 0; tp < p.R * p.S; ++tp) {
           if (!((taps >> tp) & 1u)) continue;
-          const int dy = (tp / p.S - p.R / 2) * p.dil, dx = (tp % p.S - p.S / 2) * p.dil;
+          const int dy = (tp / p.S) * p.dil - p.pad, dx = (tp % p.S) * p.dil - p.pad;
           for (int cb = 0; cb < cblocks; ++cb, ++kbg) {
             const int s = (int)(kbg % (uint32_t)p.stages);
             const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
@@ -639,7 +639,7 @@ extern "C" int eeseg_conv_debug_stats(void* device_buffer) {
 
 extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
                                     const float* shift, int64_t shift_sn, int N, int hin, int win,
-                                    int Cin, int Cout, int R, int S, int dilation, int stride,
+                                    int Cin, int Cout, int R, int S, int dilation, int stride, int pad,
                                     int relu, const void* residual, int64_t ldr, void* out,
                                     int out_dtype, int64_t ldo, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -648,7 +648,11 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   EESEG_REQUIRE(stride == 1 || stride == 2, "conv_igemm: stride %d (1 or 2)", stride);
   EESEG_REQUIRE(Cin % kBlockK == 0, "conv_igemm: Cin=%d must be a multiple of 64", Cin);
   EESEG_REQUIRE(Cout % 16 == 0, "conv_igemm: Cout=%d must be a multiple of 16", Cout);
-  EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32 && (R & 1) && (S & 1), "conv_igemm: odd kernel sizes up to 32 taps");
+  EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32, "conv_igemm: at most 32 taps");
+  if (pad < 0) {  // 'same' padding of an odd kernel
+    EESEG_REQUIRE((R & 1) && (S & 1) && R == S, "conv_igemm: pad < 0 ('same') needs an odd square kernel");
+    pad = dilation * (R / 2);
+  }
   EESEG_REQUIRE(out_dtype == EESEG_BF16 || out_dtype == EESEG_F32, "conv_igemm: out_dtype %d", out_dtype);
   const int oes = out_dtype == EESEG_F32 ? 4 : 2;
   EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
@@ -666,7 +670,7 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   const int h = (hin - 1) / stride + 1, w = (win - 1) / stride + 1;
   ConvParams p;
   p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
-  p.hin = hin; p.win = win; p.stride = stride;
+  p.hin = hin; p.win = win; p.stride = stride; p.pad = pad;
   p.has_res = residual ? 1 : 0;
   pick_tile(h, w, p.BW, p.BH);
   p.tiles_x = (w + p.BW - 1) / p.BW;

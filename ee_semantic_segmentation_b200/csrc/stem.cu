@@ -1,0 +1,107 @@
+// ResNet stem helpers: space-to-depth of the input image (so the 7x7/s2 conv runs on the tcgen05
+// implicit-GEMM kernel as a 4x4/s1 conv over 64 padded channels) and the 3x3/s2 max-pool on NHWC
+// bf16. Both are pure streaming kernels (coalesced 16 B accesses). Reference: torchvision resnet
+// conv1/bn1/relu/maxpool inside base_model[0] (from_deepv3_new.py:75-79,146).
+#include "common.cuh"
+
+namespace eeseg {
+
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, int N, int H, int W,
+                                                        int H2, int W2, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)N * H2 * W2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W2);
+    const int Y = (int)((i / W2) % H2);
+    const int n = (int)(i / ((int64_t)W2 * H2));
+    float v[12];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int yy = 2 * Y + a, xx = 2 * X + b;
+          v[(a * 2 + b) * 3 + c] = (yy < H && xx < W) ? __ldg(x + (((int64_t)n * 3 + c) * H + yy) * W + xx) : 0.f;
+        }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    w[6] = 0; w[7] = 0;
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], 0, 0);
+#pragma unroll
+    for (int k = 2; k < 8; ++k) o[k] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int N, int h,
+                                                            int w, int C, int ho, int wo,
+                                                            __nv_bfloat16* __restrict__ out) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)N * ho * wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int X = (int)((i / cv) % wo);
+    const int Y = (int)((i / ((int64_t)cv * wo)) % ho);
+    const int n = (int)(i / ((int64_t)cv * wo * ho));
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = 2 * Y + dy, xx = 2 * X + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * h + yy) * w + xx) * C) + c8);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            m[2 * k] = fmaxf(m[2 * k], __uint_as_float(w4[k] << 16));
+            m[2 * k + 1] = fmaxf(m[2 * k + 1], __uint_as_float(w4[k] & 0xffff0000u));
+          }
+        }
+      }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]);
+      o[k] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    reinterpret_cast<uint4*>(out + (((int64_t)n * ho + Y) * wo + X) * C)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace eeseg
+
+using namespace eeseg;
+
+extern "C" int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream) {
+  EESEG_REQUIRE(x && out, "stem_space_to_depth: null pointer");
+  EESEG_REQUIRE(((uintptr_t)out & 15) == 0, "stem_space_to_depth: output must be 16-byte aligned");
+  if (N <= 0) return EESEG_OK;
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const int64_t total = (int64_t)N * H2 * W2;
+  const int blocks = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  stem_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, H2, W2, (__nv_bfloat16*)out);
+  return check_launch("stem_s2d_kernel");
+}
+
+extern "C" int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream) {
+  EESEG_REQUIRE(x && out, "maxpool3x3s2: null pointer");
+  EESEG_REQUIRE(C % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                "maxpool3x3s2: C %% 8 == 0 and 16-byte aligned pointers required");
+  if (N <= 0) return EESEG_OK;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int64_t total = (int64_t)N * ho * wo * (C / 8);
+  const int blocks = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  maxpool3x3s2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, h, w, C, ho, wo,
+                                                                  (__nv_bfloat16*)out);
+  return check_launch("maxpool3x3s2_kernel");
+}

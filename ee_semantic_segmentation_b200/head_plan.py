@@ -39,7 +39,7 @@ PROFILE_TAG = "head"
 
 
 def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0, stride=1,
-               residual=None):
+               residual=None, pad=-1):
     """x bf16 NHWC [N,h,w,Cin]; wt bf16 [Cout,R,S,Cin]; out: tensor view whose data_ptr is the first
     output channel and whose pixel stride is ldo elements; residual: optional bf16 NHWC tensor of
     the output shape (added before the ReLU)."""
@@ -51,7 +51,7 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
             a.record()
         check(lib().eeseg_conv_igemm_fwd(
             x.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), shift_sn, N, h, w, Cin,
-            Cout, R, S, dilation, stride, 1 if relu else 0,
+            Cout, R, S, dilation, stride, pad, 1 if relu else 0,
             None if residual is None else residual.data_ptr(),
             0 if residual is None else residual.stride(2), out.data_ptr(), out_dtype_code, ldo,
             torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_fwd")

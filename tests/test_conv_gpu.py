@@ -140,3 +140,25 @@ def test_section_plan_vs_torchvision():
     gb = SectionPlan(sec_b.to(dev())).run(ga)
     assert gb.shape == rb.shape
     assert (gb.float().cpu() - rb).abs().max().item() < 3e-2 * rb.abs().max().item()
+
+
+def test_stem_plan_vs_torch():
+    """conv1 7x7/s2 + bn + relu + maxpool via space-to-depth + 4x4 implicit GEMM + NHWC max-pool."""
+    import torchvision
+    from ee_semantic_segmentation_b200.backbone_plan import StemPlan
+    torch.manual_seed(3)
+    r = torchvision.models.resnet50(weights=None)
+    r.bn1.running_mean.normal_(0, 0.1); r.bn1.running_var.uniform_(0.5, 1.5)
+    r.bn1.weight.data.uniform_(0.5, 1.5); r.bn1.bias.data.normal_(0, 0.1)
+    stem = torch.nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool).eval()
+    assert StemPlan.matches(list(stem))
+    for shape in [(2, 3, 513, 513), (1, 3, 97, 130)]:
+        x = torch.randn(*shape)
+        with torch.no_grad():
+            ref = stem(x)
+        stem_d = stem.to(dev())
+        got = StemPlan(stem_d[0], stem_d[1]).run(x.to(dev())).permute(0, 3, 1, 2).float().cpu()
+        stem.cpu()
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-2, err
