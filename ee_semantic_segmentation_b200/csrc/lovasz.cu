@@ -13,7 +13,8 @@
 // the bit pattern of err; payload = pixel index | fg << 31 | sign << 30), followed by a segmented
 // scan of the fg bit and one apply kernel that forms g_k from exact integer counts, accumulates
 // err*g in fp64 per tile (ordered reduction) and scatters the gradient.
-// HBM-bound, sort-dominated: 4 x (4 B hist read + 8 B read + 8 B write) per element per pass.
+// HBM-bound, sort-dominated: 4 passes x (8 B hist read + 8 B read + 8 B write) per element; the
+// scatter re-orders each tile in shared memory first so the global writes are whole runs.
 #include "common.cuh"
 
 namespace eeseg {
@@ -74,8 +75,7 @@ __global__ void __launch_bounds__(256) lv_keygen_kernel(const T* __restrict__ pr
                                                          const int64_t* __restrict__ labels,
                                                          LovaszDims d, int has_ignore,
                                                          int64_t ignore, const int* __restrict__ skip,
-                                                         uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals,
+                                                         uint2* __restrict__ kv,
                                                          T* __restrict__ dprobas) {
   // thread per pixel of the batch; loops classes so the int64 label is read once
   const int64_t P = (int64_t)d.N * d.HW;
@@ -98,14 +98,15 @@ __global__ void __launch_bounds__(256) lv_keygen_kernel(const T* __restrict__ pr
       const float diff = p - fg;
       const float err = valid ? fabsf(diff) : 0.f;
       const int64_t dst = ((int64_t)g * d.C + c) * d.L + i;
-      keys[dst] = ~__float_as_uint(err);  // ascending on ~bits == descending on err (err >= 0)
-      vals[dst] = (uint32_t)i | (fg != 0.f ? 0x80000000u : 0u) | (diff > 0.f ? 0x40000000u : 0u);
+      // key: ascending on ~bits == descending on err (err >= 0); value: index | fg << 31 | sign << 30
+      kv[dst] = make_uint2(~__float_as_uint(err),
+                           (uint32_t)i | (fg != 0.f ? 0x80000000u : 0u) | (diff > 0.f ? 0x40000000u : 0u));
     }
   }
 }
 
-// ---- LSD radix sort, one 8-bit pass = hist + scan + scatter ------------------------------------
-__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint32_t* __restrict__ keys,
+// ---- LSD radix sort, one 8-bit pass = hist + scan (2 small kernels) + scatter ----------------------
+__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint2* __restrict__ kv,
                                                               LovaszDims d, int shift,
                                                               const int* __restrict__ skip,
                                                               uint32_t* __restrict__ hist) {
@@ -115,86 +116,100 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint32_t* __r
   __shared__ unsigned h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t* k = keys + (int64_t)seg * d.L;
+  const uint2* k = kv + (int64_t)seg * d.L;
   const int64_t base = (int64_t)tile * kRsTile;
-#pragma unroll 4
-  for (int r = 0; r < kRsItems; ++r) {
+  int dg[kRsItems];
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {   // all loads first (16 independent 4 B loads in flight per thread)
     const int64_t i = base + r * kRsThreads + threadIdx.x;
-    const int dg = i < d.L ? (int)((__ldg(k + i) >> shift) & 255u) : -1;
-    unsigned peers = __match_any_sync(0xffffffffu, dg);
-    if (dg >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(h + dg, (unsigned)__popc(peers));
+    dg[r] = i < d.L ? (int)((__ldg(k + i).x >> shift) & 255u) : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    unsigned peers = __match_any_sync(0xffffffffu, dg[r]);
+    if (dg[r] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(h + dg[r], (unsigned)__popc(peers));
   }
   __syncthreads();
   hist[((int64_t)seg * 256 + threadIdx.x) * d.T + tile] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256) rs_scan_kernel(uint32_t* __restrict__ hist, int T,
-                                                       const int* __restrict__ skip,
-                                                       uint32_t* __restrict__ digit_base) {
-  // per segment: exclusive scan over tiles for every digit, then exclusive scan of digit totals
-  const int seg = blockIdx.x;
+// one warp per (segment, digit): exclusive scan of that digit's counts over the tiles
+__global__ void __launch_bounds__(256) rs_scan_tiles_kernel(uint32_t* __restrict__ hist, int T,
+                                                             const int* __restrict__ skip,
+                                                             uint32_t* __restrict__ digit_total) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);   // = seg * 256 + digit
+  const int seg = w >> 8, lane = threadIdx.x & 31;
   if (skip[seg]) return;
-  __shared__ unsigned total[256];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int dd = 0; dd < 32; ++dd) {
-    const int dg = warp * 32 + dd;
-    uint32_t* row = hist + ((int64_t)seg * 256 + dg) * T;
-    unsigned running = 0;
-    for (int t0 = 0; t0 < T; t0 += 32) {
-      const int t = t0 + lane;
-      unsigned v = t < T ? row[t] : 0u, inc = v;
+  uint32_t* row = hist + (int64_t)w * T;
+  unsigned running = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    unsigned v = t < T ? row[t] : 0u, inc = v;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
-      }
-      if (t < T) row[t] = running + inc - v;
-      running += __shfl_sync(0xffffffffu, inc, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
     }
-    if (lane == 0) total[dg] = running;
+    if (t < T) row[t] = running + inc - v;
+    running += __shfl_sync(0xffffffffu, inc, 31);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned run = 0;
-    for (int i = 0; i < 256; ++i) {
-      digit_base[seg * 256 + i] = run;
-      run += total[i];
-    }
-  }
+  if (lane == 0) digit_total[w] = running;
 }
 
+// one block per segment: exclusive scan of the 256 digit totals
+__global__ void __launch_bounds__(256) rs_scan_digits_kernel(const uint32_t* __restrict__ digit_total,
+                                                              const int* __restrict__ skip,
+                                                              uint32_t* __restrict__ digit_base) {
+  const int seg = blockIdx.x;
+  if (skip[seg]) return;
+  __shared__ unsigned wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned v = digit_total[seg * 256 + threadIdx.x];
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  unsigned off = 0;
+  for (int i = 0; i < warp; ++i) off += wsum[i];
+  digit_base[seg * 256 + threadIdx.x] = off + inc - v;
+}
+
+// Scatter: stable ranking inside the tile (warp-blocked order, match.any), then the tile is
+// re-ordered by digit in shared memory and written out run by run, so consecutive threads write
+// consecutive (key, value) pairs: full lines instead of one 32 B sector per element.
 __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(
-    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, LovaszDims d, int shift,
+    const uint2* __restrict__ in, uint2* __restrict__ out, LovaszDims d, int shift,
     const int* __restrict__ skip, const uint32_t* __restrict__ hist,
     const uint32_t* __restrict__ digit_base) {
   const int seg = blockIdx.y, tile = blockIdx.x;
   if (skip[seg]) return;
-  __shared__ unsigned cnt[kRsWarps][256];
-  __shared__ unsigned tile_off[256];
+  __shared__ unsigned cnt[kRsWarps][256];     // per-warp digit counts -> exclusive prefix over warps
+  __shared__ unsigned tile_pref[256];         // exclusive prefix of the tile's digit totals
+  __shared__ unsigned gl_off[256];            // global position of the tile's first element of a digit
+  __shared__ unsigned wsum[8];
+  __shared__ uint2 stage[kRsTile];            // 32 KB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
   const int64_t seg_off = (int64_t)seg * d.L;
   // warp-blocked order keeps the sort stable: warp w owns a contiguous run, round r is contiguous
   const int64_t wbase = (int64_t)tile * kRsTile + (int64_t)warp * (32 * kRsItems);
-  uint32_t key[kRsItems], val[kRsItems];
+  uint2 kv[kRsItems];
   unsigned lrank[kRsItems];
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const int64_t i = wbase + r * 32 + lane;
-    if (i < d.L) {
-      key[r] = __ldg(keys_in + seg_off + i);
-      val[r] = __ldg(vals_in + seg_off + i);
-    } else {
-      key[r] = 0; val[r] = 0;
-    }
+    kv[r] = i < d.L ? __ldg(in + seg_off + i) : make_uint2(0, 0);
   }
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const bool ok = wbase + r * 32 + lane < d.L;
-    const int dg = ok ? (int)((key[r] >> shift) & 255u) : -1;
+    const int dg = ok ? (int)((kv[r].x >> shift) & 255u) : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, dg);
     const int leader = __ffs(peers) - 1;
     unsigned old = 0;
@@ -216,32 +231,50 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(
       cnt[w][dg] = run;
       run += t;
     }
-    tile_off[dg] = digit_base[seg * 256 + dg] + hist[((int64_t)seg * 256 + dg) * d.T + tile];
+    // exclusive prefix of the tile's digit totals (block scan over 256 threads)
+    unsigned inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned off = 0;
+    for (int i = 0; i < warp; ++i) off += wsum[i];
+    tile_pref[dg] = off + inc - run;
+    gl_off[dg] = digit_base[seg * 256 + dg] + hist[((int64_t)seg * 256 + dg) * d.T + tile];
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     if (wbase + r * 32 + lane < d.L) {
-      const int dg = (int)((key[r] >> shift) & 255u);
-      const int64_t pos = seg_off + tile_off[dg] + cnt[warp][dg] + lrank[r];
-      keys_out[pos] = key[r];
-      vals_out[pos] = val[r];
+      const int dg = (int)((kv[r].x >> shift) & 255u);
+      stage[tile_pref[dg] + cnt[warp][dg] + lrank[r]] = kv[r];
     }
+  }
+  __syncthreads();
+  const int64_t remaining = d.L - (int64_t)tile * kRsTile;
+  const int n_valid = (int)(remaining < kRsTile ? remaining : kRsTile);
+  for (int i = threadIdx.x; i < n_valid; i += kRsThreads) {
+    const uint2 e = stage[i];
+    const int dg = (int)((e.x >> shift) & 255u);
+    out[seg_off + gl_off[dg] + ((unsigned)i - tile_pref[dg])] = e;
   }
 }
 
 // ---- segmented scan of the fg bit + Jaccard gradient + dot + gradient scatter --------------------
-__global__ void __launch_bounds__(kRsThreads) lv_fgcount_kernel(const uint32_t* __restrict__ vals,
+__global__ void __launch_bounds__(kRsThreads) lv_fgcount_kernel(const uint2* __restrict__ kv,
                                                                  LovaszDims d,
                                                                  const int* __restrict__ skip,
                                                                  uint32_t* __restrict__ tile_fg) {
   const int seg = blockIdx.y, tile = blockIdx.x;
   if (skip[seg]) return;
-  const uint32_t* v = vals + (int64_t)seg * d.L;
+  const uint2* v = kv + (int64_t)seg * d.L;
   int c = 0;
   for (int r = 0; r < kRsItems; ++r) {
     const int64_t i = (int64_t)tile * kRsTile + r * kRsThreads + threadIdx.x;
-    c += (i < d.L) ? (int)(__ldg(v + i) >> 31) : 0;
+    c += (i < d.L) ? (int)(__ldg(v + i).y >> 31) : 0;
   }
   c = warp_sum(c);
   __shared__ int s[kRsWarps];
@@ -274,7 +307,7 @@ __global__ void lv_fgscan_kernel(uint32_t* __restrict__ tile_fg, int T, const in
 
 template <typename T>
 __global__ void __launch_bounds__(kRsThreads) lv_apply_kernel(
-    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, LovaszDims d,
+    const uint2* __restrict__ kv, LovaszDims d,
     const int* __restrict__ skip, const int* __restrict__ counts, const int* __restrict__ npresent,
     const uint32_t* __restrict__ tile_fg, double* __restrict__ partial, T* __restrict__ dprobas) {
   const int seg = blockIdx.y, tile = blockIdx.x;
@@ -290,8 +323,9 @@ __global__ void __launch_bounds__(kRsThreads) lv_apply_kernel(
   for (int r = 0; r < kRsItems; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     const bool ok = i < d.L;
-    key[r] = ok ? __ldg(keys + seg_off + i) : 0xffffffffu;
-    val[r] = ok ? __ldg(vals + seg_off + i) : 0u;
+    const uint2 e = ok ? __ldg(kv + seg_off + i) : make_uint2(0xffffffffu, 0u);
+    key[r] = e.x;
+    val[r] = e.y;
     ballots[r] = __ballot_sync(0xffffffffu, ok && (val[r] >> 31));
     wtotal += __popc(ballots[r]);
   }
@@ -364,7 +398,8 @@ __global__ void lv_final_kernel(const double* __restrict__ partial, LovaszDims d
 
 // ---- workspace layout ---------------------------------------------------------------------------
 struct LovaszWs {
-  uint32_t *keys[2], *vals[2], *hist, *digit_base, *tile_fg;
+  uint2* kv[2];
+  uint32_t *hist, *digit_base, *digit_total, *tile_fg;
   double* partial;
   int *counts, *skip, *npresent;
   size_t bytes;
@@ -381,12 +416,11 @@ static LovaszWs carve(void* base, const LovaszDims& d) {
     return p;
   };
   const size_t S = (size_t)d.G * d.C, SL = S * (size_t)d.L;
-  w.keys[0] = (uint32_t*)take(SL * 4);
-  w.keys[1] = (uint32_t*)take(SL * 4);
-  w.vals[0] = (uint32_t*)take(SL * 4);
-  w.vals[1] = (uint32_t*)take(SL * 4);
+  w.kv[0] = (uint2*)take(SL * 8);
+  w.kv[1] = (uint2*)take(SL * 8);
   w.hist = (uint32_t*)take(S * 256 * (size_t)d.T * 4);
   w.digit_base = (uint32_t*)take(S * 256 * 4);
+  w.digit_total = (uint32_t*)take(S * 256 * 4);
   w.tile_fg = (uint32_t*)take(S * (size_t)d.T * 4);
   w.partial = (double*)take(S * (size_t)d.T * 8);
   w.counts = (int*)take(S * 4);
@@ -412,28 +446,29 @@ static int run_exit(const T* probas, const int64_t* labels, const LovaszDims& d,
   const int64_t P = (int64_t)d.N * d.HW;
   int kb = (int)((P + 255) / 256 < kNumSMs * 8 ? (P + 255) / 256 : kNumSMs * 8);
   lv_keygen_kernel<T><<<kb, 256, 0, stream>>>(probas, labels, d, has_ignore, ignore, w.skip,
-                                              w.keys[0], w.vals[0], dprobas);
+                                              w.kv[0], dprobas);
   int rc = check_launch("lv_keygen_kernel");
   if (rc) return rc;
   dim3 tiles(d.T, S);
   int cur = 0;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
-    rs_hist_kernel<<<tiles, kRsThreads, 0, stream>>>(w.keys[cur], d, shift, w.skip, w.hist);
+    rs_hist_kernel<<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], d, shift, w.skip, w.hist);
     if ((rc = check_launch("rs_hist_kernel"))) return rc;
-    rs_scan_kernel<<<S, 256, 0, stream>>>(w.hist, d.T, w.skip, w.digit_base);
-    if ((rc = check_launch("rs_scan_kernel"))) return rc;
-    rs_scatter_kernel<<<tiles, kRsThreads, 0, stream>>>(w.keys[cur], w.vals[cur], w.keys[cur ^ 1],
-                                                        w.vals[cur ^ 1], d, shift, w.skip, w.hist,
+    rs_scan_tiles_kernel<<<S * 32, 256, 0, stream>>>(w.hist, d.T, w.skip, w.digit_total);
+    if ((rc = check_launch("rs_scan_tiles_kernel"))) return rc;
+    rs_scan_digits_kernel<<<S, 256, 0, stream>>>(w.digit_total, w.skip, w.digit_base);
+    if ((rc = check_launch("rs_scan_digits_kernel"))) return rc;
+    rs_scatter_kernel<<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], w.kv[cur ^ 1], d, shift, w.skip, w.hist,
                                                         w.digit_base);
     if ((rc = check_launch("rs_scatter_kernel"))) return rc;
     cur ^= 1;
   }
-  lv_fgcount_kernel<<<tiles, kRsThreads, 0, stream>>>(w.vals[cur], d, w.skip, w.tile_fg);
+  lv_fgcount_kernel<<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], d, w.skip, w.tile_fg);
   if ((rc = check_launch("lv_fgcount_kernel"))) return rc;
   lv_fgscan_kernel<<<S, 32, 0, stream>>>(w.tile_fg, d.T, w.skip);
   if ((rc = check_launch("lv_fgscan_kernel"))) return rc;
-  lv_apply_kernel<T><<<tiles, kRsThreads, 0, stream>>>(w.keys[cur], w.vals[cur], d, w.skip, w.counts,
+  lv_apply_kernel<T><<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], d, w.skip, w.counts,
                                                        w.npresent, w.tile_fg, w.partial, dprobas);
   if ((rc = check_launch("lv_apply_kernel"))) return rc;
   lv_final_kernel<<<1, 256, 0, stream>>>(w.partial, d, w.skip, w.npresent, out);
