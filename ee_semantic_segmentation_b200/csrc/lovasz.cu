@@ -106,6 +106,19 @@ __global__ void __launch_bounds__(256) lv_keygen_kernel(const T* __restrict__ pr
 }
 
 // ---- LSD radix sort, one 8-bit pass = hist + scan (2 small kernels) + scatter ----------------------
+// Lanes holding the same 8-bit digit, in constant time (8 ballots) whatever the digit distribution
+// (MATCH.ANY serialises over the distinct values, i.e. it is slowest exactly on the random low bytes).
+__device__ __forceinline__ unsigned match_digit8(int dg, bool ok) {
+  unsigned peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (dg >> b) & 1;
+    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return ok ? peers : 0u;
+}
+
 __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint2* __restrict__ kv,
                                                               LovaszDims d, int shift,
                                                               const int* __restrict__ skip,
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint2* __rest
   }
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    unsigned peers = __match_any_sync(0xffffffffu, dg[r]);
+    const unsigned peers = match_digit8(dg[r], dg[r] >= 0);
     if (dg[r] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(h + dg[r], (unsigned)__popc(peers));
   }
   __syncthreads();
@@ -209,9 +222,9 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     const bool ok = wbase + r * 32 + lane < d.L;
-    const int dg = ok ? (int)((kv[r].x >> shift) & 255u) : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, dg);
-    const int leader = __ffs(peers) - 1;
+    const int dg = ok ? (int)((kv[r].x >> shift) & 255u) : 0;
+    const unsigned peers = match_digit8(dg, ok);
+    const int leader = ok ? __ffs(peers) - 1 : lane;
     unsigned old = 0;
     if (ok && lane == leader) {
       old = cnt[warp][dg];
