@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--impl", default="eeseg", choices=["eeseg", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the conv kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -204,6 +205,8 @@ def main():
     warmup = max(args.warmup, 3)
     steps = args.steps
 
+    if args.no_pdl:
+        _lib.lib().eeseg_conv_set_pdl(0)
     torch.manual_seed(0)
     net = branchyDeepv3(None, "deeplabv3_resnet50", 2, IMG, sections=SECTIONS, pretrained=False).to(dev).eval()
     eng = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=not args.no_graph)

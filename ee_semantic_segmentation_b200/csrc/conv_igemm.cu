@@ -295,6 +295,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map
+  // prefetch) overlapped the tail of the previous kernel in the stream; from here on we touch its
+  // outputs, so wait for it to complete. Our own dependents may start their prologue right away.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // tile -> (image, y0, x0, n0); identical in every role
   auto tile_coords = [&](int t, int& n_img, int& y0, int& x0, int& n0) {
@@ -630,6 +635,13 @@ static int encode_act_map(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr
 }
 
 static unsigned long long* g_conv_dbg = nullptr;
+static int g_conv_pdl = 1;
+// Programmatic dependent launch of the conv kernel on/off (default on); returns the previous setting.
+extern "C" int eeseg_conv_set_pdl(int enable) {
+  const int old = g_conv_pdl;
+  g_conv_pdl = enable ? 1 : 0;
+  return old;
+}
 // Tuning hook (not part of the product path): device buffer of [148][32] uint64 cycle counters that
 // the next conv launches fill (producer / MMA / epilogue wait times); NULL switches it off.
 extern "C" int eeseg_conv_debug_stats(void* device_buffer) {
@@ -741,7 +753,17 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
     attr_set = true;
   }
   dim3 grid((unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs));   // persistent: one CTA per SM
-  conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, tmo, tmr, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmx, tmw, tmo, tmr, p));
   return check_launch("conv_igemm_kernel");
 }
 

@@ -175,6 +175,11 @@ int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, vo
 /* 3x3 / stride-2 / pad-1 max pooling of a bf16 NHWC tensor (C % 8 == 0). */
 int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream);
 
+/* Programmatic dependent launch for eeseg_conv_igemm_fwd (prologue of launch i+1 overlaps the tail of
+ * launch i; the kernel executes griddepcontrol.wait before touching its inputs). Default on; returns
+ * the previous setting. */
+int eeseg_conv_set_pdl(int enable);
+
 /* Tuning hook: device buffer of [148][32] uint64 cycle counters (per-CTA wait times of the producer,
  * MMA and epilogue roles) filled by subsequent eeseg_conv_igemm_fwd launches; NULL switches it off. */
 int eeseg_conv_debug_stats(void* device_buffer);
