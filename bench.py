@@ -270,7 +270,31 @@ def main():
 
     for _ in range(2):
         step_e2e()
-    e2e_ms, _ = timed(step_e2e, steps)
+    if eng.use_graph:
+        # end to end through the public streaming API: pinned host batches in, per-image results out;
+        # uploads, graph replays and read-backs overlap (double-buffered inputs), all inside the timing
+        def host_batches(n):
+            for _ in range(n):
+                yield Xh, yh
+        for _ in eng.evaluate_pipelined(host_batches(3)):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        n_out = 0
+        for ex, sc in eng.evaluate_pipelined(host_batches(steps)):
+            n_out += ex.numel()
+        b2.record()
+        if world > 1:
+            eng.all_reduce()
+        barrier()
+        assert n_out == PER_GPU_BATCH * steps
+        e2e_ms = max(a.elapsed_time(b2), 0.0)
+        e2e_wall = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e2e_ms, e2e_wall - 0.5)     # events bracket the stream work; the wall clock includes the last read-back
+    else:
+        e2e_ms, _ = timed(step_e2e, steps)
 
     # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
     prof = []

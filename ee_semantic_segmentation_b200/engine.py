@@ -63,8 +63,8 @@ class EarlyExitEngine:
         g = self._capture(tuple(shape), with_targets)
         return g['X'], g['y']
 
-    def _capture(self, shape, with_targets):
-        key = (shape, with_targets)
+    def _capture(self, shape, with_targets, slot=0):
+        key = (shape, with_targets, slot)
         if key in self._graphs:
             return self._graphs[key]
         N, _, H, W = shape
@@ -92,6 +92,53 @@ class EarlyExitEngine:
         g = self._capture(tuple(shape), with_targets)
         g['graph'].replay()
         return g['out']
+
+    def evaluate_pipelined(self, host_batches):
+        """Throughput path for host-resident data: yields (exit int32 [N], scores f32 [E-1,N]) CPU
+        tensors per batch, in order. `host_batches` yields (X, y) pinned CPU tensors of one shape.
+        Two captured graphs with their own input buffers are used alternately: while graph k runs,
+        the copy stream uploads batch k+1 into the other graph's buffers, and the small per-image
+        results of batch k-1 are read back — H2D, compute and D2H overlap, nothing else changes."""
+        assert self.use_graph, "evaluate_pipelined needs use_graph=True"
+        dev = self.device
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        slots, pending = None, None
+        ev_in = [torch.cuda.Event() for _ in range(2)]     # upload of slot k finished
+        ev_free = [torch.cuda.Event() for _ in range(2)]   # graph of slot k finished reading its inputs
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        res_host = None
+        k = 0
+        for X, y in host_batches:
+            if slots is None:
+                slots = [self._capture(tuple(X.shape), True, slot=i) for i in range(2)]
+                res_host = [(torch.empty((X.shape[0],), dtype=torch.int32).pin_memory(),
+                             torch.empty((max(self.E - 1, 1), X.shape[0]), dtype=torch.float32).pin_memory())
+                            for _ in range(2)]
+                for e in ev_free:
+                    e.record(main)
+            g = slots[k & 1]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[k & 1])
+                g['X'].copy_(X, non_blocking=True)
+                g['y'].copy_(y.view_as(g['y']), non_blocking=True)
+                ev_in[k & 1].record(copy_stream)
+            main.wait_event(ev_in[k & 1])
+            g['graph'].replay()
+            ev_free[k & 1].record(main)
+            with torch.cuda.stream(copy_stream):      # results ride the copy stream too
+                copy_stream.wait_event(ev_free[k & 1])
+                res_host[k & 1][0].copy_(g['out']['exit'], non_blocking=True)
+                res_host[k & 1][1].copy_(g['out']['scores'], non_blocking=True)
+                ev_out[k & 1].record(copy_stream)
+            if pending is not None:
+                ev_out[pending].synchronize()
+                yield res_host[pending][0].clone(), res_host[pending][1].clone()
+            pending = k & 1
+            k += 1
+        if pending is not None:
+            ev_out[pending].synchronize()
+            yield res_host[pending][0].clone(), res_host[pending][1].clone()
 
     @torch.no_grad()
     def infer(self, X):

@@ -141,3 +141,23 @@ def test_mIoU_evaluator_and_operator(nets):
     op = eval_ee_deeplabv3(net, img_norm_entropy(21), -1.0, device=dev())    # never confident
     out = op(x[0].to(dev()))
     assert out["n"] == 3 and torch.equal(out["exit"], out["last"])
+
+
+def test_engine_graph_and_pipelined_match_eager(nets):
+    """CUDA-graph replay and the double-buffered streaming API give the eager engine's results."""
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine
+    port, net = nets
+    g = torch.Generator().manual_seed(24)
+    batches = [(torch.randn(2, 3, 65, 81, generator=g).pin_memory(),
+                torch.randint(0, 22, (2, 1, 65, 81), generator=g).pin_memory()) for _ in range(5)]
+    tau = 0.97
+    eager = EarlyExitEngine(net, 21, tau)
+    ref = [eager.evaluate(X.to(dev()), y.to(dev())) for X, y in batches]
+    ref = [(r["exit"].cpu(), r["scores"].cpu()) for r in ref]
+    graph = EarlyExitEngine(net, 21, tau, use_graph=True)
+    outs = list(graph.evaluate_pipelined(iter(batches)))
+    assert len(outs) == len(batches)
+    for (e1, s1), (e2, s2) in zip(ref, outs):
+        assert torch.equal(e1, e2)
+        assert torch.allclose(s1, s2, atol=1e-6)
+    assert torch.equal(graph.cm.cpu(), eager.cm.cpu()) and torch.equal(graph.counts.cpu(), eager.counts.cpu())
