@@ -101,7 +101,8 @@ class EarlyExitEngine:
         results of batch k-1 are read back — H2D, compute and D2H overlap, nothing else changes."""
         assert self.use_graph, "evaluate_pipelined needs use_graph=True"
         dev = self.device
-        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = torch.cuda.Stream(device=dev)   # uploads
+        back_stream = torch.cuda.Stream(device=dev)   # read-backs (must not queue in front of the next upload)
         main = torch.cuda.current_stream(dev)
         slots, pending = None, None
         ev_in = [torch.cuda.Event() for _ in range(2)]     # upload of slot k finished
@@ -126,11 +127,11 @@ class EarlyExitEngine:
             main.wait_event(ev_in[k & 1])
             g['graph'].replay()
             ev_free[k & 1].record(main)
-            with torch.cuda.stream(copy_stream):      # results ride the copy stream too
-                copy_stream.wait_event(ev_free[k & 1])
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(ev_free[k & 1])
                 res_host[k & 1][0].copy_(g['out']['exit'], non_blocking=True)
                 res_host[k & 1][1].copy_(g['out']['scores'], non_blocking=True)
-                ev_out[k & 1].record(copy_stream)
+                ev_out[k & 1].record(back_stream)
             if pending is not None:
                 ev_out[pending].synchronize()
                 yield res_host[pending][0].clone(), res_host[pending][1].clone()
