@@ -246,3 +246,87 @@ class EarlyExitEngine:
         res['pool'] = self.metric
         res['pool_size'] = self.size
         return res
+
+
+class ThresholdSweep:
+    """Single-pass threshold sweep: what re-running the reference's
+    `br_evaluator` (eval_br_ent.py:38-84, CLI `-t`) once per tau computes, from ONE forward per batch.
+
+    Per image the E-1 per-exit confidence scalars and the E confusion matrices (every exit's argmax
+    against the target) are computed once; each tau is then resolved on those tiny tensors with the
+    reference's rule (first early exit i >= skip whose score < tau, else the final exit). The integer
+    accumulators `cm[T, E+1, C+1, C]` / `counts[T, E+1]` are exactly what T separate evaluations would
+    give, and sum exactly across ranks (`all_reduce`)."""
+
+    def __init__(self, net, n_classes, taus, metric='ent', size=1, skip=0):
+        self.net = net
+        self.C = n_classes
+        self.E = net.n_branches + 1
+        self.metric = metric.lower()
+        assert self.metric in ('ent', 'max', 'min')
+        self.size = size if self.metric != 'ent' else 1
+        self.skip = skip
+        dev = next(net.parameters()).device
+        self.device = dev
+        self.taus = torch.as_tensor(list(taus), dtype=torch.float32, device=dev)
+        T = self.taus.numel()
+        self.cm = torch.zeros((T, self.E + 1, n_classes + 1, n_classes), dtype=torch.int64, device=dev)
+        self.counts = torch.zeros((T, self.E + 1), dtype=torch.int64, device=dev)
+
+    @torch.no_grad()
+    def update(self, X, y):
+        H, W = X.shape[-2:]
+        N = X.shape[0]
+        pool = self.metric != 'ent'
+        lows = self.net.forward_lowres(X)
+        scores = torch.full((max(self.E - 1, 1), N), float('inf'), dtype=torch.float32, device=X.device)
+        cms = []
+        for i, lo in enumerate(lows):
+            gated = i < self.E - 1 and i >= self.skip
+            res = ops.exit_gate(lo, (H, W), layout='NHWC', n_classes=self.C, want_ent=pool and gated,
+                                want_amax=True, want_score=gated and not pool)
+            if gated:
+                scores[i] = ops.entropy_pool_mean(res.ent, self.size, self.metric == 'min') if pool else res.score
+            cms.append(ops.confusion_hist(res.amax, y, self.C))
+        cms = torch.stack(cms)                                            # [E, N, C+1, C]
+        # exit taken per (tau, image): first early exit whose score is below tau, else the last exit
+        below = scores[: self.E - 1].unsqueeze(0) < self.taus.view(-1, 1, 1) if self.E > 1 else None  # [T, E-1, N]
+        if below is not None and below.shape[1] > 0:
+            first = torch.where(below.any(dim=1), below.float().argmax(dim=1), torch.full_like(below[:, 0], self.E - 1, dtype=torch.int64))
+        else:
+            first = torch.full((self.taus.numel(), N), self.E - 1, dtype=torch.int64, device=X.device)
+        onehot = torch.nn.functional.one_hot(first, self.E).to(torch.int64)   # [T, N, E]
+        per_exit = torch.einsum('tne,enab->teab', onehot, cms)
+        self.cm[:, : self.E] += per_exit
+        self.cm[:, self.E] += per_exit.sum(dim=1)
+        self.counts[:, : self.E] += onehot.sum(dim=1)
+        self.counts[:, self.E] += N
+        return scores
+
+    def all_reduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.cm)
+            dist.all_reduce(self.counts)
+
+    def results(self):
+        """One result dict per tau with the reference's keys (eval_br_ent.py:72-84)."""
+        cm, counts = self.cm.cpu(), self.counts.cpu()
+        out = []
+        for t, tau in enumerate(self.taus.cpu().tolist()):
+            def miou(m):
+                tp, fp, fn = ops.basics_from_cm(m)
+                return float((tp.double() / (tp + fp + fn).double()).sum() / self.C)
+            r = {}
+            for i in range(self.E - 1):
+                r[f'b{i+1}_mIoU'] = miou(cm[t, i])
+                r[f'b{i+1}_count'] = int(counts[t, i])
+            r['mIoU_out'] = miou(cm[t, self.E - 1])
+            r['count_out'] = int(counts[t, self.E - 1])
+            r['mIoU_gl'] = miou(cm[t, self.E])
+            r['out_gl'] = int(counts[t, self.E])
+            r['t'] = tau
+            r['pool'] = self.metric
+            r['pool_size'] = self.size
+            out.append(r)
+        return out

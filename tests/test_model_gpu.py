@@ -161,3 +161,29 @@ def test_engine_graph_and_pipelined_match_eager(nets):
         assert torch.equal(e1, e2)
         assert torch.allclose(s1, s2, atol=1e-6)
     assert torch.equal(graph.cm.cpu(), eager.cm.cpu()) and torch.equal(graph.counts.cpu(), eager.counts.cpu())
+
+
+def test_threshold_sweep_equals_per_tau_runs(nets):
+    """One-pass sweep == the per-tau evaluator, count for count."""
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine, ThresholdSweep
+    port, net = nets
+    g = torch.Generator().manual_seed(25)
+    batches = [(torch.randn(2, 3, 65, 81, generator=g).to(dev()), torch.randint(0, 22, (2, 1, 65, 81), generator=g).to(dev()))
+               for _ in range(3)]
+    probe = EarlyExitEngine(net, 21, 0.5)
+    sc = torch.cat([probe.infer(X)["scores"] for X, _ in batches], dim=1).cpu()
+    taus = [0.0, float(sc[0].median()), float(sc[1].median()), 2.0]
+    sweep = ThresholdSweep(net, 21, taus)
+    for X, y in batches:
+        sweep.update(X, y)
+    res = sweep.results()
+    for t, tau in enumerate(taus):
+        eng = EarlyExitEngine(net, 21, tau)
+        for X, y in batches:
+            eng.evaluate(X, y)
+        assert torch.equal(eng.cm.cpu(), sweep.cm[t].cpu()), tau
+        assert torch.equal(eng.counts.cpu(), sweep.counts[t].cpu()), tau
+        r = eng.results()
+        for k in ("b1_count", "b2_count", "count_out", "out_gl"):
+            assert r[k] == res[t][k]
+    assert res[0]["count_out"] == 6 and res[-1]["b1_count"] == 6
