@@ -296,7 +296,8 @@ class ThresholdSweep:
         else:
             first = torch.full((self.taus.numel(), N), self.E - 1, dtype=torch.int64, device=X.device)
         onehot = torch.nn.functional.one_hot(first, self.E).to(torch.int64)   # [T, N, E]
-        per_exit = torch.einsum('tne,enab->teab', onehot, cms)
+        # [T, E, C+1, C]; integer (CUDA has no int64 matmul): one masked sum per exit
+        per_exit = torch.stack([(onehot[:, :, e, None, None] * cms[e].unsqueeze(0)).sum(dim=1) for e in range(self.E)], dim=1)
         self.cm[:, : self.E] += per_exit
         self.cm[:, self.E] += per_exit.sum(dim=1)
         self.counts[:, : self.E] += onehot.sum(dim=1)
