@@ -39,6 +39,9 @@ PROTOTYPES = {
                                    c_p, c_p, c_p, c_sz, c_p]),
     "eeseg_conv_igemm_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                    c_i, c_i, c_i, c_i, c_p, c_i64, c_p, c_i, c_i64, c_p]),
+    "eeseg_conv_group_tiles": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "eeseg_conv_igemm_grouped": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i,
+                                       c_p, c_i64, c_i, c_p, c_i, c_p]),
     "eeseg_stem_space_to_depth": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_conv_debug_stats": (c_i, [c_p]),

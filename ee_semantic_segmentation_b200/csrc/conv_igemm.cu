@@ -31,9 +31,26 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer
 constexpr int kMaxStages = 8;
 
+constexpr int kMaxGroup = 4;   // convolutions sharing one input that can run as one grouped launch
+
+struct ConvProblem {      // what differs between the members of a group (ASPP branches)
+  int R, S, dil, pad;     // tap r reads input row out*stride + r*dil - pad
+  int ch_off;             // first output channel inside the output tensor map
+  const float* scale;
+  const float* shift;
+};
+
+struct WeightMaps {
+  CUtensorMap m[kMaxGroup];
+};
+
 struct ConvParams {
-  int N, h, w, Cin, Cout, R, S, dil;   // h, w: OUTPUT spatial size
-  int hin, win, stride, pad;           // input spatial size, stride, offset of the first tap (tap r reads in = out*stride + r*dil - pad)
+  int N, h, w, Cin, Cout;              // h, w: OUTPUT spatial size; Cout: output channels of ONE problem
+  ConvProblem pr[kMaxGroup];
+  int nprob;
+  const int32_t* schedule;             // optional work list: item = problem << 24 | tile, longest first
+  int n_items;
+  int hin, win, stride;                // input spatial size and stride
   int has_res;                         // residual tile (bf16, output shape) is TMA-prefetched and added before ReLU
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
   int main_bytes;                      // shared memory of the operand ring
@@ -44,8 +61,6 @@ struct ConvParams {
   int relu;
   int out_f32;
   int64_t shift_sn;
-  const float* scale;
-  const float* shift;
   unsigned long long* dbg;   // optional [gridDim.x][32] cycle counters (eeseg_conv_debug_stats)
 };
 
@@ -208,16 +223,16 @@ __host__ __device__ inline uint32_t tmem_cols_for(int bn) {
 }
 
 // Which taps touch at least one real pixel for the tile at (y0, x0)? bit (r*S+s).
-__device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x0) {
+__device__ __forceinline__ uint32_t live_taps(const ConvParams& p, const ConvProblem& q, int y0, int x0) {
   uint32_t m = 0;
   const int y_hi = min(y0 + p.BH, p.h), x_hi = min(x0 + p.BW, p.w);
-  for (int r = 0; r < p.R; ++r) {
-    const int dy = r * p.dil - p.pad;
+  for (int r = 0; r < q.R; ++r) {
+    const int dy = r * q.dil - q.pad;
     if ((y_hi - 1) * p.stride + dy < 0 || y0 * p.stride + dy >= p.hin) continue;
-    for (int s = 0; s < p.S; ++s) {
-      const int dx = s * p.dil - p.pad;
+    for (int s = 0; s < q.S; ++s) {
+      const int dx = s * q.dil - q.pad;
       if ((x_hi - 1) * p.stride + dx < 0 || x0 * p.stride + dx >= p.win) continue;
-      m |= 1u << (r * p.S + s);
+      m |= 1u << (r * q.S + s);
     }
   }
   return m;
@@ -230,7 +245,7 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, int y0, int x
 //                                             epilogue of tile i overlaps the main loop of tile i+1)
 //   residual tile  res_full[a]/res_empty[a]  TMA producer  <-> epilogue     (double buffered)
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ WeightMaps wmaps,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -264,13 +279,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   }
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.Cout / p.BN;
-  const int total_tiles = p.N * tiles_img * n_tiles;
+  const int total_tiles = p.n_items;   // work items: (problem, m-tile, n-tile)
   const int cblocks = p.Cin / kBlockK;
   const uint32_t ncols = tmem_cols_for(2 * p.BN);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
-    prefetch_tmap(&tmap_w);
+    for (int g = 0; g < p.nprob; ++g) prefetch_tmap(&wmaps.m[g]);
     prefetch_tmap(&tmap_out);
     if (p.has_res) prefetch_tmap(&tmap_res);
     for (int s = 0; s < p.stages; ++s) {
@@ -302,7 +317,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // tile -> (image, y0, x0, n0); identical in every role
-  auto tile_coords = [&](int t, int& n_img, int& y0, int& x0, int& n0) {
+  auto tile_coords = [&](int item_idx, int& prob, int& n_img, int& y0, int& x0, int& n0) {
+    const int item = p.schedule ? __ldg(p.schedule + item_idx) : item_idx;
+    prob = item >> 24;
+    const int t = item & 0xffffff;
     const int nt = t % n_tiles, mt = t / n_tiles;
     n_img = mt / tiles_img;
     const int trem = mt % tiles_img;
@@ -319,9 +337,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       uint32_t kbg = 0;   // k-block counter across tiles: stage = kbg % stages, phase = (kbg / stages) & 1
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        int n_img, y0, x0, n0;
-        tile_coords(t, n_img, y0, x0, n0);
-        const uint32_t taps = live_taps(p, y0, x0);
+        int prob, n_img, y0, x0, n0;
+        tile_coords(t, prob, n_img, y0, x0, n0);
+        const ConvProblem& q = p.pr[prob];
+        const uint32_t taps = live_taps(p, q, y0, x0);
         if (p.has_res) {  // residual tile: lands while the main loop runs
           const int a = it & 1;
           DBG_T(0, mbar_wait(res_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));
@@ -330,9 +349,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             tma_load_4d(res_smem + (size_t)(a * nblk_res + j) * res_blk_bytes, &tmap_res, res_full_bar + a,
                         n0 + j * 64, x0, y0, n_img);
         }
-        for (int tp = 0; tp < p.R * p.S; ++tp) {
+        for (int tp = 0; tp < q.R * q.S; ++tp) {
           if (!((taps >> tp) & 1u)) continue;
-          const int dy = (tp / p.S) * p.dil - p.pad, dx = (tp % p.S) * p.dil - p.pad;
+          const int dy = (tp / q.S) * q.dil - q.pad, dx = (tp % q.S) * q.dil - q.pad;
           for (int cb = 0; cb < cblocks; ++cb, ++kbg) {
             const int s = (int)(kbg % (uint32_t)p.stages);
             const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
@@ -341,7 +360,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             uint8_t* sb = sa + a_bytes;
             mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
             tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
-            tma_load_2d(sb, &tmap_w, full_bar + s, tp * p.Cin + cb * kBlockK, n0);
+            tma_load_2d(sb, &wmaps.m[prob], full_bar + s, tp * p.Cin + cb * kBlockK, n0);
           }
         }
       }
@@ -360,9 +379,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       uint32_t kbg = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        int n_img, y0, x0, n0;
-        tile_coords(t, n_img, y0, x0, n0);
-        const int num_kb = __popc(live_taps(p, y0, x0)) * cblocks;
+        int prob, n_img, y0, x0, n0;
+        tile_coords(t, prob, n_img, y0, x0, n0);
+        const int num_kb = __popc(live_taps(p, p.pr[prob], y0, x0)) * cblocks;
         const int a = it & 1;
         DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue drained this buffer
         tcgen05_fence_after();
@@ -393,10 +412,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   } else {
     // ===== epilogue: warps 2..9. TMEM lane quadrant = warp % 4 (hardware rule); warps 2-5 take the
     // lower half of the tile's columns, warps 6-9 the upper half =====
-    const int q = warp & 3;
+    const int quad = warp & 3;
     const int hsel = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;                    // 0..255
-    const int m = q * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
+    const int m = quad * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
     const int col_lo = hsel * (p.BN >> 1) , col_hi = p.BN < 32 ? (hsel ? 0 : p.BN) : col_lo + (p.BN >> 1);
     unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -406,15 +425,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     long long dbg_t1 = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      int n_img, y0, x0, n0;
-      tile_coords(t, n_img, y0, x0, n0);
+      int prob, n_img, y0, x0, n0;
+      tile_coords(t, prob, n_img, y0, x0, n0);
+      const ConvProblem& q = p.pr[prob];
       const int a = it & 1;
       const uint32_t aph = ((uint32_t)it >> 1) & 1u;
       // every epilogue thread passed the last barrier of the previous tile: scale/shift can change
       if (p.dbg) dbg_t1 = clock64();
       for (int i = et; i < p.BN; i += kEpiThreads) {
-        s_scale[i] = p.scale[n0 + i];
-        s_shift[i] = p.shift[(int64_t)n_img * p.shift_sn + n0 + i];
+        s_scale[i] = q.scale[n0 + i];
+        s_shift[i] = q.shift[(int64_t)n_img * p.shift_sn + n0 + i];
       }
       if (p.dbg) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
       // the staging tile is reused every tile: the previous TMA stores must have read it out
@@ -423,7 +443,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
       if (p.has_res) DBG_T(1, mbar_wait(res_full_bar + a, aph));
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN);
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
       const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
       if (p.dbg) dbg_t1 = clock64();
       for (int col = col_lo; col < col_hi; col += 16) {
@@ -506,7 +526,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (p.dbg) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
       if (et == 0) {
         for (int blk = 0; blk < p.nblk; ++blk)
-          tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, n0 + blk * p.blk_cols, x0, y0, n_img);
+          tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, q.ch_off + n0 + blk * p.blk_cols, x0, y0, n_img);
         bulk_commit();
       }
       if (p.dbg) dbg_acc[7] += (unsigned long long)(clock64() - dbg_t1);
@@ -649,45 +669,58 @@ extern "C" int eeseg_conv_debug_stats(void* device_buffer) {
   return EESEG_OK;
 }
 
-extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
-                                    const float* shift, int64_t shift_sn, int N, int hin, int win,
-                                    int Cin, int Cout, int R, int S, int dilation, int stride, int pad,
-                                    int relu, const void* residual, int64_t ldr, void* out,
-                                    int out_dtype, int64_t ldo, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  EESEG_REQUIRE(x && wt && scale && shift && out, "conv_igemm: null pointer");
+struct HostProblem {
+  const void* wt;
+  const float* scale;
+  const float* shift;
+  int R, S, dil, pad, ch_off;
+};
+
+// Common launcher: `nprob` convolutions over the same input (same Cin, Cout, stride, output tensor)
+static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t shift_sn, int N, int hin,
+                       int win, int Cin, int Cout, int stride, int relu, const void* residual, int64_t ldr,
+                       void* out, int out_dtype, int64_t ldo, int out_channels, const int32_t* schedule,
+                       int n_items, cudaStream_t stream) {
+  EESEG_REQUIRE(x && out && nprob >= 1 && nprob <= kMaxGroup, "conv_igemm: null pointer / bad group size");
   EESEG_REQUIRE(N >= 1 && hin >= 1 && win >= 1, "conv_igemm: bad sizes");
   EESEG_REQUIRE(stride == 1 || stride == 2, "conv_igemm: stride %d (1 or 2)", stride);
   EESEG_REQUIRE(Cin % kBlockK == 0, "conv_igemm: Cin=%d must be a multiple of 64", Cin);
   EESEG_REQUIRE(Cout % 16 == 0, "conv_igemm: Cout=%d must be a multiple of 16", Cout);
-  EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32, "conv_igemm: at most 32 taps");
-  if (pad < 0) {  // 'same' padding of an odd kernel
-    EESEG_REQUIRE((R & 1) && (S & 1) && R == S, "conv_igemm: pad < 0 ('same') needs an odd square kernel");
-    pad = dilation * (R / 2);
-  }
   EESEG_REQUIRE(out_dtype == EESEG_BF16 || out_dtype == EESEG_F32, "conv_igemm: out_dtype %d", out_dtype);
   const int oes = out_dtype == EESEG_F32 ? 4 : 2;
-  EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
-                    (ldo * oes) % 16 == 0,
+  EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && (ldo * oes) % 16 == 0,
                 "conv_igemm: pointers and the output pixel stride must be 16-byte aligned");
   EESEG_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && (ldr % 8) == 0 && out_dtype == EESEG_BF16 &&
-                              Cout % 64 == 0),
-                "conv_igemm: residual needs bf16 output, Cout %% 64 == 0, 16-byte alignment");
+                              Cout % 64 == 0 && nprob == 1),
+                "conv_igemm: residual needs bf16 output, Cout %% 64 == 0, 16-byte alignment, a single problem");
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     set_error("conv_igemm: cuTensorMapEncodeTiled unavailable (driver too old?)");
     return EESEG_ERR_CUDA;
   }
-  // 'same' padding = dilation*(R/2): output size (in-1)/stride+1
   const int h = (hin - 1) / stride + 1, w = (win - 1) / stride + 1;
   ConvParams p;
-  p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
-  p.hin = hin; p.win = win; p.stride = stride; p.pad = pad;
+  p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout;
+  p.hin = hin; p.win = win; p.stride = stride;
   p.has_res = residual ? 1 : 0;
+  p.nprob = nprob;
+  int kb_total = 0;
+  for (int g = 0; g < kMaxGroup; ++g) {
+    const HostProblem& q = hp[g < nprob ? g : 0];
+    EESEG_REQUIRE(q.wt && q.scale && q.shift && ((uintptr_t)q.wt & 15) == 0, "conv_igemm: null / misaligned weights");
+    EESEG_REQUIRE(q.R >= 1 && q.S >= 1 && q.R * q.S <= 32, "conv_igemm: at most 32 taps");
+    int pad = q.pad;
+    if (pad < 0) {  // 'same' padding of an odd square kernel
+      EESEG_REQUIRE((q.R & 1) && q.R == q.S, "conv_igemm: pad < 0 ('same') needs an odd square kernel");
+      pad = q.dil * (q.R / 2);
+    }
+    p.pr[g].R = q.R; p.pr[g].S = q.S; p.pr[g].dil = q.dil; p.pr[g].pad = pad; p.pr[g].ch_off = q.ch_off;
+    p.pr[g].scale = q.scale; p.pr[g].shift = q.shift;
+    if (g < nprob && q.R * q.S * (Cin / kBlockK) > kb_total) kb_total = q.R * q.S * (Cin / kBlockK);
+  }
   pick_tile(h, w, p.BW, p.BH);
   p.tiles_x = (w + p.BW - 1) / p.BW;
   p.tiles_y = (h + p.BH - 1) / p.BH;
-  const int kb_total = R * S * (Cin / kBlockK);
   // output-channel tile: a power of two (16..256) dividing Cout; shallow-K wide-N layers (ResNet
   // conv3 / projection shortcuts) are epilogue-bound: 128 columns let several CTAs share an SM
   int BN = 256;
@@ -696,7 +729,7 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
-  p.scale = scale; p.shift = shift; p.dbg = g_conv_dbg;
+  p.dbg = g_conv_dbg;
   // epilogue blocks: 128 B of output per pixel row (64 bf16 / 32 fp32 channels), swizzled; narrower
   // tiles use one dense block
   const int full_cols = 128 / oes;
@@ -708,7 +741,13 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   const size_t res_bytes = residual ? (size_t)2 * (BN / 64) * kBlockM * 128 : 0;   // double buffered
   const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
   const size_t tail_bytes = 256 + 2 * 256 * 4;   // barriers + tmem pointer (< 256 B), scale, shift
-  const int total_tiles = N * p.tiles_x * p.tiles_y * (Cout / BN);
+  const int tiles_per_problem = N * p.tiles_x * p.tiles_y * (Cout / BN);
+  const int total_tiles = tiles_per_problem * nprob;
+  EESEG_REQUIRE(tiles_per_problem < (1 << 24), "conv_igemm: too many tiles");
+  EESEG_REQUIRE(!schedule || n_items == total_tiles, "conv_igemm: schedule has %d items, expected %d", n_items, total_tiles);
+  EESEG_REQUIRE(schedule || nprob == 1, "conv_igemm: a grouped launch needs a schedule");
+  p.schedule = schedule;
+  p.n_items = total_tiles;
   // with at most one tile per CTA the ring is idle when the epilogue runs: the staging tile overlays
   // it and the ring gets the shared memory (deep-K ASPP convs: 4 stages instead of 3)
   p.overlay = total_tiles <= kNumSMs ? 1 : 0;
@@ -722,12 +761,13 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   p.main_bytes = (int)((ring + 1023) & ~(size_t)1023);
   const size_t smem_bytes = 1024 + p.main_bytes + (p.overlay ? 0 : staging_bytes) + res_bytes + tail_bytes;
 
-  CUtensorMap tmx, tmw, tmo, tmr;
+  CUtensorMap tmx, tmo, tmr;
+  WeightMaps wm;
   int rc = encode_act_map(encode, &tmx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cin, win, hin, N, Cin, kBlockK,
                           p.BW, p.BH, stride, true, "x");
   if (rc) return rc;
   rc = encode_act_map(encode, &tmo, out, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                      oes, Cout, w, h, N, ldo, p.blk_cols, p.BW, p.BH, 1, p.swz != 0, "out");
+                      oes, out_channels, w, h, N, ldo, p.blk_cols, p.BW, p.BH, 1, p.swz != 0, "out");
   if (rc) return rc;
   if (residual) {
     rc = encode_act_map(encode, &tmr, residual, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, w, h, N, ldr, 64, p.BW,
@@ -736,13 +776,14 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   } else {
     tmr = tmo;
   }
-  {
-    const cuuint64_t Kt = (cuuint64_t)R * S * Cin;
+  for (int g = 0; g < kMaxGroup; ++g) {
+    const HostProblem& q = hp[g < nprob ? g : 0];
+    const cuuint64_t Kt = (cuuint64_t)q.R * q.S * Cin;
     cuuint64_t dims[2] = {Kt, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {Kt * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tmw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wt), dims, strides, box,
+    CUresult r = encode(&wm.m[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q.wt), dims, strides, box,
                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_igemm: cuTensorMapEncodeTiled(w) failed: %d", (int)r); return EESEG_ERR_CUDA; }
@@ -763,8 +804,44 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
   attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmx, tmw, tmo, tmr, p));
+  EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmx, wm, tmo, tmr, p));
   return check_launch("conv_igemm_kernel");
+}
+
+extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale,
+                                    const float* shift, int64_t shift_sn, int N, int hin, int win,
+                                    int Cin, int Cout, int R, int S, int dilation, int stride, int pad,
+                                    int relu, const void* residual, int64_t ldr, void* out,
+                                    int out_dtype, int64_t ldo, void* stream_) {
+  HostProblem hp = {wt, scale, shift, R, S, dilation, pad, 0};
+  return launch_conv(x, &hp, 1, shift_sn, N, hin, win, Cin, Cout, stride, relu, residual, ldr, out, out_dtype,
+                     ldo, Cout, nullptr, 0, (cudaStream_t)stream_);
+}
+
+extern "C" int eeseg_conv_group_tiles(int hin, int win, int Cout, int* tiles_x, int* tiles_y, int* bw, int* bh,
+                                      int* bn) {
+  EESEG_REQUIRE(tiles_x && tiles_y && bw && bh && bn, "conv_group_tiles: null pointer");
+  pick_tile(hin, win, *bw, *bh);
+  *tiles_x = (win + *bw - 1) / *bw;
+  *tiles_y = (hin + *bh - 1) / *bh;
+  int BN = 256;   // groups contain a 3x3 (>= 9 K blocks): never the shallow-K 128-column variant
+  while (BN > 16 && (Cout % BN)) BN >>= 1;
+  *bn = BN;
+  return EESEG_OK;
+}
+
+extern "C" int eeseg_conv_igemm_grouped(const void* x, int nprob, const void* const* wt,
+                                        const float* const* scale, const float* const* shift,
+                                        const int* ksize, const int* dilation, const int* ch_off, int N,
+                                        int hin, int win, int Cin, int Cout, int relu, void* out, int64_t ldo,
+                                        int out_channels, const int32_t* schedule, int n_items, void* stream_) {
+  EESEG_REQUIRE(wt && scale && shift && ksize && dilation && ch_off, "conv_igemm_grouped: null pointer");
+  EESEG_REQUIRE(nprob >= 1 && nprob <= kMaxGroup, "conv_igemm_grouped: 1..%d problems", kMaxGroup);
+  HostProblem hp[kMaxGroup];
+  for (int g = 0; g < nprob; ++g)
+    hp[g] = HostProblem{wt[g], scale[g], shift[g], ksize[g], ksize[g], dilation[g], -1, ch_off[g]};
+  return launch_conv(x, hp, nprob, 0, N, hin, win, Cin, Cout, 1, relu, nullptr, 0, out, EESEG_BF16, ldo,
+                     out_channels, schedule, n_items, (cudaStream_t)stream_);
 }
 
 extern "C" size_t eeseg_global_avgpool_workspace_bytes(int N, int C) {

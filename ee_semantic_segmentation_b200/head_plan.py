@@ -61,6 +61,69 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
             PROFILE.append((a, b, 2 * N * ho * wo * Cout * R * S * Cin, PROFILE_TAG))
 
 
+def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
+    """Work list of a grouped conv launch: item = problem << 24 | tile, sorted by decreasing cost
+    (live taps x channel blocks — taps that fall entirely into the zero padding of a tile are skipped
+    by the kernel) and dealt to the persistent CTAs in snake order. Returns an int32 CPU tensor."""
+    import ctypes
+    import numpy as np
+    tx, ty, bw, bh, bn = (ctypes.c_int() for _ in range(5))
+    check(lib().eeseg_conv_group_tiles(h, w, cout, ctypes.byref(tx), ctypes.byref(ty), ctypes.byref(bw),
+                                       ctypes.byref(bh), ctypes.byref(bn)), "eeseg_conv_group_tiles")
+    tx, ty, bw, bh, bn = tx.value, ty.value, bw.value, bh.value, bn.value
+    n_tiles = cout // bn
+    y0 = np.arange(ty) * bh
+    x0 = np.arange(tx) * bw
+    items, costs = [], []
+    for g, (k, d) in enumerate(zip(ksizes, dils)):
+        pad = d * (k // 2)
+        off = np.arange(k) * d - pad
+        y_hi = np.minimum(y0 + bh, h)
+        x_hi = np.minimum(x0 + bw, w)
+        live_y = ((y_hi[:, None] - 1 + off[None, :] >= 0) & (y0[:, None] + off[None, :] < h)).sum(1)   # [ty]
+        live_x = ((x_hi[:, None] - 1 + off[None, :] >= 0) & (x0[:, None] + off[None, :] < w)).sum(1)   # [tx]
+        taps = live_y[:, None] * live_x[None, :]                                                      # [ty, tx]
+        cost = np.broadcast_to(taps.reshape(1, ty * tx, 1), (N, ty * tx, n_tiles)).reshape(-1) * (cin // 64)
+        tile = np.arange(N * ty * tx * n_tiles)
+        items.append((g << 24) | tile)
+        costs.append(cost)
+    items, costs = np.concatenate(items), np.concatenate(costs)
+    order = np.argsort(-costs, kind="stable")
+    items = items[order]
+    # snake order: within every round of G consecutive (sorted) items, odd rounds are reversed, so
+    # CTA c (which walks positions c, c+G, c+2G, ...) alternates between the expensive and the
+    # cheap end of consecutive rounds
+    G = min(n_ctas, len(items))
+    out = items.copy()
+    for r in range(1, (len(items) + G - 1) // G, 2):
+        seg = out[r * G:(r + 1) * G]
+        if len(seg) == G:
+            out[r * G:(r + 1) * G] = seg[::-1]
+    return torch.from_numpy(out.astype(np.int32))
+
+
+def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out, ldo, out_channels, schedule):
+    """One persistent launch for several 'same' convolutions of x (see eeseg_conv_igemm_grouped)."""
+    import ctypes
+    N, h, w, Cin = x.shape
+    n = len(wts)
+    Cout = wts[0].shape[0]
+    PA = ctypes.c_void_p * n
+    IA = ctypes.c_int * n
+    with torch.cuda.device(x.device):
+        if PROFILE is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        check(lib().eeseg_conv_igemm_grouped(
+            x.data_ptr(), n, PA(*[t.data_ptr() for t in wts]), PA(*[t.data_ptr() for t in scales]),
+            PA(*[t.data_ptr() for t in shifts]), IA(*ksizes), IA(*dils), IA(*ch_offs), N, h, w, Cin, Cout,
+            1 if relu else 0, out.data_ptr(), ldo, out_channels, schedule.data_ptr(), schedule.numel(),
+            torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_grouped")
+        if PROFILE is not None:
+            b.record()
+            PROFILE.append((a, b, sum(2 * N * h * w * Cout * k * k * Cin for k in ksizes), PROFILE_TAG))
+
+
 def global_avgpool_nhwc(xh):
     """bf16 NHWC [N,h,w,C] -> f32 [N,C] (AdaptiveAvgPool2d(1))."""
     N, h, w, C = xh.shape
@@ -74,8 +137,12 @@ def global_avgpool_nhwc(xh):
     return pooled
 
 
+GROUPED = True   # run the ASPP branch convolutions as one grouped launch
+
+
 class HeadPlan:
     def __init__(self, head):
+        self._schedules = {}
         mods = list(head.children())
         self.pre = None
         if isinstance(mods[0], nn.Conv2d):      # my_branch bottleneck 1x1 (+bias, no BN/ReLU)
@@ -132,8 +199,22 @@ class HeadPlan:
             xh = t
         nb, mid = len(self.branches), self.mid
         cat = torch.empty((N, h, w, nb * mid), dtype=torch.bfloat16, device=dev)
-        for k, (wt, s, b, dil) in enumerate(self.branches):
-            conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)
+        if GROUPED and 2 <= nb <= 4 and all(wt.shape[1] in (1, 3) for wt, _, _, _ in self.branches) \
+                and any(wt.shape[1] == 3 for wt, _, _, _ in self.branches):
+            # the ASPP branches (1x1 + atrous 3x3) as ONE persistent launch over a cost-sorted work list
+            key = (N, h, w, str(dev))
+            sched = self._schedules.get(key)
+            if sched is None:
+                sched = group_schedule(N, h, w, xh.shape[-1], mid, [wt.shape[1] for wt, _, _, _ in self.branches],
+                                       [d for _, _, _, d in self.branches]).to(dev)
+                self._schedules[key] = sched
+            conv_igemm_grouped(xh, [b[0] for b in self.branches], [b[1] for b in self.branches],
+                               [b[2] for b in self.branches], [b[0].shape[1] for b in self.branches],
+                               [b[3] for b in self.branches], [k * mid for k in range(nb)], True, cat,
+                               nb * mid, nb * mid, sched)
+        else:
+            for k, (wt, s, b, dil) in enumerate(self.branches):
+                conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)
         # pooled branch: avg-pool -> 1x1 -> BN -> ReLU, then its share of the projection, per image
         pooled = global_avgpool_nhwc(xh)
         pv = torch.relu(pooled @ self.pool_w.t() * self.pool_s + self.pool_b)   # [N, mid] (tiny GEMV)

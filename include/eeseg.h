@@ -175,6 +175,23 @@ int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, vo
 /* 3x3 / stride-2 / pad-1 max pooling of a bf16 NHWC tensor (C % 8 == 0). */
 int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream);
 
+/* Grouped form: `nprob` (<= 4) stride-1 'same' convolutions of the SAME input (the ASPP branches:
+ * 1x1 and the three atrous 3x3) as ONE persistent launch. Their tiles differ a lot in cost — a tile near
+ * the border of a 65x65 map keeps 4 of the 9 taps of a d=24 conv, an interior one all 9 — so separate
+ * launches (one wave of 144 tiles each) wait for their slowest tile; the grouped launch walks one
+ * work list over all problems, longest items first.
+ *   wt/scale/shift/ksize/dilation/ch_off: HOST arrays of length nprob (device pointers / ints);
+ *   problem g writes Cout channels at channel ch_off[g] of `out` (bf16 NHWC, pixel stride ldo,
+ *   out_channels channels in total);
+ *   schedule: DEVICE int32[n_items], item = g << 24 | tile (tile = m_tile * (Cout/BN) + n_tile in the
+ *   geometry eeseg_conv_group_tiles reports), every (g, tile) exactly once, ordered by decreasing cost. */
+int eeseg_conv_group_tiles(int hin, int win, int Cout, int* tiles_x, int* tiles_y, int* bw, int* bh, int* bn);
+int eeseg_conv_igemm_grouped(const void* x, int nprob, const void* const* wt, const float* const* scale,
+                             const float* const* shift, const int* ksize, const int* dilation,
+                             const int* ch_off, int N, int hin, int win, int Cin, int Cout, int relu,
+                             void* out, int64_t ldo, int out_channels, const int32_t* schedule, int n_items,
+                             void* stream);
+
 /* Programmatic dependent launch for eeseg_conv_igemm_fwd (prologue of launch i+1 overlaps the tail of
  * launch i; the kernel executes griddepcontrol.wait before touching its inputs). Default on; returns
  * the previous setting. */

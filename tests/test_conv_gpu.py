@@ -162,3 +162,26 @@ def test_stem_plan_vs_torch():
         assert got.shape == ref.shape, (got.shape, ref.shape)
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         assert err < 1e-2, err
+
+
+def test_grouped_conv_matches_separate_launches():
+    """The grouped ASPP launch (one persistent kernel over a cost-sorted work list) writes exactly
+    what the four separate launches write."""
+    from ee_semantic_segmentation_b200 import _lib
+    from ee_semantic_segmentation_b200.head_plan import conv_igemm, conv_igemm_grouped, group_schedule
+    g = torch.Generator().manual_seed(8)
+    N, h, w, cin, mid = 2, 65, 65, 256, 256
+    x = torch.randn(N, h, w, cin, generator=g).to(torch.bfloat16).to(dev())
+    ks, dl = [1, 3, 3, 3], [1, 12, 24, 36]
+    wts = [(torch.randn(mid, k, k, cin, generator=g) / np.sqrt(k * k * cin)).to(torch.bfloat16).to(dev()) for k in ks]
+    scs = [(torch.rand(mid, generator=g) + 0.5).to(dev()) for _ in ks]
+    shs = [torch.randn(mid, generator=g).to(dev()) for _ in ks]
+    ref = torch.empty(N, h, w, 4 * mid, dtype=torch.bfloat16, device=dev())
+    for k in range(4):
+        conv_igemm(x, wts[k], scs[k], shs[k], dl[k], True, ref[..., k * mid:], _lib.BF16, 4 * mid)
+    out = torch.zeros_like(ref)
+    sched = group_schedule(N, h, w, cin, mid, ks, dl).to(dev())
+    assert sorted(sched.tolist()) == sorted((gi << 24) | t for gi in range(4) for t in range(N * 36))
+    conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, out, 4 * mid, 4 * mid, sched)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
