@@ -55,6 +55,10 @@ struct ConvParams {
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
   int main_bytes;                      // shared memory of the operand ring
   int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
+  int direct;                          // deep-K launches: epilogue stores straight from registers (no staging
+                                       // tile), so the operand ring gets all the shared memory
+  void* out;                           // output base (direct epilogue only), pixel stride ldo elements
+  int64_t ldo;
   int BW, BH, tiles_x, tiles_y;
   int BN;          // output-channel tile (multiple of 16, <= 256)
   int stages;
@@ -259,7 +263,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t res_blk_bytes = kBlockM * 128;               // 64 bf16 channels per pixel row
   const int nblk_res = p.has_res ? p.BN / 64 : 0;
   uint8_t* stg_smem = smem + (p.overlay ? 0 : p.main_bytes);   // overlay: <= 1 tile per CTA, ring is idle by then
-  uint8_t* res_smem = smem + p.main_bytes + (p.overlay ? 0 : (size_t)p.nblk * blk_bytes);
+  uint8_t* res_smem = smem + p.main_bytes + ((p.overlay || p.direct) ? 0 : (size_t)p.nblk * blk_bytes);
   uint8_t* tail = res_smem + (size_t)2 * nblk_res * res_blk_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -438,7 +442,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       if (p.dbg) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
       // the staging tile is reused every tile: the previous TMA stores must have read it out
-      if (et == 0) DBG_T(2, bulk_wait_read(0));
+      if (et == 0 && !p.direct) DBG_T(2, bulk_wait_read(0));
       DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
@@ -487,6 +491,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (p.direct) {
+          // deep-K launch: the epilogue is a small fraction of the tile and overlaps the next main
+          // loop; store the pixel's 16 channels straight from registers
+          const int yy = y0 + m / p.BW, xx = x0 + m % p.BW;
+          if (m < p.BW * p.BH && yy < p.h && xx < p.w) {
+            const int64_t pix = ((int64_t)n_img * p.h + yy) * p.w + xx;
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + q.ch_off + n0 + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + q.ch_off + n0 + col);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&b0);
+                u.y = *reinterpret_cast<uint32_t*>(&b1);
+                u.z = *reinterpret_cast<uint32_t*>(&b2);
+                u.w = *reinterpret_cast<uint32_t*>(&b3);
+                o[j] = u;
+              }
+            }
+          }
+          continue;
+        }
         const int blk = col / p.blk_cols;
         uint8_t* orow = stg_smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
         if (p.out_f32) {
@@ -524,7 +557,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       fence_proxy_async();
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (p.dbg) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
-      if (et == 0) {
+      if (et == 0 && !p.direct) {
         for (int blk = 0; blk < p.nblk; ++blk)
           tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, q.ch_off + n0 + blk * p.blk_cols, x0, y0, n_img);
         bulk_commit();
@@ -751,7 +784,17 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   // with at most one tile per CTA the ring is idle when the epilogue runs: the staging tile overlays
   // it and the ring gets the shared memory (deep-K ASPP convs: 4 stages instead of 3)
   p.overlay = total_tiles <= kNumSMs ? 1 : 0;
-  const size_t fixed = 1024 + (p.overlay ? 0 : staging_bytes) + res_bytes + tail_bytes;
+  // multi-tile deep-K launches (every tile runs >= 16 K blocks): no staging tile, a deeper ring
+  int kb_min = 1 << 30;
+  for (int g = 0; g < nprob; ++g) {
+    // the cheapest tile of a 'same' conv still has the centre tap (and >= 4 of 9 taps for a 3x3)
+    const int taps_min = hp[g].R == 1 ? 1 : ((hp[g].R + 1) / 2) * ((hp[g].S + 1) / 2);
+    const int kb = taps_min * (Cin / kBlockK);
+    if (kb < kb_min) kb_min = kb;
+  }
+  p.direct = (!p.overlay && !residual && kb_min >= 16) ? 1 : 0;
+  p.out = out; p.ldo = ldo;
+  const size_t fixed = 1024 + ((p.overlay || p.direct) ? 0 : staging_bytes) + res_bytes + tail_bytes;
   if (fixed + stage_bytes > 227 * 1024) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -759,7 +802,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   size_t ring = stages * stage_bytes;
   if (p.overlay && ring < staging_bytes) ring = staging_bytes;
   p.main_bytes = (int)((ring + 1023) & ~(size_t)1023);
-  const size_t smem_bytes = 1024 + p.main_bytes + (p.overlay ? 0 : staging_bytes) + res_bytes + tail_bytes;
+  const size_t smem_bytes = 1024 + p.main_bytes + ((p.overlay || p.direct) ? 0 : staging_bytes) + res_bytes + tail_bytes;
 
   CUtensorMap tmx, tmo, tmr;
   WeightMaps wm;

@@ -48,3 +48,39 @@ for name, N, h, w, cin, cout, R, dil, stride, res in shapes:
     print(f"{name:22s} event {us:6.1f}us KERNEL {kern_us:6.1f}us (outside epilogue role {pro_us:4.1f}us) tiles/CTA {tiles:4.1f} | PROD total {m[2]:8.0f} wait_res_empty {m[0]:7.0f} wait_empty {m[1]:7.0f} | "
           f"MMA total {m[6]:8.0f} wait_tmem_empty {m[4]:7.0f} wait_full {m[5]:7.0f} | "
           f"EPI total {m[12]:8.0f} wait_tmem_full {m[8]:7.0f} wait_res {m[9]:7.0f} wait_store_read {m[10]:7.0f} bar1 {m[11]:6.0f} ss_load {m[13]:6.0f} colloop {m[14]:7.0f} epi_ns {m[15]:7.0f} => {m[12]/max(m[15],1):.2f} GHz", flush=True)
+
+# ---- grouped ASPP launch vs the four separate launches (kernel wall time from the dbg stamps) ----
+from ee_semantic_segmentation_b200.head_plan import conv_igemm_grouped, group_schedule
+for cin in (2048, 1024):
+    N, h, w, mid = 4, 65, 65, 256
+    x = torch.randn(N, h, w, cin, device=dev).to(torch.bfloat16)
+    ks, dl = [1, 3, 3, 3], [1, 12, 24, 36]
+    wts = [(torch.randn(mid, k, k, cin, device=dev) * 0.02).to(torch.bfloat16) for k in ks]
+    scs = [torch.ones(mid, device=dev) for _ in ks]
+    shs = [torch.zeros(mid, device=dev) for _ in ks]
+    cat = torch.empty(N, h, w, 4 * mid, dtype=torch.bfloat16, device=dev)
+    sched = group_schedule(N, h, w, cin, mid, ks, dl).to(dev)
+
+    def stamp(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        buf.zero_()
+        _lib.lib().eeseg_conv_debug_stats(buf.data_ptr())
+        fn(); torch.cuda.synchronize()
+        _lib.lib().eeseg_conv_debug_stats(None)
+        di = buf.cpu()
+        act = di[:, 17] > 0
+        return (di[act][:, 17].max() - di[act][:, 16].min()).item() / 1e3, di
+
+    tot = 0.0
+    for k in range(4):
+        us, _ = stamp(lambda: conv_igemm(x, wts[k], scs[k], shs[k], dl[k], True, cat[..., k * mid:], _lib.BF16, 4 * mid))
+        print(f"  Cin={cin} separate k={ks[k]} d={dl[k]}: {us:.1f} us")
+        tot += us
+    us, di = stamp(lambda: conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, cat, 4 * mid, 4 * mid, sched))
+    d = di.double()
+    act = d[:, 3] > 0
+    m = d[act].mean(0)
+    print(f"  Cin={cin} separate total {tot:.1f} us | GROUPED {us:.1f} us  (MMA total {m[6]:.0f} cyc, wait_full {m[5]:.0f}, wait_tmem_empty {m[4]:.0f}; "
+          f"per-CTA MMA total min/max {d[act][:,6].min():.0f}/{d[act][:,6].max():.0f})")
