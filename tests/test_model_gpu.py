@@ -187,3 +187,35 @@ def test_threshold_sweep_equals_per_tau_runs(nets):
         for k in ("b1_count", "b2_count", "count_out", "out_gl"):
             assert r[k] == res[t][k]
     assert res[0]["count_out"] == 6 and res[-1]["b1_count"] == 6
+
+
+def test_training_step_matches_torch_losses(nets):
+    """One train_epoch step (config 3: multi-exit CE, b_reduction='sum') with the eeseg loss gives the
+    same parameter update as the same step with torch.nn.CrossEntropyLoss (the reference's loss)."""
+    import copy
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    from ee_semantic_segmentation_b200.train_funcs import make_optimizer, poly_scheduler, train_epoch
+    port, net = nets
+    g = torch.Generator().manual_seed(26)
+    X = torch.randn(2, 3, 65, 65, generator=g)
+    y = torch.randint(0, 22, (2, 1, 65, 65), generator=g)
+    net_a = copy.deepcopy(net)
+    net_b = copy.deepcopy(net)
+    opt_a = make_optimizer(net_a, lr=1e-2, base_lr=1e-3)
+    assert [grp['lr'] for grp in opt_a.param_groups] == [1e-3, 1e-2, 1.1e-2]
+    sched = poly_scheduler(opt_a, 10)
+    l_a = train_epoch(net_a, [(X, y)], BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3), opt_a, dev())
+    sched.step()
+    assert opt_a.param_groups[1]['lr'] == pytest.approx(1e-2 * (1 - 1 / 10) ** .9)
+
+    class RefLoss(torch.nn.Module):      # my_pixelwise_xentropy.py:36-46 written with torch ops
+        def forward(self, y_pred, t):
+            ce = torch.nn.CrossEntropyLoss(ignore_index=21)
+            return sum(ce(y_pred[i], t.squeeze(1)) for i in range(3))
+    opt_b = make_optimizer(net_b, lr=1e-2, base_lr=1e-3)
+    l_b = train_epoch(net_b, [(X, y)], RefLoss(), opt_b, dev())
+    assert l_a.item() == pytest.approx(l_b.item(), rel=1e-4)
+    pa = torch.cat([p.detach().flatten() for p in net_a.branches.parameters()])
+    pb = torch.cat([p.detach().flatten() for p in net_b.branches.parameters()])
+    assert torch.allclose(pa, pb, rtol=1e-3, atol=1e-6)
+    net.eval()
