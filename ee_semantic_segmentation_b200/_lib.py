@@ -44,6 +44,7 @@ PROTOTYPES = {
                                        c_p, c_i64, c_i, c_p, c_i, c_p]),
     "eeseg_stem_space_to_depth": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "eeseg_dense_bn_act": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_conv_debug_stats": (c_i, [c_p]),
     "eeseg_conv_set_pdl": (c_i, [c_i]),
     "eeseg_global_avgpool_workspace_bytes": (c_sz, [c_i, c_i]),

@@ -105,3 +105,37 @@ extern "C" int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C
                                                                   (__nv_bfloat16*)out);
   return check_launch("maxpool3x3s2_kernel");
 }
+
+// ---- small dense layer for the ASPP pooled branch -----------------------------------------------
+// y[n][o] = act( (sum_k x[n][k] * W[o][k]) * scale[o] + shift[o] ), one warp per output element.
+// (AdaptiveAvgPool -> 1x1 conv -> BN -> ReLU, and its share of the ASPP projection: two launches
+// instead of a dozen tiny library kernels.)
+namespace eeseg {
+__global__ void __launch_bounds__(256) dense_bn_act_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int N, int K, int O,
+                                                            int relu, float* __restrict__ y) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= N * O) return;
+  const int n = wid / O, o = wid % O;
+  const float* xr = x + (int64_t)n * K;
+  const float* wr = W + (int64_t)o * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(xr + k), __ldg(wr + k), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc * (scale ? scale[o] : 1.f) + (shift ? shift[o] : 0.f);
+    y[(int64_t)n * O + o] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+}  // namespace eeseg
+
+extern "C" int eeseg_dense_bn_act(const float* x, const float* W, const float* scale, const float* shift, int N,
+                                  int K, int O, int relu, float* y, void* stream) {
+  EESEG_REQUIRE(x && W && y, "dense_bn_act: null pointer");
+  if (N <= 0 || O <= 0) return EESEG_OK;
+  const int warps = N * O;
+  eeseg::dense_bn_act_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, W, scale, shift, N, K, O, relu, y);
+  return eeseg::check_launch("dense_bn_act_kernel");
+}

@@ -155,44 +155,75 @@ class EarlyExitEngine:
 
     @torch.no_grad()
     def _infer(self, X):
+        if self.skip_compute:
+            return self._infer_skipping(X)
+        net = self.net
+        N, _, H, W = X.shape
+        dev = X.device
+        E = self.E
+        exit_idx = torch.full((N,), -1, dtype=torch.int32, device=dev)
+        amax_all = torch.empty((E, N, H, W), dtype=torch.uint8, device=dev)
+        scores = torch.full((max(E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)
+        pool = self.metric != 'ent'
+        Xc = X
+        for i in range(E):
+            Xc = net.run_section(i, Xc)
+            low = net._plan(i).run(Xc)
+            gated = i < E - 1 and i >= self.skip
+            res = ops.exit_gate(low, (H, W), layout='NHWC', n_classes=self.C, tau=self.tau,
+                                want_ent=pool and gated, want_amax=True, want_score=gated and not pool,
+                                amax_out=amax_all[i], score_out=scores[i] if gated and not pool else None)
+            if gated:
+                if pool:
+                    scores[i] = ops.entropy_pool_mean(res.ent, self.size, self.metric == 'min')
+                else:
+                    self.exited_px[i] += res.exited_px.sum()
+                ops.gate_decide(scores[i], self.tau, i, exit_idx, want_active=False)
+        exit_idx = torch.where(exit_idx < 0, torch.full_like(exit_idx, E - 1), exit_idx)
+        pred = amax_all[exit_idx.long(), torch.arange(N, device=dev)]     # the map of the exit each image took
+        return {'exit': exit_idx, 'pred': pred, 'scores': scores}
+
+    @torch.no_grad()
+    def _infer_skipping(self, X):
+        """Compute-skipping variant: after every gate the still-active images are compacted and only
+        they run through the next section (one 4-byte D2H per exit for the active count)."""
         net = self.net
         N, _, H, W = X.shape
         dev = X.device
         exit_idx = torch.full((N,), -1, dtype=torch.int32, device=dev)
         pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
         scores = torch.full((max(self.E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)
-        active = None   # index tensor of images still in flight (skip_compute only)
-        if True:
-            Xc = X
-            for i in range(self.E):
-                Xc = net.run_section(i, Xc)
-                low = net._plan(i).run(Xc)
-                last = i == self.E - 1
-                res = self._gate(low, (H, W), want_score=not last and i >= self.skip)
-                idx = active if active is not None else slice(None)
-                if last:
-                    still = exit_idx[idx] < 0
-                    sel = still.view(-1, 1, 1)
-                    pred[idx] = torch.where(sel, res.amax, pred[idx])
-                    exit_idx[idx] = torch.where(still, torch.full_like(exit_idx[idx], i), exit_idx[idx])
+        active = None   # index tensor of images still in flight
+        Xc = X
+        for i in range(self.E):
+            Xc = net.run_section(i, Xc)
+            low = net._plan(i).run(Xc)
+            last = i == self.E - 1
+            res = self._gate(low, (H, W), want_score=not last and i >= self.skip)
+            idx = active if active is not None else slice(None)
+            if last:
+                still = exit_idx[idx] < 0
+                sel = still.view(-1, 1, 1)
+                pred[idx] = torch.where(sel, res.amax, pred[idx])
+                exit_idx[idx] = torch.where(still, torch.full_like(exit_idx[idx], i), exit_idx[idx])
+                break
+            if i >= self.skip:
+                scores[i, idx] = res.score
+                sub = exit_idx[idx].contiguous()
+                before = sub < 0
+                al, ac = ops.gate_decide(res.score, self.tau, i, sub, want_active=True)
+                took = before & (sub == i)
+                pred[idx] = torch.where(took.view(-1, 1, 1), res.amax, pred[idx])
+                exit_idx[idx] = sub
+                if res.exited_px is not None:
+                    self.exited_px[i] += res.exited_px.sum()
+                k = int(ac.item())              # one 4-byte D2H per exit
+                if k == 0:
                     break
-                if i >= self.skip:
-                    scores[i, idx] = res.score
-                    sub = exit_idx[idx].contiguous()
-                    before = sub < 0
-                    al, ac = ops.gate_decide(res.score, self.tau, i, sub, want_active=self.skip_compute)
-                    took = before & (sub == i)
-                    pred[idx] = torch.where(took.view(-1, 1, 1), res.amax, pred[idx])
-                    exit_idx[idx] = sub
-                    self.exited_px[i] += res.exited_px.sum() if res.exited_px is not None else 0
-                    if self.skip_compute:
-                        k = int(ac.item())              # one 4-byte D2H per exit
-                        if k == 0:
-                            break
-                        if k < Xc.shape[0]:
-                            keep = al[:k].long()
-                            Xc = Xc[keep]
-                            active = keep if active is None else active[keep]
+                if k < Xc.shape[0]:
+                    keep = al[:k].long()
+                    Xc = Xc[keep]
+                    active = keep if active is None else active[keep]
         return {'exit': exit_idx, 'pred': pred, 'scores': scores}
 
     @torch.no_grad()

@@ -124,6 +124,18 @@ def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out,
             PROFILE.append((a, b, sum(2 * N * h * w * Cout * k * k * Cin for k in ksizes), PROFILE_TAG))
 
 
+def dense_bn_act(x, W, scale, shift, relu):
+    """fp32 [N,K] x [O,K]^T -> [N,O], * scale + shift, optional ReLU (eeseg_dense_bn_act)."""
+    N, K = x.shape
+    O = W.shape[0]
+    y = torch.empty((N, O), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().eeseg_dense_bn_act(x.data_ptr(), W.data_ptr(), scale.data_ptr(), shift.data_ptr(), N, K, O,
+                                       1 if relu else 0, y.data_ptr(),
+                                       torch.cuda.current_stream(x.device).cuda_stream), "eeseg_dense_bn_act")
+    return y
+
+
 def global_avgpool_nhwc(xh):
     """bf16 NHWC [N,h,w,C] -> f32 [N,C] (AdaptiveAvgPool2d(1))."""
     N, h, w, C = xh.shape
@@ -160,13 +172,13 @@ class HeadPlan:
             s, b = _fold_bn(bn)
             self.branches.append((_krsc(conv), s.contiguous(), b.contiguous(), conv.dilation[0]))
         pool = aspp.convs[-1]
-        self.pool_w = pool[1].weight.detach().float().flatten(1)           # [mid, Cin]
-        self.pool_s, self.pool_b = _fold_bn(pool[2])
+        self.pool_w = pool[1].weight.detach().float().flatten(1).contiguous()  # [mid, Cin]
+        self.pool_s, self.pool_b = (t.contiguous() for t in _fold_bn(pool[2]))
         nb = len(self.branches)
         proj = aspp.project[0].weight.detach().float().flatten(1)          # [mid, (nb+1)*mid]
         self.proj_w = proj[:, :nb * self.mid].contiguous().view(self.mid, 1, 1, nb * self.mid).to(torch.bfloat16)
         self.proj_pool_w = proj[:, nb * self.mid:].contiguous()             # [mid, mid] fp32
-        self.proj_s, self.proj_b = _fold_bn(aspp.project[1])
+        self.proj_s, self.proj_b = (t.contiguous() for t in _fold_bn(aspp.project[1]))
         self.c3_w = _krsc(conv3)
         self.c3_s, self.c3_b = _fold_bn(bn3)
         # final classifier: pad Cout to a multiple of 16 for the MMA N dimension
@@ -217,9 +229,8 @@ class HeadPlan:
                 conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)
         # pooled branch: avg-pool -> 1x1 -> BN -> ReLU, then its share of the projection, per image
         pooled = global_avgpool_nhwc(xh)
-        pv = torch.relu(pooled @ self.pool_w.t() * self.pool_s + self.pool_b)   # [N, mid] (tiny GEMV)
-        pshift = (pv @ self.proj_pool_w.t()) * self.proj_s + self.proj_b         # [N, mid]
-        pshift = pshift.contiguous()
+        pv = dense_bn_act(pooled, self.pool_w, self.pool_s, self.pool_b, True)        # [N, mid]
+        pshift = dense_bn_act(pv, self.proj_pool_w, self.proj_s, self.proj_b, False)    # [N, mid]
         y = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
         conv_igemm(cat, self.proj_w, self.proj_s, pshift, 1, True, y, BF, mid, shift_sn=mid)
         z = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)

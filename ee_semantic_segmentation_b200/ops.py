@@ -90,7 +90,7 @@ class GateResult:
 
 def exit_gate(x, out_hw=None, *, layout="NCHW", kind="logits", tau=0.0, n_classes=None,
               want_ent=False, want_amax=True, want_mask=False, want_score=True,
-              up_out=None, up_dtype=None):
+              up_out=None, up_dtype=None, amax_out=None, score_out=None):
     """Fused (bilinear up-sample ->) softmax -> normalised entropy -> argmax -> threshold.
 
     x: [N,C,h,w] (layout 'NCHW') or [N,h,w,Cp] with Cp >= C (layout 'NHWC', pass n_classes).
@@ -124,7 +124,7 @@ def exit_gate(x, out_hw=None, *, layout="NCHW", kind="logits", tau=0.0, n_classe
         if want_ent:
             res.ent = torch.empty((N, H, W), dtype=torch.float32, device=dev)
         if want_amax:
-            res.amax = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+            res.amax = amax_out if amax_out is not None else torch.empty((N, H, W), dtype=torch.uint8, device=dev)
         if want_mask:
             res.mask = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
         if want_score:
@@ -136,7 +136,7 @@ def exit_gate(x, out_hw=None, *, layout="NCHW", kind="logits", tau=0.0, n_classe
             _p(res.ent), _p(res.amax), _p(res.mask), _p(res.part_sum), _p(res.part_cnt),
             _stream(x)), "eeseg_exit_gate_pixels")
         if want_score:
-            res.score = torch.empty((N,), dtype=torch.float32, device=dev)
+            res.score = score_out if score_out is not None else torch.empty((N,), dtype=torch.float32, device=dev)
             res.exited_px = torch.empty((N,), dtype=torch.int64, device=dev)
             check(lib().eeseg_exit_gate_decide(
                 res.part_sum.data_ptr(), res.part_cnt.data_ptr(), npart, None, N, H * W, float(tau),

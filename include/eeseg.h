@@ -197,6 +197,11 @@ int eeseg_conv_igemm_grouped(const void* x, int nprob, const void* const* wt, co
  * the previous setting. */
 int eeseg_conv_set_pdl(int enable);
 
+/* Small fp32 dense layer y[n][o] = act((x[n] . W[o]) * scale[o] + shift[o]) (scale/shift optional) for the
+ * ASPP pooled branch (torchvision deeplabv3.py:70-83) and its share of the ASPP projection. */
+int eeseg_dense_bn_act(const float* x, const float* W, const float* scale, const float* shift, int N, int K,
+                       int O, int relu, float* y, void* stream);
+
 /* Tuning hook: device buffer of [148][32] uint64 cycle counters (per-CTA wait times of the producer,
  * MMA and epilogue roles) filled by subsequent eeseg_conv_igemm_fwd launches; NULL switches it off. */
 int eeseg_conv_debug_stats(void* device_buffer);
