@@ -202,7 +202,7 @@ def test_training_step_matches_torch_losses(nets):
     net_a = copy.deepcopy(net)
     net_b = copy.deepcopy(net)
     opt_a = make_optimizer(net_a, lr=1e-2, base_lr=1e-3)
-    assert [grp['lr'] for grp in opt_a.param_groups] == [1e-3, 1e-2, 1.1e-2]
+    assert [grp['lr'] for grp in opt_a.param_groups] == pytest.approx([1e-3, 1e-2, 1.1e-2])
     sched = poly_scheduler(opt_a, 10)
     l_a = train_epoch(net_a, [(X, y)], BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3), opt_a, dev())
     sched.step()
