@@ -338,7 +338,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (elect_one()) {
       unsigned long long dbg_acc[4] = {0, 0, 0, 0};
       const long long dbg_t0 = clock64();
-      uint32_t kbg = 0;   // k-block counter across tiles: stage = kbg % stages, phase = (kbg / stages) & 1
+      int s = 0;          // ring position runs across tiles; ph = parity of the number of wraps
+      uint32_t ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         int prob, n_img, y0, x0, n0;
@@ -356,15 +357,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int tp = 0; tp < q.R * q.S; ++tp) {
           if (!((taps >> tp) & 1u)) continue;
           const int dy = (tp / q.S) * q.dil - q.pad, dx = (tp % q.S) * q.dil - q.pad;
-          for (int cb = 0; cb < cblocks; ++cb, ++kbg) {
-            const int s = (int)(kbg % (uint32_t)p.stages);
-            const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
+          for (int cb = 0; cb < cblocks; ++cb) {
             DBG_T(1, mbar_wait(empty_bar + s, ph ^ 1u));
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             uint8_t* sb = sa + a_bytes;
             mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
             tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
             tma_load_2d(sb, &wmaps.m[prob], full_bar + s, tp * p.Cin + cb * kBlockK, n0);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -380,7 +380,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (elect_one()) {
       unsigned long long dbg_acc[4] = {0, 0, 0, 0};
       const long long dbg_t0 = clock64();
-      uint32_t kbg = 0;
+      int s = 0;
+      uint32_t ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         int prob, n_img, y0, x0, n0;
@@ -390,9 +391,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue drained this buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * p.BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
-          const int s = (int)(kbg % (uint32_t)p.stages);
-          const uint32_t ph = (kbg / (uint32_t)p.stages) & 1u;
+        for (int kb = 0; kb < num_kb; ++kb) {
           DBG_T(1, mbar_wait(full_bar + s, ph));
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -404,6 +403,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar + s);     // frees the smem stage when these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         umma_commit(tmem_full_bar + a);   // accumulator complete
       }
