@@ -20,6 +20,7 @@ PROTOTYPES = {
     "eeseg_last_error": (ctypes.c_char_p, []),
     "eeseg_launch_count": (c_i64, []),
     "eeseg_confusion_hist": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
+    "eeseg_exit_accumulate": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p, c_p]),
     "eeseg_exit_gate_num_partials": (c_i, [c_i, c_i]),
     "eeseg_exit_gate_pixels": (c_i, [c_p, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i,
                                      c_i, c_i, c_f, c_p, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),

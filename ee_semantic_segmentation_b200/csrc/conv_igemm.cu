@@ -592,34 +592,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 // ---- global average pool (ASPPPooling) -----------------------------------------------------------
 constexpr int kPoolSplits = 32;
 
-__global__ void avgpool_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t hw, int C,
-                                       float* __restrict__ part) {
-  // grid (C/64 chunks, splits, N); block 256 = 8 pixel lanes x 32 channel pairs (128 B rows)
+__global__ void __launch_bounds__(256) avgpool_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t hw,
+                                                               int C, float* __restrict__ part) {
+  // grid (C/64 chunks, splits, N); block 256 = 32 pixel lanes x 8 threads of 8 channels (16 B loads,
+  // one 128 B row segment per pixel lane)
   const int n = blockIdx.z, sp = blockIdx.y;
-  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
-  const int pl = threadIdx.x >> 5;
+  const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 64 + cg * 8;
   const int64_t per = (hw + kPoolSplits - 1) / kPoolSplits;
   const int64_t p0 = (int64_t)sp * per, p1 = min(p0 + per, hw);
-  float a0 = 0.f, a1 = 0.f;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
     const __nv_bfloat16* base = x + (int64_t)n * hw * C + c;
 #pragma unroll 4
-    for (int64_t p = p0 + pl; p < p1; p += 8) {
-      __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + p * C);
-      a0 += __low2float(v);
-      a1 += __high2float(v);
+    for (int64_t p = p0 + pl; p < p1; p += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * C));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[2 * k] += __uint_as_float(w4[k] << 16);
+        a[2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+      }
     }
   }
-  __shared__ float s0[8][32], s1[8][32];
-  s0[pl][threadIdx.x & 31] = a0;
-  s1[pl][threadIdx.x & 31] = a1;
+  __shared__ float sm[32][65];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sm[pl][cg * 8 + k] = a[k];
   __syncthreads();
-  if (pl == 0 && c < C) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int i = 0; i < 8; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
-    float* o = part + ((int64_t)n * kPoolSplits + sp) * C + c;
-    o[0] = t0;
-    if (c + 1 < C) o[1] = t1;
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += sm[i][threadIdx.x];   // fixed order
+    part[((int64_t)n * kPoolSplits + sp) * C + blockIdx.x * 64 + threadIdx.x] = t;
   }
 }
 
@@ -894,7 +897,7 @@ extern "C" size_t eeseg_global_avgpool_workspace_bytes(int N, int C) {
 extern "C" int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out,
                                          void* workspace, void* stream_) {
   EESEG_REQUIRE(x && out && workspace, "global_avgpool: null pointer");
-  EESEG_REQUIRE(C % 2 == 0, "global_avgpool: C must be even");
+  EESEG_REQUIRE(C % 8 == 0 && ((uintptr_t)x & 15) == 0, "global_avgpool: C %% 8 == 0 and a 16-byte aligned tensor required");
   if (N == 0) return EESEG_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   float* part = reinterpret_cast<float*>(workspace);

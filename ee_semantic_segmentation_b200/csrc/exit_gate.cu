@@ -30,6 +30,7 @@ struct GateParams {
   double* part_sum;
   int32_t* part_cnt;
   int stats;  // any of ent/amax/mask/part_* requested
+  int need_ent;  // entropy needed (ent/mask/part_*); argmax-only calls skip the softmax work
 };
 
 __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1,
@@ -147,6 +148,10 @@ __global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 
 #pragma unroll
         for (int c = 1; c < CMAX; ++c)
           if (c < C && v[c] > m) { m = v[c]; am = c; }   // first maximal index
+        if (!p.need_ent) {   // argmax only (the final exit): no softmax / entropy
+          if (p.amax) p.amax[(int64_t)n * HW + pix] = (uint8_t)am;
+          continue;
+        }
         float hn;
         if (p.in_kind == 0) {
           // H = ln S - sum e_c z_c / S with z = v - max, e = exp(z); computed in base 2
@@ -347,6 +352,7 @@ extern "C" int eeseg_exit_gate_pixels(const void* in, int in_dtype, int in_kind,
   p.up = up_logits; p.up_sn = up_sn; p.ent = ent; p.amax = amax; p.mask = mask;
   p.part_sum = part_sum; p.part_cnt = part_cnt;
   p.stats = (ent || amax || mask || part_sum || part_cnt) ? 1 : 0;
+  p.need_ent = (ent || mask || part_sum || part_cnt) ? 1 : 0;
   return dispatch_gate(p, in_dtype, up_dtype, (cudaStream_t)stream);
 }
 

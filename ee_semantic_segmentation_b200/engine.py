@@ -154,7 +154,7 @@ class EarlyExitEngine:
         return self._infer(X)
 
     @torch.no_grad()
-    def _infer(self, X):
+    def _infer(self, X, targets=None):
         if self.skip_compute:
             return self._infer_skipping(X)
         net = self.net
@@ -179,6 +179,17 @@ class EarlyExitEngine:
                 else:
                     self.exited_px[i] += res.exited_px.sum()
                 ops.gate_decide(scores[i], self.tau, i, exit_idx, want_active=False)
+        if targets is not None:
+            # one kernel: final-exit assignment, histogram of the map each image took, accumulators, pred
+            pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+            tg = targets.reshape(N, -1)
+            tg = (tg if tg.dtype == torch.int64 else tg.to(torch.int64)).contiguous()
+            with torch.cuda.device(dev):
+                ops.check(ops.lib().eeseg_exit_accumulate(
+                    amax_all.data_ptr(), tg.data_ptr(), exit_idx.data_ptr(), E, N, self.C, H * W,
+                    self.cm.data_ptr(), self.counts.data_ptr(), pred.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream), "eeseg_exit_accumulate")
+            return {'exit': exit_idx, 'pred': pred, 'scores': scores}
         exit_idx = torch.where(exit_idx < 0, torch.full_like(exit_idx, E - 1), exit_idx)
         pred = amax_all[exit_idx.long(), torch.arange(N, device=dev)]     # the map of the exit each image took
         return {'exit': exit_idx, 'pred': pred, 'scores': scores}
@@ -240,6 +251,8 @@ class EarlyExitEngine:
 
     @torch.no_grad()
     def _evaluate(self, X, y):
+        if not self.skip_compute:
+            return self._infer(X, targets=y)
         out = self._infer(X)
         cm = ops.confusion_hist(out['pred'], y, self.C)                  # [N, C+1, C]
         ex = out['exit'].long()

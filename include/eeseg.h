@@ -52,6 +52,14 @@ int64_t eeseg_launch_count(void);
 int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype, const int64_t* targets,
                          int N, int C, int64_t HW, int64_t* cm, int accumulate, void* stream);
 
+/* End-of-batch accumulation of the entropy-gated evaluator (eval_br_ent.py:57-70), one launch:
+ * image n took exit e = exit_idx[n] (a still-active -1 becomes the final exit E-1, written back); the
+ * argmax map amax_all[e][n] (uint8 [E][N][HW]) is histogrammed against targets and added to
+ * cm_acc[e] and to the global slot cm_acc[E] (int64 [E+1][C+1][C]); counts[e] and counts[E] (int64 [E+1])
+ * are incremented; pred (optional uint8 [N][HW]) receives the map of the exit taken. */
+int eeseg_exit_accumulate(const uint8_t* amax_all, const int64_t* targets, int32_t* exit_idx, int E, int N,
+                          int C, int64_t HW, int64_t* cm_acc, int64_t* counts, uint8_t* pred, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Exit gate, stage 1 (per pixel).
  * Replaces, fused: F.interpolate(bilinear, align_corners=False) (from_deepv3_new.py:149,152),
