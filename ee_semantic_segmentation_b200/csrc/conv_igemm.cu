@@ -51,10 +51,7 @@ struct ConvParams {
   const int32_t* schedule;             // optional work list: item = problem << 24 | tile, longest first
   int n_items;
   int hin, win, stride;                // input spatial size and stride
-  int has_res;                         // residual (bf16, output shape) added before ReLU: 0 none, 1 = tile TMA-prefetched
-                                       // into shared memory, 2 = read from global into registers while the MMAs run
-  const __nv_bfloat16* res;            // mode 2: residual base, pixel stride ldr elements
-  int64_t ldr;
+  int has_res;                         // residual tile (bf16, output shape) is TMA-prefetched and added before ReLU
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
   int main_bytes;                      // shared memory of the operand ring
   int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
@@ -264,7 +261,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
   const uint32_t res_blk_bytes = kBlockM * 128;               // 64 bf16 channels per pixel row
-  const int nblk_res = p.has_res == 1 ? p.BN / 64 : 0;
+  const int nblk_res = p.has_res ? p.BN / 64 : 0;
   uint8_t* stg_smem = smem + (p.overlay ? 0 : p.main_bytes);   // overlay: <= 1 tile per CTA, ring is idle by then
   uint8_t* res_smem = smem + p.main_bytes + ((p.overlay || p.direct) ? 0 : (size_t)p.nblk * blk_bytes);
   uint8_t* tail = res_smem + (size_t)2 * nblk_res * res_blk_bytes;
@@ -294,7 +291,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     prefetch_tmap(&tmap_x);
     for (int g = 0; g < p.nprob; ++g) prefetch_tmap(&wmaps.m[g]);
     prefetch_tmap(&tmap_out);
-    if (p.has_res == 1) prefetch_tmap(&tmap_res);
+    if (p.has_res) prefetch_tmap(&tmap_res);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -349,7 +346,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tile_coords(t, prob, n_img, y0, x0, n0);
         const ConvProblem& q = p.pr[prob];
         const uint32_t taps = live_taps(p, q, y0, x0);
-        if (p.has_res == 1) {  // residual tile: lands while the main loop runs
+        if (p.has_res) {  // residual tile: lands while the main loop runs
           const int a = it & 1;
           DBG_T(0, mbar_wait(res_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));
           mbar_expect_tx(res_full_bar + a, (uint32_t)nblk_res * (uint32_t)(p.BW * p.BH * 128));
@@ -447,28 +444,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // the staging tile is reused every tile: the previous TMA stores must have read it out
       if (et == 0 && !p.direct) DBG_T(2, bulk_wait_read(0));
       DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
-      // residual, mode 2: this thread's pixel row of the residual (up to 128 channels = 16 x 16 B) is
-      // fetched into registers now, while the MMAs of this tile are still running
-      uint4 rpre[16];
-      if (p.has_res == 2) {
-        const int yy = y0 + m / p.BW, xx = x0 + m % p.BW;
-        const bool live = m < p.BW * p.BH && yy < p.h && xx < p.w;
-        const uint4* rrow = reinterpret_cast<const uint4*>(
-            p.res + (((int64_t)n_img * p.h + yy) * p.w + xx) * p.ldr + q.ch_off + n0 + col_lo);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          rpre[i] = (live && col_lo + 8 * i < col_hi) ? __ldg(rrow + i) : make_uint4(0, 0, 0, 0);
-      }
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
-      if (p.has_res == 1) DBG_T(1, mbar_wait(res_full_bar + a, aph));
+      if (p.has_res) DBG_T(1, mbar_wait(res_full_bar + a, aph));
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
       const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
       if (p.dbg) dbg_t1 = clock64();
-#pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
-        const int col = col_lo + 16 * ci;
-        if (col >= col_hi) break;
+      for (int col = col_lo; col < col_hi; col += 16) {
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)col, v);
         // scale/shift for these 16 columns while the TMEM load is in flight
@@ -479,10 +461,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           sh4[j] = *reinterpret_cast<const float4*>(s_shift + col + 4 * j);
         }
         uint4 r4[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (p.has_res == 2) {
-          r4[0] = rpre[2 * ci];
-          r4[1] = rpre[2 * ci + 1];
-        } else if (p.has_res == 1) {
+        if (p.has_res) {
           const uint8_t* rrow = res_a + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
           const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
           r4[0] = *reinterpret_cast<const uint4*>(rrow + (((rk + 0) ^ (uint32_t)(m & 7)) << 4));
@@ -759,8 +738,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   ConvParams p;
   p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout;
   p.hin = hin; p.win = win; p.stride = stride;
-  p.has_res = residual ? 2 : 0;   // residual rows are prefetched into registers by the epilogue warps
-  p.res = (const __nv_bfloat16*)residual; p.ldr = ldr;
+  p.has_res = residual ? 1 : 0;
   p.nprob = nprob;
   int kb_total = 0;
   for (int g = 0; g < kMaxGroup; ++g) {
@@ -781,11 +759,10 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.tiles_y = (h + p.BH - 1) / p.BH;
   // output-channel tile: a power of two (16..256) dividing Cout; shallow-K wide-N layers (ResNet
   // conv3 / projection shortcuts) are epilogue-bound: 128 columns let several CTAs share an SM
-  // 256 columns whenever Cout allows: per MMA the operand read is A 4 KB + B N*32 B, so wider tiles need
-  // less shared-memory bandwidth per FLOP (N=128 runs at the 128 B/clk smem limit)
   int BN = 256;
+  if ((kb_total <= 8 && Cout >= 256) || residual) BN = 128;
   while (BN > 16 && (Cout % BN)) BN >>= 1;
-  (void)kb_total;
+  if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
   p.dbg = g_conv_dbg;
@@ -797,7 +774,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.row_bytes = p.blk_cols * oes;
   p.swz = p.row_bytes == 128 ? 1 : 0;
   const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
-  const size_t res_bytes = p.has_res == 1 ? (size_t)2 * (BN / 64) * kBlockM * 128 : 0;   // double buffered
+  const size_t res_bytes = residual ? (size_t)2 * (BN / 64) * kBlockM * 128 : 0;   // double buffered
   const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
   const size_t tail_bytes = 256 + 2 * 256 * 4;   // barriers + tmem pointer (< 256 B), scale, shift
   const int tiles_per_problem = N * p.tiles_x * p.tiles_y * (Cout / BN);
@@ -818,7 +795,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
     const int kb = taps_min * (Cin / kBlockK);
     if (kb < kb_min) kb_min = kb;
   }
-  p.direct = (!p.overlay && kb_min >= 16) ? 1 : 0;
+  p.direct = (!p.overlay && !residual && kb_min >= 16) ? 1 : 0;
   p.out = out; p.ldo = ldo;
   const size_t fixed = 1024 + ((p.overlay || p.direct) ? 0 : staging_bytes) + res_bytes + tail_bytes;
   if (fixed + stage_bytes > 227 * 1024) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
@@ -838,7 +815,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   rc = encode_act_map(encode, &tmo, out, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                       oes, out_channels, w, h, N, ldo, p.blk_cols, p.BW, p.BH, 1, p.swz != 0, "out");
   if (rc) return rc;
-  if (p.has_res == 1) {
+  if (residual) {
     rc = encode_act_map(encode, &tmr, residual, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, w, h, N, ldr, 64, p.BW,
                         p.BH, 1, true, "residual");
     if (rc) return rc;
