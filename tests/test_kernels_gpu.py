@@ -299,3 +299,68 @@ def test_lovasz_sort_properties_full_size():
     void = (tgt[:, 0] == C)
     assert torch.all(gd[0].permute(0, 2, 3, 1)[void] == 0)
     assert torch.isfinite(gd).all()
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_edge_empty_and_tiny_inputs():
+    from ee_semantic_segmentation_b200 import ops
+    # N = 0
+    cm = ops.confusion_hist(torch.zeros(0, 5, 4, 4, device=dev()), torch.zeros(0, 4, 4, dtype=torch.int64, device=dev()), 5)
+    assert cm.shape == (0, 6, 5)
+    # a single pixel, a single class
+    cm = ops.confusion_hist(torch.zeros(1, 1, 1, 1, device=dev()), torch.zeros(1, 1, 1, dtype=torch.int64, device=dev()), 1)
+    assert cm.tolist() == [[[1], [0]]]
+    res = ops.exit_gate(torch.randn(1, 2, 1, 1, device=dev()), (3, 5), want_ent=True)
+    assert res.ent.shape == (1, 3, 5) and torch.allclose(res.ent, res.ent[0, 0, 0])   # constant map
+    per, valid = ops.multi_exit_ce(torch.randn(1, 1, 2, 1, 1, device=dev()), torch.zeros(1, 1, 1, dtype=torch.int64, device=dev()))
+    assert int(valid) == 1 and torch.isfinite(per).all()
+
+
+@pytest.mark.parametrize("C", [2, 33, 64])
+def test_kernels_other_class_counts(C):
+    """Class counts that go through the generic (guarded) template instantiations."""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    N, H, W = 2, 37, 41
+    y = torch.randn(2, N, C, H, W, generator=g) * 2
+    tgt = torch.randint(0, C + 1, (N, H, W), generator=g)
+    yd = y.to(dev()).requires_grad_(True)
+    per, _ = ops.multi_exit_ce(yd, tgt.to(dev()), C)
+    per.sum().backward()
+    ref, rg, rper = R.br_xentropy(y.numpy(), tgt.numpy(), ignore_index=C, b_reduction="none", n_exits=2)
+    np.testing.assert_allclose(per.detach().cpu().numpy(), rper, rtol=1e-4)
+    np.testing.assert_allclose(yd.grad.cpu().numpy(), rg, rtol=1e-4, atol=1e-9)
+    cm = ops.confusion_hist(y[0].to(dev()), tgt.to(dev()), C).cpu().numpy()
+    np.testing.assert_array_equal(cm, R.confusion_matrix(R.argmax_first(y[0].numpy().reshape(N, C, -1), 1),
+                                                          tgt.numpy().reshape(N, -1), C))
+    res = ops.exit_gate(y[0].to(dev()), None, want_ent=True)
+    ent = np.stack([R.pixel_norm_entropy(R.softmax_c(y[0, n].numpy(), 0), C) for n in range(N)])
+    np.testing.assert_allclose(res.ent.cpu().numpy(), ent, atol=3e-5)
+
+
+def test_lovasz_all_void_and_single_class():
+    from ee_semantic_segmentation_b200 import ops
+    y = torch.randn(1, 1, 4, 6, 7, device=dev(), requires_grad=True)
+    void = torch.full((1, 6, 7), 4, dtype=torch.int64, device=dev())
+    per = ops.lovasz_multi_exit(y, void, ignore=4)
+    per.sum().backward()
+    assert per.item() == 0.0 and torch.all(y.grad == 0)        # lovaszsoftmax.py:179-181: only void -> 0
+    one = torch.zeros((1, 6, 7), dtype=torch.int64, device=dev())
+    y2 = torch.rand(1, 1, 4, 6, 7, device=dev())
+    per = ops.lovasz_multi_exit(y2, one, ignore=4)
+    ref, _ = R.lovasz_softmax(y2[0].cpu().numpy(), one.cpu().numpy(), ignore=4)
+    assert per.item() == pytest.approx(float(ref), rel=1e-5)
+
+
+def test_lovasz_cityscapes_crop_vs_oracle():
+    """BASELINE config 4 shape (19 classes, 768x768 crop), one exit, against the numpy oracle."""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    y = torch.randn(1, 1, 19, 768, 768, generator=g)
+    tgt = blocky(g, 1, 19, 768, 768)
+    yd = y.to(dev()).requires_grad_(True)
+    per = ops.lovasz_multi_exit(yd, tgt.to(dev()), ignore=19)
+    per.sum().backward()
+    ref, rg = R.lovasz_softmax(y[0].numpy(), tgt.numpy(), ignore=19)
+    assert per.item() == pytest.approx(float(ref), rel=1e-4)
+    np.testing.assert_allclose(yd.grad[0].cpu().numpy(), rg, rtol=2e-3, atol=1e-9)

@@ -221,3 +221,28 @@ def test_training_step_matches_torch_losses(nets):
     pb = torch.cat([p.detach().flatten() for p in net_b.branches.parameters()])
     assert torch.allclose(pa, pb, rtol=1e-3, atol=1e-6)
     net.eval()
+
+
+def test_cityscapes_shaped_full_res_sweep():
+    """BASELINE config 5 shape: 19 classes, one 1024x2048 image (128x256 feature maps, 16x8 conv tiles),
+    threshold sweep + integer confusion matrices; heads checked against the fp32 PyTorch modules."""
+    from ee_semantic_segmentation_b200.engine import ThresholdSweep
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    torch.manual_seed(5)
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=[16, 3, 1], num_classes=19, pretrained=False).to(dev()).eval()
+    g = torch.Generator().manual_seed(27)
+    X = torch.randn(1, 3, 1024, 2048, generator=g).to(dev())
+    y = torch.randint(0, 20, (1, 1, 1024, 2048), generator=g).to(dev())
+    lows = net.forward_lowres(X)
+    assert [tuple(l.shape) for l in lows] == [(1, 128, 256, 32)] * 3
+    with torch.no_grad():                       # fp32 reference of the first head on the same features
+        feat = net.run_section(0, X)
+        ref = net.branches[0](feat.float())
+    got = lows[0][..., :19].permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
+    sweep = ThresholdSweep(net, 19, [0.0, 0.5, 2.0])
+    sweep.update(X, y)
+    res = sweep.results()
+    assert [r["out_gl"] for r in res] == [1, 1, 1]
+    assert res[0]["count_out"] == 1 and res[2]["b1_count"] == 1
+    assert int(sweep.cm[:, -1].sum()) == 3 * 1024 * 2048       # every pixel counted once per tau
