@@ -40,6 +40,8 @@ def confusion_hist(pred, targets, n_classes, out=None, accumulate=False):
     _cuda(pred, "pred")
     C = int(n_classes)
     N = pred.shape[0]
+    if N == 0:      # empty batch: nothing to launch
+        return out if out is not None else torch.zeros((0, C + 1, C), dtype=torch.int64, device=pred.device)
     with torch.cuda.device(pred.device):
         if pred.dtype in (torch.uint8, torch.int64):
             kind = 1 if pred.dtype == torch.uint8 else 2
