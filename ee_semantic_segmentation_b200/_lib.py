@@ -48,6 +48,7 @@ PROTOTYPES = {
     "eeseg_dense_bn_act": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_conv_debug_stats": (c_i, [c_p]),
     "eeseg_conv_set_pdl": (c_i, [c_i]),
+    "eeseg_conv_timing": (c_i, [c_p, c_i]),
     "eeseg_global_avgpool_workspace_bytes": (c_sz, [c_i, c_i]),
     "eeseg_global_avgpool_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_p, c_p, c_p]),
 }

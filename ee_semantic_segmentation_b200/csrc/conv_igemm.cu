@@ -66,6 +66,7 @@ struct ConvParams {
   int out_f32;
   int64_t shift_sn;
   unsigned long long* dbg;   // optional [gridDim.x][32] cycle counters (eeseg_conv_debug_stats)
+  unsigned long long* tslot; // optional {min start, max end} wall-clock ns of this launch (eeseg_conv_timing)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -276,10 +277,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* s_shift = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.dbg && threadIdx.x == 0) {   // kernel-entry wall clock (ns) of this CTA
+  if ((p.dbg || p.tslot) && threadIdx.x == 0) {   // kernel-entry wall clock (ns) of this CTA
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    p.dbg[(size_t)blockIdx.x * 32 + 16] = g;
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 32 + 16] = g;
+    if (p.tslot) atomicMin(p.tslot, g);
   }
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.Cout / p.BN;
@@ -582,10 +584,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
                  : "memory");
   }
-  if (p.dbg && threadIdx.x == 0) {   // kernel-exit wall clock (ns)
+  if ((p.dbg || p.tslot) && threadIdx.x == 0) {   // kernel-exit wall clock (ns)
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    p.dbg[(size_t)blockIdx.x * 32 + 17] = g;
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 32 + 17] = g;
+    if (p.tslot) atomicMax(p.tslot + 1, g);
   }
 }
 
@@ -692,6 +695,18 @@ static int encode_act_map(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr
 
 static unsigned long long* g_conv_dbg = nullptr;
 static int g_conv_pdl = 1;
+static unsigned long long* g_conv_tbuf = nullptr;
+static int g_conv_tcap = 0, g_conv_tnext = 0;
+// Measurement hook: every following conv launch i records {first CTA start, last CTA end} in wall-clock
+// nanoseconds (%globaltimer) at buffer[2*i], buffer[2*i+1] (i < capacity; the caller initialises starts
+// to UINT64_MAX and ends to 0). NULL switches it off. Returns the number of launches recorded so far.
+extern "C" int eeseg_conv_timing(void* device_buffer, int capacity) {
+  const int n = g_conv_tnext;
+  g_conv_tbuf = reinterpret_cast<unsigned long long*>(device_buffer);
+  g_conv_tcap = device_buffer ? capacity : 0;
+  g_conv_tnext = 0;
+  return n;
+}
 // Programmatic dependent launch of the conv kernel on/off (default on); returns the previous setting.
 extern "C" int eeseg_conv_set_pdl(int enable) {
   const int old = g_conv_pdl;
@@ -766,6 +781,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
   p.dbg = g_conv_dbg;
+  p.tslot = (g_conv_tbuf && g_conv_tnext < g_conv_tcap) ? g_conv_tbuf + 2 * (size_t)(g_conv_tnext++) : nullptr;
   // epilogue blocks: 128 B of output per pixel row (64 bf16 / 32 fp32 channels), swizzled; narrower
   // tiles use one dense block
   const int full_cols = 128 / oes;

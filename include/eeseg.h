@@ -210,6 +210,11 @@ int eeseg_conv_set_pdl(int enable);
 int eeseg_dense_bn_act(const float* x, const float* W, const float* scale, const float* shift, int N, int K,
                        int O, int relu, float* y, void* stream);
 
+/* Measurement hook: following eeseg_conv_igemm_* launches record {first CTA start, last CTA end} in
+ * wall-clock ns (%globaltimer) at buffer[2*i], buffer[2*i+1] (uint64, i < capacity; initialise starts to
+ * UINT64_MAX and ends to 0). NULL switches it off; returns how many launches were recorded. */
+int eeseg_conv_timing(void* device_buffer, int capacity);
+
 /* Tuning hook: device buffer of [148][32] uint64 cycle counters (per-CTA wait times of the producer,
  * MMA and epilogue roles) filled by subsequent eeseg_conv_igemm_fwd launches; NULL switches it off. */
 int eeseg_conv_debug_stats(void* device_buffer);
