@@ -57,8 +57,9 @@ class BottleneckPlan:
 class StemPlan:
     """conv1 7x7/s2/p3 (3->64) + bn1 + relu + maxpool 3x3/s2/p1 of torchvision's ResNet on the eeseg
     kernels: the fp32 NCHW image is space-to-depth'ed (2x2 -> 12 channels, zero-padded to the 64-channel
-    MMA K block) so the stride-2 7x7 conv is a stride-1 4x4 implicit GEMM with the first tap at offset
-    -2 (input row 2y-3+r = 2(y+t-2)+a with r = 2t+a-1); BatchNorm and ReLU are the conv epilogue; the
+    MMA K block together with the 4 horizontal taps: channel u*12 + (a*2+b)*3 + c) so the stride-2 7x7 conv
+    is a stride-1 4x1 implicit GEMM (4 K blocks) with the first tap at row offset -2 (input row
+    2y-3+r = 2(y+t-2)+a with r = 2t+a-1); BatchNorm and ReLU are the conv epilogue; the
     max-pool is one streaming kernel. Replaces a cuDNN conv + 3 elementwise kernels on a 4x larger
     intermediate."""
 
@@ -66,7 +67,7 @@ class StemPlan:
         dev = conv.weight.device
         W = conv.weight.detach().float()                         # [64, 3, 7, 7]
         cout = W.shape[0]
-        w2 = torch.zeros((cout, 4, 4, 64), dtype=torch.float32, device=dev)
+        w2 = torch.zeros((cout, 4, 1, 64), dtype=torch.float32, device=dev)
         for t in range(4):
             for a in range(2):
                 r = 2 * t + a - 1
@@ -77,8 +78,8 @@ class StemPlan:
                         q = 2 * u + b - 1
                         if not 0 <= q <= 6:
                             continue
-                        ch = (a * 2 + b) * 3
-                        w2[:, t, u, ch:ch + 3] = W[:, :, r, q]
+                        ch = u * 12 + (a * 2 + b) * 3
+                        w2[:, t, 0, ch:ch + 3] = W[:, :, r, q]
         self.w = w2.to(torch.bfloat16).contiguous()
         s, b = _fold_bn(bn)
         self.s, self.b = s.contiguous(), b.contiguous()

@@ -34,7 +34,8 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxGroup = 4;   // convolutions sharing one input that can run as one grouped launch
 
 struct ConvProblem {      // what differs between the members of a group (ASPP branches)
-  int R, S, dil, pad;     // tap r reads input row out*stride + r*dil - pad
+  int R, S, dil, pad;     // tap (r,s) reads input (y*stride + r*dil - pad_y, x*stride + s*dil - pad_x) where the
+                          // pad applies along every kernel dimension with more than one tap
   int ch_off;             // first output channel inside the output tensor map
   const float* scale;
   const float* shift;
@@ -233,10 +234,10 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, const ConvPro
   uint32_t m = 0;
   const int y_hi = min(y0 + p.BH, p.h), x_hi = min(x0 + p.BW, p.w);
   for (int r = 0; r < q.R; ++r) {
-    const int dy = r * q.dil - q.pad;
+    const int dy = r * q.dil - (q.R > 1 ? q.pad : 0);
     if ((y_hi - 1) * p.stride + dy < 0 || y0 * p.stride + dy >= p.hin) continue;
     for (int s = 0; s < q.S; ++s) {
-      const int dx = s * q.dil - q.pad;
+      const int dx = s * q.dil - (q.S > 1 ? q.pad : 0);
       if ((x_hi - 1) * p.stride + dx < 0 || x0 * p.stride + dx >= p.win) continue;
       m |= 1u << (r * q.S + s);
     }
@@ -363,7 +364,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         for (int tp = 0; tp < q.R * q.S; ++tp) {
           if (!((taps >> tp) & 1u)) continue;
-          const int dy = (tp / q.S) * q.dil - q.pad, dx = (tp % q.S) * q.dil - q.pad;
+          const int dy = (tp / q.S) * q.dil - (q.R > 1 ? q.pad : 0), dx = (tp % q.S) * q.dil - (q.S > 1 ? q.pad : 0);
           for (int cb = 0; cb < cblocks; ++cb) {
             DBG_T(1, mbar_wait(empty_bar + s, ph ^ 1u));
             uint8_t* sa = smem + (size_t)s * stage_bytes;

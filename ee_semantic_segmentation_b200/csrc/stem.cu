@@ -1,5 +1,5 @@
-// ResNet stem helpers: space-to-depth of the input image (so the 7x7/s2 conv runs on the tcgen05
-// implicit-GEMM kernel as a 4x4/s1 conv over 64 padded channels) and the 3x3/s2 max-pool on NHWC
+// ResNet stem helpers: space-to-depth + horizontal tap unrolling of the input image (so the 7x7/s2 conv
+// runs on the tcgen05 implicit-GEMM kernel as a 4x1/s1 conv over 48 of 64 channels: 4 K blocks) and the 3x3/s2 max-pool on NHWC
 // bf16. Both are pure streaming kernels (coalesced 16 B accesses). Reference: torchvision resnet
 // conv1/bn1/relu/maxpool inside base_model[0] (from_deepv3_new.py:75-79,146).
 #include "common.cuh"
@@ -8,34 +8,39 @@ namespace eeseg {
 
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, int N, int H, int W,
                                                         int H2, int W2, __nv_bfloat16* __restrict__ out) {
+  // one thread per output pixel (n, Y, X): 4 horizontal taps x (2x2 space-to-depth x 3 channels) = 48
+  // values from input rows 2Y, 2Y+1 and columns 2(X-2) .. 2(X+1)+1, then 16 zero channels
   const int64_t total = (int64_t)N * H2 * W2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int X = (int)(i % W2);
     const int Y = (int)((i / W2) % H2);
     const int n = (int)(i / ((int64_t)W2 * H2));
-    float v[12];
+    uint32_t w[32];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int u = 0; u < 4; ++u) {
+      float v[12];
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int yy = 2 * Y + a, xx = 2 * X + b;
-          v[(a * 2 + b) * 3 + c] = (yy < H && xx < W) ? __ldg(x + (((int64_t)n * 3 + c) * H + yy) * W + xx) : 0.f;
-        }
-    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
-    uint32_t w[8];
+        for (int b = 0; b < 2; ++b)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-      w[k] = *reinterpret_cast<uint32_t*>(&b2);
+          for (int c = 0; c < 3; ++c) {
+            const int yy = 2 * Y + a, xx = 2 * (X + u - 2) + b;
+            v[(a * 2 + b) * 3 + c] =
+                (yy < H && xx >= 0 && xx < W) ? __ldg(x + (((int64_t)n * 3 + c) * H + yy) * W + xx) : 0.f;
+          }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        w[u * 6 + k] = *reinterpret_cast<uint32_t*>(&b2);
+      }
     }
-    w[6] = 0; w[7] = 0;
-    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    o[1] = make_uint4(w[4], w[5], 0, 0);
 #pragma unroll
-    for (int k = 2; k < 8; ++k) o[k] = make_uint4(0, 0, 0, 0);
+    for (int k = 24; k < 32; ++k) w[k] = 0;
+    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
   }
 }
 

@@ -163,7 +163,8 @@ int eeseg_lovasz_fwd_bwd(const void* probas, int dtype, int64_t exit_stride, con
  *   wt  bf16 [Cout][R][S][Cin]             (Cout % 16 == 0; tiled by <= 256 output channels)
  *   y = act( scale[co] * conv(x, wt; dilation, stride, pad) + shift[n?][co] + residual )
  *       tap (r,s) of output (y,x) reads input (y*stride + r*dilation - pad, x*stride + s*dilation - pad),
- *       zero outside the image; pad < 0 = 'same' padding dilation*(R/2) of an odd square kernel;
+ *       zero outside the image (the pad applies along each kernel dimension that has more than one tap);
+ *       pad < 0 = 'same' padding dilation*(R/2) of an odd square kernel;
  *       output spatial size (hin-1)/stride+1 x (win-1)/stride+1
  *   shift_sn: image stride of `shift` in elements (0 = shared by all images)
  *   residual: optional bf16 NHWC tensor of the OUTPUT shape (pixel stride ldr), or NULL. It is added
@@ -178,9 +179,10 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
                          void* out, int out_dtype, int64_t ldo, void* stream);
 
 /* ResNet stem helpers (base_model[0][0:4], torchvision resnet.py conv1/bn1/relu/maxpool):
- * space-to-depth of the fp32 NCHW image so that the 7x7 / stride-2 / pad-3 convolution becomes a
- * 4x4 / stride-1 / pad-2 implicit GEMM: out bf16 NHWC [N][(H+1)/2][(W+1)/2][64], channel
- * (a*2+b)*3+c = x[n][c][2Y+a][2X+b] (zero outside the image and for channels >= 12). */
+ * space-to-depth (2x2) plus horizontal tap unrolling of the fp32 NCHW image, so that the 7x7 / stride-2 /
+ * pad-3 convolution becomes a 4x1 / stride-1 / pad-2 implicit GEMM with K = 4 taps x 64 channels:
+ * out bf16 NHWC [N][(H+1)/2][(W+1)/2][64], channel u*12 + (a*2+b)*3 + c = x[n][c][2Y+a][2(X+u-2)+b]
+ * for u in 0..3 (zero outside the image and for channels >= 48). */
 int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream);
 /* 3x3 / stride-2 / pad-1 max pooling of a bf16 NHWC tensor (C % 8 == 0). */
 int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream);
