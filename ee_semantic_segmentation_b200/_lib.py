@@ -5,7 +5,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeeseg_b200.so")
+LIB_PATH = os.environ.get("EESEG_LIB") or os.path.join(_HERE, "libeeseg_b200.so")   # EESEG_LIB: A/B builds while tuning
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "eeseg.h")
 
 _lib = None

@@ -65,6 +65,19 @@ __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) {
   __stcs(reinterpret_cast<unsigned short*>(p), *reinterpret_cast<unsigned short*>(&b));
 }
 
+// Plane addressing: element (c, p) of an image lives at base + c*HW + p. With the plane stride as a
+// 32-bit BYTE count and c a compile-time constant the address is ONE widening multiply-add
+// (IMAD.WIDE.U32) per access; 64-bit HW arithmetic costs 3-4 instructions per access and made v3.0 of
+// this kernel half issue-bound (ncu: 578 warp instructions per pixel-exit, issue slots 50 % busy).
+template <typename T>
+__device__ __forceinline__ const T* plane_ptr(const T* base, uint32_t c, uint32_t plane_bytes) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (uint64_t)c * plane_bytes);
+}
+template <typename T>
+__device__ __forceinline__ T* plane_ptr(T* base, uint32_t c, uint32_t plane_bytes) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + (uint64_t)c * plane_bytes);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

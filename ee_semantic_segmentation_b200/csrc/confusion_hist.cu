@@ -7,7 +7,6 @@
 // blocky label maps of segmentation data do not serialise on one bank, then flushed once per block
 // with 64-bit global atomics.
 #include "common.cuh"
-#include "plane_stream.cuh"
 
 namespace eeseg {
 
@@ -78,98 +77,63 @@ __global__ void __launch_bounds__(256) cm_from_logits_kernel(const T* __restrict
   hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
 }
 
-// Streaming variant (the default for logits): class planes staged through shared memory with
-// bulk-TMA copies (plane_stream.cuh), one persistent CTA per SM, several tiles in flight.
-template <typename T, int TILE>
-__global__ void __launch_bounds__(TILE, 2) cm_from_logits_stream_kernel(
-    const T* __restrict__ logits, const int64_t* __restrict__ targets, int C, int64_t HW, int copies,
-    unsigned long long* __restrict__ cm, const uint8_t* __restrict__ limit_logits,
-    const uint8_t* __restrict__ limit_targets, int stages) {
-  extern __shared__ __align__(128) uint8_t hs_smem[];
-  constexpr int ES = (int)sizeof(T);
-  constexpr int rb = ps::row_bytes(TILE, ES), rbt = ps::row_bytes(TILE, 8);
-  const int stage_bytes = C * rb + rbt;
-  uint64_t* full = reinterpret_cast<uint64_t*>(hs_smem + (size_t)stages * stage_bytes);
-  uint64_t* done = full + 4;   // every thread has read its pixel out of a stage
-  unsigned* hist = reinterpret_cast<unsigned*>(full + 8);
-  constexpr int NW = TILE / 32;   // row r is owned by warp r % NW, lane r / NW
-  const int my_row = (int)(threadIdx.x & 31) * NW + (int)(threadIdx.x >> 5);
-  const int bins = (C + 1) * C;
-  for (int i = threadIdx.x; i < copies * bins; i += TILE) hist[i] = 0;
-  unsigned* h = hist + ((threadIdx.x >> 5) % copies) * bins;
-
-  const int n = blockIdx.y;
-  const uint8_t* base_b = reinterpret_cast<const uint8_t*>(logits + (int64_t)n * C * HW);
-  const uint8_t* tg_b = reinterpret_cast<const uint8_t*>(targets + (int64_t)n * HW);
-  const int num_tiles = (int)((HW + TILE - 1) / TILE);
-  const int my_count = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto issue = [&](int k) {   // the owner of row r issues it (r < C: class plane, r == C: targets)
-    const int r = my_row;
-    if (r > C) return;
-    const int s = k % stages;
-    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
-    const int count = (int)min((int64_t)TILE, HW - p0);
-    uint8_t* st = hs_smem + (size_t)s * stage_bytes;
-    if (r < C) ps::issue_tile<ES>(st + (size_t)r * rb, rb, full + s, base_b + (int64_t)r * HW * ES, 0, 1, p0, count, limit_logits);
-    else ps::issue_tile<8>(st + (size_t)C * rb, rbt, full + s, tg_b, 0, 1, p0, count, limit_targets);
-  };
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      ps::mbar_init(full + s, C + 1);
-      ps::mbar_init(done + s, TILE);
-    }
-    ps::fence_barrier_init();
+// torch.argmax treats NaN as the maximum and returns the first one. Kept out of line (and re-reading
+// the pixel) so that the hot loop carries no NaN bookkeeping.
+template <typename T>
+__device__ __noinline__ int first_nan_class(const T* px, int C, uint32_t plane_bytes) {
+  for (int c = 0; c < C; ++c) {
+    const float v = ldf(plane_ptr(px, (uint32_t)c, plane_bytes));
+    if (v != v) return c;
   }
-  __syncthreads();
-  for (int k = 0; k < stages && k < my_count; ++k) issue(k);
-  const uint32_t delta = (uint32_t)(((uint64_t)HW * ES) & 15);
-  for (int k = 0; k < my_count; ++k) {
-    const int s = k % stages;
-    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
-    const int64_t p = p0 + threadIdx.x;
-    const uint8_t* st = hs_smem + (size_t)s * stage_bytes;
-    ps::mbar_wait(full + s, (uint32_t)(k / stages) & 1u);
-    const uint32_t a0 = (uint32_t)((uintptr_t)(base_b + p0 * ES) & 15);
-    const uint32_t t0 = (uint32_t)((uintptr_t)(tg_b + p0 * 8) & 15);
-    const uint32_t stu = ps::smem_u32(st);
-    constexpr int P = 16 / ES;   // the plane misalignment pattern repeats every P classes
-    uint32_t rowbase[P];
+  return 0;
+}
+
+// Default for logits: thread = PIX pixels (strided by the block), all C class values of those pixels
+// loaded into registers before the first compare (PIX x C independent plane-coalesced loads in flight
+// per thread, no staging). tools/ub_stream.cu: 79 % of the HBM copy peak with PIX = 2, against 44 %
+// for the bulk-TMA shared-memory ring it replaces and 71 % / 60 % for PIX = 1 / 4.
+// CMAX 32 = register capacity with a runtime class count, otherwise the exact count (19, 21).
+template <typename T, int CMAX, int PIX, int THREADS>
+__global__ void __launch_bounds__(THREADS) cm_from_logits_direct_kernel(
+    const T* __restrict__ logits, const int64_t* __restrict__ targets, int C, int64_t HW, int copies,
+    unsigned long long* __restrict__ cm) {
+  if (CMAX != 32) C = CMAX;
+  extern __shared__ unsigned hist[];
+  const int bins = (C + 1) * C;
+  for (int i = threadIdx.x; i < copies * bins; i += THREADS) hist[i] = 0;
+  unsigned* h = hist + ((threadIdx.x >> 5) % copies) * bins;
+  const int n = blockIdx.y;
+  const T* base = logits + (int64_t)n * C * HW;
+  const int64_t p0 = (int64_t)blockIdx.x * (THREADS * PIX) + threadIdx.x;
+  const uint32_t pb = (uint32_t)HW * (uint32_t)sizeof(T);   // plane stride in bytes (< 2^32, checked on the host)
+  float v[PIX][CMAX];
+  int64_t t[PIX];
 #pragma unroll
-    for (int r = 0; r < P; ++r) rowbase[r] = stu + ((a0 + (uint32_t)r * delta) & 15u) + threadIdx.x * ES;
-    int key = -1;
-    if (p < HW) {
-      int64_t t;
-      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t) : "r"(stu + (uint32_t)C * rb + t0 + threadIdx.x * 8));
-      float best = -INFINITY;
-      int arg = 0;
-      for (int c0 = 0; c0 < C; c0 += P) {
+  for (int j = 0; j < PIX; ++j) {
+    const int64_t p = p0 + j * THREADS;
+    t[j] = p < HW ? __ldg(targets + (int64_t)n * HW + p) : -1;
 #pragma unroll
-        for (int r = 0; r < P; ++r) {
-          const int c = c0 + r;
-          if (c < C) {
-            float v;
-            if constexpr (ES == 4) {
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(rowbase[r] + (uint32_t)c * rb));
-            } else {
-              unsigned short u;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(rowbase[r] + (uint32_t)c * rb));
-              v = __uint_as_float(((uint32_t)u) << 16);
-            }
-            // torch.argmax: first maximal index, NaN counts as the maximum
-            const bool take = (v > best) || (v != v && best == best) || (c == 0);
-            if (take) { best = v; arg = c; }
-          }
-        }
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) v[j][c] = p < HW ? ldf_stream(plane_ptr(base + p, (uint32_t)c, pb)) : 0.f;
+  }
+  __syncthreads();   // histogram zeroed (the loads above are already in flight)
+#pragma unroll
+  for (int j = 0; j < PIX; ++j) {
+    const int64_t p = p0 + j * THREADS;
+    // torch.argmax: first maximal index, NaN counts as the maximum. One unordered compare per class
+    // ("greater or NaN") is exact as long as the running best is not NaN; the rare NaN pixel is redone.
+    float best = v[j][0];
+    int arg = 0;
+#pragma unroll
+    for (int c = 1; c < CMAX; ++c)
+      if (c < C) {
+        const bool take = !(v[j][c] <= best);
+        best = take ? v[j][c] : best;
+        arg = take ? c : arg;
       }
-      const int tt = (t >= 0 && t < C) ? (int)t : C;
-      key = tt * C + arg;
-    }
-    ps::mbar_arrive(done + s);  // this thread has read its pixel
-    if (my_row <= C && k + stages < my_count) {   // only the row owners wait before refilling the stage
-      ps::mbar_wait(done + s, (uint32_t)(k / stages) & 1u);
-      issue(k + stages);
-    }
-    hist_add(h, key);
+    if (best != best) arg = first_nan_class(base + p, C, pb);   // rare; out of line, re-reads the pixel
+    const int tt = (t[j] >= 0 && t[j] < C) ? (int)t[j] : C;
+    hist_add(h, p < HW ? tt * C + arg : -1);   // whole warps reach this together (match.any)
   }
   hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
 }
@@ -317,36 +281,24 @@ extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype,
         cm_from_logits_global_kernel<__nv_bfloat16><<<g2, 256, 0, stream>>>((const __nv_bfloat16*)pred, targets, C, HW, cmu);
       return check_launch("cm_from_logits_global_kernel");
     }
-    {
-      // streaming path: one persistent CTA per SM, bulk-TMA staged planes
-      constexpr int kTile = 512;
-      const int es = dtype == EESEG_F32 ? 4 : 2;
-      const size_t stage_bytes = (size_t)C * ps::row_bytes(kTile, es) + ps::row_bytes(kTile, 8);
-      int hcopies = copies < 4 ? copies : 4;
-      const size_t fixed = 8 * sizeof(uint64_t) + (size_t)hcopies * bytes1;
-      int stages = (int)((112 * 1024 - fixed) / stage_bytes);   // two CTAs per SM
-      if (stages > 3) stages = 3;
-      if (stages >= 2 && C + 1 <= kTile && stages <= 4) {
-        const size_t smem = stages * stage_bytes + fixed;
-        int64_t per_img = 2 * kNumSMs / N;
-        if (per_img < 1) per_img = 1;
-        const int64_t tiles = (HW + kTile - 1) / kTile;
-        dim3 sgrid((unsigned)(per_img < tiles ? per_img : tiles), (unsigned)N);
-        const uintptr_t end_l = ((uintptr_t)pred + (size_t)N * C * HW * es + 15) & ~(uintptr_t)15;
-        const uintptr_t end_t = ((uintptr_t)(targets + (int64_t)N * HW) + 15) & ~(uintptr_t)15;
-        if (dtype == EESEG_F32) {
-          auto kern = cm_from_logits_stream_kernel<float, kTile>;
-          EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          kern<<<sgrid, kTile, smem, stream>>>((const float*)pred, targets, C, HW, hcopies, cmu,
-                                               (const uint8_t*)end_l, (const uint8_t*)end_t, stages);
-        } else {
-          auto kern = cm_from_logits_stream_kernel<__nv_bfloat16, kTile>;
-          EESEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          kern<<<sgrid, kTile, smem, stream>>>((const __nv_bfloat16*)pred, targets, C, HW, hcopies, cmu,
-                                               (const uint8_t*)end_l, (const uint8_t*)end_t, stages);
-        }
-        return check_launch("cm_from_logits_stream_kernel");
+    if (C <= 32 && HW < (1ll << 29)) {
+      constexpr int kT = 256, kP = 2;
+      int dcopies = copies < kT / 32 ? copies : kT / 32;
+      dim3 dgrid((unsigned)((HW + kT * kP - 1) / (kT * kP)), (unsigned)N);
+      const size_t sm = (size_t)dcopies * bytes1;
+#define EESEG_HIST_CASE(T, CM)                                                                             \
+  cm_from_logits_direct_kernel<T, CM, kP, kT><<<dgrid, kT, sm, stream>>>((const T*)pred, targets, C, HW, dcopies, cmu)
+      if (dtype == EESEG_F32) {
+        if (C == 21) EESEG_HIST_CASE(float, 21);
+        else if (C == 19) EESEG_HIST_CASE(float, 19);
+        else EESEG_HIST_CASE(float, 32);
+      } else {
+        if (C == 21) EESEG_HIST_CASE(__nv_bfloat16, 21);
+        else if (C == 19) EESEG_HIST_CASE(__nv_bfloat16, 19);
+        else EESEG_HIST_CASE(__nv_bfloat16, 32);
       }
+#undef EESEG_HIST_CASE
+      return check_launch("cm_from_logits_direct_kernel");
     }
     if (dtype == EESEG_F32)
       cm_from_logits_kernel<float, kPix><<<grid, kThreads, copies * bytes1, stream>>>(

@@ -81,20 +81,32 @@ __device__ __forceinline__ void lerp_row(const TI* __restrict__ row, int off0, i
 }
 
 template <typename TI, typename TO, int CMAX, bool INTERP, bool NHWC_VEC>
-__global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 3 : 1))) gate_kernel(const GateParams p) {
-  const int X = blockIdx.x * kGateThreads + threadIdx.x;
-  const int n = blockIdx.z;
-  const int Y0 = blockIdx.y * kRowsPerStrip;
+#ifndef EESEG_GATE_MINB
+#define EESEG_GATE_MINB 4
+#endif
+__global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? EESEG_GATE_MINB : (CMAX <= 32 ? 3 : 1))) gate_kernel(const GateParams p) {
+  // Work item = one WARP: 32 consecutive columns x kRowsPerStrip rows of one image. Items are dealt to
+  // warps from a flat index, so a 513-wide image costs 17 warps per strip (not 5 blocks of 4 warps with
+  // 3 of the last block's warps parked at a barrier — ncu: 19 % of stall samples), and there is no
+  // block barrier: every warp writes its own ordered partial.
+  const int xgroups = (p.W + 31) >> 5, strips = (p.H + kRowsPerStrip - 1) / kRowsPerStrip;
+  const int item = blockIdx.x * (kGateThreads / 32) + (int)(threadIdx.x >> 5);
+  if (item >= xgroups * strips * p.N) return;   // whole warp
+  const int n = item / (xgroups * strips);
+  const int irem = item - n * (xgroups * strips);   // partial slot inside the image: strip-major
+  const int X = (irem % xgroups) * 32 + (int)(threadIdx.x & 31);
+  const int Y0 = (irem / xgroups) * kRowsPerStrip;
   const int Y1 = min(Y0 + kRowsPerStrip, p.H);
   const bool live = X < p.W;
   const int C = cmax_is_exact(CMAX) ? CMAX : p.C;
   const TI* in = reinterpret_cast<const TI*>(p.in) + (int64_t)n * p.in_sn;
   TO* up = p.up ? reinterpret_cast<TO*>(p.up) + (int64_t)n * p.up_sn : nullptr;
   const int64_t HW = (int64_t)p.H * p.W;
+  const uint32_t upb = (uint32_t)HW * (uint32_t)sizeof(TO);   // output plane stride in bytes (< 2^32, host-checked)
   const float inv_lnC = C > 1 ? 1.f / logf((float)C) : 0.f;
   constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
-  double acc_ent = 0.0;
+  float acc_ent = 0.f;   // <= kRowsPerStrip values in [0,1]: exact enough in fp32, widened once below
   int acc_cnt = 0;
 
   float top[CMAX], bot[CMAX];
@@ -137,17 +149,23 @@ __global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 
           if (c < C) v[c] = ldf_stream(r + (int64_t)c * p.in_sc);
       }
       const int64_t pix = (int64_t)Y * p.W + X;
-      if (up) {
+      if (up) {   // one widening multiply-add per plane address (see plane_ptr)
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) stf(up + c * HW + pix, v[c]);
+          if (c < C) stf(plane_ptr(up + pix, (uint32_t)c, upb), v[c]);
       }
       if (p.stats) {
+        // max with 3-input FMNMX, then the first index that equals it (2 instructions per class instead
+        // of the 3 of a compare-select-select chain). A NaN logit poisons the entropy anyway.
         float m = v[0];
-        int am = 0;
 #pragma unroll
         for (int c = 1; c < CMAX; ++c)
-          if (c < C && v[c] > m) { m = v[c]; am = c; }   // first maximal index
+          if (c < C) m = fmaxf(m, v[c]);
+        int am = 0;
+#pragma unroll
+        for (int c = CMAX - 1; c >= 1; --c)
+          if (c < C) am = (v[c] == m) ? c : am;
+        am = (v[0] == m) ? 0 : am;
         if (!p.need_ent) {   // argmax only (the final exit): no softmax / entropy
           if (p.amax) p.amax[(int64_t)n * HW + pix] = (uint8_t)am;
           continue;
@@ -156,15 +174,16 @@ __global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 
         if (p.in_kind == 0) {
           // H = ln S - sum e_c z_c / S with z = v - max, e = exp(z); computed in base 2
           const float m2 = m * kLog2e;
-          float S = 0.f, T = 0.f;
+          float Sa[3] = {0.f, 0.f, 0.f}, Ta[3] = {0.f, 0.f, 0.f};   // three interleaved chains (ILP)
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
             if (c < C) {
               const float z2 = fmaf(v[c], kLog2e, -m2);   // (v - m) * log2(e) <= 0
               const float e = ex2_approx(z2);
-              S += e;
-              T = fmaf(e, z2, T);                          // e == 0 contributes 0 (entr(0) = 0)
+              Sa[c % 3] += e;
+              Ta[c % 3] = fmaf(e, z2, Ta[c % 3]);          // e == 0 contributes 0 (entr(0) = 0)
             }
+          const float S = (Sa[0] + Sa[1]) + Sa[2], T = (Ta[0] + Ta[1]) + Ta[2];
           hn = (__log2f(S) - __fdividef(T, S)) * (kLn2 * inv_lnC);
         } else {
           float S = 0.f;
@@ -185,26 +204,19 @@ __global__ void __launch_bounds__(kGateThreads, (CMAX <= 24 ? 4 : (CMAX <= 32 ? 
         if (p.amax) p.amax[(int64_t)n * HW + pix] = (uint8_t)am;
         const bool below = hn < p.tau;
         if (p.mask) p.mask[(int64_t)n * HW + pix] = below ? 1 : 0;
-        acc_ent += (double)hn;
+        acc_ent += hn;
         acc_cnt += below ? 1 : 0;
       }
     }
   }
 
   if (p.part_sum || p.part_cnt) {
-    __shared__ double s_sum[kGateThreads / 32];
-    __shared__ int s_cnt[kGateThreads / 32];
-    double ws = warp_sum(acc_ent);
-    int wc = warp_sum(acc_cnt);
-    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = ws; s_cnt[threadIdx.x >> 5] = wc; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      int k = 0;
-      for (int i = 0; i < kGateThreads / 32; ++i) { t += s_sum[i]; k += s_cnt[i]; }
-      const int64_t slot = (int64_t)n * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x;
-      if (p.part_sum) p.part_sum[slot] = t;
-      if (p.part_cnt) p.part_cnt[slot] = k;
+    const double ws = warp_sum((double)acc_ent);
+    const int wc = warp_sum(acc_cnt);
+    if ((threadIdx.x & 31) == 0) {
+      const int64_t slot = (int64_t)n * (xgroups * strips) + irem;
+      if (p.part_sum) p.part_sum[slot] = ws;
+      if (p.part_cnt) p.part_cnt[slot] = wc;
     }
   }
 }
@@ -289,7 +301,8 @@ __global__ void decide_kernel(const float* __restrict__ score, int N, float tau,
 
 template <typename TI, typename TO>
 static int launch_gate(const GateParams& p, bool interp, bool vec, cudaStream_t stream) {
-  dim3 grid((p.W + kGateThreads - 1) / kGateThreads, (p.H + kRowsPerStrip - 1) / kRowsPerStrip, p.N);
+  const int64_t items = (int64_t)((p.W + 31) / 32) * ((p.H + kRowsPerStrip - 1) / kRowsPerStrip) * p.N;
+  dim3 grid((unsigned)((items + kGateThreads / 32 - 1) / (kGateThreads / 32)));
 #define EESEG_GATE_CASE(CM)                                                                        \
   if (p.C <= CM) {                                                                                  \
     if (interp && vec) gate_kernel<TI, TO, CM, true, true><<<grid, kGateThreads, 0, stream>>>(p);   \
@@ -328,7 +341,7 @@ static int dispatch_gate(const GateParams& p, int in_dtype, int up_dtype, cudaSt
 using namespace eeseg;
 
 extern "C" int eeseg_exit_gate_num_partials(int H, int W) {
-  return ((W + kGateThreads - 1) / kGateThreads) * ((H + kRowsPerStrip - 1) / kRowsPerStrip);
+  return ((W + 31) / 32) * ((H + kRowsPerStrip - 1) / kRowsPerStrip);
 }
 
 extern "C" int eeseg_exit_gate_pixels(const void* in, int in_dtype, int in_kind, int64_t in_sn,
@@ -344,6 +357,7 @@ extern "C" int eeseg_exit_gate_pixels(const void* in, int in_dtype, int in_kind,
   EESEG_REQUIRE(!amax || C <= 256, "exit_gate: uint8 argmax needs C <= 256");
   EESEG_REQUIRE((int64_t)h * in_sy < (1ll << 31) && (int64_t)w * in_sx < (1ll << 31) && (int64_t)C * in_sc < (1ll << 31),
                 "exit_gate: one low-res image must span fewer than 2^31 elements");
+  EESEG_REQUIRE((int64_t)H * W < (1ll << 29), "exit_gate: H*W must be < 2^29 pixels");
   if (N == 0) return EESEG_OK;
   GateParams p;
   p.in = in; p.in_sn = in_sn; p.in_sc = in_sc; p.in_sy = in_sy; p.in_sx = in_sx;

@@ -234,8 +234,8 @@ def multi_exit_ce(y, targets, ignore_index=-100, coef=None):
     _cuda(targets, "targets")
     if y.dim() < 4:
         raise ValueError("y_pred must be [E,N,C,...]")
-    if not y.is_contiguous() or y.data_ptr() % 16:
-        y = y.clone(memory_format=torch.contiguous_format)   # gradient buffer shares the 16 B phase
+    if not y.is_contiguous():
+        y = y.contiguous()
     E, N = y.shape[:2]
     tg = targets.reshape(N, -1)
     if tg.dtype != torch.int64:
