@@ -29,28 +29,51 @@ sys.path.insert(0, ROOT)
 
 SECTIONS = [16, 3, 1]      # SURVEY.md §3.1 probe: n=2 -> heads on Cin = 1024, 2048
 N_CLASSES = 21
-IMG = 513
+IMG = 513                  # int (square) or (H, W)
 PER_GPU_BATCH = 4
 TAU = 0.5
+METRIC = "early_exit_images_per_sec_513"
+WORKLOAD_NAME = "synthetic VOC 21-class 513x513"
+
+# --workload: the default is the configuration BASELINE.json's metric is quoted on (configs[1] at one
+# GPU's share); "cityscapes" is configs[4]'s shape (full-resolution 1024x2048, 19 classes)
+WORKLOADS = {
+    "voc513": dict(N_CLASSES=21, IMG=513, PER_GPU_BATCH=4, METRIC="early_exit_images_per_sec_513",
+                   WORKLOAD_NAME="synthetic VOC 21-class 513x513"),
+    "cityscapes": dict(N_CLASSES=19, IMG=(1024, 2048), PER_GPU_BATCH=2, METRIC="early_exit_images_per_sec_1024x2048",
+                       WORKLOAD_NAME="synthetic Cityscapes-shaped 19-class 1024x2048"),
+}
 
 
-def synth_batch(rank, n, img=IMG, n_classes=N_CLASSES):
+def set_workload(name):
+    globals().update(WORKLOADS[name])
+
+
+def img_hw(img=None):
+    img = IMG if img is None else img
+    return (img, img) if isinstance(img, int) else tuple(img)
+
+
+def synth_batch(rank, n, img=None, n_classes=None):
     """seed 1234+rank, randn images, blocky labels at 1/16 resolution, 5 % void."""
     import torch
     import torch.nn.functional as F
+    H, W = img_hw(img)
+    n_classes = N_CLASSES if n_classes is None else n_classes
     g = torch.Generator().manual_seed(1234 + rank)
-    X = torch.randn(n, 3, img, img, generator=g)
-    low = torch.randint(0, n_classes, (n, 1, (img + 15) // 16, (img + 15) // 16), generator=g)
-    y = F.interpolate(low.float(), size=(img, img), mode="nearest").long()
-    void = torch.rand(n, 1, img, img, generator=g) < 0.05
+    X = torch.randn(n, 3, H, W, generator=g)
+    low = torch.randint(0, n_classes, (n, 1, (H + 15) // 16, (W + 15) // 16), generator=g)
+    y = F.interpolate(low.float(), size=(H, W), mode="nearest").long()
+    void = torch.rand(n, 1, H, W, generator=g) < 0.05
     y = torch.where(void, torch.full_like(y, n_classes), y)
     return X, y
 
 
-def head_flops(h, w, n, cins, n_classes=N_CLASSES):
+def head_flops(h, w, n, cins, n_classes=None):
     """Nominal dense FLOPs (2*M*N*K, no discount for taps in the zero padding) of the implicit-GEMM
     launches of one step: per head 1x1 + 3 atrous 3x3 (Cin->256), projection (4*256->256, the pooled
     branch enters as a shift), 3x3 256->256, final 1x1 256->Cpad."""
+    n_classes = N_CLASSES if n_classes is None else n_classes
     M = n * h * w
     cp = (n_classes + 15) // 16 * 16
     tot = 0
@@ -123,6 +146,18 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch from the committed ncu capture of one
+    step of the default workload (profiles/r01_conv_traffic.json); None for other workloads."""
+    if METRIC != "early_exit_images_per_sec_513":
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+            return json.load(f)["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, sample_images=2):
     """The reference's CPU path (oracle port: torchvision fp32 model + numpy/scipy-style entropy gate
@@ -130,7 +165,7 @@ def cpu_reference_run(steps, warmup, sample_images=2):
     import torch
     from oracle import model_port
     torch.set_num_threads(os.cpu_count() or 1)
-    net = model_port.build_port(SECTIONS, seed=0).eval()
+    net = model_port.build_port(SECTIONS, seed=0, num_classes=N_CLASSES).eval()
     X, y = synth_batch(0, sample_images)
     times = []
     for it in range(warmup + steps):
@@ -142,7 +177,7 @@ def cpu_reference_run(steps, warmup, sample_images=2):
     mean = sum(times) / len(times)
     return {"value": sample_images / mean, "unit": "images/s", "cores": torch.get_num_threads(),
             "kind": "port", "ms_per_step": mean * 1e3,
-            "sample": f"{sample_images} images of 513x513 per step x {steps} steps (+{warmup} warm-up), "
+            "sample": f"{sample_images} images of {img_hw()[0]}x{img_hw()[1]} per step x {steps} steps (+{warmup} warm-up), "
                       f"fp32, 3 exits, oracle/model_port.evaluate_batch_cpu"}
 
 
@@ -154,7 +189,7 @@ def run_reference(args):
     warmup = max(1, min(args.warmup, 1))
     cb = cpu_reference_run(steps, warmup)
     line = {
-        "impl": "reference", "metric": "early_exit_images_per_sec_513", "value": cb["value"], "unit": "images/s",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
@@ -168,7 +203,7 @@ def run_reference(args):
 
 def workload_config(n_gpus):
     return {"workload": "BranchyDeepLabV3 ResNet-50, 3 exits (sections 16/3/1, heads Cin 1024/2048/2048), "
-                        "entropy-threshold early-exit inference, synthetic VOC 21-class 513x513",
+                        f"entropy-threshold early-exit inference, {WORKLOAD_NAME}",
             "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "tau": TAU,
             "parallelism": f"dp{n_gpus}", "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -179,10 +214,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="eeseg", choices=["eeseg", "reference"])
+    ap.add_argument("--workload", default="voc513", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the conv kernel")
     args = ap.parse_args()
+    set_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -208,7 +245,8 @@ def main():
     if args.no_pdl:
         _lib.lib().eeseg_conv_set_pdl(0)
     torch.manual_seed(0)
-    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, IMG, sections=SECTIONS, pretrained=False).to(dev).eval()
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, img_hw()[0], sections=SECTIONS, pretrained=False,
+                        num_classes=N_CLASSES).to(dev).eval()
     eng = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=not args.no_graph)
     Xh, yh = synth_batch(rank, PER_GPU_BATCH)
     Xh, yh = Xh.pin_memory(), yh.pin_memory()
@@ -308,6 +346,20 @@ def main():
     else:
         e2e_ms, _ = timed(step_e2e, steps)
 
+    # ---- an early-exit operating point: tau between the middle first-exit scores of the batch, so
+    # half of the images leave at exit 1; timed through the compute-skipping engine (still-active
+    # images are compacted after every gate: later sections run on fewer images)
+    sc0 = eng.evaluate(Xd, yd)["scores"][0].float().cpu().sort().values
+    mid = (len(sc0) - 1) // 2
+    tau_mid = float((sc0[mid] + sc0[mid + 1]) / 2) if len(sc0) > 1 else float(sc0[0]) + 1.0
+    eng_skip = EarlyExitEngine(net, N_CLASSES, tau_mid, skip_compute=True)
+    for _ in range(3):
+        eng_skip.evaluate(Xd, yd)
+    eng_skip.reset()
+    skip_ms, _ = timed(lambda: eng_skip.evaluate(Xd, yd), steps)
+    skip_counts = [int(v) for v in eng_skip.counts.cpu()]
+    skip_px = [int(v) for v in eng_skip.exited_px.cpu()]
+
     # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
     prof = []
     eng_prof = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=False)   # same kernels, launched eagerly
@@ -327,6 +379,19 @@ def main():
         prof_steps.append((sa, sb))
     torch.cuda.synchronize()
     head_plan.PROFILE = None
+    # the same launches on the kernel's own clock (%globaltimer: first CTA start -> last CTA end of every
+    # launch, no events between the launches, so programmatic dependent launch overlaps as in the graph)
+    tcap = 512
+    tbuf = torch.zeros((tcap, 2), dtype=torch.int64, device=dev)
+    tbuf[:, 0] = torch.iinfo(torch.int64).max
+    torch.cuda.synchronize()
+    _lib.lib().eeseg_conv_timing(tbuf.data_ptr(), tcap)
+    torch.cuda._sleep(int(2e7))
+    eng_prof.evaluate(Xd, yd)
+    torch.cuda.synchronize()
+    n_t = _lib.lib().eeseg_conv_timing(None, 0)
+    tb = tbuf[:n_t].cpu()
+    inkernel_ms = float((tb[:, 1] - tb[:, 0]).sum()) / 1e6
     prof_step_ms = sum(a.elapsed_time(b) for a, b in prof_steps)
     clocks = sampler.stop() if rank == 0 else {}
     conv_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
@@ -335,23 +400,23 @@ def main():
     head_fl = sum(p[2] for p in prof if p[3] == "head")
     n_conv = len(prof)
 
-    t = torch.tensor([dev_ms, e2e_ms, conv_ms, head_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, conv_ms, head_ms, skip_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, conv_ms, head_ms = (float(v) for v in t.cpu())
+    dev_ms, e2e_ms, conv_ms, head_ms, skip_ms = (float(v) for v in t.cpu())
 
     if rank == 0:
         peaks = measured_peaks()
         imgs = PER_GPU_BATCH * world * steps
-        h = (IMG - 1) // 8 + 1
-        assert head_fl == head_flops(h, h, PER_GPU_BATCH, [1024, 2048, 2048]) * steps, "head FLOP model out of date"
+        fh, fw = ((d - 1) // 8 + 1 for d in img_hw())
+        assert head_fl == head_flops(fh, fw, PER_GPU_BATCH, [1024, 2048, 2048]) * steps, "head FLOP model out of date"
         fl = conv_fl
         achieved = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         head_tf = head_fl / (head_ms * 1e-3) / 1e12 if head_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
         res = eng.results()
         line = {
-            "metric": "early_exit_images_per_sec_513", "value": imgs / (dev_ms * 1e-3), "unit": "images/s",
+            "metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(world),
@@ -366,7 +431,7 @@ def main():
             "roofline": {"kernel": f"conv_igemm_kernel (tcgen05 implicit GEMM, {n_conv // steps} launches/step: "
                                    "exit heads + ResNet bottlenecks)",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": conv_traffic(),
                          "exit_heads_only": {"achieved": head_tf, "frac": head_tf / peak,
                                              "ms_per_step": head_ms / steps, "flops_per_step": head_fl / steps},
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
@@ -375,10 +440,23 @@ def main():
                          "timing": "CUDA events around every conv launch of an eagerly launched step (GPU parked first so "
                                    "launches are back to back); the per-launch events cost ~15 % over the graph replay",
                          "eager_event_step_ms": prof_step_ms / steps,
+                         "in_kernel_clock": {"conv_ms_per_step": inkernel_ms,
+                                             "achieved": (fl / steps) / (inkernel_ms * 1e-3) / 1e12 if inkernel_ms > 0 else None,
+                                             "frac": (fl / steps) / (inkernel_ms * 1e-3) / 1e12 / peak if inkernel_ms > 0 else None,
+                                             "how": "sum over one step's conv launches of (last CTA end - first CTA start) on "
+                                                    "%globaltimer, launches not separated by events"},
                          "flops_per_step": fl / steps},
             "clocks": clocks,
             "wall_ms_timed_region": wall_ms,
             "exit_stats": {k: res[k] for k in ("b1_count", "b2_count", "count_out", "out_gl")},
+            "early_exit_operating_point": {
+                "tau": tau_mid, "value": imgs / (skip_ms * 1e-3), "unit": "images/s", "ms_per_step": skip_ms / steps,
+                "mode": "skip_compute engine (eager launches, one 4-byte D2H per gate for the active count), rank 0 counters",
+                "images_per_exit": skip_counts[:-1],
+                "pct_images_exited_early": 100.0 * sum(skip_counts[:-2]) / max(1, skip_counts[-1]),
+                "pct_pixels_below_tau_per_gate": [100.0 * px / max(1, PER_GPU_BATCH * steps * img_hw()[0] * img_hw()[1])
+                                                  for px in skip_px[:-1]],
+            },
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_reference_run(steps=3, warmup=1)

@@ -27,6 +27,9 @@ static inline int ce_grid_x(int E, int N, int64_t HW) {
 
 __global__ void count_valid_kernel(const int64_t* __restrict__ targets, int64_t total, int C,
                                    int64_t ignore, unsigned long long* __restrict__ out) {
+  // programmatic dependent launch: the CE kernel behind us may start loading logits right away; it
+  // waits (griddepcontrol.wait) for this grid to finish before it reads the count
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   int cnt = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -91,6 +94,9 @@ __global__ void __launch_bounds__(kCeThreads) ce_kernel(
     vt[j] = 0.f;
     if (ok) vt[j] = ldf(plane_ptr(logits + (int64_t)(eg + j) * exit_stride + (int64_t)n * C * HW + p, t, pb));
   }
+  // everything above touched only tensors that were complete before the preceding kernel in the
+  // stream (count_valid_kernel) started; its result is needed from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float vinv = 0.f;
   if (dlogits) vinv = 1.f / (float)(*valid_count);   // valid == 0 -> inf; only ok pixels use it
   float loss[EB];
@@ -170,41 +176,56 @@ __global__ void scale_exits_kernel(T* __restrict__ d, int64_t exit_stride, int64
     stf(p + i, ldf(p + i) * r);
 }
 
+template <typename T, int CMAX, int EB>
+static int launch_ce_one(dim3 grid, bool pdl, const T* logits, int64_t exit_stride, const int64_t* targets, int e0,
+                         int N, int C, int64_t HW, int64_t ignore, const float* coef, const int64_t* valid_count,
+                         T* dlogits, double* part, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kCeThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EESEG_CUDA(cudaLaunchKernelEx(&cfg, ce_kernel<T, CMAX, EB>, logits, exit_stride, targets, e0, N, C, HW, ignore, coef,
+                                valid_count, dlogits, part));
+  return check_launch("ce_kernel");
+}
+
+// `pdl`: the launch directly follows count_valid_kernel in the stream and may overlap it
 template <typename T, int CMAX, int EBMAX>
 static int launch_ce_cfg(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                          int C, int64_t HW, int64_t ignore, const float* coef,
-                         const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
+                         const int64_t* valid_count, T* dlogits, double* part, bool pdl, cudaStream_t stream) {
   // exits in groups of 3 (2, 1 for the remainder): a thread holds the logits of all exits of a group
   const unsigned gx = (unsigned)ce_grid_x(E, N, HW);
   int e0 = 0;
   if (EBMAX >= 3 && E >= 3) {
-    ce_kernel<T, CMAX, (EBMAX >= 3 ? 3 : 1)><<<dim3(gx, N, E / 3), kCeThreads, 0, stream>>>(
-        logits, exit_stride, targets, 0, N, C, HW, ignore, coef, valid_count, dlogits, part);
-    int rc = check_launch("ce_kernel");
+    int rc = launch_ce_one<T, CMAX, (EBMAX >= 3 ? 3 : 1)>(dim3(gx, N, E / 3), pdl, logits, exit_stride, targets, 0, N, C, HW,
+                                                         ignore, coef, valid_count, dlogits, part, stream);
     if (rc) return rc;
     e0 = E / 3 * 3;
+    pdl = false;
   }
-  if (EBMAX >= 2 && E - e0 == 2) {
-    ce_kernel<T, CMAX, (EBMAX >= 2 ? 2 : 1)><<<dim3(gx, N, 1), kCeThreads, 0, stream>>>(
-        logits, exit_stride, targets, e0, N, C, HW, ignore, coef, valid_count, dlogits, part);
-    return check_launch("ce_kernel");
-  }
-  if (E - e0 >= 1) {
-    ce_kernel<T, CMAX, 1><<<dim3(gx, N, E - e0), kCeThreads, 0, stream>>>(
-        logits, exit_stride, targets, e0, N, C, HW, ignore, coef, valid_count, dlogits, part);
-    return check_launch("ce_kernel");
-  }
+  if (EBMAX >= 2 && E - e0 == 2)
+    return launch_ce_one<T, CMAX, (EBMAX >= 2 ? 2 : 1)>(dim3(gx, N, 1), pdl, logits, exit_stride, targets, e0, N, C, HW, ignore,
+                                                       coef, valid_count, dlogits, part, stream);
+  if (E - e0 >= 1)
+    return launch_ce_one<T, CMAX, 1>(dim3(gx, N, E - e0), pdl, logits, exit_stride, targets, e0, N, C, HW, ignore, coef,
+                                     valid_count, dlogits, part, stream);
   return EESEG_OK;
 }
 
 template <typename T>
 static int launch_ce(const T* logits, int64_t exit_stride, const int64_t* targets, int E, int N,
                      int C, int64_t HW, int64_t ignore, const float* coef,
-                     const int64_t* valid_count, T* dlogits, double* part, cudaStream_t stream) {
-  if (C == 21) return launch_ce_cfg<T, 21, 3>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
-  if (C == 19) return launch_ce_cfg<T, 19, 3>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
-  if (C <= 32) return launch_ce_cfg<T, 32, 2>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
-  if (C <= 64) return launch_ce_cfg<T, 64, 1>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, stream);
+                     const int64_t* valid_count, T* dlogits, double* part, bool pdl, cudaStream_t stream) {
+  if (C == 21) return launch_ce_cfg<T, 21, 3>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, pdl, stream);
+  if (C == 19) return launch_ce_cfg<T, 19, 3>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, pdl, stream);
+  if (C <= 32) return launch_ce_cfg<T, 32, 2>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, pdl, stream);
+  if (C <= 64) return launch_ce_cfg<T, 64, 1>(logits, exit_stride, targets, E, N, C, HW, ignore, coef, valid_count, dlogits, part, pdl, stream);
   set_error("multi_exit_ce: C=%d > 64 classes is not supported by this build", C);
   return EESEG_ERR_UNSUPPORTED;
 }
@@ -239,11 +260,11 @@ extern "C" int eeseg_multi_exit_ce_fwd(const void* logits, int dtype, int64_t ex
   double* part = reinterpret_cast<double*>(workspace);
   if (dtype == EESEG_F32)
     rc = launch_ce<float>((const float*)logits, exit_stride, targets, E, N, C, HW, ignore_index,
-                          coef, valid_count, (float*)dlogits, part, stream);
+                          coef, valid_count, (float*)dlogits, part, true, stream);
   else
     rc = launch_ce<__nv_bfloat16>((const __nv_bfloat16*)logits, exit_stride, targets, E, N, C, HW,
                                   ignore_index, coef, valid_count, (__nv_bfloat16*)dlogits, part,
-                                  stream);
+                                  true, stream);
   if (rc) return rc;
   ce_finalize_kernel<<<E, 256, 0, stream>>>(part, N * ce_grid_x(E, N, HW), valid_count, per_exit);
   return check_launch("ce_finalize_kernel");
@@ -261,10 +282,10 @@ extern "C" int eeseg_multi_exit_ce_bwd(const void* logits, int dtype, int64_t ex
   EESEG_REQUIRE(dtype == EESEG_F32 || dtype == EESEG_BF16, "multi_exit_ce_bwd: dtype %d", dtype);
   if (dtype == EESEG_F32)
     return launch_ce<float>((const float*)logits, exit_stride, targets, E, N, C, HW, ignore_index, g,
-                            valid_count, (float*)dlogits, nullptr, stream);
+                            valid_count, (float*)dlogits, nullptr, false, stream);
   return launch_ce<__nv_bfloat16>((const __nv_bfloat16*)logits, exit_stride, targets, E, N, C, HW,
                                   ignore_index, g, valid_count, (__nv_bfloat16*)dlogits, nullptr,
-                                  stream);
+                                  false, stream);
 }
 
 extern "C" int eeseg_scale_exits(void* dlogits, int dtype, int64_t exit_stride, int E,
