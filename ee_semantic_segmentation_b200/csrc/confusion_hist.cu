@@ -77,15 +77,20 @@ __global__ void __launch_bounds__(256) cm_from_logits_kernel(const T* __restrict
   hist_flush(hist, copies, bins, cm + (int64_t)n * bins);
 }
 
-// torch.argmax treats NaN as the maximum and returns the first one. Kept out of line (and re-reading
-// the pixel) so that the hot loop carries no NaN bookkeeping.
+// torch.argmax treats NaN as the maximum and returns the first one. Pixels with a NaN (or inf - inf)
+// logit are redone here, out of line and re-reading the pixel, so that the hot loop carries no NaN
+// bookkeeping beyond one add per class.
 template <typename T>
-__device__ __noinline__ int first_nan_class(const T* px, int C, uint32_t plane_bytes) {
-  for (int c = 0; c < C; ++c) {
+__device__ __noinline__ int argmax_with_nan(const T* px, int C, uint32_t plane_bytes) {
+  float best = ldf(px);
+  int arg = 0;
+  if (best != best) return 0;
+  for (int c = 1; c < C; ++c) {
     const float v = ldf(plane_ptr(px, (uint32_t)c, plane_bytes));
     if (v != v) return c;
+    if (v > best) { best = v; arg = c; }
   }
-  return 0;
+  return arg;
 }
 
 // Default for logits: thread = PIX pixels (strided by the block), all C class values of those pixels
@@ -120,18 +125,20 @@ __global__ void __launch_bounds__(THREADS) cm_from_logits_direct_kernel(
 #pragma unroll
   for (int j = 0; j < PIX; ++j) {
     const int64_t p = p0 + j * THREADS;
-    // torch.argmax: first maximal index, NaN counts as the maximum. One unordered compare per class
-    // ("greater or NaN") is exact as long as the running best is not NaN; the rare NaN pixel is redone.
-    float best = v[j][0];
+    // torch.argmax: first maximal index, NaN counts as the maximum. Hot loop: one compare + two selects
+    // per class; the running sum (FMA pipe, off the compare/select pipe) turns NaN if any logit is NaN
+    // (or for inf - inf) and sends that rare pixel to the exact out-of-line path.
+    float best = v[j][0], nan_probe = v[j][0];
     int arg = 0;
 #pragma unroll
     for (int c = 1; c < CMAX; ++c)
       if (c < C) {
-        const bool take = !(v[j][c] <= best);
+        const bool take = v[j][c] > best;
         best = take ? v[j][c] : best;
         arg = take ? c : arg;
+        nan_probe += v[j][c];
       }
-    if (best != best) arg = first_nan_class(base + p, C, pb);   // rare; out of line, re-reads the pixel
+    if (nan_probe != nan_probe && p < HW) arg = argmax_with_nan(base + p, C, pb);
     const int tt = (t[j] >= 0 && t[j] < C) ? (int)t[j] : C;
     hist_add(h, p < HW ? tt * C + arg : -1);   // whole warps reach this together (match.any)
   }

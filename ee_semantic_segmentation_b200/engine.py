@@ -27,6 +27,8 @@ class EarlyExitEngine:
         reads the active count on the host)."""
         assert not (use_graph and skip_compute), "CUDA-graph replay needs a static step"
         self.use_graph = use_graph
+        self.overlap_gates = True      # early-exit gates on a side stream, overlapping the next section
+        self._side = None
         self._graphs = {}
         self.net = net
         self.C = n_classes
@@ -43,6 +45,11 @@ class EarlyExitEngine:
         self.cm = torch.zeros((self.E + 1, n_classes + 1, n_classes), dtype=torch.int64, device=dev)
         self.counts = torch.zeros((self.E + 1,), dtype=torch.int64, device=dev)
         self.exited_px = torch.zeros((self.E,), dtype=torch.int64, device=dev)
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def reset(self):
         self.cm.zero_(); self.counts.zero_(); self.exited_px.zero_()
@@ -165,20 +172,39 @@ class EarlyExitEngine:
         amax_all = torch.empty((E, N, H, W), dtype=torch.uint8, device=dev)
         scores = torch.full((max(E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)
         pool = self.metric != 'ent'
+        # The gate of an early exit (up-sample + entropy + decision, ~35 us of small kernels) does not feed
+        # the next backbone section: it runs on a side stream, forked when the head's low-res logits are
+        # ready and joined before the final accumulation, so it overlaps the next section's convolutions
+        # (the gate CTAs need no shared memory and fit next to the persistent conv CTAs). Captured into the
+        # CUDA graph as a parallel branch; all gates share the one side stream, so decisions stay ordered.
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream()
+        keep = []          # tensors produced on `main` and read on `side` stay referenced until the join
+        forked = False
         Xc = X
         for i in range(E):
             Xc = net.run_section(i, Xc)
             low = net._plan(i).run(Xc)
             gated = i < E - 1 and i >= self.skip
-            res = ops.exit_gate(low, (H, W), layout='NHWC', n_classes=self.C, tau=self.tau,
-                                want_ent=pool and gated, want_amax=True, want_score=gated and not pool,
-                                amax_out=amax_all[i], score_out=scores[i] if gated and not pool else None)
-            if gated:
-                if pool:
-                    scores[i] = ops.entropy_pool_mean(res.ent, self.size, self.metric == 'min')
-                else:
-                    self.exited_px[i] += res.exited_px.sum()
-                ops.gate_decide(scores[i], self.tau, i, exit_idx, want_active=False)
+            on_side = self.overlap_gates and i < E - 1
+            if on_side:
+                side.wait_stream(main)
+                keep.append(low)
+                forked = True
+            with torch.cuda.stream(side if on_side else main):
+                res = ops.exit_gate(low, (H, W), layout='NHWC', n_classes=self.C, tau=self.tau,
+                                    want_ent=pool and gated, want_amax=True, want_score=gated and not pool,
+                                    amax_out=amax_all[i], score_out=scores[i] if gated and not pool else None)
+                if gated:
+                    if pool:
+                        scores[i] = ops.entropy_pool_mean(res.ent, self.size, self.metric == 'min')
+                    else:
+                        self.exited_px[i] += res.exited_px.sum()
+                    ops.gate_decide(scores[i], self.tau, i, exit_idx, want_active=False)
+                if on_side:
+                    keep.append(res)
+        if forked:
+            main.wait_stream(side)
         if targets is not None:
             # one kernel: final-exit assignment, histogram of the map each image took, accumulators, pred
             pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)

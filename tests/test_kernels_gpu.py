@@ -364,3 +364,91 @@ def test_lovasz_cityscapes_crop_vs_oracle():
     ref, rg = R.lovasz_softmax(y[0].numpy(), tgt.numpy(), ignore=19)
     assert per.item() == pytest.approx(float(ref), rel=1e-4)
     np.testing.assert_allclose(yd.grad[0].cpu().numpy(), rg, rtol=2e-3, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------ code paths of the
+# register-resident streaming kernels (exit groups of 3/2/1, ragged block tails, NaN argmax)
+@pytest.mark.parametrize("E", [1, 2, 4, 5, 7])
+@pytest.mark.parametrize("C,dtype", [(21, torch.float32), (19, torch.bfloat16), (7, torch.float32), (40, torch.float32)])
+def test_ce_exit_groups_and_weights_vs_oracle(E, C, dtype):
+    """E exits run as launches of 3-, 2- and 1-exit groups (one thread holds a group's logits): every
+    split, with per-exit weights, an odd plane size (unaligned planes) and a ragged last block."""
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    g = torch.Generator().manual_seed(100 + E + C)
+    N, H, W = 2, 37, 29                       # 1073 pixels: odd, not a multiple of the 256-pixel block
+    y = (torch.randn(E, N, C, H, W, generator=g) * 4).to(dtype)
+    tgt = blocky(g, N, C, H, W, void_frac=0.2, cell=5)
+    w = [float(v) for v in torch.rand(E, generator=g) + 0.5]
+    yd = y.to(dev()).requires_grad_(True)
+    loss = BrXEntropyLoss(ignore_index=C, b_reduction="sum", n_exits=E, weights=w)(yd, tgt.to(dev()))
+    loss.backward()
+    ref_loss, ref_grad, _ = R.br_xentropy(y.float().numpy(), tgt.numpy(), ignore_index=C, b_reduction="sum",
+                                          n_exits=E, weights=w)
+    rtol = 1e-4 if dtype == torch.float32 else 1e-2
+    np.testing.assert_allclose(loss.item(), ref_loss, rtol=rtol)
+    np.testing.assert_allclose(yd.grad.float().cpu().numpy(), ref_grad, rtol=rtol,
+                               atol=1e-9 if dtype == torch.float32 else 2e-6)
+
+
+def test_ce_target_class_gradient_is_softmax_minus_one():
+    """The target class is written twice by its thread (softmax*g, then softmax*g - g): the second store
+    must win, for every class index including 0 and C-1."""
+    from ee_semantic_segmentation_b200 import ops
+    C, H, W = 21, 3, 21
+    y = torch.zeros(3, 1, C, H, W, device=dev())                       # uniform softmax = 1/C
+    tgt = (torch.arange(H * W, device=dev()) % C).view(1, H, W)
+    yd = y.requires_grad_(True)
+    per, valid = ops.multi_exit_ce(yd, tgt, -100)
+    per.sum().backward()
+    gr = yd.grad.cpu().numpy() * (H * W)
+    onehot = np.eye(C, dtype=np.float32)[tgt.cpu().numpy()[0]].transpose(2, 0, 1)   # [C,H,W]
+    for e in range(3):
+        np.testing.assert_allclose(gr[e, 0], 1.0 / C - onehot, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(per.detach().cpu().numpy(), np.log(C), rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_confusion_hist_nan_and_ragged_tail(dtype):
+    """torch.argmax semantics: NaN is the maximum, the FIRST NaN / first maximum wins; 513*3 pixels leave
+    a ragged last block (2 pixels per thread, 512 per block)."""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    N, C, H, W = 2, 21, 3, 513
+    lg = torch.randn(N, C, H, W, generator=g).to(dtype)
+    lg[0, 5, 1, 7] = float("nan")
+    lg[0, 9, 1, 7] = float("nan")             # first NaN (class 5) wins
+    lg[1, 20, 2, 512] = float("nan")          # last pixel of the image, last class
+    lg[1, 0, 0, 0] = float("nan")
+    lg[0, 3, 0, 100] = lg[0, :, 0, 100].float().max().to(dtype) + 1
+    lg[0, 11, 0, 100] = lg[0, 3, 0, 100]      # tie: class 3 wins
+    tgt = torch.randint(0, C + 1, (N, H, W), generator=g)
+    cm = ops.confusion_hist(lg.to(dev()), tgt.to(dev()), C).cpu()
+    pred = lg.float().argmax(1)
+    assert pred[0, 1, 7] == 5 and pred[1, 2, 512] == 20 and pred[1, 0, 0] == 0 and pred[0, 0, 100] == 3
+    ref = torch.zeros(N, C + 1, C, dtype=torch.int64)
+    for n in range(N):
+        ref[n].view(-1).index_add_(0, (tgt[n].clamp(max=C) * C + pred[n]).view(-1), torch.ones(H * W, dtype=torch.int64))
+    assert torch.equal(cm, ref)
+
+
+@pytest.mark.parametrize("H,W", [(9, 31), (17, 33), (8, 64), (23, 97)])
+def test_gate_warp_items_ragged_shapes(H, W):
+    """The gate deals (32 columns x 8 rows) items to warps from a flat index: widths around the 32-column
+    group size, heights around the 8-row strip, partial sums in item order."""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(H * 100 + W)
+    N, C, h, w = 3, 21, 5, 7
+    low = torch.randn(N, C, h, w, generator=g) * 3
+    res = ops.exit_gate(low.to(dev()), (H, W), tau=0.8, want_ent=True, want_mask=True, up_dtype=torch.float32)
+    up = R.bilinear_upsample(low.numpy(), (H, W))
+    ent = np.stack([R.pixel_norm_entropy(R.softmax_c(u, 0), C) for u in up])
+    np.testing.assert_allclose(res.up_logits.cpu().numpy(), up, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(res.ent.cpu().numpy(), ent, atol=1e-4)
+    np.testing.assert_allclose(res.score.cpu().numpy(), ent.reshape(N, -1).mean(1), atol=1e-5)
+    near = np.abs(ent - 0.8) < 1e-4
+    assert np.all((res.mask.cpu().numpy() == (ent < 0.8)) | near)
+    am = res.amax.cpu().numpy()
+    top2 = np.sort(up, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-4          # argmax is unambiguous
+    assert np.all((am == up.argmax(1)) | ~clear)
+    assert int(res.exited_px.sum()) == int(res.mask.sum())
