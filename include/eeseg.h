@@ -178,6 +178,32 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
                          int dilation, int stride, int pad, int relu, const void* residual, int64_t ldr,
                          void* out, int out_dtype, int64_t ldo, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training: gradients of the stride-1 'same' convolutions of the exit heads (the backward of the
+ * DeepLabHead / ASPP convolutions under train_epoch, train_funcs.py:22-27; the reference gets them from
+ * autograd through cuDNN).
+ *
+ * eeseg_conv_igemm_wgrad:  dW[co][r][s][ci] = sum_{n,y,x} dY[n,y,x,co] * X[n, y+r*dil-pad, x+s*dil-pad, ci]
+ *   tcgen05 implicit GEMM with the pixels as the contraction dimension (both operands MN-major, TMA boxes of
+ *   NHWC tensors; the tap is a coordinate offset, zero fill = padding).
+ *   x  bf16 NHWC [N][h][w][Cin] (Cin % 64 == 0);  dy bf16 NHWC, pixel stride ldy, dy_channels channels in
+ *   total, this convolution's Cout (% 128 == 0) channels starting at co_off;  dw fp32 [Cout][R][S][Cin]
+ *   (overwritten; summed with atomics when the pixel dimension is split over CTAs to fill the GPU).
+ *
+ * eeseg_conv_igemm_dgrad:  dX = conv(dY, W'), W'[ci][r][s][co] = W[co][R-1-r][S-1-s][ci], on the forward
+ *   kernel. dy bf16 NHWC contiguous [N][h][w][Cout] (Cout % 64 == 0), wt bf16 [Cout][R][S][Cin]
+ *   (Cin % 16 == 0), dx bf16 / fp32 NHWC with pixel stride lddx; workspace of
+ *   eeseg_conv_igemm_dgrad_workspace_bytes bytes (the transformed weights), 256-byte aligned.
+ * eeseg_conv_weight_rot180_t: the weight transform alone ([Cout][R][S][Cin] -> [Cin][R][S][Cout], taps
+ *   rotated by 180 degrees), for callers that cache it.
+ * ---------------------------------------------------------------------------------------------- */
+int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
+                           int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* stream);
+size_t eeseg_conv_igemm_dgrad_workspace_bytes(int Cin, int Cout, int R, int S);
+int eeseg_conv_igemm_dgrad(const void* dy, const void* wt, int N, int h, int w, int Cin, int Cout, int R, int S,
+                           int dilation, void* dx, int dx_dtype, int64_t lddx, void* workspace, void* stream);
+int eeseg_conv_weight_rot180_t(const void* w, int Cout, int R, int S, int Cin, void* out, void* stream);
+
 /* ResNet stem helpers (base_model[0][0:4], torchvision resnet.py conv1/bn1/relu/maxpool):
  * space-to-depth (2x2) plus horizontal tap unrolling of the fp32 NCHW image, so that the 7x7 / stride-2 /
  * pad-3 convolution becomes a 4x1 / stride-1 / pad-2 implicit GEMM with K = 4 taps x 64 channels:

@@ -32,7 +32,7 @@ def test_every_header_symbol_is_exported_and_bound(libpath):
 
 def test_pure_host_entry_points(libpath):
     l = _lib.lib()
-    assert l.eeseg_exit_gate_num_partials(513, 513) == 5 * 65
+    assert l.eeseg_exit_gate_num_partials(513, 513) == 17 * 65   # 32-column groups x 8-row strips
     assert l.eeseg_multi_exit_ce_workspace_bytes(3, 2, 513 * 513) > 0
     assert l.eeseg_lovasz_workspace_bytes(3, 1, 19, 768 * 768) >= 16 * 19 * 768 * 768
     assert _lib.launch_count() == 0

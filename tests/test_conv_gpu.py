@@ -187,3 +187,60 @@ def test_grouped_conv_matches_separate_launches():
     conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, out, 4 * mid, 4 * mid, sched)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+# ------------------------------------------------------------------------------------ training: gradients
+def run_conv_grads(N, h, w, Cin, Cout, R, dil, seed=0, co_off=0, extra=0):
+    """eeseg_conv_igemm_wgrad / _dgrad against autograd through F.conv2d in fp32 on the same bf16-rounded
+    operands. dY may be a channel window [co_off, co_off+Cout) of a wider NHWC buffer (extra channels)."""
+    import ctypes
+    from ee_semantic_segmentation_b200 import _lib
+    from ee_semantic_segmentation_b200._lib import check, lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, h, w, Cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(Cout, R, R, Cin, generator=g) / np.sqrt(R * R * Cin)).to(torch.bfloat16)
+    dy_full = torch.randn(N, h, w, Cout + extra, generator=g).to(torch.bfloat16)
+    dy = dy_full[..., co_off:co_off + Cout]
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.conv2d(xr, wr, padding=dil * (R // 2), dilation=dil).backward(dy.float().permute(0, 3, 1, 2))
+    ref_dw = wr.grad.permute(0, 2, 3, 1)          # [Cout][R][S][Cin]
+    ref_dx = xr.grad.permute(0, 2, 3, 1)          # NHWC
+    xd, wd, dyd = x.to(dev()), wt.to(dev()), dy_full.to(dev())
+    st = torch.cuda.current_stream().cuda_stream
+    dw = torch.full((Cout, R, R, Cin), 7.0, dtype=torch.float32, device=dev())
+    check(lib().eeseg_conv_igemm_wgrad(xd.data_ptr(), dyd.data_ptr(), Cout + extra, Cout + extra, co_off, N, h, w, Cin, Cout,
+                                       R, R, dil, dw.data_ptr(), st), "wgrad")
+    e_w = (dw.cpu() - ref_dw).abs().max().item() / (ref_dw.abs().max().item() + 1e-9)
+    e_x = None
+    if extra == 0:
+        ws = torch.empty(lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, R), dtype=torch.uint8, device=dev())
+        dx = torch.empty(N, h, w, Cin, dtype=torch.float32, device=dev())
+        check(lib().eeseg_conv_igemm_dgrad(dyd.data_ptr(), wd.data_ptr(), N, h, w, Cin, Cout, R, R, dil, dx.data_ptr(),
+                                           _lib.F32, Cin, ws.data_ptr(), st), "dgrad")
+        e_x = (dx.cpu() - ref_dx).abs().max().item() / (ref_dx.abs().max().item() + 1e-9)
+    torch.cuda.synchronize()
+    return e_w, e_x
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=1, h=16, w=8, Cin=64, Cout=128, R=1, dil=1),             # one exact 128-pixel tile, one MMA block
+    dict(N=1, h=16, w=8, Cin=256, Cout=128, R=3, dil=1),            # taps, zero fill
+    dict(N=2, h=65, w=65, Cin=128, Cout=256, R=3, dil=1),           # ragged 11x11 tiles (7 zero rows per box), K split
+    dict(N=1, h=65, w=65, Cin=192, Cout=128, R=3, dil=12),          # 64-wide ci tiles
+    dict(N=2, h=65, w=65, Cin=256, Cout=256, R=3, dil=36),          # most (tap, tile) pairs all padding
+    dict(N=2, h=33, w=47, Cin=512, Cout=256, R=1, dil=1),           # 1x1, deep K split
+    dict(N=1, h=24, w=40, Cin=320, Cout=256, R=1, dil=1, co_off=64, extra=128),   # dY is a window of a wider buffer
+])
+def test_conv_wgrad_dgrad_vs_autograd(cfg):
+    e_w, e_x = run_conv_grads(**cfg)
+    assert e_w < 5e-3, ("wgrad", e_w)      # fp32 accumulation of bf16 products: far inside the 1e-2 bf16 bound
+    assert e_x is None or e_x < 5e-3, ("dgrad", e_x)
+
+
+def test_conv_grads_aspp_shapes():
+    """The ASPP shapes of the 513x513 training crop (65x65 maps): Cin = 2048, d = 24; the projection K = 1280."""
+    e_w, e_x = run_conv_grads(N=2, h=65, w=65, Cin=2048, Cout=256, R=3, dil=24, seed=3)
+    assert e_w < 5e-3 and e_x < 5e-3, (e_w, e_x)
+    e_w, e_x = run_conv_grads(N=2, h=65, w=65, Cin=1280, Cout=256, R=1, dil=1, seed=4)
+    assert e_w < 5e-3 and e_x < 5e-3, (e_w, e_x)
