@@ -30,7 +30,7 @@ from torch.nn import functional as F
 from torch.utils.flop_counter import FlopCounterMode
 from torchvision.models.segmentation.deeplabv3 import ASPP, DeepLabHead
 
-from . import ops
+from . import head_train, ops
 from .backbone_plan import SectionPlan, supported as _section_supported
 from .head_plan import HeadPlan
 
@@ -128,6 +128,7 @@ class branchyDeepv3(nn.Module):
         self._section_plans = {}
         self.fast_inference = True     # eval-mode CUDA forward on the eeseg kernels
         self.fast_backbone = True      # ... including the ResNet bottlenecks of the sections
+        self.fast_training_heads = True   # autograd forward: head convolutions (fwd/dgrad/wgrad) on eeseg kernels
 
     # ---- construction helpers ---------------------------------------------------------------------
     @staticmethod
@@ -232,15 +233,24 @@ class branchyDeepv3(nn.Module):
         with tch.autocast('cuda', dtype=tch.bfloat16):
             return sec(X.contiguous(memory_format=tch.channels_last))
 
+    def _head_autograd(self, head, X):
+        """head(X) with autograd: the head's convolutions (forward, input and weight gradients) on the
+        eeseg tcgen05 kernels when fast_training_heads is set and the head has the DeepLabHead layout,
+        else the PyTorch modules (cuDNN)."""
+        if self.fast_training_heads and X.is_cuda and head_train.head_supported(head):
+            return head_train.head_forward_train(head, X)
+        return head(X)
+
     def _forward_torch(self, X):
-        """The reference data flow on PyTorch modules (used for training / autograd)."""
+        """The reference data flow with autograd (training): backbone sections on the PyTorch modules,
+        exit heads through _head_autograd."""
         outputs = []
         inp_shape = X.shape[-2:]
         for i in range(self.n_branches):
             X = self.base_model[i](X)
-            br = self.branches[i](X)
+            br = self._head_autograd(self.branches[i], X)
             outputs.append(F.interpolate(br, size=inp_shape, mode='bilinear', align_corners=False).unsqueeze(0))
-        y = self.classifier(self.base_model[-1](X))
+        y = self._head_autograd(self.classifier, self.base_model[-1](X))
         outputs.append(F.interpolate(y, size=inp_shape, mode='bilinear', align_corners=False).unsqueeze(0))
         return tch.cat(outputs)
 

@@ -1,0 +1,116 @@
+"""Training-mode forward/backward of a DeepLabHead / my_branch exit head with its convolutions on the
+eeseg tcgen05 kernels (forward `eeseg_conv_igemm_fwd`, input gradient `eeseg_conv_igemm_dgrad`, weight
+gradient `eeseg_conv_igemm_wgrad`) — what autograd through cuDNN computes for
+`branches[i](X)` / `classifier(X)` (from_deepv3_new.py:147,151) inside `train_epoch`
+(train_funcs.py:22-27).
+
+Activations of the head are bf16 NHWC; BatchNorm (batch statistics), ReLU, Dropout, the pooled ASPP branch
+and the final Cout = num_classes 1x1 convolution stay on the PyTorch modules (they are the parameter
+containers and bandwidth-bound glue: 0.03 % of the head's FLOPs), so state-dict layout, running statistics
+and RNG consumption are those of the reference modules. Weight gradients are returned in fp32 in the
+parameter's own [Cout,Cin,R,S] layout.
+"""
+import torch
+from torch import nn
+from torchvision.models.segmentation.deeplabv3 import ASPP
+
+from . import _lib
+from ._lib import check, lib
+
+_UNIT = {}
+
+
+def _unit_scale_shift(dev, n):
+    key = (dev, n)
+    if key not in _UNIT:
+        _UNIT[key] = (torch.ones(n, dtype=torch.float32, device=dev), torch.zeros(n, dtype=torch.float32, device=dev))
+    return _UNIT[key]
+
+
+class ConvIgemmFn(torch.autograd.Function):
+    """y = conv2d(x, weight; stride 1, 'same' padding dilation*(R//2), no bias) on NHWC bf16 activations.
+    x [N,h,w,Cin] bf16 contiguous (Cin % 64 == 0); weight: the nn.Conv2d parameter [Cout,Cin,R,S]
+    (Cout % 128 == 0 for the weight gradient). Returns [N,h,w,Cout] bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, dilation):
+        from .head_plan import conv_igemm
+        x = x.contiguous()
+        N, h, w, Cin = x.shape
+        wt = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)     # [Cout,R,S,Cin]
+        Cout = wt.shape[0]
+        out = torch.empty((N, h, w, Cout), dtype=torch.bfloat16, device=x.device)
+        one, zero = _unit_scale_shift(x.device, Cout)
+        conv_igemm(x, wt, one, zero, dilation, False, out, _lib.BF16, Cout)
+        ctx.save_for_backward(x, wt)
+        ctx.dilation = dilation
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wt = ctx.saved_tensors
+        N, h, w, Cin = x.shape
+        Cout, R, S, _ = wt.shape
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        dy = dy.contiguous()
+        dx = dw = None
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            if ctx.needs_input_grad[0]:
+                ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, S),), dtype=torch.uint8,
+                                 device=x.device)
+                dx = torch.empty_like(x)
+                check(lib().eeseg_conv_igemm_dgrad(dy.data_ptr(), wt.data_ptr(), N, h, w, Cin, Cout, R, S, ctx.dilation,
+                                                   dx.data_ptr(), _lib.BF16, Cin, ws.data_ptr(), st), "eeseg_conv_igemm_dgrad")
+            if ctx.needs_input_grad[1]:
+                dwk = torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
+                check(lib().eeseg_conv_igemm_wgrad(x.data_ptr(), dy.data_ptr(), Cout, Cout, 0, N, h, w, Cin, Cout, R, S,
+                                                   ctx.dilation, dwk.data_ptr(), st), "eeseg_conv_igemm_wgrad")
+                dw = dwk.permute(0, 3, 1, 2)                                             # the parameter's layout
+        return dx, dw, None
+
+
+def _conv_ok(conv):
+    """Shapes the three kernels take: stride 1, 'same' padding, no groups/bias, channel multiples."""
+    k, d = conv.kernel_size[0], conv.dilation[0]
+    return (isinstance(conv, nn.Conv2d) and conv.bias is None and conv.groups == 1 and conv.stride == (1, 1)
+            and conv.kernel_size[0] == conv.kernel_size[1] and (k & 1) and conv.dilation[0] == conv.dilation[1]
+            and conv.padding == (d * (k // 2), d * (k // 2)) and conv.padding_mode == 'zeros'
+            and conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0)
+
+
+def head_supported(head):
+    """DeepLabHead / my_branch without bottleneck: Sequential(ASPP, Conv3x3, BN, ReLU, Conv1x1)."""
+    if not (isinstance(head, nn.Sequential) and len(head) == 5 and isinstance(head[0], ASPP)):
+        return False
+    aspp = head[0]
+    convs = [m[0] for m in list(aspp.convs)[:-1]] + [aspp.project[0], head[1]]
+    return all(_conv_ok(c) for c in convs) and isinstance(head[4], nn.Conv2d)
+
+
+def _nhwc(t):
+    """[N,C,h,w] (any memory format) -> contiguous [N,h,w,C] bf16."""
+    return t.to(dtype=torch.bfloat16, memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+
+def _conv(xh, conv):
+    """NHWC bf16 in -> NCHW-shaped (channels_last) bf16 out, as the following BatchNorm2d expects."""
+    return ConvIgemmFn.apply(xh, conv.weight, conv.dilation[0]).permute(0, 3, 1, 2)
+
+
+def head_forward_train(head, x):
+    """head(x) with autograd, x [N,Cin,h,w] (fp32 or bf16, any memory format) -> logits [N,C,h,w] fp32."""
+    aspp = head[0]
+    xh = _nhwc(x)
+    outs = []
+    for m in list(aspp.convs)[:-1]:                      # 1x1 and the atrous 3x3 branches: conv, BN, ReLU
+        outs.append(m[2](m[1](_conv(xh, m[0]))))
+    pooled = aspp.convs[-1](x)                           # ASPPPooling on the PyTorch modules ([N,256,h,w])
+    outs.append(pooled.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
+    cat = torch.cat(outs, dim=1)
+    y = _conv(_nhwc(cat), aspp.project[0])
+    for m in list(aspp.project)[1:]:                     # BN, ReLU, Dropout(0.5)
+        y = m(y)
+    y = head[3](head[2](_conv(_nhwc(y), head[1])))       # 3x3, BN, ReLU
+    return head[4](y.float())                            # final 1x1 (+bias) to num_classes

@@ -223,6 +223,46 @@ def test_training_step_matches_torch_losses(nets):
     net.eval()
 
 
+def test_training_heads_on_eeseg_convs_match_torch_autograd(nets):
+    """Training forward/backward with the head convolutions on the tcgen05 kernels (fwd, dgrad, wgrad; bf16
+    activations) against the same step on the PyTorch modules (fp32 autograd through cuDNN): loss and logits
+    within the bf16 bound, gradients of head AND backbone parameters (the latter flow through dgrad) close in
+    direction and size. Dropout is switched off so both runs see the same network."""
+    import copy
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    port, net = nets
+    g = torch.Generator().manual_seed(31)
+    X = torch.randn(2, 3, 129, 129, generator=g).to(dev())
+    y = torch.randint(0, 22, (2, 1, 129, 129), generator=g).to(dev())
+    loss_fn = BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3)
+    runs = {}
+    for fast in (True, False):
+        m = copy.deepcopy(net).train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        m.fast_training_heads = fast
+        out = m(X)
+        l = loss_fn(out, y)
+        l.backward()
+        runs[fast] = (out.detach(), l.item(),
+                      torch.cat([p.grad.flatten() for p in m.branches.parameters()] +
+                                [p.grad.flatten() for p in m.classifier.parameters()]),
+                      torch.cat([p.grad.flatten() for p in m.base_model.parameters()]),
+                      {k: v.clone() for k, v in m.state_dict().items() if k.endswith('running_var') and 'branches' in k})
+    (of, lf, ghf, gbf, rvf), (ot, lt, ght, gbt, rvt) = runs[True], runs[False]
+    assert abs(lf - lt) < 1e-2 * abs(lt), (lf, lt)
+    for e in range(3):
+        assert (of[e] - ot[e]).abs().max().item() < 3e-2 * ot[e].abs().max().item()
+    cos = lambda a, b: torch.nn.functional.cosine_similarity(a.double(), b.double(), dim=0).item()
+    assert cos(ghf, ght) > 0.995 and cos(gbf, gbt) > 0.99, (cos(ghf, ght), cos(gbf, gbt))
+    assert abs(ghf.norm().item() / ght.norm().item() - 1) < 3e-2
+    assert abs(gbf.norm().item() / gbt.norm().item() - 1) < 5e-2
+    for k in rvf:          # BatchNorm running statistics were updated by the same modules
+        assert torch.allclose(rvf[k], rvt[k], rtol=5e-2, atol=1e-4), k
+    net.eval()
+
+
 def test_cityscapes_shaped_full_res_sweep():
     """BASELINE config 5 shape: 19 classes, one 1024x2048 image (128x256 feature maps, 16x8 conv tiles),
     threshold sweep + integer confusion matrices; heads checked against the fp32 PyTorch modules."""
