@@ -251,6 +251,36 @@ def main():
             ems = timeit(lambda i: F.relu(F.conv2d(xc, wc, padding=dil * (R // 2), dilation=dil)), 5, flush)
             row(f"conv_igemm {name} (N=4, 65x65)", ms, flops=fl, eager_ms=ems, note="nominal dense FLOPs; eager = cuDNN bf16 channels_last")
 
+    # ---------------- conv gradients (training) ----------------
+    if want("grad"):
+        for (cin, cout, R, dil, name) in [(2048, 256, 3, 12, "ASPP 3x3 d=12 Cin=2048"), (2048, 256, 3, 36, "ASPP 3x3 d=36 Cin=2048"),
+                                          (2048, 256, 1, 1, "ASPP 1x1 Cin=2048"), (1280, 256, 1, 1, "project 1x1 K=1280"),
+                                          (256, 256, 3, 1, "head 3x3 256->256")]:
+            x = torch.randn(N, h, w, cin, device=dev).to(torch.bfloat16)
+            wt = (torch.randn(cout, R, R, cin, device=dev) * 0.02).to(torch.bfloat16)
+            dy = torch.randn(N, h, w, cout, device=dev).to(torch.bfloat16)
+            dw = torch.empty(cout, R, R, cin, dtype=torch.float32, device=dev)
+            dx = torch.empty(N, h, w, cin, dtype=torch.bfloat16, device=dev)
+            ws = torch.empty(lib().eeseg_conv_igemm_dgrad_workspace_bytes(cin, cout, R, R), dtype=torch.uint8, device=dev)
+            fl = 2 * N * h * w * cout * cin * R * R
+            ms = timeit(lambda i: check(lib().eeseg_conv_igemm_wgrad(x.data_ptr(), dy.data_ptr(), cout, cout, 0, N, h, w, cin, cout,
+                                                                     R, R, dil, dw.data_ptr(), stream()), "wgrad"), args.iters, flush)
+            xc = x.permute(0, 3, 1, 2).float().requires_grad_(True)
+            wc = wt.permute(0, 3, 1, 2).float().requires_grad_(True)
+            dyc = dy.permute(0, 3, 1, 2).float()
+            torch.backends.cudnn.allow_tf32 = True
+            def eager_w(i):
+                return torch.autograd.grad(F.conv2d(xc, wc, padding=dil * (R // 2), dilation=dil), wc, dyc)
+            row(f"conv wgrad {name} (N=4, 65x65)", ms, flops=fl, eager_ms=timeit(eager_w, 3, flush),
+                note="nominal dense FLOPs; eager = autograd through cuDNN, TF32 allowed (fwd + wgrad)")
+            ms = timeit(lambda i: check(lib().eeseg_conv_igemm_dgrad(dy.data_ptr(), wt.data_ptr(), N, h, w, cin, cout, R, R, dil,
+                                                                     dx.data_ptr(), _lib.BF16, cin, ws.data_ptr(), stream()), "dgrad"),
+                        args.iters, flush)
+            def eager_x(i):
+                return torch.autograd.grad(F.conv2d(xc, wc, padding=dil * (R // 2), dilation=dil), xc, dyc)
+            row(f"conv dgrad {name} (N=4, 65x65), incl. weight transform", ms, flops=fl, eager_ms=timeit(eager_x, 3, flush),
+                note="nominal dense FLOPs; eager = autograd through cuDNN, TF32 allowed (fwd + dgrad)")
+
     out = {"peaks": peaks, "method": f"CUDA events around {REPS} back-to-back calls on a parked GPU, buffers rotated over sets larger than L2 "
                                      "(conv / Lovasz / eager rows: single call after a read flush of L2); mean of the faster half", "rows": rows}
     if args.out:
