@@ -29,6 +29,7 @@ PROTOTYPES = {
                                      c_p, c_p, c_p]),
     "eeseg_upsample_bilinear": (c_i, [c_p, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i, c_i,
                                       c_i, c_p, c_i, c_i64, c_p]),
+    "eeseg_upsample_bilinear_bwd": (c_i, [c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_multi_exit_ce_workspace_bytes": (c_sz, [c_i, c_i, c_i64]),
     "eeseg_multi_exit_ce_fwd": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i64, c_i64, c_p, c_p,
                                       c_p, c_p, c_p, c_p]),

@@ -299,6 +299,52 @@ __global__ void decide_kernel(const float* __restrict__ score, int N, float tau,
   }
 }
 
+// Adjoint of the bilinear up-sampling (F.interpolate backward, from_deepv3_new.py:149,152 under autograd):
+//   dlow[n,c,y,x] = sum_{Y,X} wy(Y,y) * wx(X,x) * dout[n,c,Y,X]
+// in GATHER form: one thread per low-res pixel walks the (at most ~2*scale+2)^2 output pixels that
+// interpolate from it, in a fixed order — no atomics, bit-reproducible (ATen's kernel scatters with atomics).
+// Lanes = consecutive low-res x, so a warp reads contiguous row segments of the dout plane.
+__device__ __forceinline__ float up_weight(int dst, float scale, int in_size, int src_idx) {
+  int i0, i1;
+  float l0, l1;
+  src_index(dst, scale, in_size, i0, i1, l0, l1);
+  return (i0 == src_idx ? l0 : 0.f) + (i1 == src_idx ? l1 : 0.f);   // both when the window is clamped to the edge
+}
+
+__device__ __forceinline__ void up_range(int src_idx, float scale, int in_size, int out_size, int& lo, int& hi) {
+  // outputs whose source coordinate lies in (src_idx-1, src_idx+1), widened by one (weights are re-checked)
+  const float inv = 1.f / scale;
+  lo = max((int)floorf(((float)src_idx - 1.f + 0.5f) * inv - 0.5f) - 1, 0);
+  hi = min((int)ceilf(((float)src_idx + 1.f + 0.5f) * inv - 0.5f) + 1, out_size - 1);
+  if (src_idx == in_size - 1) hi = out_size - 1;   // clamped tail
+  if (src_idx == 0) lo = 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) upsample_bwd_kernel(const T* __restrict__ dout, int64_t planes, int h, int w, int H,
+                                                           int W, float scale_y, float scale_x, float* __restrict__ dlow) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  const int64_t plane = blockIdx.z;
+  if (x >= w) return;
+  int Ylo, Yhi, Xlo, Xhi;
+  up_range(y, scale_y, h, H, Ylo, Yhi);
+  up_range(x, scale_x, w, W, Xlo, Xhi);
+  const T* g = dout + plane * (int64_t)H * W;
+  float acc = 0.f;
+  for (int Y = Ylo; Y <= Yhi; ++Y) {
+    const float wy = up_weight(Y, scale_y, h, y);
+    if (wy == 0.f) continue;
+    float row = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      const float wx = up_weight(X, scale_x, w, x);
+      if (wx != 0.f) row = fmaf(wx, ldf(g + (int64_t)Y * W + X), row);
+    }
+    acc = fmaf(wy, row, acc);
+  }
+  dlow[(plane * h + y) * (int64_t)w + x] = acc;
+}
+
 template <typename TI, typename TO>
 static int launch_gate(const GateParams& p, bool interp, bool vec, cudaStream_t stream) {
   const int64_t items = (int64_t)((p.W + 31) / 32) * ((p.H + kRowsPerStrip - 1) / kRowsPerStrip) * p.N;
@@ -408,6 +454,30 @@ extern "C" int eeseg_exit_gate_decide(const double* part_sum, const int32_t* par
   if (exit_idx) {
     decide_kernel<<<1, 256, 0, stream>>>(score, N, tau, less_than, exit_id, exit_idx, active_list, active_count);
     return check_launch("decide_kernel");
+  }
+  return EESEG_OK;
+}
+
+extern "C" int eeseg_upsample_bilinear_bwd(const void* dout, int dtype, int64_t planes, int h, int w, int H, int W,
+                                           float* dlow, void* stream) {
+  EESEG_REQUIRE(dout && dlow, "upsample_bwd: null pointer");
+  EESEG_REQUIRE(planes >= 0 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && h <= 65535 && planes <= 0x7fffffff,
+                "upsample_bwd: bad sizes");
+  EESEG_REQUIRE(dtype == EESEG_F32 || dtype == EESEG_BF16, "upsample_bwd: dtype %d", dtype);
+  if (planes == 0) return EESEG_OK;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  // grid.z carries the planes in chunks of 65535
+  for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
+    const int64_t np = planes - p0 < 65535 ? planes - p0 : 65535;
+    dim3 grid((w + 127) / 128, h, (unsigned)np);
+    if (dtype == EESEG_F32)
+      upsample_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)dout + p0 * (int64_t)H * W, np, h, w, H, W,
+                                                                        sy, sx, dlow + p0 * (int64_t)h * w);
+    else
+      upsample_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)dout + p0 * (int64_t)H * W, np, h, w, H, W, sy, sx, dlow + p0 * (int64_t)h * w);
+    int rc = check_launch("upsample_bwd_kernel");
+    if (rc) return rc;
   }
   return EESEG_OK;
 }

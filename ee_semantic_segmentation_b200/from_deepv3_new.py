@@ -241,6 +241,13 @@ class branchyDeepv3(nn.Module):
             return head_train.head_forward_train(head, X)
         return head(X)
 
+    def _upsample_autograd(self, y, size):
+        """F.interpolate(bilinear, align_corners=False) with autograd: eeseg kernels (fused forward, gather-form
+        deterministic backward) on CUDA when fast_training_heads is set, else ATen."""
+        if self.fast_training_heads and y.is_cuda:
+            return ops.upsample_bilinear_autograd(y, size)
+        return F.interpolate(y, size=size, mode='bilinear', align_corners=False)
+
     def _forward_torch(self, X):
         """The reference data flow with autograd (training): backbone sections on the PyTorch modules,
         exit heads through _head_autograd."""
@@ -249,9 +256,9 @@ class branchyDeepv3(nn.Module):
         for i in range(self.n_branches):
             X = self.base_model[i](X)
             br = self._head_autograd(self.branches[i], X)
-            outputs.append(F.interpolate(br, size=inp_shape, mode='bilinear', align_corners=False).unsqueeze(0))
+            outputs.append(self._upsample_autograd(br, inp_shape).unsqueeze(0))
         y = self._head_autograd(self.classifier, self.base_model[-1](X))
-        outputs.append(F.interpolate(y, size=inp_shape, mode='bilinear', align_corners=False).unsqueeze(0))
+        outputs.append(self._upsample_autograd(y, inp_shape).unsqueeze(0))
         return tch.cat(outputs)
 
     def _use_fast(self, X):

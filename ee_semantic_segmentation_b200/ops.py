@@ -184,6 +184,37 @@ def upsample_bilinear(x, out_hw, out=None, out_dtype=None, layout="NCHW", n_clas
     return r.up_logits
 
 
+class _UpsampleBilinear(torch.autograd.Function):
+    """F.interpolate(x, size, mode='bilinear', align_corners=False) for NCHW fp32 x with autograd: forward
+    on eeseg_upsample_bilinear, backward on the gather-form adjoint kernel (deterministic)."""
+
+    @staticmethod
+    def forward(ctx, x, out_hw):
+        ctx.in_hw = tuple(x.shape[-2:])
+        ctx.out_hw = (int(out_hw[0]), int(out_hw[1]))
+        return upsample_bilinear(x.contiguous(), ctx.out_hw)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        N, C = g.shape[:2]
+        h, w = ctx.in_hw
+        H, W = ctx.out_hw
+        dx = torch.empty((N, C, h, w), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib().eeseg_upsample_bilinear_bwd(g.data_ptr(), _dt(g), N * C, h, w, H, W, dx.data_ptr(), _stream(g)),
+                  "eeseg_upsample_bilinear_bwd")
+        return dx, None
+
+
+def upsample_bilinear_autograd(x, out_hw):
+    """Differentiable bilinear up-sampling of an NCHW fp32 CUDA tensor on the eeseg kernels."""
+    _cuda(x, "x")
+    if x.dtype != torch.float32:
+        x = x.float()
+    return _UpsampleBilinear.apply(x, out_hw)
+
+
 # --------------------------------------------------------------------------------------------------
 # multi-exit cross-entropy
 # --------------------------------------------------------------------------------------------------

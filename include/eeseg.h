@@ -111,6 +111,12 @@ int eeseg_upsample_bilinear(const void* in, int in_dtype,
                             int64_t in_sn, int64_t in_sc, int64_t in_sy, int64_t in_sx,
                             int N, int C, int h, int w, int H, int W,
                             void* out, int out_dtype, int64_t out_sn, void* stream);
+/* Adjoint of eeseg_upsample_bilinear (the backward of F.interpolate(..., mode='bilinear', align_corners=False)
+ * at from_deepv3_new.py:149,152 in training): dlow[p][y][x] = sum_{Y,X} wy(Y,y) wx(X,x) dout[p][Y][X] over
+ * `planes` = N*C contiguous planes. Gather form, fixed summation order (bit-reproducible; ATen scatters with
+ * atomics). dout fp32 / bf16 [planes][H][W]; dlow fp32 [planes][h][w]. */
+int eeseg_upsample_bilinear_bwd(const void* dout, int dtype, int64_t planes, int h, int w, int H, int W,
+                                float* dlow, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-exit pixelwise cross-entropy.

@@ -452,3 +452,27 @@ def test_gate_warp_items_ragged_shapes(H, W):
     clear = (top2[:, 1] - top2[:, 0]) > 1e-4          # argmax is unambiguous
     assert np.all((am == up.argmax(1)) | ~clear)
     assert int(res.exited_px.sum()) == int(res.mask.sum())
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 65, 65, 513, 513), (1, 19, 33, 40, 129, 157), (2, 3, 5, 4, 5, 4),
+                                   (1, 2, 7, 9, 3, 5), (1, 4, 1, 1, 6, 7), (1, 2, 129, 129, 513, 513)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upsample_backward_vs_aten(shape, dtype):
+    """Adjoint of the bilinear up-sampling (gather form) against autograd through ATen's F.interpolate in fp64
+    on the same gradient; up- and down-sampling ratios, clamped borders, 1x1 sources."""
+    from ee_semantic_segmentation_b200 import ops
+    N, C, h, w, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    low = torch.randn(N, C, h, w, generator=g)
+    go = torch.randn(N, C, H, W, generator=g).to(dtype)
+    ref_in = low.double().requires_grad_(True)
+    torch.nn.functional.interpolate(ref_in, size=(H, W), mode="bilinear", align_corners=False).backward(go.double())
+    x = low.to(dev()).requires_grad_(True)
+    y = ops.upsample_bilinear_autograd(x, (H, W))
+    y.backward(go.to(dev()).float() if dtype == torch.float32 else go.to(dev()))
+    got = x.grad.cpu().double()
+    np.testing.assert_allclose(got.numpy(), ref_in.grad.numpy(), rtol=2e-5, atol=2e-5 * float(ref_in.grad.abs().max()))
+    # determinism: bit-identical on a second run
+    x2 = low.to(dev()).requires_grad_(True)
+    ops.upsample_bilinear_autograd(x2, (H, W)).backward(go.to(dev()).float() if dtype == torch.float32 else go.to(dev()))
+    assert torch.equal(x.grad, x2.grad)
