@@ -1,0 +1,47 @@
+"""Training-mode forward/backward of a backbone section (`base_model[i]`, from_deepv3_new.py:146,151 inside
+`train_epoch`, train_funcs.py:22-27): every stride-1 'same' convolution of the torchvision ResNet
+`Bottleneck`s whose channel counts fit the tensor-core tiles (Cin % 64 == 0, Cout % 128 == 0 — all of layer2-4
+but the two stride-2 convolutions of layer2.0, and the 1x1 expansions / projection of layer1) runs forward,
+input-gradient and weight-gradient on the eeseg tcgen05 kernels (head_train.ConvIgemmFn); activations are bf16
+channels_last end to end. BatchNorm (batch statistics, running-stat updates), ReLU, the residual add, the
+7x7 stem, the max-pool and the few unsupported convolutions (64-channel outputs of layer1, stride 2) stay on
+the PyTorch modules under bf16 autocast: parameters, buffers and state-dict layout are the reference's.
+Master weights and their gradients stay fp32 (mixed precision); the reference trains in fp32 with TF32
+allowed (train_funcs.py:117-118) — parity is within the bf16 bound of north_star and is tested as such.
+"""
+import torch
+from torch import nn
+from torchvision.models.resnet import Bottleneck
+
+from .head_train import ConvIgemmFn, _conv_ok
+
+
+def _conv(x, conv):
+    """x: [N,C,h,w] bf16 channels_last -> conv(x) in the same format."""
+    if _conv_ok(conv):
+        return ConvIgemmFn.apply(x.permute(0, 2, 3, 1), conv.weight, conv.dilation[0]).permute(0, 3, 1, 2)
+    return conv(x)       # under autocast: cuDNN bf16
+
+
+def bottleneck_forward_train(blk, x):
+    """torchvision.models.resnet.Bottleneck.forward with the supported convolutions on ConvIgemmFn."""
+    identity = x
+    out = blk.relu(blk.bn1(_conv(x, blk.conv1)))
+    out = blk.relu(blk.bn2(_conv(out, blk.conv2)))
+    out = blk.bn3(_conv(out, blk.conv3))
+    if blk.downsample is not None:
+        identity = blk.downsample[1](_conv(x, blk.downsample[0]))
+    out = out + identity
+    return blk.relu(out)
+
+
+def section_forward_train(section, x):
+    """section(x) with autograd. x: fp32/bf16 NCHW (any memory format) -> bf16 channels_last."""
+    x = x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        for unit in section:
+            if isinstance(unit, Bottleneck) and len(unit.downsample or [0, 0]) == 2:
+                x = bottleneck_forward_train(unit, x)
+            else:
+                x = unit(x)
+    return x

@@ -30,7 +30,7 @@ from torch.nn import functional as F
 from torch.utils.flop_counter import FlopCounterMode
 from torchvision.models.segmentation.deeplabv3 import ASPP, DeepLabHead
 
-from . import head_train, ops
+from . import backbone_train, head_train, ops
 from .backbone_plan import SectionPlan, supported as _section_supported
 from .head_plan import HeadPlan
 
@@ -129,6 +129,7 @@ class branchyDeepv3(nn.Module):
         self.fast_inference = True     # eval-mode CUDA forward on the eeseg kernels
         self.fast_backbone = True      # ... including the ResNet bottlenecks of the sections
         self.fast_training_heads = True   # autograd forward: head convolutions (fwd/dgrad/wgrad) on eeseg kernels
+        self.fast_training_backbone = True   # ... and the Bottleneck convolutions of the sections (bf16 activations)
 
     # ---- construction helpers ---------------------------------------------------------------------
     @staticmethod
@@ -237,14 +238,21 @@ class branchyDeepv3(nn.Module):
         """head(X) with autograd: the head's convolutions (forward, input and weight gradients) on the
         eeseg tcgen05 kernels when fast_training_heads is set and the head has the DeepLabHead layout,
         else the PyTorch modules (cuDNN)."""
-        if self.fast_training_heads and X.is_cuda and head_train.head_supported(head):
+        if self.fast_training_heads and self.training and X.is_cuda and head_train.head_supported(head):
             return head_train.head_forward_train(head, X)
         return head(X)
+
+    def _section_autograd(self, section, X):
+        """base_model[i](X) with autograd: Bottleneck convolutions on the eeseg kernels in bf16 when
+        fast_training_backbone is set (backbone_train.py), else the PyTorch modules in the input dtype."""
+        if self.fast_training_backbone and self.training and X.is_cuda:
+            return backbone_train.section_forward_train(section, X)
+        return section(X)
 
     def _upsample_autograd(self, y, size):
         """F.interpolate(bilinear, align_corners=False) with autograd: eeseg kernels (fused forward, gather-form
         deterministic backward) on CUDA when fast_training_heads is set, else ATen."""
-        if self.fast_training_heads and y.is_cuda:
+        if self.fast_training_heads and self.training and y.is_cuda:
             return ops.upsample_bilinear_autograd(y, size)
         return F.interpolate(y, size=size, mode='bilinear', align_corners=False)
 
@@ -254,10 +262,10 @@ class branchyDeepv3(nn.Module):
         outputs = []
         inp_shape = X.shape[-2:]
         for i in range(self.n_branches):
-            X = self.base_model[i](X)
+            X = self._section_autograd(self.base_model[i], X)
             br = self._head_autograd(self.branches[i], X)
             outputs.append(self._upsample_autograd(br, inp_shape).unsqueeze(0))
-        y = self._head_autograd(self.classifier, self.base_model[-1](X))
+        y = self._head_autograd(self.classifier, self._section_autograd(self.base_model[-1], X))
         outputs.append(self._upsample_autograd(y, inp_shape).unsqueeze(0))
         return tch.cat(outputs)
 

@@ -242,6 +242,7 @@ def test_training_heads_on_eeseg_convs_match_torch_autograd(nets):
             if isinstance(mod, torch.nn.Dropout):
                 mod.p = 0.0
         m.fast_training_heads = fast
+        m.fast_training_backbone = False
         out = m(X)
         l = loss_fn(out, y)
         l.backward()
@@ -260,6 +261,65 @@ def test_training_heads_on_eeseg_convs_match_torch_autograd(nets):
     assert abs(gbf.norm().item() / gbt.norm().item() - 1) < 5e-2
     for k in rvf:          # BatchNorm running statistics were updated by the same modules
         assert torch.allclose(rvf[k], rvt[k], rtol=5e-2, atol=1e-4), k
+    net.eval()
+
+
+def test_training_backbone_on_eeseg_convs_matches_torch_autograd(nets):
+    """Backbone sections in training with the Bottleneck convolutions on the tcgen05 kernels (forward, dgrad,
+    wgrad; bf16 activations, fp32 master weights and gradients) against the SAME PyTorch modules under bf16
+    autocast (cuDNN): identical rounding points, so outputs and every gradient agree tightly. (Against fp32 a
+    random-init train-mode ResNet amplifies bf16 rounding by ~1.15x per block — 1 % after the first block, 50 %
+    after twenty, identically for cuDNN-bf16 and for these kernels — so fp32 is only checked on the loss.)"""
+    import copy
+    from ee_semantic_segmentation_b200 import backbone_train
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    port, net = nets
+    g = torch.Generator().manual_seed(33)
+    X = torch.randn(4, 3, 129, 129, generator=g).to(dev())
+    # block by block (a whole section would only measure the amplification): every Bottleneck variant of the
+    # backbone — 64-channel layer1 convs and the stride-2 block stay on cuDNN inside, dilations 1 / 2 / 4,
+    # projection shortcuts
+    from torchvision.models.resnet import Bottleneck
+    blocks = [u for sec in net.base_model for u in sec if isinstance(u, Bottleneck)]
+    assert len(blocks) == 16
+    for bi in (0, 1, 3, 4, 7, 8, 13, 14):
+        blk_a = copy.deepcopy(blocks[bi]).train()
+        blk_b = copy.deepcopy(blocks[bi]).train()
+        cin = blk_a.conv1.in_channels
+        hw = 33 if bi < 4 else 17
+        x0 = torch.randn(4, cin, hw, hw, generator=g).to(dev()).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        xa = x0.clone().requires_grad_(True)
+        xb = x0.clone().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            ya = backbone_train.bottleneck_forward_train(blk_a, xa)
+            yb = blk_b(xb)
+        assert ya.dtype == yb.dtype == torch.bfloat16 and ya.shape == yb.shape
+        rel = ((ya.float() - yb.float()).norm() / yb.float().norm()).item()
+        assert rel < 1e-2, (bi, rel)
+        go = torch.randn(yb.shape, generator=g).to(dev()).to(torch.bfloat16)
+        ya.backward(go)
+        yb.backward(go)
+        cos = lambda a, b: torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+        assert cos(xa.grad, xb.grad) > 0.999, (bi, cos(xa.grad, xb.grad))
+        for (n, pa), (_, pb) in zip(blk_a.named_parameters(), blk_b.named_parameters()):
+            assert cos(pa.grad, pb.grad) > 0.999, (bi, n, cos(pa.grad, pb.grad))
+            assert abs(pa.grad.norm().item() / (pb.grad.norm().item() + 1e-12) - 1) < 2e-2, (bi, n)
+        for (n, ba), (_, bb) in zip(blk_a.named_buffers(), blk_b.named_buffers()):     # BN running statistics
+            if ba.dtype.is_floating_point:
+                assert torch.allclose(ba, bb, rtol=2e-2, atol=1e-3), (bi, n)
+    # whole model: loss next to the fp32 PyTorch-module step, every parameter gets a finite gradient
+    y = torch.randint(0, 22, (4, 1, 129, 129), generator=g).to(dev())
+    loss_fn = BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3)
+    losses = {}
+    for fast in (True, False):
+        m = copy.deepcopy(net).train()
+        m.fast_training_heads = m.fast_training_backbone = fast
+        torch.manual_seed(5)
+        l = loss_fn(m(X), y)
+        l.backward()
+        losses[fast] = l.item()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    assert abs(losses[True] - losses[False]) < 2e-2 * abs(losses[False]), losses
     net.eval()
 
 
