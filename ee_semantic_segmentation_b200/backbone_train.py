@@ -2,10 +2,11 @@
 `train_epoch`, train_funcs.py:22-27): every stride-1 'same' convolution of the torchvision ResNet
 `Bottleneck`s whose channel counts fit the tensor-core tiles (Cin % 64 == 0, Cout % 128 == 0 — all of layer2-4
 but the two stride-2 convolutions of layer2.0, and the 1x1 expansions / projection of layer1) runs forward,
-input-gradient and weight-gradient on the eeseg tcgen05 kernels (head_train.ConvIgemmFn); activations are bf16
-channels_last end to end. BatchNorm (batch statistics, running-stat updates), ReLU, the residual add, the
-7x7 stem, the max-pool and the few unsupported convolutions (64-channel outputs of layer1, stride 2) stay on
-the PyTorch modules under bf16 autocast: parameters, buffers and state-dict layout are the reference's.
+input-gradient and weight-gradient on the eeseg tcgen05 kernels (head_train.ConvIgemmFn); BatchNorm (batch
+statistics, running-stat updates) + residual add + ReLU run as one fused eeseg node per BatchNorm
+(bn_train.BnActFn); activations are bf16 channels_last end to end. The 7x7 stem (conv, BN, ReLU, max-pool) and the
+few unsupported convolutions (64-channel outputs of layer1, stride 2) stay on the PyTorch modules under bf16
+autocast: parameters, buffers and state-dict layout are the reference's.
 Master weights and their gradients stay fp32 (mixed precision); the reference trains in fp32 with TF32
 allowed (train_funcs.py:117-118) — parity is within the bf16 bound of north_star and is tested as such.
 """
@@ -13,6 +14,7 @@ import torch
 from torch import nn
 from torchvision.models.resnet import Bottleneck
 
+from .bn_train import bn_act
 from .head_train import ConvIgemmFn, _conv_ok
 
 
@@ -26,13 +28,12 @@ def _conv(x, conv):
 def bottleneck_forward_train(blk, x):
     """torchvision.models.resnet.Bottleneck.forward with the supported convolutions on ConvIgemmFn."""
     identity = x
-    out = blk.relu(blk.bn1(_conv(x, blk.conv1)))
-    out = blk.relu(blk.bn2(_conv(out, blk.conv2)))
-    out = blk.bn3(_conv(out, blk.conv3))
+    out = bn_act(_conv(x, blk.conv1), blk.bn1, True)
+    out = bn_act(_conv(out, blk.conv2), blk.bn2, True)
     if blk.downsample is not None:
-        identity = blk.downsample[1](_conv(x, blk.downsample[0]))
-    out = out + identity
-    return blk.relu(out)
+        identity = bn_act(_conv(x, blk.downsample[0]), blk.downsample[1], False)
+    # bn3 + residual add + ReLU: one pass
+    return bn_act(_conv(out, blk.conv3), blk.bn3, True, residual=identity)
 
 
 def section_forward_train(section, x):

@@ -4,10 +4,10 @@ gradient `eeseg_conv_igemm_wgrad`) — what autograd through cuDNN computes for
 `branches[i](X)` / `classifier(X)` (from_deepv3_new.py:147,151) inside `train_epoch`
 (train_funcs.py:22-27).
 
-Activations of the head are bf16 NHWC; BatchNorm (batch statistics), ReLU, Dropout, the pooled ASPP branch
-and the final Cout = num_classes 1x1 convolution stay on the PyTorch modules (they are the parameter
-containers and bandwidth-bound glue: 0.03 % of the head's FLOPs), so state-dict layout, running statistics
-and RNG consumption are those of the reference modules. Weight gradients are returned in fp32 in the
+Activations of the head are bf16 NHWC; BatchNorm (batch statistics) + ReLU run as fused eeseg nodes
+(bn_train.BnActFn) on the modules' own parameters and running-statistic buffers; Dropout, the pooled ASPP branch
+and the final Cout = num_classes 1x1 convolution stay on the PyTorch modules (0.03 % of the head's FLOPs), so
+state-dict layout, running statistics and RNG consumption are those of the reference modules. Weight gradients are returned in fp32 in the
 parameter's own [Cout,Cin,R,S] layout.
 """
 import torch
@@ -104,8 +104,9 @@ def head_forward_train(head, x):
     aspp = head[0]
     xh = _nhwc(x)
     outs = []
-    for m in list(aspp.convs)[:-1]:                      # 1x1 and the atrous 3x3 branches: conv, BN, ReLU
-        outs.append(m[2](m[1](_conv(xh, m[0]))))
+    from .bn_train import bn_act
+    for m in list(aspp.convs)[:-1]:                      # 1x1 and the atrous 3x3 branches: conv, BN + ReLU
+        outs.append(bn_act(_conv(xh, m[0]), m[1], True))
     # ASPPPooling on its PyTorch modules (global average pool, 1x1 conv, BN, ReLU). Its "bilinear" up-sampling
     # of a 1x1 map (deeplabv3.py:83) is a broadcast: expand() instead of F.interpolate, whose backward is a plain
     # sum instead of ATen's atomic scatter onto one pixel (0.42 ms per head at 65x65)
@@ -116,8 +117,8 @@ def head_forward_train(head, x):
     pooled = pooled.to(torch.bfloat16).expand(-1, -1, x.shape[-2], x.shape[-1]).contiguous(memory_format=torch.channels_last)
     outs.append(pooled)
     cat = torch.cat(outs, dim=1)
-    y = _conv(_nhwc(cat), aspp.project[0])
-    for m in list(aspp.project)[1:]:                     # BN, ReLU, Dropout(0.5)
+    y = bn_act(_conv(_nhwc(cat), aspp.project[0]), aspp.project[1], True)   # projection, BN + ReLU
+    for m in list(aspp.project)[3:]:                     # Dropout(0.5)
         y = m(y)
-    y = head[3](head[2](_conv(_nhwc(y), head[1])))       # 3x3, BN, ReLU
+    y = bn_act(_conv(_nhwc(y), head[1]), head[2], True)  # 3x3, BN + ReLU
     return head[4](y.float())                            # final 1x1 (+bias) to num_classes

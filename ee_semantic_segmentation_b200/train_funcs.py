@@ -57,3 +57,55 @@ def poly_scheduler(optimizer, num_epochs, lr=None, min_lr=None):
         n0 = num_epochs * w / (1 - w)
         return optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda k: (1 - k / (num_epochs + n0)) ** .9)
     return optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda k: (1 - k / num_epochs) ** .9)
+
+
+class GraphedTrainStep:
+    """One training step — forward, loss, backward, optimizer.step() — captured into ONE CUDA graph and replayed
+    per batch: the ~650 kernel launches of a step (eeseg conv / BatchNorm / loss kernels, optimizer) cost one
+    graph launch instead of Python + driver time each, which is what bounds the eager step once the kernels are
+    fast (24 ms wall for 20 ms of GPU work at batch 4, 513x513).
+
+    Same arithmetic as the body of `train_epoch` (train_funcs.py:22-27) for a fixed batch shape. The warm-up
+    steps needed before capture run on the example batch and are rolled back (parameters, BatchNorm buffers,
+    momentum), so the first replay is the first real update. Learning-rate changes made by a scheduler are baked
+    into the graph: call `recapture()` after `scheduler.step()` (the reference steps it once per epoch)."""
+
+    def __init__(self, net, loss, optimizer, X, y, warmup=3):
+        self.net, self.loss_fn, self.opt = net, loss, optimizer
+        self.X, self.y = X.clone(), y.clone()
+        net.train()
+        saved = [t.detach().clone() for t in list(net.parameters()) + list(net.buffers())]
+        cur = tch.cuda.current_stream()
+        side = tch.cuda.Stream()
+        side.wait_stream(cur)
+        with tch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        cur.wait_stream(side)
+        with tch.no_grad():
+            for t, s in zip(list(net.parameters()) + list(net.buffers()), saved):
+                t.copy_(s)
+            for st in optimizer.state.values():          # momentum buffers must exist before capture: zero them
+                for v in st.values():
+                    if isinstance(v, tch.Tensor):
+                        v.zero_()
+        self.recapture()
+
+    def _step(self):
+        self.opt.zero_grad(set_to_none=True)
+        l = self.loss_fn(self.net(self.X), self.y)
+        l.mean().backward()
+        self.opt.step()
+        return l
+
+    def recapture(self):
+        self.graph = tch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with tch.cuda.graph(self.graph):
+            self.loss = self._step().detach()
+
+    def __call__(self, X, y):
+        self.X.copy_(X, non_blocking=True)
+        self.y.copy_(y.view_as(self.y), non_blocking=True)
+        self.graph.replay()
+        return self.loss

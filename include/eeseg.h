@@ -210,6 +210,26 @@ int eeseg_conv_igemm_dgrad(const void* dy, const void* wt, int N, int h, int w, 
                            int dilation, void* dx, int dx_dtype, int64_t lddx, void* workspace, void* stream);
 int eeseg_conv_weight_rot180_t(const void* w, int Cout, int R, int S, int Cin, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm2d (+ residual add) (+ ReLU) on NHWC bf16 activations — the nn.BatchNorm2d / ReLU /
+ * `out += identity` modules of DeepLabHead, ASPP and the ResNet Bottlenecks as they run under net.train() in
+ * train_epoch (train_funcs.py:12-33).  x, y, residual, dy, dx, dres: bf16 [P = N*h*w][C], C % 64 == 0.
+ *   fwd:  mean/var over the P pixels per channel (biased variance inside the normalisation),
+ *         y = act(gamma*(x-mean)*invstd + beta (+ residual)), act = ReLU if relu else identity;
+ *         running_mean/var (optional) <- (1-momentum)*running + momentum*(mean / unbiased variance);
+ *         save_mean, save_invstd fp32 [C] for the backward.
+ *   bwd:  dy' = dy * [y > 0] (relu; needs y),  dbeta = sum dy',  dgamma = sum dy'*xhat,
+ *         dx = gamma*invstd*(dy' - dbeta/P - xhat*dgamma/P),  dres (optional) = dy'.
+ *   Fixed summation order (bit-reproducible). workspace: eeseg_bn_train_workspace_bytes(C) bytes, 16 B aligned.
+ * ---------------------------------------------------------------------------------------------- */
+size_t eeseg_bn_train_workspace_bytes(int C);
+int eeseg_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, int relu, const void* residual, void* y,
+                       float* save_mean, float* save_invstd, void* workspace, void* stream);
+int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
+                       const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres,
+                       float* dgamma, float* dbeta, void* workspace, void* stream);
+
 /* ResNet stem helpers (base_model[0][0:4], torchvision resnet.py conv1/bn1/relu/maxpool):
  * space-to-depth (2x2) plus horizontal tap unrolling of the fp32 NCHW image, so that the 7x7 / stride-2 /
  * pad-3 convolution becomes a 4x1 / stride-1 / pad-2 implicit GEMM with K = 4 taps x 64 channels:

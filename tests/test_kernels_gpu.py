@@ -476,3 +476,47 @@ def test_upsample_backward_vs_aten(shape, dtype):
     x2 = low.to(dev()).requires_grad_(True)
     ops.upsample_bilinear_autograd(x2, (H, W)).backward(go.to(dev()).float() if dtype == torch.float32 else go.to(dev()))
     assert torch.equal(x.grad, x2.grad)
+
+
+@pytest.mark.parametrize("N,C,h,w", [(4, 64, 33, 33), (2, 256, 17, 17), (1, 2048, 9, 9), (3, 128, 5, 7)])
+@pytest.mark.parametrize("relu,res", [(True, False), (False, False), (True, True)])
+def test_bn_train_fwd_bwd_vs_torch(N, C, h, w, relu, res):
+    """Fused training BatchNorm (+ residual) (+ ReLU) against nn.BatchNorm2d in fp32 on the same bf16-rounded
+    inputs: output, running statistics, dx, dresidual, dgamma, dbeta."""
+    import copy
+    from ee_semantic_segmentation_b200.bn_train import bn_act
+    g = torch.Generator().manual_seed(N * 1000 + C + h)
+    x = (torch.randn(N, C, h, w, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    r = torch.randn(N, C, h, w, generator=g).to(torch.bfloat16) if res else None
+    go = torch.randn(N, C, h, w, generator=g).to(torch.bfloat16)
+    bn_ref = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn_ref.bias.copy_(torch.randn(C, generator=g) * 0.3)
+        bn_ref.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+    bn = copy.deepcopy(bn_ref).to(dev()).train()
+    bn_ref.train()
+    xr = x.float().requires_grad_(True)
+    rr = r.float().requires_grad_(True) if res else None
+    yr = bn_ref(xr)
+    if res:
+        yr = yr + rr
+    if relu:
+        yr = yr.relu()
+    yr.backward(go.float())
+    xd = x.to(dev()).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    rd = r.to(dev()).contiguous(memory_format=torch.channels_last).requires_grad_(True) if res else None
+    yd = bn_act(xd, bn, relu, residual=rd)
+    yd.backward(go.to(dev()))
+    assert yd.dtype == torch.bfloat16 and yd.shape == yr.shape
+    np.testing.assert_allclose(yd.detach().float().cpu().numpy(), yr.detach().numpy(), rtol=1e-2, atol=2e-2)
+    np.testing.assert_allclose(bn.running_mean.cpu().numpy(), bn_ref.running_mean.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), bn_ref.running_var.numpy(), rtol=1e-4, atol=1e-5)
+    assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked) == 1
+    # gradients: the ReLU mask can differ where the bf16-rounded output is exactly at 0 -> compare in the L2 sense
+    rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-12)).item()
+    assert rel(xd.grad.float().cpu(), xr.grad) < 1e-2
+    assert rel(bn.weight.grad.cpu(), bn_ref.weight.grad) < 5e-3
+    assert rel(bn.bias.grad.cpu(), bn_ref.bias.grad) < 5e-3
+    if res:
+        assert rel(rd.grad.float().cpu(), rr.grad) < 1e-2

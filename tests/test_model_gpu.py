@@ -323,6 +323,43 @@ def test_training_backbone_on_eeseg_convs_matches_torch_autograd(nets):
     net.eval()
 
 
+def test_graphed_train_step_matches_eager_steps(nets):
+    """train_funcs.GraphedTrainStep (one CUDA graph per step) applies the same updates as the eager loop of
+    train_epoch: two steps each on identical copies, Dropout off, same batches; the warm-up it runs before the
+    capture is rolled back."""
+    import copy
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    from ee_semantic_segmentation_b200.train_funcs import GraphedTrainStep, make_optimizer, train_epoch
+    port, net = nets
+    g = torch.Generator().manual_seed(41)
+    batches = [(torch.randn(2, 3, 97, 97, generator=g).to(dev()), torch.randint(0, 22, (2, 1, 97, 97), generator=g).to(dev()))
+               for _ in range(2)]
+    loss_fn = BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3)
+    nets2 = []
+    for _ in range(2):
+        m = copy.deepcopy(net).train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        nets2.append(m)
+    na, nb = nets2
+    opt_a = make_optimizer(na, lr=1e-2, base_lr=1e-3)
+    l_eager = [train_epoch(na, [b], loss_fn, opt_a, dev()).item() for b in batches]
+    opt_b = make_optimizer(nb, lr=1e-2, base_lr=1e-3)
+    step = GraphedTrainStep(nb, loss_fn, opt_b, *batches[0])
+    l_graph = [step(*b).item() for b in batches]
+    assert l_graph == pytest.approx(l_eager, rel=2e-3)
+    pa = torch.cat([p.detach().flatten() for p in na.parameters()])
+    pb = torch.cat([p.detach().flatten() for p in nb.parameters()])
+    assert ((pa - pb).norm() / pa.norm()).item() < 1e-4
+    for (n, ba), (_, bb) in zip(na.named_buffers(), nb.named_buffers()):
+        if ba.dtype.is_floating_point:
+            assert torch.allclose(ba, bb, rtol=1e-2, atol=1e-3), n
+        else:
+            assert torch.equal(ba, bb), n          # num_batches_tracked: 2, the warm-up was rolled back
+    net.eval()
+
+
 def test_cityscapes_shaped_full_res_sweep():
     """BASELINE config 5 shape: 19 classes, one 1024x2048 image (128x256 feature maps, 16x8 conv tiles),
     threshold sweep + integer confusion matrices; heads checked against the fp32 PyTorch modules."""

@@ -2,7 +2,8 @@
 """Training-step throughput (BASELINE configs[2]: multi-exit weighted pixelwise CE, synthetic VOC 513x513
 crops; configs[3]: Lovasz branchy loss, 19-class 768x768 crops) on one GPU:
 
-  eeseg       : head convolutions fwd/dgrad/wgrad on the tcgen05 kernels + fused multi-exit loss kernel
+  eeseg-graph : eeseg with the whole step (fwd, loss, bwd, SGD) replayed as one CUDA graph (train_funcs.GraphedTrainStep)
+  eeseg       : backbone + head convolutions fwd/dgrad/wgrad on the tcgen05 kernels, fused BatchNorm/ReLU and loss kernels
   eeseg-loss  : PyTorch-module heads (cuDNN) + fused multi-exit loss kernel
   torch       : the reference's GPU path — PyTorch modules + torch losses (TF32 allowed, train_funcs.py:117-118)
 
@@ -22,7 +23,7 @@ import bench  # noqa: E402
 from ee_semantic_segmentation_b200.branchy_seg_losses import LovaszSoftmax  # noqa: E402
 from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3  # noqa: E402
 from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss  # noqa: E402
-from ee_semantic_segmentation_b200.train_funcs import make_optimizer  # noqa: E402
+from ee_semantic_segmentation_b200.train_funcs import GraphedTrainStep, make_optimizer  # noqa: E402
 
 
 def torch_lovasz(probas, labels, ignore):
@@ -62,11 +63,12 @@ def main():
     X, y = bench.synth_batch(0, args.batch, img=img, n_classes=C)
     X, y = X.to(dev), y.to(dev)
     rows = []
-    for mode in ("eeseg", "eeseg-loss", "torch"):
+    ap_modes = ("eeseg-graph", "eeseg", "eeseg-loss", "torch")
+    for mode in ap_modes:
         torch.manual_seed(0)
         net = branchyDeepv3(None, "deeplabv3_resnet50", 2, img, sections=bench.SECTIONS, pretrained=False,
                             num_classes=C).to(dev).train()
-        net.fast_training_heads = mode == "eeseg"
+        net.fast_training_heads = net.fast_training_backbone = mode in ("eeseg", "eeseg-graph")
         opt = make_optimizer(net, lr=1e-3, base_lr=1e-4)
         if mode == "torch":
             if args.config == "ce":
@@ -85,6 +87,9 @@ def main():
             l.backward()
             opt.step()
             return l
+        if mode == "eeseg-graph":
+            gstep = GraphedTrainStep(net, loss_fn, opt, X, y)
+            step = lambda: gstep(X, y)
         for _ in range(3):
             l = step()
         torch.cuda.synchronize()
