@@ -41,7 +41,8 @@ PROTOTYPES = {
                                    c_p, c_p, c_p, c_sz, c_p]),
     "eeseg_conv_igemm_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                    c_i, c_i, c_i, c_i, c_p, c_i64, c_p, c_i, c_i64, c_p]),
-    "eeseg_conv_igemm_wgrad": (c_i, [c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "eeseg_conv_igemm_wgrad_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
+    "eeseg_conv_igemm_wgrad": (c_i, [c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "eeseg_conv_igemm_dgrad_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "eeseg_conv_igemm_dgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i64, c_p, c_p]),
     "eeseg_conv_weight_rot180_t": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),

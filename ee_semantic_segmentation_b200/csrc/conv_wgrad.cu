@@ -14,9 +14,12 @@
 //   rows 121..127 of every box are zeroed once and never written again (0 x 0 adds nothing to the K sum).
 // * One CTA = one (tap, 128-co block, BN-ci block, K split): it walks its pixel tiles through a TMA ring
 //   (warp 0), issues 8 UMMA 128xBNx16 per tile (warp 1, fp32 accumulator in TMEM), and warps 2-5 write the
-//   accumulator to dW (fp32; atomically when the K dimension is split across CTAs to fill the 148 SMs).
+//   accumulator to dW in fp32 — or, when the K dimension is split across CTAs to fill the 148 SMs, to its own
+//   partial buffer, summed afterwards in a fixed order (fp32 atomics cost 36 of 55 us on a 1x1 Cin=2048 layer and
+//   made dW irreproducible).
 // Pixel tiles for which the shifted window lies entirely in the padding are skipped.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -34,8 +37,8 @@ struct WgradParams {
   int BN, nblocks, mblocks, ksplit;
   int stages;
   int co_off;       // first channel of this conv inside the dY tensor map
-  float* dw;
-  int atomic;       // ksplit > 1: accumulate with atomics into a zeroed dW
+  float* dw;        // ksplit == 1: dW itself; else the partial buffer [ksplit][Cout][R*S][Cin]
+  int64_t part_stride;   // elements between the partial buffers of consecutive K splits
 };
 
 __host__ __device__ inline uint32_t tmem_cols_for_wg(int bn) { return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u; }
@@ -161,7 +164,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const int co = mb * 128 + m;
-    float* row = p.dw + ((int64_t)co * (p.R * p.S) + tap) * p.Cin + (int64_t)nb * p.BN;
+    float* row = p.dw + (int64_t)ks * p.part_stride + ((int64_t)co * (p.R * p.S) + tap) * p.Cin + (int64_t)nb * p.BN;
     if (n_live > 0) {
       mbar_wait(acc_bar, 0);
       tcgen05_fence_after();
@@ -170,17 +173,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)col, v);
         tmem_ld_wait();
-        if (p.atomic) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(row + col + j, __uint_as_float(v[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(row + col)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<float4*>(row + col)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
-    } else if (!p.atomic) {
+    } else {
       for (int col = 0; col < p.BN; col += 4) *reinterpret_cast<float4*>(row + col) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tcgen05_fence_before();
@@ -210,6 +208,18 @@ __global__ void weight_rot180_t_kernel(const __nv_bfloat16* __restrict__ w, int 
   }
 }
 
+// dW = sum over K splits of the partial buffers, fixed order (deterministic)
+__global__ void wgrad_reduce_kernel(const float4* __restrict__ part, int ksplit, int64_t n4, float4* __restrict__ dw) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = part[i];
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 b = part[(int64_t)k * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dw[i] = a;
+  }
+}
+
 __global__ void fill_scale_shift_kernel(float* scale, float* shift, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { scale[i] = 1.f; shift[i] = 0.f; }
@@ -219,24 +229,7 @@ __global__ void fill_scale_shift_kernel(float* scale, float* shift, int n) {
 
 using namespace eeseg;
 
-extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
-                                      int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  EESEG_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
-  EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_wgrad: bad sizes");
-  EESEG_REQUIRE(Cin % 64 == 0, "conv_wgrad: Cin=%d must be a multiple of 64", Cin);
-  EESEG_REQUIRE(Cout % 128 == 0, "conv_wgrad: Cout=%d must be a multiple of 128", Cout);
-  EESEG_REQUIRE(R >= 1 && S >= 1 && (R & 1) && (S & 1) && R * S <= 32, "conv_wgrad: odd kernel sizes with at most 32 taps");
-  EESEG_REQUIRE(dilation >= 1, "conv_wgrad: dilation %d", dilation);
-  EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw & 15) == 0 && (ldy % 8) == 0,
-                "conv_wgrad: pointers and the dY pixel stride must be 16-byte aligned");
-  EESEG_REQUIRE(co_off >= 0 && co_off + Cout <= dy_channels && dy_channels <= ldy, "conv_wgrad: channel window outside dY");
-  EncodeTiledFn encode = get_encode();
-  if (!encode) { set_error("conv_wgrad: cuTensorMapEncodeTiled unavailable"); return EESEG_ERR_CUDA; }
-  WgradParams p;
-  p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
-  p.pad = dilation * (R / 2);   // 'same' (square kernels: R == S for the padded dimension)
-  EESEG_REQUIRE(R == S || R == 1 || S == 1, "conv_wgrad: square or 1-D kernels");
+static int wgrad_geometry(int N, int h, int w, int Cin, int Cout, int R, int S, WgradParams& p) {
   pick_tile(h, w, p.BW, p.BH);
   p.tiles_x = (w + p.BW - 1) / p.BW;
   p.tiles_y = (h + p.BH - 1) / p.BH;
@@ -248,10 +241,46 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   int ksplit = kNumSMs / base_items;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > total_pt) ksplit = total_pt;
+  if (const char* e = getenv("EESEG_WGRAD_KSPLIT")) {   // tuning hook
+    const int v = atoi(e);
+    if (v >= 1 && v <= total_pt) ksplit = v;
+  }
   p.ksplit = ksplit;
-  p.atomic = ksplit > 1 ? 1 : 0;
+  return base_items;
+}
+
+extern "C" size_t eeseg_conv_igemm_wgrad_workspace_bytes(int N, int h, int w, int Cin, int Cout, int R, int S) {
+  if (N < 1 || h < 1 || w < 1 || Cin < 64 || Cout < 128 || R < 1 || S < 1) return 256;
+  WgradParams p;
+  wgrad_geometry(N, h, w, Cin, Cout, R, S, p);
+  return (p.ksplit > 1 ? (size_t)p.ksplit * Cout * R * S * Cin * sizeof(float) : 0) + 256;
+}
+
+extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
+                                      int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* workspace,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EESEG_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
+  EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_wgrad: bad sizes");
+  EESEG_REQUIRE(Cin % 64 == 0, "conv_wgrad: Cin=%d must be a multiple of 64", Cin);
+  EESEG_REQUIRE(Cout % 128 == 0, "conv_wgrad: Cout=%d must be a multiple of 128", Cout);
+  EESEG_REQUIRE(R >= 1 && S >= 1 && (R & 1) && (S & 1) && R * S <= 32, "conv_wgrad: odd kernel sizes with at most 32 taps");
+  EESEG_REQUIRE(dilation >= 1, "conv_wgrad: dilation %d", dilation);
+  EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw & 15) == 0 && (ldy % 8) == 0 &&
+                ((uintptr_t)workspace & 15) == 0, "conv_wgrad: pointers and the dY pixel stride must be 16-byte aligned");
+  EESEG_REQUIRE(co_off >= 0 && co_off + Cout <= dy_channels && dy_channels <= ldy, "conv_wgrad: channel window outside dY");
+  EESEG_REQUIRE(R == S || R == 1 || S == 1, "conv_wgrad: square or 1-D kernels");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("conv_wgrad: cuTensorMapEncodeTiled unavailable"); return EESEG_ERR_CUDA; }
+  WgradParams p;
+  p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.dil = dilation;
+  p.pad = dilation * (R / 2);   // 'same'
+  const int base_items = wgrad_geometry(N, h, w, Cin, Cout, R, S, p);
+  const int64_t dw_elems = (int64_t)Cout * R * S * Cin;
+  EESEG_REQUIRE(p.ksplit == 1 || workspace, "conv_wgrad: this shape splits the pixels over %d CTAs and needs the workspace", p.ksplit);
   p.co_off = co_off;
-  p.dw = dw;
+  p.dw = p.ksplit > 1 ? reinterpret_cast<float*>(workspace) : dw;
+  p.part_stride = p.ksplit > 1 ? dw_elems : 0;
   const size_t stage_bytes = (size_t)(2 + p.BN / 64) * kWgBox;
   int stages = (int)((227 * 1024 - 1024 - 256) / stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
@@ -264,14 +293,20 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   if (rc) return rc;
   rc = encode_act_map(encode, &tmx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cin, w, h, N, Cin, 64, p.BW, p.BH, 1, true, "x");
   if (rc) return rc;
-  if (p.atomic) EESEG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * R * S * Cin, stream));
   static bool attr_set = false;
   if (!attr_set) {
     EESEG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_wgrad_kernel<<<base_items * ksplit, kWgThreads, smem_bytes, stream>>>(tmdy, tmx, p);
-  return check_launch("conv_wgrad_kernel");
+  conv_wgrad_kernel<<<base_items * p.ksplit, kWgThreads, smem_bytes, stream>>>(tmdy, tmx, p);
+  rc = check_launch("conv_wgrad_kernel");
+  if (rc || p.ksplit == 1) return rc;
+  const int64_t n4 = dw_elems / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), p.ksplit, n4,
+                                                           reinterpret_cast<float4*>(dw));
+  return check_launch("wgrad_reduce_kernel");
 }
 
 extern "C" int eeseg_conv_weight_rot180_t(const void* w, int Cout, int R, int S, int Cin, void* out, void* stream_) {

@@ -332,13 +332,29 @@ __global__ void __launch_bounds__(128) upsample_bwd_kernel(const T* __restrict__
   up_range(x, scale_x, w, W, Xlo, Xhi);
   const T* g = dout + plane * (int64_t)H * W;
   float acc = 0.f;
+  // horizontal weights once per thread (the window is <= 2*scale + 4 wide: 20 for the 8x up-sampling of the heads)
+  constexpr int kMaxWin = 24;
+  float wxs[kMaxWin];
+  const int nx = Xhi - Xlo + 1;
+  const bool cached = nx <= kMaxWin;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kMaxWin; ++i) wxs[i] = i < nx ? up_weight(Xlo + i, scale_x, w, x) : 0.f;
+  }
   for (int Y = Ylo; Y <= Yhi; ++Y) {
     const float wy = up_weight(Y, scale_y, h, y);
     if (wy == 0.f) continue;
+    const T* grow = g + (int64_t)Y * W + Xlo;
     float row = 0.f;
-    for (int X = Xlo; X <= Xhi; ++X) {
-      const float wx = up_weight(X, scale_x, w, x);
-      if (wx != 0.f) row = fmaf(wx, ldf(g + (int64_t)Y * W + X), row);
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < kMaxWin; ++i)
+        if (i < nx) row = fmaf(wxs[i], ldf(grow + i), row);
+    } else {
+      for (int X = Xlo; X <= Xhi; ++X) {
+        const float wx = up_weight(X, scale_x, w, x);
+        if (wx != 0.f) row = fmaf(wx, ldf(grow + (X - Xlo)), row);
+      }
     }
     acc = fmaf(wy, row, acc);
   }

@@ -65,8 +65,10 @@ class ConvIgemmFn(torch.autograd.Function):
                                                    dx.data_ptr(), _lib.BF16, Cin, ws.data_ptr(), st), "eeseg_conv_igemm_dgrad")
             if ctx.needs_input_grad[1]:
                 dwk = torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
+                wws = torch.empty((lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, Cin, Cout, R, S),), dtype=torch.uint8,
+                                  device=x.device)
                 check(lib().eeseg_conv_igemm_wgrad(x.data_ptr(), dy.data_ptr(), Cout, Cout, 0, N, h, w, Cin, Cout, R, S,
-                                                   ctx.dilation, dwk.data_ptr(), st), "eeseg_conv_igemm_wgrad")
+                                                   ctx.dilation, dwk.data_ptr(), wws.data_ptr(), st), "eeseg_conv_igemm_wgrad")
                 dw = dwk.permute(0, 3, 1, 2)                                             # the parameter's layout
         return dx, dw, None
 

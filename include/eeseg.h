@@ -194,7 +194,9 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
  *   NHWC tensors; the tap is a coordinate offset, zero fill = padding).
  *   x  bf16 NHWC [N][h][w][Cin] (Cin % 64 == 0);  dy bf16 NHWC, pixel stride ldy, dy_channels channels in
  *   total, this convolution's Cout (% 128 == 0) channels starting at co_off;  dw fp32 [Cout][R][S][Cin]
- *   (overwritten; summed with atomics when the pixel dimension is split over CTAs to fill the GPU).
+ *   (overwritten). When the pixel dimension is split over CTAs to fill the GPU every split writes its own partial
+ *   dW into `workspace` (eeseg_conv_igemm_wgrad_workspace_bytes bytes, 16 B aligned) and a second kernel sums them
+ *   in a fixed order: bit-reproducible, no atomics.
  *
  * eeseg_conv_igemm_dgrad:  dX = conv(dY, W'), W'[ci][r][s][co] = W[co][R-1-r][S-1-s][ci], on the forward
  *   kernel. dy bf16 NHWC contiguous [N][h][w][Cout] (Cout % 64 == 0), wt bf16 [Cout][R][S][Cin]
@@ -203,8 +205,10 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
  * eeseg_conv_weight_rot180_t: the weight transform alone ([Cout][R][S][Cin] -> [Cin][R][S][Cout], taps
  *   rotated by 180 degrees), for callers that cache it.
  * ---------------------------------------------------------------------------------------------- */
+size_t eeseg_conv_igemm_wgrad_workspace_bytes(int N, int h, int w, int Cin, int Cout, int R, int S);
 int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
-                           int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* stream);
+                           int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* workspace,
+                           void* stream);
 size_t eeseg_conv_igemm_dgrad_workspace_bytes(int Cin, int Cout, int R, int S);
 int eeseg_conv_igemm_dgrad(const void* dy, const void* wt, int N, int h, int w, int Cin, int Cout, int R, int S,
                            int dilation, void* dx, int dx_dtype, int64_t lddx, void* workspace, void* stream);

@@ -209,8 +209,13 @@ def run_conv_grads(N, h, w, Cin, Cout, R, dil, seed=0, co_off=0, extra=0):
     xd, wd, dyd = x.to(dev()), wt.to(dev()), dy_full.to(dev())
     st = torch.cuda.current_stream().cuda_stream
     dw = torch.full((Cout, R, R, Cin), 7.0, dtype=torch.float32, device=dev())
+    wws = torch.empty(lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, Cin, Cout, R, R), dtype=torch.uint8, device=dev())
     check(lib().eeseg_conv_igemm_wgrad(xd.data_ptr(), dyd.data_ptr(), Cout + extra, Cout + extra, co_off, N, h, w, Cin, Cout,
-                                       R, R, dil, dw.data_ptr(), st), "wgrad")
+                                       R, R, dil, dw.data_ptr(), wws.data_ptr(), st), "wgrad")
+    dw2 = torch.empty_like(dw)      # split-K partials are summed in a fixed order: bit-reproducible
+    check(lib().eeseg_conv_igemm_wgrad(xd.data_ptr(), dyd.data_ptr(), Cout + extra, Cout + extra, co_off, N, h, w, Cin, Cout,
+                                       R, R, dil, dw2.data_ptr(), wws.data_ptr(), st), "wgrad")
+    assert torch.equal(dw, dw2)
     e_w = (dw.cpu() - ref_dw).abs().max().item() / (ref_dw.abs().max().item() + 1e-9)
     e_x = None
     if extra == 0:

@@ -263,8 +263,10 @@ def main():
             dx = torch.empty(N, h, w, cin, dtype=torch.bfloat16, device=dev)
             ws = torch.empty(lib().eeseg_conv_igemm_dgrad_workspace_bytes(cin, cout, R, R), dtype=torch.uint8, device=dev)
             fl = 2 * N * h * w * cout * cin * R * R
+            wws = torch.empty(lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, cin, cout, R, R), dtype=torch.uint8, device=dev)
             ms = timeit(lambda i: check(lib().eeseg_conv_igemm_wgrad(x.data_ptr(), dy.data_ptr(), cout, cout, 0, N, h, w, cin, cout,
-                                                                     R, R, dil, dw.data_ptr(), stream()), "wgrad"), args.iters, flush)
+                                                                     R, R, dil, dw.data_ptr(), wws.data_ptr(), stream()), "wgrad"),
+                        args.iters, flush)
             xc = x.permute(0, 3, 1, 2).float().requires_grad_(True)
             wc = wt.permute(0, 3, 1, 2).float().requires_grad_(True)
             dyc = dy.permute(0, 3, 1, 2).float()
