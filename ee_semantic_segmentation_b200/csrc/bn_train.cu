@@ -17,7 +17,7 @@
 namespace eeseg {
 
 constexpr int kBnThreads = 256;      // 8 channel groups (8 channels each) x 32 pixel lanes
-constexpr int kBnMaxSplits = 64;
+constexpr int kBnMaxSplits = 512;
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -93,17 +93,26 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const __nv_bfloat
   }
 }
 
-// mean / invstd / folded scale-shift / running statistics from the partial sums (one thread per channel)
+// Sum of the `splits` partials of quantity q for channel c by ONE WARP in a fixed order: lane l adds partials
+// l, l+32, ... in fp64, then a fixed shuffle tree. Every lane returns the total.
+__device__ __forceinline__ double bn_warp_total(const float* __restrict__ partial, int splits, int C, int c, int q) {
+  double t = 0.0;
+  for (int i = (int)(threadIdx.x & 31); i < splits; i += 32) t += (double)partial[((int64_t)i * 2 + q) * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+// mean / invstd / folded scale-shift / running statistics from the partial sums (one warp per channel)
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int splits, int C, int64_t P,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                          float eps, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                          float* __restrict__ fa, float* __restrict__ fb) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-#pragma unroll 8
-  for (int i = 0; i < splits; ++i) { s += partial[((int64_t)i * 2) * C + c]; ss += partial[((int64_t)i * 2 + 1) * C + c]; }
+  const double s = bn_warp_total(partial, splits, C, c, 0), ss = bn_warp_total(partial, splits, C, c, 1);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / (double)P;
   double var = ss / (double)P - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -124,18 +133,20 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ res, int64_t total8, int C,
                                                        const float* __restrict__ fa, const float* __restrict__ fb, int relu,
                                                        __nv_bfloat16* __restrict__ y) {
-  // total8 = P*C/8 groups of 8 channels; a thread's channel offset is constant when the stride is a multiple of C/8
+  // total8 = P*C/8 groups of 8 channels. The host sizes the grid so that the grid stride is a multiple of C/8:
+  // a thread then keeps the same 8 channels for its whole loop and their constants stay in registers
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int c8 = C >> 3;
+  const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % c8) * 8;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(fa + c)), a1 = __ldg(reinterpret_cast<const float4*>(fa + c + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(fb + c)), b1 = __ldg(reinterpret_cast<const float4*>(fb + c + 4));
+  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll 2
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
-    const int c = (int)(i % c8) * 8;
     float xv[8], rv[8], o[8];
     unpack8(ld16_stream(x + i * 8), xv);
     if (res) unpack8(ld16_stream(res + i * 8), rv);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(fa + c)), a1 = __ldg(reinterpret_cast<const float4*>(fa + c + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(fb + c)), b1 = __ldg(reinterpret_cast<const float4*>(fb + c + 4));
-    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float v = fmaf(av[k], xv[k], bv[k]);
@@ -151,10 +162,10 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int sp
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
                                        float* __restrict__ c2, float* __restrict__ fa) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int i = 0; i < splits; ++i) { s += partial[((int64_t)i * 2) * C + c]; ss += partial[((int64_t)i * 2 + 1) * C + c]; }
+  const double s = bn_warp_total(partial, splits, C, c, 0), ss = bn_warp_total(partial, splits, C, c, 1);
+  if ((threadIdx.x & 31) != 0) return;
   if (dbeta) dbeta[c] = (float)s;
   if (dgamma) dgamma[c] = (float)ss;
   // dx = a*(dy' - s/P - xhat*ss/P) = a*dy' + k1 + k2*x with xhat = (x - mean)*invstd
@@ -171,20 +182,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ fa, const float* __restrict__ k1,
                                                            const float* __restrict__ k2, int relu,
                                                            __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;   // a multiple of C/8 (see bn_apply_kernel)
   const int c8 = C >> 3;
+  const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % c8) * 8;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(fa + c)), a1 = __ldg(reinterpret_cast<const float4*>(fa + c + 4));
+  const float4 p0 = __ldg(reinterpret_cast<const float4*>(k1 + c)), p1 = __ldg(reinterpret_cast<const float4*>(k1 + c + 4));
+  const float4 q0 = __ldg(reinterpret_cast<const float4*>(k2 + c)), q1 = __ldg(reinterpret_cast<const float4*>(k2 + c + 4));
+  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll 2
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
-    const int c = (int)(i % c8) * 8;
     float g[8], xv[8], yv[8], o[8], r[8];
     unpack8(ld16_stream(dy + i * 8), g);
     unpack8(ld16_stream(x + i * 8), xv);
     if (relu) unpack8(ld16_stream(y + i * 8), yv);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(fa + c)), a1 = __ldg(reinterpret_cast<const float4*>(fa + c + 4));
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(k1 + c)), p1 = __ldg(reinterpret_cast<const float4*>(k1 + c + 4));
-    const float4 q0 = __ldg(reinterpret_cast<const float4*>(k2 + c)), q1 = __ldg(reinterpret_cast<const float4*>(k2 + c + 4));
-    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float gg = (!relu || yv[k] > 0.f) ? g[k] : 0.f;
@@ -194,6 +206,18 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(o);
     if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(r);
   }
+}
+
+// number of 256-thread blocks of the apply kernels: about 16 per SM, and blocks*256 a multiple of C/8
+static unsigned bn_apply_blocks(int64_t total8, int C) {
+  const int c8 = C >> 3;
+  int64_t unit = 1;                       // smallest block count with (unit*256) % c8 == 0
+  while ((unit * 256) % c8) ++unit;
+  int64_t blocks = (total8 + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  blocks = (blocks + unit - 1) / unit * unit;
+  return (unsigned)blocks;
 }
 
 static int bn_splits(int64_t P, int C) {
@@ -236,14 +260,12 @@ extern "C" int eeseg_bn_train_fwd(const void* x, int64_t P, int C, const float* 
                                                                        nullptr, 0, partial);
   int rc = check_launch("bn_reduce_kernel<stats>");
   if (rc) return rc;
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, splits, C, P, gamma, beta, running_mean, running_var,
+  bn_stats_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partial, splits, C, P, gamma, beta, running_mean, running_var,
                                                               momentum, eps, save_mean, save_invstd, fa, fb);
   rc = check_launch("bn_stats_finalize_kernel");
   if (rc) return rc;
   const int64_t total8 = P * C / 8;
-  int64_t blocks = (total8 + 255) / 256;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  bn_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, total8, C, fa, fb,
+  bn_apply_kernel<<<bn_apply_blocks(total8, C), 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, total8, C, fa, fb,
                                                        relu, (__nv_bfloat16*)y);
   return check_launch("bn_apply_kernel");
 }
@@ -265,14 +287,12 @@ extern "C" int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, 
                                                                        relu, partial);
   int rc = check_launch("bn_reduce_kernel<bwd>");
   if (rc) return rc;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, splits, C, P, gamma, save_mean, save_invstd, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partial, splits, C, P, gamma, save_mean, save_invstd, dgamma, dbeta,
                                                               c1, c2, fa);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
   const int64_t total8 = P * C / 8;
-  int64_t blocks = (total8 + 255) / 256;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+  bn_bwd_apply_kernel<<<bn_apply_blocks(total8, C), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                            (const __nv_bfloat16*)y, total8, C, fa, c1, c2, relu,
                                                            (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
   return check_launch("bn_bwd_apply_kernel");

@@ -283,6 +283,54 @@ def main():
             row(f"conv dgrad {name} (N=4, 65x65), incl. weight transform", ms, flops=fl, eager_ms=timeit(eager_x, 3, flush),
                 note="nominal dense FLOPs; eager = autograd through cuDNN, TF32 allowed (fwd + dgrad)")
 
+    # ---------------- training BatchNorm (+residual) (+ReLU) and up-sampling backward ----------------
+    if want("bn"):
+        for (Nb, Cb, hb, wb, name) in [(4, 256, 129, 129, "layer1 out 4x256x129x129"), (4, 1024, 65, 65, "layer3 out 4x1024x65x65"),
+                                       (4, 256, 65, 65, "head 4x256x65x65")]:
+            P = Nb * hb * wb
+            xs = [torch.randn(P, Cb, device=dev).to(torch.bfloat16) for _ in range(ROT)]
+            rs = [torch.randn(P, Cb, device=dev).to(torch.bfloat16) for _ in range(ROT)]
+            ys = [torch.empty(P, Cb, device=dev, dtype=torch.bfloat16) for _ in range(ROT)]
+            dxs = [torch.empty(P, Cb, device=dev, dtype=torch.bfloat16) for _ in range(ROT)]
+            gam, bet = torch.ones(Cb, device=dev), torch.zeros(Cb, device=dev)
+            rm, rv = torch.zeros(Cb, device=dev), torch.ones(Cb, device=dev)
+            mean, istd = torch.empty(Cb, device=dev), torch.empty(Cb, device=dev)
+            dg, db = torch.empty(Cb, device=dev), torch.empty(Cb, device=dev)
+            ws = torch.empty(lib().eeseg_bn_train_workspace_bytes(Cb), dtype=torch.uint8, device=dev)
+            def fwd(i):
+                k = i % ROT
+                check(lib().eeseg_bn_train_fwd(xs[k].data_ptr(), P, Cb, gam.data_ptr(), bet.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1,
+                                               1e-5, 1, rs[k].data_ptr(), ys[k].data_ptr(), mean.data_ptr(), istd.data_ptr(),
+                                               ws.data_ptr(), stream()), "bn_fwd")
+            def bwd(i):
+                k = i % ROT
+                check(lib().eeseg_bn_train_bwd(rs[k].data_ptr(), xs[k].data_ptr(), ys[k].data_ptr(), P, Cb, gam.data_ptr(), mean.data_ptr(),
+                                               istd.data_ptr(), 1, dxs[k].data_ptr(), ys[(k + 1) % ROT].data_ptr(), dg.data_ptr(),
+                                               db.data_ptr(), ws.data_ptr(), stream()), "bn_bwd")
+            fwd(0)
+            bn = torch.nn.BatchNorm2d(Cb).to(dev).train()
+            xc = [t.view(Nb, hb, wb, Cb).permute(0, 3, 1, 2) for t in xs]
+            rc = [t.view(Nb, hb, wb, Cb).permute(0, 3, 1, 2) for t in rs]
+            def eager_f(i):
+                return torch.relu(bn(xc[i % ROT]) + rc[i % ROT])
+            ms = timeit(fwd, args.iters)
+            row(f"bn_train fwd (+residual +ReLU) {name}", ms, P * Cb * 2 * 4, eager_ms=timeit(eager_f, 5),
+                note="stats + apply: x read twice, residual read, y written; eager = ATen channels_last bf16 BN + add + relu")
+            ms = timeit(bwd, args.iters)
+            row(f"bn_train bwd (+residual +ReLU) {name}", ms, P * Cb * 2 * 8,
+                note="reduce + apply: dy, x, y read twice, dx and dresidual written")
+            del xs, rs, ys, dxs
+        E = 3
+        gos = [torch.randn(N, C, H, W, device=dev) for _ in range(ROT)]
+        dlow = torch.empty(N, C, h, w, device=dev)
+        ms = timeit(lambda i: check(lib().eeseg_upsample_bilinear_bwd(gos[i % ROT].data_ptr(), 0, N * C, h, w, H, W, dlow.data_ptr(),
+                                                                      stream()), "upbwd"), args.iters)
+        lowr = torch.randn(N, C, h, w, device=dev, requires_grad=True)
+        def eager_u(i):
+            return torch.autograd.grad(F.interpolate(lowr, size=(H, W), mode="bilinear", align_corners=False), lowr, gos[i % ROT])
+        row("upsample_bilinear backward (gather, deterministic) N=4 C=21 513x513 -> 65x65", ms, N * C * (H * W + h * w) * 4,
+            eager_ms=timeit(eager_u, 5), note="eager = ATen forward + atomic-scatter backward")
+
     out = {"peaks": peaks, "method": f"CUDA events around {REPS} back-to-back calls on a parked GPU, buffers rotated over sets larger than L2 "
                                      "(conv / Lovasz / eager rows: single call after a read flush of L2); mean of the faster half", "rows": rows}
     if args.out:
