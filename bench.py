@@ -363,6 +363,7 @@ def main():
     # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
     prof = []
     eng_prof = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=False)   # same kernels, launched eagerly
+    eng_prof.overlap_gates = False     # gates in stream order: nothing shares the SMs with the conv kernel being timed
     eng_prof.evaluate(Xd, yd)
     head_plan.PROFILE = prof
     barrier()
