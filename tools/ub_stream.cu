@@ -194,6 +194,9 @@ static float time_it(F f, int iters = 20) {
   return ms / iters;
 }
 
+extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype, const int64_t* targets, int N, int C, int64_t HW,
+                                    int64_t* cm, int accumulate, void* stream);
+
 int main() {
   constexpr int E = 3, N = 4, C = 21;
   const int64_t HW = 513 * 513;
@@ -234,6 +237,12 @@ int main() {
     auto hrun = [&](auto kern, dim3 grid, int T) { kern<<<grid, T>>>(x + (int64_t)(k++ % E) * N * C * HW, tg, HW, cm); };
 #define HDR(PIX, T) rep("hist_direct PIX=" #PIX " threads=" #T, time_it([&] { hrun(hist_direct<C, PIX, T>, dim3((HW + T * PIX - 1) / (T * PIX), N), T); }), hist_bytes)
     HDR(1, 128); HDR(1, 256); HDR(2, 128); HDR(2, 256); HDR(4, 128); HDR(4, 256);
+    // the product kernel through the C ABI, same buffers and timing loop
+    int kk = 0;
+    rep("product eeseg_confusion_hist (accumulate)", time_it([&] {
+          eeseg_confusion_hist(x + (int64_t)(kk++ % E) * N * C * HW, 0, 0, tg, N, C, HW, (int64_t*)cm, 1, nullptr); }), hist_bytes);
+    rep("product eeseg_confusion_hist (memset + kernel)", time_it([&] {
+          eeseg_confusion_hist(x + (int64_t)(kk++ % E) * N * C * HW, 0, 0, tg, N, C, HW, (int64_t*)cm, 0, nullptr); }), hist_bytes);
   }
   return 0;
 }
