@@ -19,7 +19,6 @@
 //   made dW irreproducible).
 // Pixel tiles for which the shifted window lies entirely in the padding are skipped.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -241,10 +240,6 @@ static int wgrad_geometry(int N, int h, int w, int Cin, int Cout, int R, int S, 
   int ksplit = kNumSMs / base_items;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > total_pt) ksplit = total_pt;
-  if (const char* e = getenv("EESEG_WGRAD_KSPLIT")) {   // tuning hook
-    const int v = atoi(e);
-    if (v >= 1 && v <= total_pt) ksplit = v;
-  }
   p.ksplit = ksplit;
   return base_items;
 }
