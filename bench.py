@@ -363,7 +363,8 @@ def main():
     # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
     prof = []
     eng_prof = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=False)   # same kernels, launched eagerly
-    eng_prof.overlap_gates = False     # gates in stream order: nothing shares the SMs with the conv kernel being timed
+    eng_prof.overlap_gates = False     # gates and pooled branches in stream order: nothing shares the SMs with the
+    head_plan.OVERLAP_POOLED = False   # conv kernel being timed
     eng_prof.evaluate(Xd, yd)
     head_plan.PROFILE = prof
     barrier()
@@ -393,6 +394,7 @@ def main():
     n_t = _lib.lib().eeseg_conv_timing(None, 0)
     tb = tbuf[:n_t].cpu()
     inkernel_ms = float((tb[:, 1] - tb[:, 0]).sum()) / 1e6
+    head_plan.OVERLAP_POOLED = True
     prof_step_ms = sum(a.elapsed_time(b) for a, b in prof_steps)
     clocks = sampler.stop() if rank == 0 else {}
     conv_ms = sum(p[0].elapsed_time(p[1]) for p in prof)

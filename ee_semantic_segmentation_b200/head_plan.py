@@ -150,6 +150,16 @@ def global_avgpool_nhwc(xh):
 
 
 GROUPED = True   # run the ASPP branch convolutions as one grouped launch
+OVERLAP_POOLED = True   # pooled ASPP branch on a side stream, next to the grouped ASPP launch
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = str(dev)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 class HeadPlan:
@@ -211,6 +221,18 @@ class HeadPlan:
             xh = t
         nb, mid = len(self.branches), self.mid
         cat = torch.empty((N, h, w, nb * mid), dtype=torch.bfloat16, device=dev)
+        # The pooled branch (avg-pool -> 1x1 -> BN -> ReLU, then its share of the projection, per image: ~35 us of
+        # four small launches) needs only the head input, like the ASPP convolutions: it runs on a side stream
+        # (a parallel branch of the captured graph) while the grouped ASPP launch — whose CTAs leave ~28 KB of
+        # shared memory and half of the register file free — occupies the main stream; joined before the projection.
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if OVERLAP_POOLED else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            pooled = global_avgpool_nhwc(xh)
+            pv = dense_bn_act(pooled, self.pool_w, self.pool_s, self.pool_b, True)        # [N, mid]
+            pshift = dense_bn_act(pv, self.proj_pool_w, self.proj_s, self.proj_b, False)    # [N, mid]
         if GROUPED and 2 <= nb <= 4 and all(wt.shape[1] in (1, 3) for wt, _, _, _ in self.branches) \
                 and any(wt.shape[1] == 3 for wt, _, _, _ in self.branches):
             # the ASPP branches (1x1 + atrous 3x3) as ONE persistent launch over a cost-sorted work list
@@ -227,10 +249,8 @@ class HeadPlan:
         else:
             for k, (wt, s, b, dil) in enumerate(self.branches):
                 conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)
-        # pooled branch: avg-pool -> 1x1 -> BN -> ReLU, then its share of the projection, per image
-        pooled = global_avgpool_nhwc(xh)
-        pv = dense_bn_act(pooled, self.pool_w, self.pool_s, self.pool_b, True)        # [N, mid]
-        pshift = dense_bn_act(pv, self.proj_pool_w, self.proj_s, self.proj_b, False)    # [N, mid]
+        if side is not main:
+            main.wait_stream(side)
         y = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
         conv_igemm(cat, self.proj_w, self.proj_s, pshift, 1, True, y, BF, mid, shift_sn=mid)
         z = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
