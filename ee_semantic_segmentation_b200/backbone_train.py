@@ -1,11 +1,11 @@
 """Training-mode forward/backward of a backbone section (`base_model[i]`, from_deepv3_new.py:146,151 inside
 `train_epoch`, train_funcs.py:22-27): every stride-1 'same' convolution of the torchvision ResNet
-`Bottleneck`s whose channel counts fit the tensor-core tiles (Cin % 64 == 0, Cout % 128 == 0 — all of layer2-4
-but the two stride-2 convolutions of layer2.0, and the 1x1 expansions / projection of layer1) runs forward,
+`Bottleneck`s whose channel counts fit the tensor-core tiles (Cin % 64 == 0, Cout % 64 == 0 — all of layer1-4
+but the two stride-2 convolutions of layer2.0) runs forward,
 input-gradient and weight-gradient on the eeseg tcgen05 kernels (head_train.ConvIgemmFn); BatchNorm (batch
 statistics, running-stat updates) + residual add + ReLU run as one fused eeseg node per BatchNorm
 (bn_train.BnActFn); activations are bf16 channels_last end to end. The 7x7 stem (conv, BN, ReLU, max-pool) and the
-few unsupported convolutions (64-channel outputs of layer1, stride 2) stay on the PyTorch modules under bf16
+two stride-2 convolutions of layer2.0 stay on the PyTorch modules under bf16
 autocast: parameters, buffers and state-dict layout are the reference's.
 Master weights and their gradients stay fp32 (mixed precision); the reference trains in fp32 with TF32
 allowed (train_funcs.py:117-118) — parity is within the bf16 bound of north_star and is tested as such.

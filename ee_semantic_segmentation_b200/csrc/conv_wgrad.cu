@@ -164,6 +164,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     const int m = quad * 32 + lane;
     const int co = mb * 128 + m;
     float* row = p.dw + (int64_t)ks * p.part_stride + ((int64_t)co * (p.R * p.S) + tap) * p.Cin + (int64_t)nb * p.BN;
+    const bool store = co < p.Cout;   // rows past Cout (64-channel layers) hold zeros and have no destination
     if (n_live > 0) {
       mbar_wait(acc_bar, 0);
       tcgen05_fence_after();
@@ -172,12 +173,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)col, v);
         tmem_ld_wait();
+        if (!store) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           reinterpret_cast<float4*>(row + col)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
-    } else {
+    } else if (store) {
       for (int col = 0; col < p.BN; col += 4) *reinterpret_cast<float4*>(row + col) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tcgen05_fence_before();
@@ -234,7 +236,8 @@ static int wgrad_geometry(int N, int h, int w, int Cin, int Cout, int R, int S, 
   p.tiles_y = (h + p.BH - 1) / p.BH;
   p.BN = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
   p.nblocks = Cin / p.BN;
-  p.mblocks = Cout / 128;
+  p.mblocks = (Cout + 127) / 128;   // Cout = 64: the upper half of the 128-row tile reads channels past the end of dY
+                                    // (TMA zero fill) and is not stored
   const int base_items = R * S * p.nblocks * p.mblocks;
   const int total_pt = N * p.tiles_x * p.tiles_y;
   int ksplit = kNumSMs / base_items;
@@ -245,7 +248,7 @@ static int wgrad_geometry(int N, int h, int w, int Cin, int Cout, int R, int S, 
 }
 
 extern "C" size_t eeseg_conv_igemm_wgrad_workspace_bytes(int N, int h, int w, int Cin, int Cout, int R, int S) {
-  if (N < 1 || h < 1 || w < 1 || Cin < 64 || Cout < 128 || R < 1 || S < 1) return 256;
+  if (N < 1 || h < 1 || w < 1 || Cin < 64 || Cout < 64 || R < 1 || S < 1) return 256;
   WgradParams p;
   wgrad_geometry(N, h, w, Cin, Cout, R, S, p);
   return (p.ksplit > 1 ? (size_t)p.ksplit * Cout * R * S * Cin * sizeof(float) : 0) + 256;
@@ -258,7 +261,7 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   EESEG_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
   EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_wgrad: bad sizes");
   EESEG_REQUIRE(Cin % 64 == 0, "conv_wgrad: Cin=%d must be a multiple of 64", Cin);
-  EESEG_REQUIRE(Cout % 128 == 0, "conv_wgrad: Cout=%d must be a multiple of 128", Cout);
+  EESEG_REQUIRE(Cout % 64 == 0, "conv_wgrad: Cout=%d must be a multiple of 64", Cout);
   EESEG_REQUIRE(R >= 1 && S >= 1 && (R & 1) && (S & 1) && R * S <= 32, "conv_wgrad: odd kernel sizes with at most 32 taps");
   EESEG_REQUIRE(dilation >= 1, "conv_wgrad: dilation %d", dilation);
   EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw & 15) == 0 && (ldy % 8) == 0 &&

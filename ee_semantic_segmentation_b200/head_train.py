@@ -30,7 +30,7 @@ def _unit_scale_shift(dev, n):
 class ConvIgemmFn(torch.autograd.Function):
     """y = conv2d(x, weight; stride 1, 'same' padding dilation*(R//2), no bias) on NHWC bf16 activations.
     x [N,h,w,Cin] bf16 contiguous (Cin % 64 == 0); weight: the nn.Conv2d parameter [Cout,Cin,R,S]
-    (Cout % 128 == 0 for the weight gradient). Returns [N,h,w,Cout] bf16."""
+    (Cout % 64 == 0). Returns [N,h,w,Cout] bf16."""
 
     @staticmethod
     def forward(ctx, x, weight, dilation):
@@ -79,7 +79,7 @@ def _conv_ok(conv):
     return (isinstance(conv, nn.Conv2d) and conv.bias is None and conv.groups == 1 and conv.stride == (1, 1)
             and conv.kernel_size[0] == conv.kernel_size[1] and (k & 1) and conv.dilation[0] == conv.dilation[1]
             and conv.padding == (d * (k // 2), d * (k // 2)) and conv.padding_mode == 'zeros'
-            and conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0)
+            and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0)
 
 
 def head_supported(head):

@@ -193,7 +193,7 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
  *   tcgen05 implicit GEMM with the pixels as the contraction dimension (both operands MN-major, TMA boxes of
  *   NHWC tensors; the tap is a coordinate offset, zero fill = padding).
  *   x  bf16 NHWC [N][h][w][Cin] (Cin % 64 == 0);  dy bf16 NHWC, pixel stride ldy, dy_channels channels in
- *   total, this convolution's Cout (% 128 == 0) channels starting at co_off;  dw fp32 [Cout][R][S][Cin]
+ *   total, this convolution's Cout (% 64 == 0) channels starting at co_off;  dw fp32 [Cout][R][S][Cin]
  *   (overwritten). When the pixel dimension is split over CTAs to fill the GPU every split writes its own partial
  *   dW into `workspace` (eeseg_conv_igemm_wgrad_workspace_bytes bytes, 16 B aligned) and a second kernel sums them
  *   in a fixed order: bit-reproducible, no atomics.

@@ -236,6 +236,9 @@ def run_conv_grads(N, h, w, Cin, Cout, R, dil, seed=0, co_off=0, extra=0):
     dict(N=2, h=65, w=65, Cin=256, Cout=256, R=3, dil=36),          # most (tap, tile) pairs all padding
     dict(N=2, h=33, w=47, Cin=512, Cout=256, R=1, dil=1),           # 1x1, deep K split
     dict(N=1, h=24, w=40, Cin=320, Cout=256, R=1, dil=1, co_off=64, extra=128),   # dY is a window of a wider buffer
+    dict(N=2, h=33, w=33, Cin=64, Cout=64, R=3, dil=1),             # layer1: 64 output channels = half a 128-row tile
+    dict(N=2, h=33, w=33, Cin=256, Cout=64, R=1, dil=1),
+    dict(N=1, h=17, w=17, Cin=128, Cout=192, R=1, dil=1, co_off=64, extra=64),    # ragged last co block inside a wider dY
 ])
 def test_conv_wgrad_dgrad_vs_autograd(cfg):
     e_w, e_x = run_conv_grads(**cfg)
