@@ -1,11 +1,10 @@
 """Training-mode forward/backward of a backbone section (`base_model[i]`, from_deepv3_new.py:146,151 inside
-`train_epoch`, train_funcs.py:22-27): every stride-1 'same' convolution of the torchvision ResNet
-`Bottleneck`s whose channel counts fit the tensor-core tiles (Cin % 64 == 0, Cout % 64 == 0 — all of layer1-4
-but the two stride-2 convolutions of layer2.0) runs forward,
+`train_epoch`, train_funcs.py:22-27): every convolution of the torchvision ResNet `Bottleneck`s (Cin, Cout
+multiples of 64; stride 1, or 2 in layer2.0) runs forward,
 input-gradient and weight-gradient on the eeseg tcgen05 kernels (head_train.ConvIgemmFn); BatchNorm (batch
 statistics, running-stat updates) + residual add + ReLU run as one fused eeseg node per BatchNorm
-(bn_train.BnActFn); activations are bf16 channels_last end to end. The 7x7 stem (conv, BN, ReLU, max-pool) and the
-two stride-2 convolutions of layer2.0 stay on the PyTorch modules under bf16
+(bn_train.BnActFn); activations are bf16 channels_last end to end. The 7x7 stem (conv, BN, ReLU, max-pool: 3 input
+channels) stays on the PyTorch modules under bf16
 autocast: parameters, buffers and state-dict layout are the reference's.
 Master weights and their gradients stay fp32 (mixed precision); the reference trains in fp32 with TF32
 allowed (train_funcs.py:117-118) — parity is within the bf16 bound of north_star and is tested as such.
@@ -21,7 +20,7 @@ from .head_train import ConvIgemmFn, _conv_ok
 def _conv(x, conv):
     """x: [N,C,h,w] bf16 channels_last -> conv(x) in the same format."""
     if _conv_ok(conv):
-        return ConvIgemmFn.apply(x.permute(0, 2, 3, 1), conv.weight, conv.dilation[0]).permute(0, 3, 1, 2)
+        return ConvIgemmFn.apply(x.permute(0, 2, 3, 1), conv.weight, conv.dilation[0], conv.stride[0]).permute(0, 3, 1, 2)
     return conv(x)       # under autocast: cuDNN bf16
 
 

@@ -28,22 +28,28 @@ def _unit_scale_shift(dev, n):
 
 
 class ConvIgemmFn(torch.autograd.Function):
-    """y = conv2d(x, weight; stride 1, 'same' padding dilation*(R//2), no bias) on NHWC bf16 activations.
+    """y = conv2d(x, weight; stride 1 or 2, padding dilation*(R//2), no bias) on NHWC bf16 activations.
     x [N,h,w,Cin] bf16 contiguous (Cin % 64 == 0); weight: the nn.Conv2d parameter [Cout,Cin,R,S]
-    (Cout % 64 == 0). Returns [N,h,w,Cout] bf16."""
+    (Cout % 64 == 0). Returns [N,ho,wo,Cout] bf16, ho = (h-1)//stride + 1.
+
+    Stride 2 (layer2.0 of the ResNet): the forward kernel strides its TMA boxes; the backward inserts zeros
+    between the rows / columns of dY (a [N,h,w,Cout] tensor, 3 of 4 pixels zero) and runs the stride-1 input- and
+    weight-gradient kernels on it — the transposed convolution and the strided correlation are exactly those."""
 
     @staticmethod
-    def forward(ctx, x, weight, dilation):
+    def forward(ctx, x, weight, dilation, stride=1):
         from .head_plan import conv_igemm
         x = x.contiguous()
         N, h, w, Cin = x.shape
         wt = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)     # [Cout,R,S,Cin]
         Cout = wt.shape[0]
-        out = torch.empty((N, h, w, Cout), dtype=torch.bfloat16, device=x.device)
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+        out = torch.empty((N, ho, wo, Cout), dtype=torch.bfloat16, device=x.device)
         one, zero = _unit_scale_shift(x.device, Cout)
-        conv_igemm(x, wt, one, zero, dilation, False, out, _lib.BF16, Cout)
+        conv_igemm(x, wt, one, zero, dilation, False, out, _lib.BF16, Cout, stride=stride)
         ctx.save_for_backward(x, wt)
         ctx.dilation = dilation
+        ctx.stride = stride
         return out
 
     @staticmethod
@@ -53,6 +59,10 @@ class ConvIgemmFn(torch.autograd.Function):
         Cout, R, S, _ = wt.shape
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
+        if ctx.stride != 1:
+            up = torch.zeros((N, h, w, Cout), dtype=torch.bfloat16, device=x.device)
+            up[:, ::ctx.stride, ::ctx.stride] = dy
+            dy = up
         dy = dy.contiguous()
         dx = dw = None
         with torch.cuda.device(x.device):
@@ -70,13 +80,13 @@ class ConvIgemmFn(torch.autograd.Function):
                 check(lib().eeseg_conv_igemm_wgrad(x.data_ptr(), dy.data_ptr(), Cout, Cout, 0, N, h, w, Cin, Cout, R, S,
                                                    ctx.dilation, dwk.data_ptr(), wws.data_ptr(), st), "eeseg_conv_igemm_wgrad")
                 dw = dwk.permute(0, 3, 1, 2)                                             # the parameter's layout
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 def _conv_ok(conv):
-    """Shapes the three kernels take: stride 1, 'same' padding, no groups/bias, channel multiples."""
+    """Shapes the three kernels take: stride 1 or 2, padding dilation*(k//2), no groups/bias, channel multiples."""
     k, d = conv.kernel_size[0], conv.dilation[0]
-    return (isinstance(conv, nn.Conv2d) and conv.bias is None and conv.groups == 1 and conv.stride == (1, 1)
+    return (isinstance(conv, nn.Conv2d) and conv.bias is None and conv.groups == 1 and conv.stride in ((1, 1), (2, 2))
             and conv.kernel_size[0] == conv.kernel_size[1] and (k & 1) and conv.dilation[0] == conv.dilation[1]
             and conv.padding == (d * (k // 2), d * (k // 2)) and conv.padding_mode == 'zeros'
             and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0)
@@ -98,7 +108,7 @@ def _nhwc(t):
 
 def _conv(xh, conv):
     """NHWC bf16 in -> NCHW-shaped (channels_last) bf16 out, as the following BatchNorm2d expects."""
-    return ConvIgemmFn.apply(xh, conv.weight, conv.dilation[0]).permute(0, 3, 1, 2)
+    return ConvIgemmFn.apply(xh, conv.weight, conv.dilation[0], conv.stride[0]).permute(0, 3, 1, 2)
 
 
 def head_forward_train(head, x):

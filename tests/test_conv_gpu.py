@@ -252,3 +252,30 @@ def test_conv_grads_aspp_shapes():
     assert e_w < 5e-3 and e_x < 5e-3, (e_w, e_x)
     e_w, e_x = run_conv_grads(N=2, h=65, w=65, Cin=1280, Cout=256, R=1, dil=1, seed=4)
     assert e_w < 5e-3 and e_x < 5e-3, (e_w, e_x)
+
+
+@pytest.mark.parametrize("cfg", [dict(Cin=128, Cout=128, R=3, h=33, w=33), dict(Cin=256, Cout=512, R=1, h=33, w=33),
+                                 dict(Cin=64, Cout=128, R=3, h=24, w=30)])
+def test_conv_autograd_stride2_vs_torch(cfg):
+    """ConvIgemmFn with stride 2 (layer2.0 of the ResNet): forward on strided TMA boxes, backward through the
+    zero-inserted dY on the stride-1 gradient kernels, against autograd through F.conv2d (odd and even sizes)."""
+    from ee_semantic_segmentation_b200.head_train import ConvIgemmFn
+    Cin, Cout, R, h, w = cfg["Cin"], cfg["Cout"], cfg["R"], cfg["h"], cfg["w"]
+    g = torch.Generator().manual_seed(Cin + Cout + R)
+    x = torch.randn(2, h, w, Cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(Cout, Cin, R, R, generator=g) / np.sqrt(R * R * Cin)).to(torch.bfloat16).float()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    go = torch.randn(2, ho, wo, Cout, generator=g).to(torch.bfloat16)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=2, padding=R // 2)
+    assert yr.shape[-2:] == (ho, wo)
+    yr.backward(go.float().permute(0, 3, 1, 2))
+    xd = x.to(dev()).requires_grad_(True)
+    wd = wt.to(dev()).requires_grad_(True)
+    yd = ConvIgemmFn.apply(xd, wd, 1, 2)
+    yd.backward(go.to(dev()))
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert rel(yd.detach().float().cpu(), yr.detach().permute(0, 2, 3, 1)) < 1e-2
+    assert rel(xd.grad.float().cpu(), xr.grad.permute(0, 2, 3, 1)) < 1e-2
+    assert rel(wd.grad.cpu(), wr.grad) < 5e-3

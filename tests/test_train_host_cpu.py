@@ -11,7 +11,8 @@ def test_conv_routing_rules_match_the_kernel_constraints():
     ok = nn.Conv2d(256, 256, 3, padding=2, dilation=2, bias=False)
     assert _conv_ok(ok)
     assert not _conv_ok(nn.Conv2d(256, 256, 3, padding=1, dilation=2, bias=False))      # not 'same'
-    assert not _conv_ok(nn.Conv2d(256, 256, 3, stride=2, padding=1, bias=False))        # stride 2 (layer2.0)
+    assert _conv_ok(nn.Conv2d(256, 256, 3, stride=2, padding=1, bias=False))            # stride 2 (layer2.0)
+    assert not _conv_ok(nn.Conv2d(256, 256, 3, stride=4, padding=1, bias=False))
     assert _conv_ok(nn.Conv2d(256, 64, 1, bias=False))                                  # 64 output channels (layer1)
     assert not _conv_ok(nn.Conv2d(256, 96, 1, bias=False))                              # Cout % 64
     assert not _conv_ok(nn.Conv2d(3, 128, 7, padding=3, bias=False))                    # Cin % 64 (stem)
@@ -23,8 +24,8 @@ def test_conv_routing_rules_match_the_kernel_constraints():
 
 
 def test_resnet50_backbone_routing_counts():
-    """Of the 52 Bottleneck convolutions of the DeepLab ResNet-50 backbone (stride 8), 50 take the eeseg tiles;
-    the 2 stride-2 convolutions of layer2.0 do not."""
+    """All 52 Bottleneck convolutions of the DeepLab ResNet-50 backbone (stride 8) take the eeseg tiles; the stem's
+    7x7 convolution (3 input channels) does not."""
     import torchvision
     from torchvision.models.resnet import Bottleneck
     from ee_semantic_segmentation_b200.head_train import _conv_ok
@@ -32,8 +33,8 @@ def test_resnet50_backbone_routing_counts():
     convs = [m for blk in bb.modules() if isinstance(blk, Bottleneck) for m in blk.modules() if isinstance(m, nn.Conv2d)]
     assert len(convs) == 52
     bad = [c for c in convs if not _conv_ok(c)]
-    assert len(bad) == 2
-    assert sorted((c.out_channels, c.stride[0]) for c in bad) == [(128, 2), (512, 2)]
+    assert len(bad) == 0
+    assert not _conv_ok(bb.conv1)
 
 
 def test_training_kernels_refuse_cpu_tensors():
