@@ -1,7 +1,11 @@
-"""Drop-in for the hot-path part of the reference's branchy_seg_losses.py: the multi-exit wrapper
-`BrSegLoss` (:9-38) and the branchy `LovaszSoftmax` (:133-159). All exits are handled by one call
-into csrc/lovasz.cu instead of a Python loop of per-class torch.sort calls.
-Dice/Jaccard/Tversky/FocalTversky/Focal bodies are out of scope."""
+"""Drop-in for the reference's branchy_seg_losses.py: the multi-exit wrapper `BrSegLoss` (:9-38), the branchy
+`LovaszSoftmax` (:133-159; one call into csrc/lovasz.cu for all exits instead of a Python loop of per-class
+torch.sort calls) and the overlap family `DiceLoss` (:40-48), `JaccardLoss` (:50-77), `TverskyLoss` (:79-103),
+`FocalTverskyLoss` (:105-113): one streaming pass over the logits of ALL exits (csrc/soft_overlap.cu) produces
+the per-exit / image / class sums, and the reference's formulas are applied verbatim on those small tensors —
+instead of materialising softmax and int64 one-hot tensors [N,HW,C] per exit. Tversky works on the arg-max map
+(no gradient reaches the logits, as in the reference) and comes from the confusion-matrix kernel.
+`FocalLoss` (:115-131) is not provided."""
 import torch as tch
 from torch import nn
 
@@ -24,9 +28,14 @@ class BrSegLoss(SegLoss):
     def _compute_loss(self, y_pred, targets):
         pass
 
+    def _compute_all(self, y_pred, targets):
+        """Per-exit losses of all exits at once, [E, ...] (subclasses on the eeseg kernels override this)."""
+        return tch.cat([self._compute_loss(y_pred[i], targets).unsqueeze(0) for i in range(y_pred.shape[0])])
+
     def forward(self, y_pred, targets):
-        losses = [self._compute_loss(y_pred[i], targets).unsqueeze(0) for i in range(self.n)]
-        losses = tch.cat(losses)
+        if y_pred.shape[0] < self.n:
+            raise IndexError(f'index {self.n - 1} is out of bounds for dimension 0 with size {y_pred.shape[0]}')
+        losses = self._compute_all(y_pred[:self.n], targets)
         dim = list(range(1, len(losses.shape)))
         if self.reduction == 'mean':
             losses = losses.mean(dim=dim)
@@ -35,6 +44,82 @@ class BrSegLoss(SegLoss):
         else:
             return losses
         return tch.dot(self.weights.to(device=losses.device), losses)
+
+
+def _no_void(s_t, n_pixels):
+    """F.one_hot(targets, num_classes=C) of the reference raises on labels outside [0,C) (branchy_seg_losses.py:44,92)."""
+    if float(s_t.sum()) != float(n_pixels):
+        raise RuntimeError("Class values must be smaller than num_classes.")
+
+
+class DiceLoss(BrSegLoss):
+    """1 - (2*sum p*t + smooth) / (sum (p + t) + smooth) per image (branchy_seg_losses.py:40-48)."""
+
+    def _compute_all(self, y_pred, targets):
+        s_pt, s_p, s_t = ops.soft_overlap_sums(y_pred, targets)
+        _no_void(s_t, targets.numel())
+        num = 2 * s_pt.sum(dim=2) + self.smooth                      # [E,N]
+        den = (s_p + s_t.unsqueeze(0)).sum(dim=2) + self.smooth
+        return 1 - num / den
+
+    def _compute_loss(self, y_pred, targets):
+        return self._compute_all(y_pred.unsqueeze(0), targets)[0]
+
+
+class JaccardLoss(BrSegLoss):
+    """1 - (I + smooth)/(U + smooth) per image and class, class 0 scaled by downgrad_bg; void labels (>= C) are
+    dropped (branchy_seg_losses.py:50-77)."""
+
+    def __init__(self, smooth=1e-6, reduction='mean', n_branches=0, downgrad_bg=1.):
+        super().__init__(smooth, reduction, n_branches)
+        self.downgrad_bg = downgrad_bg if 0 <= downgrad_bg <= 1. else 1.
+
+    def _compute_all(self, y_pred, targets):
+        s_pt, s_p, s_t = ops.soft_overlap_sums(y_pred, targets)
+        intersection = s_pt                                          # [E,N,C]
+        total = s_p + s_t.unsqueeze(0)
+        union = total - intersection
+        IoU = (intersection + self.smooth) / (union + self.smooth)
+        if self.downgrad_bg:
+            loss = 1 - IoU
+            scale = tch.ones(loss.shape[-1], dtype=loss.dtype, device=loss.device)
+            scale[0] = self.downgrad_bg
+            return loss * scale
+        return (1 - IoU).sum(dim=-1)
+
+    def _compute_loss(self, y_pred, targets):
+        return self._compute_all(y_pred.unsqueeze(0), targets)[0]
+
+
+class TverskyLoss(BrSegLoss):
+    """1 - (TP + s)/(TP + alpha*FP + beta*FN + s) per image and class on the ARG-MAX map (branchy_seg_losses.py:79-103);
+    TP/FP/FN from the confusion-matrix kernel."""
+
+    def __init__(self, smooth=1e-6, alpha=.5, beta=.5, reduction='mean', n_branches=1, weights=None):
+        super().__init__(smooth, reduction, n_branches, weights)
+        self.alpha = alpha
+        self.beta = beta
+
+    def _forward_imp(self, y_pred, targets):
+        N, C = y_pred.shape[:2]
+        cm = ops.confusion_hist(y_pred, targets, C)                  # [N, C+1, C]
+        if int(cm[:, C].sum()) != 0:
+            raise RuntimeError("Class values must be smaller than num_classes.")
+        TP, FP, FN = (t.to(tch.float32) for t in ops.basics_from_cm(cm))
+        tversky_idx = (TP + self.smooth) / (TP + self.alpha * FP + self.beta * FN + self.smooth)
+        return 1 - tversky_idx
+
+    def _compute_loss(self, y_pred, targets):
+        return self._forward_imp(y_pred, targets)
+
+
+class FocalTverskyLoss(TverskyLoss):
+    def __init__(self, smooth=1e-6, alpha=.5, beta=.5, gamma=1., reduction='mean', n_branches=1, weights=None):
+        super().__init__(smooth, alpha, beta, reduction, n_branches, weights)
+        self.gamma = gamma
+
+    def _compute_loss(self, y_pred, targets):
+        return self._forward_imp(y_pred, targets) ** self.gamma
 
 
 class LovaszSoftmax(nn.Module):

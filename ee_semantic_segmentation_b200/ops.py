@@ -295,6 +295,64 @@ def multi_exit_ce_backward_unfused(y, targets, ignore_index, g, valid):
 
 
 # --------------------------------------------------------------------------------------------------
+# soft-overlap sums (Dice / Jaccard family)
+# --------------------------------------------------------------------------------------------------
+class _SoftOverlap(torch.autograd.Function):
+    """(S_pt, S_p, S_t) of eeseg_soft_overlap_fwd for y [E,N,C,HW...]; differentiable in y through S_pt and S_p."""
+
+    @staticmethod
+    def forward(ctx, y, targets):
+        E, N, C = y.shape[:3]
+        HW = y[0, 0, 0].numel()
+        dev = y.device
+        with torch.cuda.device(dev):
+            sums = torch.empty((E, N, 3, C), dtype=torch.float32, device=dev)
+            ws = torch.empty((lib().eeseg_soft_overlap_workspace_bytes(E, N, C, HW),), dtype=torch.uint8, device=dev)
+            check(lib().eeseg_soft_overlap_fwd(y.data_ptr(), _dt(y), y.stride(0), targets.data_ptr(), E, N, C, HW,
+                                               sums.data_ptr(), ws.data_ptr(), _stream(y)), "eeseg_soft_overlap_fwd")
+        ctx.save_for_backward(y, targets)
+        s_t = sums[0, :, 2]
+        ctx.mark_non_differentiable(s_t)
+        return sums[:, :, 0], sums[:, :, 1], s_t
+
+    @staticmethod
+    def backward(ctx, g_pt, g_p, _g_t):
+        y, targets = ctx.saved_tensors
+        E, N, C = y.shape[:3]
+        HW = y[0, 0, 0].numel()
+        zeros = None
+        if g_pt is None or g_p is None:
+            zeros = torch.zeros((E, N, C), dtype=torch.float32, device=y.device)
+        a = (zeros if g_pt is None else g_pt).contiguous().float()
+        b = (zeros if g_p is None else g_p).contiguous().float()
+        dy = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            check(lib().eeseg_soft_overlap_bwd(y.data_ptr(), _dt(y), y.stride(0), targets.data_ptr(), E, N, C, HW,
+                                               a.data_ptr(), b.data_ptr(), dy.data_ptr(), _stream(y)), "eeseg_soft_overlap_bwd")
+        return dy, None
+
+
+def soft_overlap_sums(y, targets):
+    """y [E,N,C,*spatial] f32/bf16 CUDA logits, targets [N,(1,)*spatial] integer labels. Returns
+    S_pt [E,N,C] = sum_px softmax(y)[c]*[t==c], S_p [E,N,C] = sum_px softmax(y)[c], S_t [N,C] = sum_px [t==c]
+    (fp32; labels outside [0,C) match no class). Differentiable with respect to y."""
+    _cuda(y, "y_pred")
+    _cuda(targets, "targets")
+    if y.dim() < 4:
+        raise ValueError("y_pred must be [E,N,C,...]")
+    if not y.is_contiguous():
+        y = y.contiguous()
+    N = y.shape[1]
+    tg = targets.reshape(N, -1)
+    if tg.dtype != torch.int64:
+        tg = tg.to(torch.int64)
+    tg = tg.contiguous()
+    if tg.shape[1] != y[0, 0, 0].numel():
+        raise ValueError(f"targets {tuple(targets.shape)} do not match logits {tuple(y.shape)}")
+    return _SoftOverlap.apply(y, tg)
+
+
+# --------------------------------------------------------------------------------------------------
 # Lovasz-softmax
 # --------------------------------------------------------------------------------------------------
 class _Lovasz(torch.autograd.Function):

@@ -215,6 +215,21 @@ int eeseg_conv_igemm_dgrad(const void* dy, const void* wt, int N, int h, int w, 
 int eeseg_conv_weight_rot180_t(const void* w, int Cout, int R, int S, int Cin, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Soft-overlap sums of the branchy Dice / Jaccard losses (BSL.DiceLoss / BSL.JaccardLoss._compute_loss,
+ * branchy_seg_losses.py:40-77, under BrSegLoss.forward :24-38) and their gradient.
+ *   logits [E][N][C][HW] (f32 / bf16, exit stride in elements), targets int64 [N][HW] (values outside [0,C) match no class)
+ *   fwd: sums f32 [E][N][3][C] = { sum_px p_c [t==c],  sum_px p_c,  sum_px [t==c] },  p = softmax over C
+ *   bwd: dlogits[e,n,c,px] = p_c * (g_c - sum_k p_k g_k),  g_c = dsum_p[e,n,c] + dsum_pt[e,n,c] [t==c]
+ *        (dsum_pt, dsum_p f32 [E][N][C]: the loss formula's derivatives with respect to the first two sums)
+ *   workspace: eeseg_soft_overlap_workspace_bytes bytes. Fixed summation order (bit-reproducible).
+ * ---------------------------------------------------------------------------------------------- */
+size_t eeseg_soft_overlap_workspace_bytes(int E, int N, int C, int64_t HW);
+int eeseg_soft_overlap_fwd(const void* logits, int dtype, int64_t exit_stride, const int64_t* targets, int E, int N,
+                           int C, int64_t HW, float* sums, void* workspace, void* stream);
+int eeseg_soft_overlap_bwd(const void* logits, int dtype, int64_t exit_stride, const int64_t* targets, int E, int N,
+                           int C, int64_t HW, const float* dsum_pt, const float* dsum_p, void* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training-mode BatchNorm2d (+ residual add) (+ ReLU) on NHWC bf16 activations — the nn.BatchNorm2d / ReLU /
  * `out += identity` modules of DeepLabHead, ASPP and the ResNet Bottlenecks as they run under net.train() in
  * train_epoch (train_funcs.py:12-33).  x, y, residual, dy, dx, dres: bf16 [P = N*h*w][C], C % 64 == 0.

@@ -236,6 +236,85 @@ def br_xentropy(y_pred, targets, ignore_index=-100, b_reduction="mean", n_exits=
 
 
 # ----------------------------------------------------------------------------------------------
+# Overlap family of branchy_seg_losses.py: Dice :40-48, Jaccard :50-77, Tversky :79-103,
+# FocalTversky :105-113, under BrSegLoss.forward :24-38. Values and (Dice / Jaccard) gradients w.r.t. the logits.
+# ----------------------------------------------------------------------------------------------
+def _overlap_sums(logits, targets):
+    """logits [N,C,H,W] -> p [N,C,HW] (softmax), one-hot t [N,C,HW] (labels outside [0,C) match no class)."""
+    y = np.asarray(logits, dtype=np.float32)
+    N, C = y.shape[:2]
+    p = softmax_c(y.reshape(N, C, -1).astype(np.float64), 1)
+    t = np.asarray(targets).reshape(N, -1)
+    oh = (t[:, None, :] == np.arange(C)[None, :, None]).astype(np.float64)
+    return p, oh, t
+
+
+def _softmax_backward(p, g):
+    """dL/dz for z -> softmax -> p with dL/dp = g (both [N,C,HW])."""
+    return p * (g - (p * g).sum(axis=1, keepdims=True))
+
+
+def dice_loss(logits, targets, smooth=1e-6):
+    """DiceLoss._compute_loss (branchy_seg_losses.py:40-48): [N] losses and d sum(loss*w)/dlogits for w = 1."""
+    p, oh, t = _overlap_sums(logits, targets)
+    C = p.shape[1]
+    if ((t < 0) | (t >= C)).any():
+        raise RuntimeError("Class values must be smaller than num_classes.")   # F.one_hot, :44
+    num = 2 * (p * oh).sum(axis=(1, 2)) + smooth
+    den = (p + oh).sum(axis=(1, 2)) + smooth
+    loss = 1 - num / den
+    g = (-(2 * oh) / den[:, None, None] + (num / den ** 2)[:, None, None])       # d loss_n / d p
+    return loss.astype(np.float32), _softmax_backward(p, g).reshape(np.asarray(logits).shape)
+
+
+def jaccard_loss(logits, targets, smooth=1e-6, downgrad_bg=1.0):
+    """JaccardLoss._compute_loss (:55-77): [N,C] (or [N] when downgrad_bg is falsy) and the gradient of its sum."""
+    p, oh, _ = _overlap_sums(logits, targets)
+    inter = (p * oh).sum(axis=-1)
+    total = (p + oh).sum(axis=-1)
+    union = total - inter
+    iou = (inter + smooth) / (union + smooth)
+    scale = np.ones(p.shape[1])
+    if downgrad_bg:
+        scale[0] = downgrad_bg
+        loss = (1 - iou) * scale
+    else:
+        loss = (1 - iou).sum(axis=-1)
+    # d(1-iou)/dp = -[oh*(union+s) - (inter+s)*(1-oh)] / (union+s)^2
+    u = (union + smooth)[:, :, None]
+    g = -(oh * u - (inter + smooth)[:, :, None] * (1 - oh)) / u ** 2 * scale[None, :, None]
+    return loss.astype(np.float32), _softmax_backward(p, g).reshape(np.asarray(logits).shape)
+
+
+def tversky_loss(logits, targets, smooth=1e-6, alpha=.5, beta=.5, gamma=None):
+    """TverskyLoss._forward_imp (:85-100) on the arg-max map; gamma -> FocalTverskyLoss (:110-113). [N,C]."""
+    y = np.asarray(logits, dtype=np.float32)
+    N, C = y.shape[:2]
+    t = np.asarray(targets).reshape(N, -1)
+    if ((t < 0) | (t >= C)).any():
+        raise RuntimeError("Class values must be smaller than num_classes.")   # F.one_hot, :92
+    pred = argmax_first(y.reshape(N, C, -1), 1)
+    cls = np.arange(C)[None, :, None]
+    P, T = (pred[:, None, :] == cls), (t[:, None, :] == cls)
+    TP = (P & T).sum(-1).astype(np.float32)
+    FP = (P & ~T).sum(-1).astype(np.float32)
+    FN = (~P & T).sum(-1).astype(np.float32)
+    loss = 1 - (TP + np.float32(smooth)) / (TP + np.float32(alpha) * FP + np.float32(beta) * FN + np.float32(smooth))
+    return loss if gamma is None else loss ** np.float32(gamma)
+
+
+def br_seg_loss(per_exit, reduction="mean", weights=None):
+    """BrSegLoss.forward (:24-38) on the stacked per-exit losses [E, ...]."""
+    l = np.asarray(per_exit, dtype=np.float32)
+    if reduction == "none":
+        return l
+    dims = tuple(range(1, l.ndim))
+    r = l.mean(axis=dims, dtype=np.float32) if reduction == "mean" else l.sum(axis=dims, dtype=np.float32)
+    w = np.ones(l.shape[0], np.float32) if weights is None else np.asarray(weights, np.float32)
+    return np.float32(np.dot(w, r))
+
+
+# ----------------------------------------------------------------------------------------------
 # A10  lovasz_grad / lovasz_softmax_flat / flatten_probas   (lovaszsoftmax.py:19-31,172-219)
 # ----------------------------------------------------------------------------------------------
 def lovasz_grad(gt_sorted):

@@ -520,3 +520,61 @@ def test_bn_train_fwd_bwd_vs_torch(N, C, h, w, relu, res):
     assert rel(bn.bias.grad.cpu(), bn_ref.bias.grad) < 5e-3
     if res:
         assert rel(rd.grad.float().cpu(), rr.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ Dice / Jaccard / Tversky
+def test_overlap_losses_golden(golden):
+    """BSL.DiceLoss / JaccardLoss / TverskyLoss / FocalTverskyLoss on the soft-overlap and histogram kernels against
+    the unmodified reference's values and autograd gradients (tests/golden/overlap_losses.npz)."""
+    from ee_semantic_segmentation_b200 import branchy_seg_losses as BSL
+    G = golden("overlap_losses")
+    y = torch.from_numpy(G["y_pred"]).to(dev())
+    t = torch.from_numpy(G["targets"]).to(dev())
+    tv = torch.from_numpy(G["targets_void"]).to(dev())
+    cases = {
+        "dice_mean": (BSL.DiceLoss(n_branches=2), t),
+        "dice_sum_w": (BSL.DiceLoss(reduction="sum", n_branches=2, weights=[0.5, 1.0, 2.0]), t),
+        "jaccard_mean": (BSL.JaccardLoss(n_branches=2), t),
+        "jaccard_void_bg": (BSL.JaccardLoss(n_branches=2, downgrad_bg=0.3), tv),
+        "jaccard_nobg_sum": (BSL.JaccardLoss(reduction="sum", n_branches=1, downgrad_bg=0.0), tv),
+    }
+    for tag, (fn, tgt) in cases.items():
+        yy = y.clone().requires_grad_(True)
+        l = fn(yy, tgt)
+        l.backward()
+        np.testing.assert_allclose(l.item(), G[f"{tag}_loss"], rtol=1e-4, err_msg=tag)
+        np.testing.assert_allclose(yy.grad.cpu().numpy(), G[f"{tag}_grad"], rtol=1e-3, atol=1e-8, err_msg=tag)
+    np.testing.assert_allclose(BSL.DiceLoss(reduction="none", n_branches=2)(y, t).cpu().numpy(), G["dice_none"], rtol=1e-4)
+    np.testing.assert_allclose(BSL.JaccardLoss(reduction="none", n_branches=2)(y, tv).cpu().numpy(), G["jaccard_none"], rtol=1e-4)
+    np.testing.assert_allclose(BSL.TverskyLoss(alpha=0.3, beta=0.7, n_branches=2)(y, t).item(), G["tversky_mean"], rtol=1e-5)
+    np.testing.assert_allclose(BSL.TverskyLoss(reduction="none", n_branches=2)(y, t).cpu().numpy(), G["tversky_none"], rtol=1e-6)
+    np.testing.assert_allclose(BSL.FocalTverskyLoss(gamma=0.75, n_branches=2)(y, t).item(), G["focal_tversky_mean"], rtol=1e-5)
+    for bad in (BSL.DiceLoss(n_branches=2), BSL.TverskyLoss(n_branches=2)):      # F.one_hot(num_classes=C) of the reference
+        with pytest.raises(RuntimeError, match="smaller than num_classes"):
+            bad(y, tv)
+
+
+@pytest.mark.parametrize("C,dtype", [(21, torch.float32), (19, torch.bfloat16), (40, torch.float32)])
+def test_overlap_sums_full_size_vs_oracle(C, dtype):
+    """Soft-overlap sums and the gradient they carry, at 513x513 (odd planes, ragged last block), against the oracle."""
+    from ee_semantic_segmentation_b200 import branchy_seg_losses as BSL
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    E, N, H, W = 2, 2, (513 if C != 40 else 61), (513 if C != 40 else 47)
+    y = (torch.randn(E, N, C, H, W, generator=g) * 3).to(dtype)
+    tgt = blocky(g, N, C, H, W)
+    s_pt, s_p, s_t = ops.soft_overlap_sums(y.to(dev()), tgt.to(dev()))
+    p = torch.softmax(y.double(), 2).view(E, N, C, -1)
+    oh = (tgt.view(N, 1, -1) == torch.arange(C).view(1, C, 1)).double()
+    rtol = 1e-4 if dtype == torch.float32 else 2e-3
+    np.testing.assert_allclose(s_pt.cpu().numpy(), (p * oh).sum(-1).numpy(), rtol=rtol, atol=1e-3)
+    np.testing.assert_allclose(s_p.cpu().numpy(), p.sum(-1).numpy(), rtol=rtol)
+    assert torch.equal(s_t.cpu().double(), oh.sum(-1))
+    yd = y.to(dev()).requires_grad_(True)
+    l = BSL.JaccardLoss(n_branches=E - 1, downgrad_bg=0.5)(yd, tgt.to(dev()))
+    l.backward()
+    ls, gs = zip(*(R.jaccard_loss(y[e].float().numpy(), tgt.numpy(), downgrad_bg=0.5) for e in range(E)))
+    np.testing.assert_allclose(l.item(), R.br_seg_loss(np.stack(ls)), rtol=rtol)
+    ref_g = np.stack(gs) / (N * C)
+    got = yd.grad.float().cpu().numpy()
+    assert np.abs(got - ref_g).max() < (1e-3 if dtype == torch.float32 else 2e-2) * np.abs(ref_g).max()

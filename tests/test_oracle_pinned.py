@@ -145,3 +145,41 @@ def test_br_evaluator_vs_reference(golden):
         assert cnt[-2] == int(d[f"{key}/count_out"]) and cnt[-1] == int(d[f"{key}/out_gl"])
         a, b = float(acc[-1].compute()), float(d[f"{key}/mIoU_gl"])
         assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, abs=1e-6), key
+
+
+def test_overlap_losses_oracle_vs_reference_golden(golden):
+    """Dice / Jaccard / Tversky / FocalTversky restatements against the unmodified reference's values and autograd
+    gradients (tests/golden/overlap_losses.npz, oracle/make_golden_overlap.py)."""
+    G = golden("overlap_losses")
+    y, t, tv = G["y_pred"], G["targets"], G["targets_void"]
+    E = y.shape[0]
+
+    def stack(fn, tgt, n, **kw):
+        ls, gs = zip(*(fn(y[e], tgt, **kw) for e in range(n)))
+        return np.stack(ls), np.stack(gs)
+    l, g = stack(R.dice_loss, t, E)
+    np.testing.assert_allclose(l, G["dice_none"], rtol=1e-5)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["dice_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / l.shape[1], G["dice_mean_grad"], rtol=1e-4, atol=1e-9)
+    w = np.array([0.5, 1.0, 2.0], np.float32)
+    np.testing.assert_allclose(R.br_seg_loss(l, "sum", w), G["dice_sum_w_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g * w[:, None, None, None, None], G["dice_sum_w_grad"], rtol=1e-4, atol=1e-9)
+    l, g = stack(R.jaccard_loss, t, E)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["jaccard_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / (l.shape[1] * l.shape[2]), G["jaccard_mean_grad"], rtol=1e-4, atol=1e-9)
+    l, g = stack(R.jaccard_loss, tv, E, downgrad_bg=0.3)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["jaccard_void_bg_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / (l.shape[1] * l.shape[2]), G["jaccard_void_bg_grad"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(stack(R.jaccard_loss, tv, E)[0], G["jaccard_none"], rtol=1e-5)
+    l, g = stack(R.jaccard_loss, tv, 2, downgrad_bg=0.0)
+    np.testing.assert_allclose(R.br_seg_loss(l, "sum"), G["jaccard_nobg_sum_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g, G["jaccard_nobg_sum_grad"][:2], rtol=1e-4, atol=1e-9)
+    assert np.all(G["jaccard_nobg_sum_grad"][2] == 0)
+    tl = np.stack([R.tversky_loss(y[e], t) for e in range(E)])
+    np.testing.assert_allclose(tl, G["tversky_none"], rtol=1e-6)
+    tl = np.stack([R.tversky_loss(y[e], t, alpha=0.3, beta=0.7) for e in range(E)])
+    np.testing.assert_allclose(R.br_seg_loss(tl), G["tversky_mean"], rtol=1e-5)
+    tl = np.stack([R.tversky_loss(y[e], t, gamma=0.75) for e in range(E)])
+    np.testing.assert_allclose(R.br_seg_loss(tl), G["focal_tversky_mean"], rtol=1e-5)
+    with pytest.raises(RuntimeError):
+        R.dice_loss(y[0], tv)        # void label: F.one_hot(num_classes=C) raises in the reference
