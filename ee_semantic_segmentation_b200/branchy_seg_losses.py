@@ -5,7 +5,7 @@ torch.sort calls) and the overlap family `DiceLoss` (:40-48), `JaccardLoss` (:50
 the per-exit / image / class sums, and the reference's formulas are applied verbatim on those small tensors —
 instead of materialising softmax and int64 one-hot tensors [N,HW,C] per exit. Tversky works on the arg-max map
 (no gradient reaches the logits, as in the reference) and comes from the confusion-matrix kernel.
-`FocalLoss` (:115-131) is not provided."""
+`FocalLoss` (:115-131) is one streaming pass over all exits (csrc/focal.cu) with the gradient fused into it."""
 import torch as tch
 from torch import nn
 
@@ -120,6 +120,66 @@ class FocalTverskyLoss(TverskyLoss):
 
     def _compute_loss(self, y_pred, targets):
         return self._forward_imp(y_pred, targets) ** self.gamma
+
+
+class FocalLoss(BrSegLoss):
+    """-(1 - p_t)^gamma * log p_t per pixel, times alpha[targets] when alpha is given (branchy_seg_losses.py:115-131).
+    As in the reference, targets are [N,1,H,W] (`probs.gather(1, targets)`) with labels in [0,C), and the alpha product
+    broadcasts the [N,H,W] loss against alpha[targets] of shape [N,1,H,W] to [N,N,H,W] (:128-129): every image's loss is
+    weighted by the alpha of EVERY image at that pixel. Reproduced as a per-pixel weight sum_i alpha[t_i] inside the kernel
+    for 'mean' / 'sum'; reduction='none' returns the reference's [E,N,(N,)H,W] tensor."""
+
+    def __init__(self, alpha=None, gamma=2, smooth=1e-6, reduction='mean', n_branches=1, weights=None):
+        super().__init__(smooth, reduction, n_branches, weights)
+        self.alpha = alpha
+        self.gamma = gamma
+
+    def _check(self, y_pred, targets):
+        N, C = y_pred.shape[1:3]
+        if targets.dim() != y_pred.dim() - 1 or targets.shape[0] != N or targets.shape[1] != 1 \
+                or tuple(targets.shape[2:]) != tuple(y_pred.shape[3:]):
+            raise RuntimeError(f'gather(): targets must be [N,1,H,W] for logits {tuple(y_pred.shape[1:])}, '
+                               f'got {tuple(targets.shape)}')
+        if targets.is_floating_point():
+            targets = targets.to(tch.int64)
+        if bool(((targets < 0) | (targets >= C)).any()):
+            raise RuntimeError('index out of range in gather(): labels must be in [0, C)')
+        return targets
+
+    def _alpha_map(self, targets, device):
+        alpha = tch.as_tensor(self.alpha, dtype=tch.float32, device=device)
+        return alpha, alpha[targets.to(tch.int64)]                  # [N,1,H,W]
+
+    def _compute_all(self, y_pred, targets):
+        targets = self._check(y_pred, targets)
+        E, N = y_pred.shape[:2]
+        loss = ops.focal_map(y_pred, targets, self.gamma).view(E, N, *y_pred.shape[3:])
+        if self.alpha is not None:
+            loss = loss.unsqueeze(1) * self._alpha_map(targets, loss.device)[1].unsqueeze(0)    # [E,N,N,H,W]
+        return loss
+
+    def _compute_loss(self, y_pred, targets):
+        return self._compute_all(y_pred.unsqueeze(0), targets)[0]
+
+    def forward(self, y_pred, targets):
+        if self.reduction not in ('mean', 'sum'):
+            return super().forward(y_pred, targets)
+        if y_pred.shape[0] < self.n:
+            raise IndexError(f'index {self.n - 1} is out of bounds for dimension 0 with size {y_pred.shape[0]}')
+        y_pred = y_pred[:self.n]
+        targets = self._check(y_pred, targets)
+        N = y_pred.shape[1]
+        count = targets.numel()
+        alpha = pixw = None
+        if self.alpha is not None:
+            alpha, amap = self._alpha_map(targets, y_pred.device)
+            if N > 1:
+                alpha, pixw = None, amap.sum(dim=0).reshape(-1)      # sum_i alpha[t_i] per pixel position
+                count *= N
+        w = self.weights.to(device=y_pred.device)
+        scale = 1.0 / count if self.reduction == 'mean' else 1.0
+        sums = ops.focal_sums(y_pred, targets, self.gamma, alpha=alpha, pixel_weight=pixw, coef=w.detach() * scale)
+        return tch.dot(w, sums * scale)
 
 
 class LovaszSoftmax(nn.Module):

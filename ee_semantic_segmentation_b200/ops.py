@@ -353,6 +353,108 @@ def soft_overlap_sums(y, targets):
 
 
 # --------------------------------------------------------------------------------------------------
+# focal loss
+# --------------------------------------------------------------------------------------------------
+def _focal_call(y, tg, gamma, alpha, pixw, coef, per_exit, loss_map, dy):
+    E, N, C = y.shape[:3]
+    HW = y[0, 0, 0].numel()
+    if pixw is None:
+        pw, pes, pis = None, 0, 0
+    else:
+        pw = pixw
+        pes = pw.stride(0) if pw.dim() == 3 else 0
+        pis = pw.stride(-2) if pw.dim() >= 2 else 0
+    with torch.cuda.device(y.device):
+        ws = torch.empty((lib().eeseg_focal_workspace_bytes(E, N, HW),), dtype=torch.uint8, device=y.device)
+        check(lib().eeseg_focal_fwd(y.data_ptr(), _dt(y), y.stride(0), tg.data_ptr(), E, N, C, HW, float(gamma),
+                                    _p(alpha), _p(pw), pes, pis, _p(coef), per_exit.data_ptr(), _p(loss_map), _p(dy),
+                                    ws.data_ptr(), _stream(y)), "eeseg_focal_fwd")
+
+
+class _FocalSum(torch.autograd.Function):
+    """per_exit[e] = sum over (n, px) of the weighted focal loss; the same pass writes d per_exit/dy scaled by `coef`
+    (the upstream gradient the caller is about to apply; backward rescales on the device only if it differs)."""
+
+    @staticmethod
+    def forward(ctx, y, tg, gamma, alpha, pixw, coef):
+        E = y.shape[0]
+        per_exit = torch.empty((E,), dtype=torch.float32, device=y.device)
+        dy = torch.empty_like(y) if y.requires_grad else None
+        _focal_call(y, tg, gamma, alpha, pixw, coef, per_exit, None, dy)
+        ctx.dy = dy
+        ctx.save_for_backward(coef)
+        return per_exit
+
+    @staticmethod
+    def backward(ctx, g):
+        dy = ctx.dy
+        (coef,) = ctx.saved_tensors
+        if dy is None:
+            return None, None, None, None, None, None
+        g = g.contiguous().float()
+        with torch.cuda.device(dy.device):
+            check(lib().eeseg_scale_exits(dy.data_ptr(), _dt(dy), dy.stride(0), dy.shape[0], dy[0].numel(),
+                                          g.data_ptr(), coef.data_ptr(), _stream(dy)), "eeseg_scale_exits")
+        ctx.dy = None
+        return dy, None, None, None, None, None
+
+
+class _FocalMap(torch.autograd.Function):
+    """loss[e,n,px] (reduction='none'); backward is a second pass with the incoming gradient map as pixel weight."""
+
+    @staticmethod
+    def forward(ctx, y, tg, gamma):
+        E, N = y.shape[:2]
+        loss_map = torch.empty((E, N, tg.shape[1]), dtype=torch.float32, device=y.device)
+        per_exit = torch.empty((E,), dtype=torch.float32, device=y.device)
+        _focal_call(y, tg, gamma, None, None, None, per_exit, loss_map, None)
+        ctx.save_for_backward(y, tg)
+        ctx.gamma = gamma
+        return loss_map
+
+    @staticmethod
+    def backward(ctx, g):
+        y, tg = ctx.saved_tensors
+        dy = torch.empty_like(y)
+        per_exit = torch.empty((y.shape[0],), dtype=torch.float32, device=y.device)
+        _focal_call(y, tg, ctx.gamma, None, g.contiguous().float(), None, per_exit, None, dy)
+        return dy, None, None
+
+
+def _focal_args(y, targets):
+    _cuda(y, "y_pred")
+    _cuda(targets, "targets")
+    if y.dim() < 4:
+        raise ValueError("y_pred must be [E,N,C,...]")
+    if not y.is_contiguous():
+        y = y.contiguous()
+    tg = targets.reshape(y.shape[1], -1)
+    if tg.dtype != torch.int64:
+        tg = tg.to(torch.int64)
+    tg = tg.contiguous()
+    if tg.shape[1] != y[0, 0, 0].numel():
+        raise ValueError(f"targets {tuple(targets.shape)} do not match logits {tuple(y.shape)}")
+    return y, tg
+
+
+def focal_sums(y, targets, gamma=2.0, alpha=None, pixel_weight=None, coef=None):
+    """y [E,N,C,*spatial] f32/bf16 CUDA logits, targets [N,(1,)*spatial] labels in [0,C). Returns f32 [E]:
+    sum over (n, px) of -alpha[t] * w * (1 - p_t)^gamma * log p_t. alpha f32 [C] and pixel_weight f32 [HW] / [N,HW] /
+    [E,N,HW] are optional; coef f32 [E] is the expected upstream gradient per exit (default ones)."""
+    y, tg = _focal_args(y, targets)
+    dev = y.device
+    f = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    coef = torch.ones((y.shape[0],), dtype=torch.float32, device=dev) if coef is None else f(coef)
+    return _FocalSum.apply(y, tg, float(gamma), f(alpha), f(pixel_weight), coef)
+
+
+def focal_map(y, targets, gamma=2.0):
+    """Per-pixel focal loss f32 [E,N,HW] (no class weights), differentiable in y."""
+    y, tg = _focal_args(y, targets)
+    return _FocalMap.apply(y, tg, float(gamma))
+
+
+# --------------------------------------------------------------------------------------------------
 # Lovasz-softmax
 # --------------------------------------------------------------------------------------------------
 class _Lovasz(torch.autograd.Function):

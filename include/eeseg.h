@@ -230,6 +230,21 @@ int eeseg_soft_overlap_bwd(const void* logits, int dtype, int64_t exit_stride, c
                            int C, int64_t HW, const float* dsum_pt, const float* dsum_p, void* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Branchy focal loss (BSL.FocalLoss._compute_loss, branchy_seg_losses.py:122-131, under BrSegLoss.forward :24-38):
+ *   loss[e,n,px] = -alpha[t] * w[e,n,px] * (1 - p_t)^gamma * log p_t,  p = softmax(logits[e,n,:,px]),  t = targets[n,px] in [0,C)
+ *   w = pixel_weight[e*pw_exit_stride + n*pw_image_stride + px] (optional f32; stride 0 = broadcast): the reference's
+ *   broadcast `loss * alpha[targets]` product (:128-129) and the upstream gradient map of reduction='none';
+ *   per_exit_sum f32 [E] = sum over (n,px) of loss (ordered fp64 partials);  loss_map (optional) f32 [E][N][HW];
+ *   dlogits (optional, logits' dtype) = coef[e] * d loss / d logits  (coef folds the reduction and the exit weight);
+ *   alpha (optional) f32 [C];  workspace: eeseg_focal_workspace_bytes bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t eeseg_focal_workspace_bytes(int E, int N, int64_t HW);
+int eeseg_focal_fwd(const void* logits, int dtype, int64_t exit_stride, const int64_t* targets, int E, int N, int C,
+                    int64_t HW, float gamma, const float* alpha, const float* pixel_weight, int64_t pw_exit_stride,
+                    int64_t pw_image_stride, const float* coef, float* per_exit_sum, float* loss_map, void* dlogits,
+                    void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training-mode BatchNorm2d (+ residual add) (+ ReLU) on NHWC bf16 activations — the nn.BatchNorm2d / ReLU /
  * `out += identity` modules of DeepLabHead, ASPP and the ResNet Bottlenecks as they run under net.train() in
  * train_epoch (train_funcs.py:12-33).  x, y, residual, dy, dx, dres: bf16 [P = N*h*w][C], C % 64 == 0.

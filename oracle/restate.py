@@ -237,7 +237,8 @@ def br_xentropy(y_pred, targets, ignore_index=-100, b_reduction="mean", n_exits=
 
 # ----------------------------------------------------------------------------------------------
 # Overlap family of branchy_seg_losses.py: Dice :40-48, Jaccard :50-77, Tversky :79-103,
-# FocalTversky :105-113, under BrSegLoss.forward :24-38. Values and (Dice / Jaccard) gradients w.r.t. the logits.
+# FocalTversky :105-113, Focal :115-131, under BrSegLoss.forward :24-38. Values and (Dice / Jaccard / Focal) gradients
+# w.r.t. the logits.
 # ----------------------------------------------------------------------------------------------
 def _overlap_sums(logits, targets):
     """logits [N,C,H,W] -> p [N,C,HW] (softmax), one-hot t [N,C,HW] (labels outside [0,C) match no class)."""
@@ -301,6 +302,37 @@ def tversky_loss(logits, targets, smooth=1e-6, alpha=.5, beta=.5, gamma=None):
     FN = (~P & T).sum(-1).astype(np.float32)
     loss = 1 - (TP + np.float32(smooth)) / (TP + np.float32(alpha) * FP + np.float32(beta) * FN + np.float32(smooth))
     return loss if gamma is None else loss ** np.float32(gamma)
+
+
+def focal_loss(logits, targets, gamma=2.0, alpha=None):
+    """FocalLoss._compute_loss (branchy_seg_losses.py:122-131). logits [N,C,H,W], targets [N,1,H,W] in [0,C).
+    Returns the reference's loss tensor — [N,H,W], or [N,N,H,W] when alpha is given: `loss * alpha[targets]` broadcasts
+    [N,H,W] against [N,1,H,W] (:128-129), out[i,j] = loss[j] * alpha[t_i] — and the gradient of its SUM w.r.t. logits."""
+    y = np.asarray(logits, dtype=np.float64)
+    N, C = y.shape[:2]
+    t = np.asarray(targets)
+    if t.ndim != y.ndim or t.shape[1] != 1 or t.shape[0] != N or t.shape[2:] != y.shape[2:]:
+        raise RuntimeError("gather(): index shape")                               # probs.gather(1, targets), :126
+    t = t.astype(np.int64)
+    if ((t < 0) | (t >= C)).any():
+        raise RuntimeError("index out of range in gather()")
+    lsm = y - y.max(axis=1, keepdims=True)
+    lsm = lsm - np.log(np.exp(lsm).sum(axis=1, keepdims=True))                    # log_softmax, :124
+    p = np.exp(lsm)
+    lp = np.take_along_axis(lsm, t, axis=1)[:, 0]                                 # [N,H,W]
+    pt = np.exp(lp)
+    loss = -((1 - pt) ** gamma) * lp
+    # d loss / d lp = gamma (1-pt)^(gamma-1) pt lp - (1-pt)^gamma ;  d lp / d z_c = [c == t] - p_c
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dl = np.where(pt < 1, gamma * (1 - pt) ** (gamma - 1) * pt * lp, 0.0) - (1 - pt) ** gamma if gamma else -np.ones_like(lp)
+    w = np.ones_like(lp)
+    if alpha is not None:
+        a_t = np.asarray(alpha, dtype=np.float64)[t]                              # [N,1,H,W]
+        loss = loss[None] * a_t                                                   # [N(i),N(j),H,W]
+        w = np.broadcast_to(a_t.sum(axis=0), lp.shape)                            # every image j: sum_i alpha[t_i]
+    oh = (np.arange(C)[None, :, None, None] == t)
+    grad = (dl * w)[:, None] * (oh - p)
+    return loss.astype(np.float32), grad
 
 
 def br_seg_loss(per_exit, reduction="mean", weights=None):

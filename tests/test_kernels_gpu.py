@@ -578,3 +578,67 @@ def test_overlap_sums_full_size_vs_oracle(C, dtype):
     ref_g = np.stack(gs) / (N * C)
     got = yd.grad.float().cpu().numpy()
     assert np.abs(got - ref_g).max() < (1e-3 if dtype == torch.float32 else 2e-2) * np.abs(ref_g).max()
+
+
+# ------------------------------------------------------------------------------------ Focal
+def test_focal_loss_golden(golden):
+    """BSL.FocalLoss on csrc/focal.cu against the unmodified reference's values and autograd gradients
+    (tests/golden/focal_loss.npz), including the reference's [N,N,H,W] alpha broadcast and reduction='none'."""
+    from ee_semantic_segmentation_b200 import branchy_seg_losses as BSL
+    G = golden("focal_loss")
+    y = torch.from_numpy(G["y_pred"]).to(dev())
+    t = torch.from_numpy(G["targets"]).to(dev())
+    alpha = torch.from_numpy(G["alpha"]).to(dev())
+    cases = {
+        "g2_mean": (BSL.FocalLoss(n_branches=2), y, t),
+        "g15_sum_w": (BSL.FocalLoss(gamma=1.5, reduction="sum", n_branches=2, weights=[0.5, 1.0, 2.0]), y, t),
+        "g0_mean": (BSL.FocalLoss(gamma=0, n_branches=1), y, t),
+        "g05_mean": (BSL.FocalLoss(gamma=0.5, n_branches=2), y, t),
+        "alpha_mean": (BSL.FocalLoss(alpha=alpha, n_branches=2), y, t),
+        "alpha_sum": (BSL.FocalLoss(alpha=alpha, gamma=1, reduction="sum", n_branches=2), y, t),
+        "alpha_n1_mean": (BSL.FocalLoss(alpha=alpha, n_branches=2), y[:, :1].contiguous(), t[:1]),
+    }
+    for tag, (fn, yy, tgt) in cases.items():
+        yy = yy.clone().requires_grad_(True)
+        l = fn(yy, tgt)
+        l.backward()
+        np.testing.assert_allclose(l.item(), G[f"{tag}_loss"], rtol=1e-4, err_msg=tag)
+        ref = G[f"{tag}_grad"]
+        assert np.abs(yy.grad.cpu().numpy() - ref).max() < 1e-4 * np.abs(ref).max(), tag
+    np.testing.assert_allclose(BSL.FocalLoss(reduction="none", n_branches=2)(y, t).cpu().numpy(), G["g2_none"],
+                               rtol=1e-4, atol=1e-6)
+    yy = y.clone().requires_grad_(True)
+    ln = BSL.FocalLoss(alpha=alpha, reduction="none", n_branches=2)(yy, t)
+    assert ln.shape == G["alpha_none"].shape
+    np.testing.assert_allclose(ln.detach().cpu().numpy(), G["alpha_none"], rtol=1e-4, atol=1e-6)
+    (ln * torch.from_numpy(G["alpha_none_up"]).to(dev())).sum().backward()
+    ref = G["alpha_none_grad"]
+    assert np.abs(yy.grad.cpu().numpy() - ref).max() < 1e-4 * np.abs(ref).max()
+    with pytest.raises(RuntimeError, match="gather"):
+        BSL.FocalLoss(n_branches=2)(y, t[:, 0])                   # [N,H,W] targets
+    with pytest.raises(RuntimeError, match="out of range"):
+        BSL.FocalLoss(n_branches=2)(y, torch.full_like(t, 7))     # void label
+    with pytest.raises(IndexError):
+        BSL.FocalLoss(n_branches=3)(y, t)
+
+
+@pytest.mark.parametrize("C,dtype", [(21, torch.float32), (19, torch.bfloat16), (40, torch.float32)])
+def test_focal_full_size_vs_oracle(C, dtype):
+    """Focal loss and gradient at 513x513 (odd planes, ragged last block) against the oracle."""
+    from ee_semantic_segmentation_b200 import branchy_seg_losses as BSL
+    g = torch.Generator().manual_seed(100 + C)
+    E, N, H, W = 2, 2, (513 if C != 40 else 61), (513 if C != 40 else 47)
+    y = (torch.randn(E, N, C, H, W, generator=g) * 3).to(dtype)
+    tgt = blocky(g, N, C, H, W, void_frac=0.0)
+    alpha = torch.rand(C, generator=g) + 0.5
+    yd = y.to(dev()).requires_grad_(True)
+    l = BSL.FocalLoss(alpha=alpha.to(dev()), gamma=2, n_branches=E - 1, weights=[0.4, 1.0])(yd, tgt.to(dev()))
+    l.backward()
+    ls, gs = zip(*(R.focal_loss(y[e].float().numpy(), tgt.numpy(), gamma=2, alpha=alpha.numpy()) for e in range(E)))
+    w = np.array([0.4, 1.0])
+    ref_l = float(sum(w[e] * ls[e].astype(np.float64).mean() for e in range(E)))
+    rtol = 1e-4 if dtype == torch.float32 else 5e-3
+    np.testing.assert_allclose(l.item(), ref_l, rtol=rtol)
+    ref_g = np.stack(gs) * w[:, None, None, None, None] / ls[0].size
+    got = yd.grad.float().cpu().numpy()
+    assert np.abs(got - ref_g).max() < (1e-4 if dtype == torch.float32 else 1e-2) * np.abs(ref_g).max()

@@ -183,3 +183,44 @@ def test_overlap_losses_oracle_vs_reference_golden(golden):
     np.testing.assert_allclose(R.br_seg_loss(tl), G["focal_tversky_mean"], rtol=1e-5)
     with pytest.raises(RuntimeError):
         R.dice_loss(y[0], tv)        # void label: F.one_hot(num_classes=C) raises in the reference
+
+
+def test_focal_loss_oracle_vs_reference_golden(golden):
+    """FocalLoss restatement (incl. the reference's [N,N,H,W] alpha broadcast) against the unmodified reference's values
+    and autograd gradients (tests/golden/focal_loss.npz, oracle/make_golden_focal.py)."""
+    G = golden("focal_loss")
+    y, t, alpha = G["y_pred"], G["targets"], G["alpha"]
+
+    def run(n, yy=y, tt=t, **kw):
+        ls, gs = zip(*(R.focal_loss(yy[e], tt, **kw) for e in range(n)))
+        return np.stack(ls), np.stack(gs)
+    l, g = run(3)
+    np.testing.assert_allclose(l, G["g2_none"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["g2_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / l[0].size, G["g2_mean_grad"], rtol=1e-4, atol=1e-8)
+    w = np.array([0.5, 1.0, 2.0], np.float32)
+    l, g = run(3, gamma=1.5)
+    np.testing.assert_allclose(R.br_seg_loss(l, "sum", w), G["g15_sum_w_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g * w[:, None, None, None, None], G["g15_sum_w_grad"], rtol=1e-4, atol=1e-6)
+    l, g = run(2, gamma=0)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["g0_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / l[0].size, G["g0_mean_grad"][:2], rtol=1e-4, atol=1e-8)
+    assert np.all(G["g0_mean_grad"][2] == 0)
+    l, g = run(3, gamma=0.5)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["g05_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / l[0].size, G["g05_mean_grad"], rtol=1e-4, atol=1e-8)
+    l, g = run(3, alpha=alpha)
+    assert l.shape == G["alpha_none"].shape == (3, 2, 2, 13, 17)
+    np.testing.assert_allclose(l, G["alpha_none"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["alpha_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / l[0].size, G["alpha_mean_grad"], rtol=1e-4, atol=1e-8)
+    l, g = run(3, alpha=alpha, gamma=1)
+    np.testing.assert_allclose(R.br_seg_loss(l, "sum"), G["alpha_sum_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g, G["alpha_sum_grad"], rtol=1e-4, atol=1e-6)
+    l, g = run(3, yy=y[:, :1], tt=t[:1], alpha=alpha)
+    np.testing.assert_allclose(R.br_seg_loss(l), G["alpha_n1_mean_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g / l[0].size, G["alpha_n1_mean_grad"], rtol=1e-4, atol=1e-8)
+    with pytest.raises(RuntimeError):
+        R.focal_loss(y[0], t[:, 0])          # [N,H,W] targets: gather() needs [N,1,H,W]
+    with pytest.raises(RuntimeError):
+        R.focal_loss(y[0], np.full_like(t, 7))
