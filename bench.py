@@ -352,13 +352,29 @@ def main():
     sc0 = eng.evaluate(Xd, yd)["scores"][0].float().cpu().sort().values
     mid = (len(sc0) - 1) // 2
     tau_mid = float((sc0[mid] + sc0[mid + 1]) / 2) if len(sc0) > 1 else float(sc0[0]) + 1.0
-    eng_skip = EarlyExitEngine(net, N_CLASSES, tau_mid, skip_compute=True)
+    eng_skip_eager = EarlyExitEngine(net, N_CLASSES, tau_mid, skip_compute=True)
+    for _ in range(3):
+        eng_skip_eager.evaluate(Xd, yd)
+    skip_eager_ms, _ = timed(lambda: eng_skip_eager.evaluate(Xd, yd), steps)
+    # the same engine with one CUDA graph per (exit stage, still-active image count); the host reads the
+    # 4-byte active count after each gate and replays the next stage's graph of that size
+    eng_skip = EarlyExitEngine(net, N_CLASSES, tau_mid, skip_compute=True, use_graph=not args.no_graph)
     for _ in range(3):
         eng_skip.evaluate(Xd, yd)
     eng_skip.reset()
     skip_ms, _ = timed(lambda: eng_skip.evaluate(Xd, yd), steps)
     skip_counts = [int(v) for v in eng_skip.counts.cpu()]
     skip_px = [int(v) for v in eng_skip.exited_px.cpu()]
+    skip_e2e_ms = None
+    if eng_skip.use_graph:
+        for _ in eng_skip.evaluate_pipelined(host_batches(3)):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        for ex, sc in eng_skip.evaluate_pipelined(host_batches(steps)):
+            pass
+        torch.cuda.synchronize()
+        skip_e2e_ms = (time.perf_counter() - t0) * 1e3
 
     # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
     prof = []
@@ -454,7 +470,11 @@ def main():
             "exit_stats": {k: res[k] for k in ("b1_count", "b2_count", "count_out", "out_gl")},
             "early_exit_operating_point": {
                 "tau": tau_mid, "value": imgs / (skip_ms * 1e-3), "unit": "images/s", "ms_per_step": skip_ms / steps,
-                "mode": "skip_compute engine (eager launches, one 4-byte D2H per gate for the active count), rank 0 counters",
+                "mode": "skip_compute engine, one CUDA graph per (exit stage, active image count), one 4-byte D2H per gate "
+                        "for the active count; rank 0 counters" if eng_skip.use_graph else "skip_compute engine, eager launches",
+                "e2e": {"value": imgs / (skip_e2e_ms * 1e-3), "unit": "images/s",
+                        "how": "pinned host batches through evaluate_pipelined, rank 0 wall clock (x world size)"} if skip_e2e_ms else None,
+                "eager_launch_value": imgs / (skip_eager_ms * 1e-3),
                 "images_per_exit": skip_counts[:-1],
                 "pct_images_exited_early": 100.0 * sum(skip_counts[:-2]) / max(1, skip_counts[-1]),
                 "pct_pixels_below_tau_per_gate": [100.0 * px / max(1, PER_GPU_BATCH * steps * img_hw()[0] * img_hw()[1])

@@ -23,9 +23,9 @@ class EarlyExitEngine:
                  use_graph=False):
         """use_graph: capture the whole (static) step — backbone sections, heads, gates, decision,
         histogram — into one CUDA graph per input shape and replay it; removes the per-launch host
-        overhead of the ~700 launches of a step. Not available with skip_compute (the compaction
-        reads the active count on the host)."""
-        assert not (use_graph and skip_compute), "CUDA-graph replay needs a static step"
+        overhead of the ~700 launches of a step. With skip_compute the step is captured as one
+        graph per (exit stage, number of still-active images) instead: after each gate the host reads
+        the 4-byte active count and replays the next stage's graph of that size (_skip_state)."""
         self.use_graph = use_graph
         self.overlap_gates = True      # early-exit gates on a side stream, overlapping the next section
         self._side = None
@@ -67,8 +67,19 @@ class EarlyExitEngine:
     def static_inputs(self, shape, with_targets=True):
         """Graph mode: the device buffers the captured step reads. Fill them (e.g. H2D copies
         straight from pinned memory) and call replay() to avoid an extra device copy."""
-        g = self._capture(tuple(shape), with_targets)
+        g = self._slot(tuple(shape), with_targets)
         return g['X'], g['y']
+
+    def _slot(self, shape, with_targets, slot=0):
+        if self.skip_compute:
+            return self._skip_state(shape, with_targets, slot)
+        return self._capture(shape, with_targets, slot)
+
+    def _replay_slot(self, g):
+        if self.skip_compute:
+            return self._run_skip_graphs(g)
+        g['graph'].replay()
+        return g['out']
 
     def _capture(self, shape, with_targets, slot=0):
         key = (shape, with_targets, slot)
@@ -96,16 +107,15 @@ class EarlyExitEngine:
         return g
 
     def replay(self, shape, with_targets=True):
-        g = self._capture(tuple(shape), with_targets)
-        g['graph'].replay()
-        return g['out']
+        return self._replay_slot(self._slot(tuple(shape), with_targets))
 
     def evaluate_pipelined(self, host_batches):
         """Throughput path for host-resident data: yields (exit int32 [N], scores f32 [E-1,N]) CPU
         tensors per batch, in order. `host_batches` yields (X, y) pinned CPU tensors of one shape.
         Two captured graphs with their own input buffers are used alternately: while graph k runs,
         the copy stream uploads batch k+1 into the other graph's buffers, and the small per-image
-        results of batch k-1 are read back — H2D, compute and D2H overlap, nothing else changes."""
+        results of batch k-1 are read back — H2D, compute and D2H overlap, nothing else changes.
+        With skip_compute the "graph" of a slot is its chain of stage graphs (a 4-byte host read per gate)."""
         assert self.use_graph, "evaluate_pipelined needs use_graph=True"
         dev = self.device
         copy_stream = torch.cuda.Stream(device=dev)   # uploads
@@ -116,10 +126,11 @@ class EarlyExitEngine:
         ev_free = [torch.cuda.Event() for _ in range(2)]   # graph of slot k finished reading its inputs
         ev_out = [torch.cuda.Event() for _ in range(2)]
         res_host = None
-        k = 0
-        for X, y in host_batches:
+
+        def upload(k, X, y):
+            nonlocal slots, res_host
             if slots is None:
-                slots = [self._capture(tuple(X.shape), True, slot=i) for i in range(2)]
+                slots = [self._slot(tuple(X.shape), True, slot=i) for i in range(2)]
                 res_host = [(torch.empty((X.shape[0],), dtype=torch.int32).pin_memory(),
                              torch.empty((max(self.E - 1, 1), X.shape[0]), dtype=torch.float32).pin_memory())
                             for _ in range(2)]
@@ -131,8 +142,20 @@ class EarlyExitEngine:
                 g['X'].copy_(X, non_blocking=True)
                 g['y'].copy_(y.view_as(g['y']), non_blocking=True)
                 ev_in[k & 1].record(copy_stream)
+
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is not None:
+            upload(0, *nxt)
+        k = 0
+        while nxt is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                # slot (k+1)&1 was last read by batch k-1, whose results were handed out in the previous iteration
+                upload(k + 1, *nxt)
+            g = slots[k & 1]
             main.wait_event(ev_in[k & 1])
-            g['graph'].replay()
+            self._replay_slot(g)              # skip mode blocks the host at every gate: the next upload is already queued
             ev_free[k & 1].record(main)
             with torch.cuda.stream(back_stream):
                 back_stream.wait_event(ev_free[k & 1])
@@ -148,11 +171,124 @@ class EarlyExitEngine:
             ev_out[pending].synchronize()
             yield res_host[pending][0].clone(), res_host[pending][1].clone()
 
+    # ------------------------------------------------------------------------------------------
+    # compute-skipping + CUDA graphs: one graph per (stage i, active images n)
+    # ------------------------------------------------------------------------------------------
+    def _skip_state(self, shape, with_targets, slot=0):
+        """Static buffers of the staged step for one input shape: the input of every backbone section
+        (`xin[i]`, its first n rows hold the compacted still-active images), their original batch
+        positions (`act[i]`), the per-image results, and a pinned host word per gate for the count."""
+        key = ('skip', shape, with_targets, slot)
+        st = self._graphs.get(key)
+        if st is not None:
+            return st
+        N, _, H, W = shape
+        dev, E = self.device, self.E
+        X = torch.zeros(shape, dtype=torch.float32, device=dev)
+        xin, Xc = [X], X
+        for i in range(E - 1):                 # one eager pass: shapes of the section boundaries (+ plan warm-up)
+            Xc = self.net.run_section(i, Xc)
+            xin.append(torch.empty_like(Xc))
+        st = {
+            'X': X, 'xin': xin,
+            'y': torch.full((N, 1, H, W), self.C, dtype=torch.int64, device=dev) if with_targets else None,
+            'act': [torch.arange(N, dtype=torch.int64, device=dev)] +
+                   [torch.zeros((N,), dtype=torch.int64, device=dev) for _ in range(E - 1)],
+            'cnt_host': torch.zeros((E,), dtype=torch.int32).pin_memory(),
+            'pool': torch.cuda.graph_pool_handle(), 'stages': {}, 'ev': torch.cuda.Event(),
+            'out': {'exit': torch.full((N,), -1, dtype=torch.int32, device=dev),
+                    'pred': torch.zeros((N, H, W), dtype=torch.uint8, device=dev),
+                    'scores': torch.full((max(E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)},
+        }
+        self._graphs[key] = st
+        return st
+
+    def _skip_stage(self, st, i, n):
+        """Stage i on the n still-active images: section, head, gate, decision; results scattered to the images'
+        batch positions; survivors gathered to the front of the next section's input. Static shapes only."""
+        net, E, out = self.net, self.E, st['out']
+        N, H, W = out['pred'].shape
+        last = i == E - 1
+        if i == 0:
+            out['exit'].fill_(-1)
+            out['scores'].fill_(float('inf'))
+        Xin, act = st['xin'][i][:n], st['act'][i][:n]
+        Xc = net.run_section(i, Xin)
+        low = net._plan(i).run(Xc)
+        gated = not last and i >= self.skip
+        res = self._gate(low, (H, W), want_score=gated)
+        if last:
+            out['pred'].index_copy_(0, act, res.amax)
+            out['exit'].index_fill_(0, act, i)
+        elif gated:
+            out['scores'][i].index_copy_(0, act, res.score)
+            sub = torch.full((n,), -1, dtype=torch.int32, device=Xc.device)
+            al, ac = ops.gate_decide(res.score, self.tau, i, sub, want_active=True)
+            took = (sub == i).view(-1, 1, 1)
+            out['pred'].index_copy_(0, act, torch.where(took, res.amax, out['pred'].index_select(0, act)))
+            out['exit'].index_copy_(0, act, sub)
+            if res.exited_px is not None:
+                self.exited_px[i] += res.exited_px.sum()
+            keep = al.long().clamp_(0, n - 1)      # entries past the active count are don't-cares
+            torch.index_select(Xc, 0, keep, out=st['xin'][i + 1][:n])      # one pass: survivors to the front
+            torch.index_select(act, 0, keep, out=st['act'][i + 1][:n])
+            st['cnt_host'][i:i + 1].copy_(ac, non_blocking=True)
+        else:
+            st['xin'][i + 1][:n].copy_(Xc)
+            st['act'][i + 1][:n].copy_(act)
+
+    def _skip_final(self, st):
+        out = st['out']
+        cm = ops.confusion_hist(out['pred'], st['y'], self.C)            # [N, C+1, C]
+        ex = out['exit'].long()
+        self.cm.index_add_(0, ex, cm)
+        self.cm[-1] += cm.sum(dim=0)
+        self.counts.index_add_(0, ex, torch.ones_like(ex))
+        self.counts[-1] += ex.numel()
+
+    def _skip_graph(self, st, key, fn):
+        g = st['stages'].get(key)
+        if g is None:
+            dev = self.device
+            saved = (self.cm.clone(), self.counts.clone(), self.exited_px.clone())
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):      # warm-up on the real buffers: every stage is idempotent but for the accumulators
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=st['pool']):
+                fn()
+            self.cm.copy_(saved[0]); self.counts.copy_(saved[1]); self.exited_px.copy_(saved[2])
+            st['stages'][key] = g
+        return g
+
+    def _run_skip_graphs(self, st):
+        """Replay the stage graphs of one batch whose inputs are already in st['X'] / st['y']."""
+        n = st['X'].shape[0]
+        main = torch.cuda.current_stream(self.device)
+        for i in range(self.E):
+            self._skip_graph(st, (i, n), lambda: self._skip_stage(st, i, n)).replay()
+            if i < self.E - 1 and i >= self.skip:
+                st['ev'].record(main)
+                st['ev'].synchronize()           # the one host read per gate: 4 bytes
+                n = int(st['cnt_host'][i])
+                if n == 0:
+                    break
+        if st['y'] is not None:
+            self._skip_graph(st, 'final', lambda: self._skip_final(st)).replay()
+        return st['out']
+
     @torch.no_grad()
     def infer(self, X):
         """X [N,3,H,W] on the device. Returns dict: 'exit' int32 [N] (0-based exit taken),
         'pred' uint8 [N,H,W] (argmax map of that exit), 'scores' f32 [E-1,N]. In graph mode the
         returned tensors are the graph's static outputs (overwritten by the next call)."""
+        if self.use_graph and self.skip_compute:
+            st = self._skip_state(tuple(X.shape), False)
+            st['X'].copy_(X, non_blocking=True)
+            return self._run_skip_graphs(st)
         if self.use_graph:
             g = self._capture(tuple(X.shape), False)
             g['X'].copy_(X, non_blocking=True)
@@ -267,6 +403,11 @@ class EarlyExitEngine:
     def evaluate(self, X, y):
         """infer + integer confusion matrices of the exit taken: accumulates self.cm[e] for the exit
         each image left at and self.cm[-1] globally (the accumulators of eval_br_ent.py:39,61-69)."""
+        if self.use_graph and self.skip_compute:
+            st = self._skip_state(tuple(X.shape), True)
+            st['X'].copy_(X, non_blocking=True)
+            st['y'].copy_(y.view_as(st['y']), non_blocking=True)
+            return self._run_skip_graphs(st)
         if self.use_graph:
             g = self._capture(tuple(X.shape), True)
             g['X'].copy_(X, non_blocking=True)

@@ -93,6 +93,42 @@ def test_engine_decisions_and_confusion_vs_oracle(nets):
         assert r["out_gl"] == N and set(r) >= {"b1_mIoU", "b1_count", "b2_mIoU", "mIoU_out", "mIoU_gl", "t", "pool", "pool_size"}
 
 
+def test_engine_graphed_skipping_equals_eager_skipping(nets):
+    """skip_compute + use_graph (one CUDA graph per exit stage and active-image count, 4-byte host read per gate)
+    against the eager compute-skipping engine: same exits, maps, scores, confusion matrices and counters, over
+    several batches (graphs reused) and thresholds that make all / some / no images leave early."""
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine
+    _, net = nets
+    g = torch.Generator().manual_seed(31)
+    N = 4
+    batches = [(torch.randn(N, 3, 97, 113, generator=g).to(dev()), torch.randint(0, 22, (N, 1, 97, 113), generator=g).to(dev()))
+               for _ in range(3)]
+    sc = EarlyExitEngine(net, 21, 0.5).evaluate(*batches[0])["scores"].cpu()
+    taus = [0.0, float(sc[0].median()), float(sc.max()) + 1e-3, float((sc[0].min() + sc[0].sort().values[1]) / 2)]
+    for tau in taus:
+        eager = EarlyExitEngine(net, 21, tau, skip_compute=True)
+        graphed = EarlyExitEngine(net, 21, tau, skip_compute=True, use_graph=True)
+        for rep in range(2):                        # second round: every graph already captured
+            for X, y in batches:
+                a = eager.evaluate(X, y)
+                b = graphed.evaluate(X, y)
+                assert torch.equal(a["exit"], b["exit"])
+                assert torch.equal(a["pred"], b["pred"])
+                took = a["exit"].cpu()
+                for k in range(N):                   # scores of the gates an image actually reached
+                    for i in range(min(int(took[k]) + 1, 2)):
+                        assert float(a["scores"][i, k]) == float(b["scores"][i, k])
+        assert torch.equal(eager.cm, graphed.cm)
+        assert torch.equal(eager.counts, graphed.counts)
+        assert torch.equal(eager.exited_px, graphed.exited_px)
+        assert int(graphed.counts[-1]) == 2 * 3 * N
+    # inference-only entry
+    graphed = EarlyExitEngine(net, 21, taus[1], skip_compute=True, use_graph=True)
+    eager = EarlyExitEngine(net, 21, taus[1], skip_compute=True)
+    a, b = eager.infer(batches[1][0]), graphed.infer(batches[1][0])
+    assert torch.equal(a["exit"], b["exit"]) and torch.equal(a["pred"], b["pred"])
+
+
 def test_br_evaluator_golden(golden):
     """The reference's br_evaluator result dicts (fake 3-exit net, several tau / pool modes)."""
     from ee_semantic_segmentation_b200.eval_br_ent import br_evaluator
