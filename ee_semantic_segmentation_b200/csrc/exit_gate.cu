@@ -299,6 +299,30 @@ __global__ void decide_kernel(const float* __restrict__ score, int N, float tau,
   }
 }
 
+// Batch compaction after a gate: dst[j] = src[active_list[j]] for j < *active_count (all n rows when the count pointer is
+// null) — the still-active images' activations moved to the front of the next backbone section's input. Rows are whole
+// images (tens of MB): 16-byte vectors, grid.y = destination row, grid-stride along the row; rows past the count cost nothing.
+__global__ void __launch_bounds__(256) compact_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                           const int32_t* __restrict__ list,
+                                                           const int32_t* __restrict__ count, int n_src, int64_t row_vecs) {
+  const int j = blockIdx.y;
+  if (count && j >= *count) return;
+  const int sidx = list[j];
+  if (sidx < 0 || sidx >= n_src) return;
+  const uint4* s = src + (int64_t)sidx * row_vecs;
+  uint4* d = dst + (int64_t)j * row_vecs;
+  const int64_t step = (int64_t)gridDim.x * 256 * 4;
+  for (int64_t v = (int64_t)blockIdx.x * 1024 + threadIdx.x; v < row_vecs; v += step) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u * 256 < row_vecs) r[u] = __ldcs(s + v + u * 256);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u * 256 < row_vecs) d[v + u * 256] = r[u];
+  }
+}
+
 // Adjoint of the bilinear up-sampling (F.interpolate backward, from_deepv3_new.py:149,152 under autograd):
 //   dlow[n,c,y,x] = sum_{Y,X} wy(Y,y) * wx(X,x) * dout[n,c,Y,X]
 // in GATHER form: one thread per low-res pixel walks the (at most ~2*scale+2)^2 output pixels that
@@ -472,6 +496,23 @@ extern "C" int eeseg_exit_gate_decide(const double* part_sum, const int32_t* par
     return check_launch("decide_kernel");
   }
   return EESEG_OK;
+}
+
+extern "C" int eeseg_compact_rows(const void* src, void* dst, const int32_t* active_list, const int32_t* active_count,
+                                  int n_src, int n_dst, int64_t row_bytes, void* stream) {
+  EESEG_REQUIRE(src && dst && active_list, "compact_rows: null pointer");
+  EESEG_REQUIRE(n_src >= 0 && n_dst >= 0 && n_dst <= 65535 && row_bytes >= 0, "compact_rows: bad sizes");
+  EESEG_REQUIRE((row_bytes & 15) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0,
+                "compact_rows: rows must be 16-byte multiples and 16-byte aligned");
+  if (n_dst == 0 || row_bytes == 0) return EESEG_OK;
+  const int64_t row_vecs = row_bytes >> 4;
+  int64_t bx = (row_vecs + 1023) / 1024;
+  const int64_t cap = (8 * kNumSMs + n_dst - 1) / n_dst;      // ~8 blocks per SM over all rows
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  compact_rows_kernel<<<dim3((unsigned)bx, (unsigned)n_dst), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, (uint4*)dst, active_list, active_count, n_src, row_vecs);
+  return check_launch("compact_rows_kernel");
 }
 
 extern "C" int eeseg_upsample_bilinear_bwd(const void* dout, int dtype, int64_t planes, int h, int w, int H, int W,

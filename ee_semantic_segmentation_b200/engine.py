@@ -230,12 +230,19 @@ class EarlyExitEngine:
             if res.exited_px is not None:
                 self.exited_px[i] += res.exited_px.sum()
             keep = al.long().clamp_(0, n - 1)      # entries past the active count are don't-cares
-            torch.index_select(Xc, 0, keep, out=st['xin'][i + 1][:n])      # one pass: survivors to the front
+            ops.compact_rows(self._dense_rows(Xc), al, ac, self._dense_rows(st['xin'][i + 1][:n]))   # survivors to the front
             torch.index_select(act, 0, keep, out=st['act'][i + 1][:n])
             st['cnt_host'][i:i + 1].copy_(ac, non_blocking=True)
         else:
             st['xin'][i + 1][:n].copy_(Xc)
             st['act'][i + 1][:n].copy_(act)
+
+    @staticmethod
+    def _dense_rows(t):
+        """[n, ...] view whose rows are dense in memory (channels_last NCHW tensors are NHWC underneath)."""
+        if t.dim() == 4 and t.shape[0] and not t[0].is_contiguous() and t.is_contiguous(memory_format=torch.channels_last):
+            return t.permute(0, 2, 3, 1)
+        return t
 
     def _skip_final(self, st):
         out = st['out']

@@ -177,6 +177,22 @@ def gate_decide(score, tau, exit_id, exit_idx, less_than=True, want_active=True)
     return al, ac
 
 
+def compact_rows(src, active_list, active_count, out):
+    """out[j] = src[active_list[j]] for j < active_count (device-side count; rows past it are left untouched).
+    src [n, ...] and out [m, ...] dense rows of equal size; active_list int32 [>= m]."""
+    _cuda(src, "src")
+    if src.shape[1:] != out.shape[1:] or src.dtype != out.dtype:
+        raise ValueError("compact_rows: row shapes / dtypes differ")
+    if src.shape[0] and (src.stride(0) != src[0].numel() or not src[0].is_contiguous()) or \
+            out.shape[0] and (out.stride(0) != out[0].numel() or not out[0].is_contiguous()):
+        raise ValueError("compact_rows: rows must be dense")
+    row_bytes = (src[0].numel() if src.shape[0] else 0) * src.element_size()
+    with torch.cuda.device(src.device):
+        check(lib().eeseg_compact_rows(src.data_ptr(), out.data_ptr(), active_list.data_ptr(), _p(active_count),
+                                       src.shape[0], out.shape[0], row_bytes, _stream(src)), "eeseg_compact_rows")
+    return out
+
+
 def upsample_bilinear(x, out_hw, out=None, out_dtype=None, layout="NCHW", n_classes=None):
     """F.interpolate(x, size=out_hw, mode='bilinear', align_corners=False) into planes [N,C,H,W]."""
     r = exit_gate(x, out_hw, layout=layout, n_classes=n_classes, want_amax=False, want_score=False,

@@ -105,6 +105,14 @@ int eeseg_exit_gate_decide(const double* part_sum, const int32_t* part_cnt, int 
                            int exit_id, int32_t* exit_idx, float* score_out, int64_t* exited_px,
                            int32_t* active_list, int32_t* active_count, void* stream);
 
+/* Batch compaction after a gate (the compute-skipping form of ee_dnn_op_ne.py:80-101, which always runs the tail):
+ *   dst[j][:] = src[active_list[j]][:]  for j < *active_count (j < n_dst when active_count == NULL)
+ * rows of row_bytes bytes (16-byte multiple, 16-byte aligned): the activations of the images still active after an
+ * exit, moved to the front of the next backbone section's input. active_list / active_count as written by
+ * eeseg_exit_gate_decide; list entries outside [0, n_src) are skipped. */
+int eeseg_compact_rows(const void* src, void* dst, const int32_t* active_list, const int32_t* active_count,
+                       int n_src, int n_dst, int64_t row_bytes, void* stream);
+
 /* Plain bilinear up-sampling of E stacked low-res logit tensors into [.. ][C][H][W] planes
  * (the reference's forward return value, from_deepv3_new.py:149-155, without the cat copy). */
 int eeseg_upsample_bilinear(const void* in, int in_dtype,

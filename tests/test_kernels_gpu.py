@@ -642,3 +642,25 @@ def test_focal_full_size_vs_oracle(C, dtype):
     ref_g = np.stack(gs) * w[:, None, None, None, None] / ls[0].size
     got = yd.grad.float().cpu().numpy()
     assert np.abs(got - ref_g).max() < (1e-4 if dtype == torch.float32 else 1e-2) * np.abs(ref_g).max()
+
+
+# ------------------------------------------------------------------------------------ batch compaction
+@pytest.mark.parametrize("dtype,row", [(torch.bfloat16, (65, 65, 1024)), (torch.float32, (3, 5, 4)), (torch.uint8, (16,))])
+def test_compact_rows(dtype, row):
+    """dst[j] = src[list[j]] for j < count; rows past the device-side count stay untouched (bit-exact copy)."""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n = 5
+    src = (torch.randn((n,) + row, generator=g) * 50).to(dtype).to(dev())
+    for lst in ([0, 1, 2, 3, 4], [1, 3], [4], []):
+        al = torch.tensor(lst + [0x7fffffff] * (n - len(lst)), dtype=torch.int32, device=dev())   # garbage past the count
+        ac = torch.tensor([len(lst)], dtype=torch.int32, device=dev())
+        out = torch.full_like(src, 7)
+        ops.compact_rows(src, al, ac, out)
+        assert torch.equal(out[:len(lst)], src[lst])
+        assert bool((out[len(lst):] == 7).all())
+    out = torch.full_like(src[:3], 7)
+    ops.compact_rows(src, torch.tensor([4, 0, 2], dtype=torch.int32, device=dev()), None, out)   # no count: all rows of dst
+    assert torch.equal(out, src[[4, 0, 2]])
+    with pytest.raises(RuntimeError):
+        ops.compact_rows(src.cpu(), al, ac, out)

@@ -50,6 +50,19 @@ def main():
     torch.cuda.synchronize()
     rows["final_us"] = round(a.elapsed_time(b) / 20 * 1e3, 1)
     print(json.dumps(rows))
+    if "--profile" in sys.argv:
+        from torch.profiler import ProfilerActivity, profile
+        g = st['stages'][(1, N)]
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                g.replay()
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_time_total > 0), key=lambda e: e.time_range.start)
+        per = len(evs) // 5
+        t0 = evs[-per].time_range.start
+        for e in evs[-per:]:
+            print(f"{e.time_range.start - t0:9.1f} {e.device_time_total:8.1f}  {e.name[:90]}")
 
 
 if __name__ == "__main__":
