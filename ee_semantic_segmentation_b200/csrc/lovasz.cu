@@ -87,20 +87,33 @@ __global__ void __launch_bounds__(256) lv_keygen_kernel(const T* __restrict__ pr
     const bool valid = !(has_ignore && lab == ignore);
     const int g = d.G == 1 ? 0 : n;
     const int64_t i = d.G == 1 ? q : pix;  // index inside the segment
-    for (int c = 0; c < d.C; ++c) {
-      const int64_t src = ((int64_t)n * d.C + c) * d.HW + pix;
-      if (skip[g * d.C + c]) {
-        if (dprobas) stf(dprobas + src, 0.f);
-        continue;
+    // classes in chunks of 4: the chunk's loads are issued before the first use (the loop is latency bound otherwise)
+    for (int c0 = 0; c0 < d.C; c0 += 4) {
+      float pv[4];
+      bool sk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u;
+        sk[u] = c >= d.C || skip[g * d.C + c] != 0;
+        pv[u] = sk[u] ? 0.f : ldf_stream(probas + ((int64_t)n * d.C + c) * d.HW + pix);
       }
-      const float p = ldf_stream(probas + src);
-      const float fg = (lab == c) ? 1.f : 0.f;
-      const float diff = p - fg;
-      const float err = valid ? fabsf(diff) : 0.f;
-      const int64_t dst = ((int64_t)g * d.C + c) * d.L + i;
-      // key: ascending on ~bits == descending on err (err >= 0); value: index | fg << 31 | sign << 30
-      kv[dst] = make_uint2(~__float_as_uint(err),
-                           (uint32_t)i | (fg != 0.f ? 0x80000000u : 0u) | (diff > 0.f ? 0x40000000u : 0u));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u;
+        if (c >= d.C) break;
+        const int64_t src = ((int64_t)n * d.C + c) * d.HW + pix;
+        if (sk[u]) {
+          if (dprobas) stf(dprobas + src, 0.f);
+          continue;
+        }
+        const float fg = (lab == c) ? 1.f : 0.f;
+        const float diff = pv[u] - fg;
+        const float err = valid ? fabsf(diff) : 0.f;
+        const int64_t dst = ((int64_t)g * d.C + c) * d.L + i;
+        // key: ascending on ~bits == descending on err (err >= 0); value: index | fg << 31 | sign << 30
+        kv[dst] = make_uint2(~__float_as_uint(err),
+                             (uint32_t)i | (fg != 0.f ? 0x80000000u : 0u) | (diff > 0.f ? 0x40000000u : 0u));
+      }
     }
   }
 }
@@ -119,6 +132,12 @@ __device__ __forceinline__ unsigned match_digit8(int dg, bool ok) {
   return ok ? peers : 0u;
 }
 
+// Tile histograms. Counting goes through per-warp private shared-memory histograms with plain atomics: random digits
+// (the mantissa bytes) spread over the banks and cost ~1 instruction per element, where digit matching by ballots made the
+// kernel ALU bound (ncu: math-pipe throttle the top stall, 31 % of HBM peak). Concentrated digits (kTop: the sign/exponent
+// byte takes a handful of values, so the atomics would serialise 32-way) are aggregated with MATCH.ANY first, which is
+// cheap exactly when there are few distinct values; a warp whose 32 digits coincide adds them with one atomic either way.
+template <bool kTop>
 __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint2* __restrict__ kv,
                                                               LovaszDims d, int shift,
                                                               const int* __restrict__ skip,
@@ -126,24 +145,40 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint2* __rest
   // hist[seg][digit][tile]
   const int seg = blockIdx.y, tile = blockIdx.x;
   if (skip[seg]) return;
-  __shared__ unsigned h[256];
-  h[threadIdx.x] = 0;
+  __shared__ unsigned h[kRsWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 0; w < kRsWarps; ++w) h[w][threadIdx.x] = 0;
   __syncthreads();
   const uint2* k = kv + (int64_t)seg * d.L;
   const int64_t base = (int64_t)tile * kRsTile;
   int dg[kRsItems];
 #pragma unroll
-  for (int r = 0; r < kRsItems; ++r) {   // all loads first (16 independent 4 B loads in flight per thread)
+  for (int r = 0; r < kRsItems; ++r) {   // all loads first (16 independent loads in flight per thread)
     const int64_t i = base + r * kRsThreads + threadIdx.x;
-    dg[r] = i < d.L ? (int)((__ldg(k + i).x >> shift) & 255u) : -1;
+    dg[r] = i < d.L ? (int)((__ldg(k + i).x >> shift) & 255u) : 256;
   }
+  unsigned* hw = h[warp];
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
-    const unsigned peers = match_digit8(dg[r], dg[r] >= 0);
-    if (dg[r] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(h + dg[r], (unsigned)__popc(peers));
+    if (kTop) {
+      const unsigned peers = __match_any_sync(0xffffffffu, dg[r]);
+      if (dg[r] < 256 && lane == __ffs(peers) - 1) atomicAdd(hw + dg[r], (unsigned)__popc(peers));
+    } else {
+      int same;
+      __match_all_sync(0xffffffffu, dg[r], &same);
+      if (same) {
+        if (lane == 0 && dg[r] < 256) atomicAdd(hw + dg[r], 32u);
+      } else if (dg[r] < 256) {
+        atomicAdd(hw + dg[r], 1u);
+      }
+    }
   }
   __syncthreads();
-  hist[((int64_t)seg * 256 + threadIdx.x) * d.T + tile] = h[threadIdx.x];
+  unsigned t = 0;
+#pragma unroll
+  for (int w = 0; w < kRsWarps; ++w) t += h[w][threadIdx.x];
+  hist[((int64_t)seg * 256 + threadIdx.x) * d.T + tile] = t;
 }
 
 // one warp per (segment, digit): exclusive scan of that digit's counts over the tiles
@@ -194,7 +229,7 @@ __global__ void __launch_bounds__(256) rs_scan_digits_kernel(const uint32_t* __r
 // Scatter: stable ranking inside the tile (warp-blocked order, match.any), then the tile is
 // re-ordered by digit in shared memory and written out run by run, so consecutive threads write
 // consecutive (key, value) pairs: full lines instead of one 32 B sector per element.
-__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(
+__global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(
     const uint2* __restrict__ in, uint2* __restrict__ out, LovaszDims d, int shift,
     const int* __restrict__ skip, const uint32_t* __restrict__ hist,
     const uint32_t* __restrict__ digit_base) {
@@ -466,7 +501,10 @@ static int run_exit(const T* probas, const int64_t* labels, const LovaszDims& d,
   int cur = 0;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
-    rs_hist_kernel<<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], d, shift, w.skip, w.hist);
+    if (pass == 3)
+      rs_hist_kernel<true><<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], d, shift, w.skip, w.hist);
+    else
+      rs_hist_kernel<false><<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], d, shift, w.skip, w.hist);
     if ((rc = check_launch("rs_hist_kernel"))) return rc;
     rs_scan_tiles_kernel<<<S * 32, 256, 0, stream>>>(w.hist, d.T, w.skip, w.digit_total);
     if ((rc = check_launch("rs_scan_tiles_kernel"))) return rc;
