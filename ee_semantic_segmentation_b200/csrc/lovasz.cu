@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(256) rs_scan_digits_kernel(const uint32_t* __r
 // Scatter: stable ranking inside the tile (warp-blocked order, match.any), then the tile is
 // re-ordered by digit in shared memory and written out run by run, so consecutive threads write
 // consecutive (key, value) pairs: full lines instead of one 32 B sector per element.
+template <bool kMatchAny>
 __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(
     const uint2* __restrict__ in, uint2* __restrict__ out, LovaszDims d, int shift,
     const int* __restrict__ skip, const uint32_t* __restrict__ hist,
@@ -258,7 +259,8 @@ __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(
   for (int r = 0; r < kRsItems; ++r) {
     const bool ok = wbase + r * 32 + lane < d.L;
     const int dg = ok ? (int)((kv[r].x >> shift) & 255u) : 0;
-    const unsigned peers = match_digit8(dg, ok);
+    const unsigned peers = kMatchAny ? (__match_any_sync(0xffffffffu, ok ? dg : 256) & (ok ? 0xffffffffu : 0u))
+                                     : match_digit8(dg, ok);
     const int leader = ok ? __ffs(peers) - 1 : lane;
     unsigned old = 0;
     if (ok && lane == leader) {
@@ -510,8 +512,12 @@ static int run_exit(const T* probas, const int64_t* labels, const LovaszDims& d,
     if ((rc = check_launch("rs_scan_tiles_kernel"))) return rc;
     rs_scan_digits_kernel<<<S, 256, 0, stream>>>(w.digit_total, w.skip, w.digit_base);
     if ((rc = check_launch("rs_scan_digits_kernel"))) return rc;
-    rs_scatter_kernel<<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], w.kv[cur ^ 1], d, shift, w.skip, w.hist,
-                                                        w.digit_base);
+    if (pass == 3)   // the sign/exponent byte: few distinct digits per warp, MATCH.ANY beats the 8-ballot match there (only)
+      rs_scatter_kernel<true><<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], w.kv[cur ^ 1], d, shift, w.skip, w.hist,
+                                                                w.digit_base);
+    else
+      rs_scatter_kernel<false><<<tiles, kRsThreads, 0, stream>>>(w.kv[cur], w.kv[cur ^ 1], d, shift, w.skip, w.hist,
+                                                                 w.digit_base);
     if ((rc = check_launch("rs_scatter_kernel"))) return rc;
     cur ^= 1;
   }
