@@ -262,7 +262,8 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_wgrad: bad sizes");
   EESEG_REQUIRE(Cin % 64 == 0, "conv_wgrad: Cin=%d must be a multiple of 64", Cin);
   EESEG_REQUIRE(Cout % 64 == 0, "conv_wgrad: Cout=%d must be a multiple of 64", Cout);
-  EESEG_REQUIRE(R >= 1 && S >= 1 && (R & 1) && (S & 1) && R * S <= 32, "conv_wgrad: odd kernel sizes with at most 32 taps");
+  // even kernel sizes (the space-to-depth'ed 4x1 stem) use the same rule pad = dilation * (R / 2), i.e. the forward's pad = 2
+  EESEG_REQUIRE(R >= 1 && S >= 1 && R * S <= 32, "conv_wgrad: at most 32 taps");
   EESEG_REQUIRE(dilation >= 1, "conv_wgrad: dilation %d", dilation);
   EESEG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw & 15) == 0 && (ldy % 8) == 0 &&
                 ((uintptr_t)workspace & 15) == 0, "conv_wgrad: pointers and the dY pixel stride must be 16-byte aligned");

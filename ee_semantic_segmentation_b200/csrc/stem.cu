@@ -83,9 +83,128 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
   }
 }
 
+// Training max-pool: forward also records which of the 9 window taps won (first maximum in row-major window order,
+// ATen's rule: a later tap wins only if strictly greater), backward gathers: an input pixel belongs to at most 2x2
+// windows and receives dOut of those whose recorded tap points at it — fixed order, no atomics.
+__global__ void __launch_bounds__(256) maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ x, int N, int h,
+                                                                int w, int C, int ho, int wo,
+                                                                __nv_bfloat16* __restrict__ out,
+                                                                uint8_t* __restrict__ idx) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)N * ho * wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int X = (int)((i / cv) % wo);
+    const int Y = (int)((i / ((int64_t)cv * wo)) % ho);
+    const int n = (int)(i / ((int64_t)cv * wo * ho));
+    float m[8];
+    uint32_t bits[8];
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; bits[k] = 0xff80u; arg[k] = 0; }
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = 2 * Y + dy, xx = 2 * X + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * h + yy) * w + xx) * C) + c8);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+          const int tap = (dy + 1) * 3 + (dx + 1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t b = (k & 1) ? (w4[k >> 1] >> 16) : (w4[k >> 1] & 0xffffu);
+            const float v = __uint_as_float(b << 16);
+            if (v > m[k] || v != v) { m[k] = v; bits[k] = b; arg[k] = tap; }
+          }
+        }
+      }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = bits[2 * k] | (bits[2 * k + 1] << 16);
+    const int64_t opix = ((int64_t)n * ho + Y) * wo + X;
+    reinterpret_cast<uint4*>(out + opix * C)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lo |= (uint32_t)arg[k] << (8 * k); hi |= (uint32_t)arg[4 + k] << (8 * k); }
+    reinterpret_cast<uint2*>(idx + opix * C)[c8] = make_uint2(lo, hi);
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                                const uint8_t* __restrict__ idx, int N, int h, int w,
+                                                                int C, int ho, int wo, __nv_bfloat16* __restrict__ dx) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)N * h * w * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int x = (int)((i / cv) % w);
+    const int y = (int)((i / ((int64_t)cv * w)) % h);
+    const int n = (int)(i / ((int64_t)cv * w * h));
+    float g[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = 0.f;
+    // windows (Y, X) with |2Y - y| <= 1: Y in [ceil((y-1)/2), floor((y+1)/2)]
+    const int Y0 = y >> 1, Y1 = (y + 1) >> 1, X0 = x >> 1, X1 = (x + 1) >> 1;   // equal when y (x) is even
+    for (int Y = Y0; Y <= Y1; ++Y) {
+      if (Y >= ho) continue;
+      for (int X = X0; X <= X1; ++X) {
+        if (X >= wo) continue;
+        const int tap = (y - 2 * Y + 1) * 3 + (x - 2 * X + 1);
+        const int64_t opix = ((int64_t)n * ho + Y) * wo + X;
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(idx + opix * C) + c8);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + opix * C) + c8);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ak = (int)(((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xffu);
+          const uint32_t b = (k & 1) ? (w4[k >> 1] & 0xffff0000u) : (w4[k >> 1] << 16);
+          if (ak == tap) g[k] += __uint_as_float(b);
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
+      o[k] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    reinterpret_cast<uint4*>(dx + (((int64_t)n * h + y) * w + x) * C)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace eeseg
 
 using namespace eeseg;
+
+extern "C" int eeseg_maxpool3x3s2_nhwc_train(const void* x, int N, int h, int w, int C, void* out, void* idx, void* stream) {
+  EESEG_REQUIRE(x && out && idx, "maxpool3x3s2_train: null pointer");
+  EESEG_REQUIRE(C % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 && ((uintptr_t)idx & 7) == 0,
+                "maxpool3x3s2_train: C %% 8 == 0 and aligned pointers required");
+  if (N <= 0) return EESEG_OK;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int64_t total = (int64_t)N * ho * wo * (C / 8);
+  const int blocks = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  maxpool3x3s2_idx_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, h, w, C, ho, wo,
+                                                                      (__nv_bfloat16*)out, (uint8_t*)idx);
+  return check_launch("maxpool3x3s2_idx_kernel");
+}
+
+extern "C" int eeseg_maxpool3x3s2_nhwc_bwd(const void* dout, const void* idx, int N, int h, int w, int C, void* dx,
+                                           void* stream) {
+  EESEG_REQUIRE(dout && idx && dx, "maxpool3x3s2_bwd: null pointer");
+  EESEG_REQUIRE(C % 8 == 0 && (((uintptr_t)dout | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)idx & 7) == 0,
+                "maxpool3x3s2_bwd: C %% 8 == 0 and aligned pointers required");
+  if (N <= 0) return EESEG_OK;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int64_t total = (int64_t)N * h * w * (C / 8);
+  const int blocks = (int)((total + 255) / 256 < kNumSMs * 16 ? (total + 255) / 256 : kNumSMs * 16);
+  maxpool3x3s2_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (const uint8_t*)idx, N, h, w,
+                                                                      C, ho, wo, (__nv_bfloat16*)dx);
+  return check_launch("maxpool3x3s2_bwd_kernel");
+}
 
 extern "C" int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream) {
   EESEG_REQUIRE(x && out, "stem_space_to_depth: null pointer");

@@ -199,7 +199,9 @@ int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* scale, cons
  *
  * eeseg_conv_igemm_wgrad:  dW[co][r][s][ci] = sum_{n,y,x} dY[n,y,x,co] * X[n, y+r*dil-pad, x+s*dil-pad, ci]
  *   tcgen05 implicit GEMM with the pixels as the contraction dimension (both operands MN-major, TMA boxes of
- *   NHWC tensors; the tap is a coordinate offset, zero fill = padding).
+ *   NHWC tensors; the tap is a coordinate offset, zero fill = padding). pad = dil * (R / 2) along every kernel
+ *   dimension with more than one tap ('same' for odd kernels; R = 4, S = 1 is the space-to-depth'ed ResNet stem,
+ *   whose forward runs with pad = 2).
  *   x  bf16 NHWC [N][h][w][Cin] (Cin % 64 == 0);  dy bf16 NHWC, pixel stride ldy, dy_channels channels in
  *   total, this convolution's Cout (% 64 == 0) channels starting at co_off;  dw fp32 [Cout][R][S][Cin]
  *   (overwritten). When the pixel dimension is split over CTAs to fill the GPU every split writes its own partial
@@ -280,6 +282,13 @@ int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, int64_t P, 
 int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream);
 /* 3x3 / stride-2 / pad-1 max pooling of a bf16 NHWC tensor (C % 8 == 0). */
 int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream);
+
+/* Training max-pool 3x3 / stride 2 / pad 1 (torchvision resnet `maxpool` under net.train(), from_deepv3_new.py:146):
+ * forward also writes idx u8 [N][ho][wo][C], the winning window tap 0..8 (row-major; first maximum, NaN wins — ATen's
+ * rule); backward gathers dx[n][y][x][c] = sum of dout over the <= 2x2 windows whose idx points at (y,x): fixed
+ * order, no atomics. x / dx bf16 NHWC [N][h][w][C], out / dout [N][ho][wo][C], C % 8 == 0. */
+int eeseg_maxpool3x3s2_nhwc_train(const void* x, int N, int h, int w, int C, void* out, void* idx, void* stream);
+int eeseg_maxpool3x3s2_nhwc_bwd(const void* dout, const void* idx, int N, int h, int w, int C, void* dx, void* stream);
 
 /* Grouped form: `nprob` (<= 4) stride-1 'same' convolutions of the SAME input (the ASPP branches:
  * 1x1 and the three atrous 3x3) as ONE persistent launch. Their tiles differ a lot in cost — a tile near

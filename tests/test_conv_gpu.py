@@ -279,3 +279,68 @@ def test_conv_autograd_stride2_vs_torch(cfg):
     assert rel(yd.detach().float().cpu(), yr.detach().permute(0, 2, 3, 1)) < 1e-2
     assert rel(xd.grad.float().cpu(), xr.grad.permute(0, 2, 3, 1)) < 1e-2
     assert rel(wd.grad.cpu(), wr.grad) < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 33, 37, 64), (1, 64, 64, 128), (2, 1, 5, 8)])
+def test_maxpool_train_fwd_bwd_vs_torch(shape):
+    """MaxPool2d(3, 2, 1) on NHWC bf16: values, the recorded winning tap (ties: first maximum in window order, as
+    ATen; the inputs are quantised so ties are frequent) and the gather-form backward against autograd."""
+    from ee_semantic_segmentation_b200.backbone_train import MaxPool3x3s2Fn
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 2).round().clamp_(min=0).to(torch.bfloat16)     # post-ReLU-like, many ties
+    N, h, w, C = shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    go = torch.randn(N, ho, wo, C, generator=g).to(torch.bfloat16)
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    yr.backward(go.float().permute(0, 3, 1, 2))
+    xd = x.to(dev()).requires_grad_(True)
+    yd = MaxPool3x3s2Fn.apply(xd)
+    yd.backward(go.to(dev()))
+    assert torch.equal(yd.detach().float().cpu(), yr.detach().permute(0, 2, 3, 1))
+    ref = xr.grad.permute(0, 2, 3, 1)
+    got = xd.grad.float().cpu()
+    # up to 4 bf16 gradients are summed in fp32 and rounded once
+    assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert torch.equal(got != 0, ref.to(torch.bfloat16).float() != 0) or (got - ref).abs().max().item() < 1e-2
+
+
+def test_stem_train_vs_torch_modules():
+    """Training stem (conv1 7x7/s2 as the space-to-depth 4x1 implicit GEMM, BatchNorm batch statistics + ReLU, max-pool)
+    on the eeseg kernels against autograd through the fp32 PyTorch modules: output, conv / BN parameter gradients
+    and the running statistics."""
+    import copy
+    import torchvision
+    from ee_semantic_segmentation_b200 import backbone_train
+    torch.manual_seed(5)
+    r = torchvision.models.resnet50(weights=None)
+    r.bn1.weight.data.uniform_(0.5, 1.5); r.bn1.bias.data.normal_(0, 0.2)
+    stem_ref = torch.nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool).train()
+    stem_dev = copy.deepcopy(stem_ref).to(dev()).train()
+    for shape in [(2, 3, 129, 161), (1, 3, 64, 96)]:
+        x = torch.randn(*shape)
+        stem_ref.zero_grad(); stem_dev.zero_grad()
+        yr = stem_ref(x)
+        go = torch.randn_like(yr)
+        yr.backward(go)
+        assert backbone_train.stem_supported(list(stem_dev), x.to(dev()))
+        yd = backbone_train.section_forward_train(stem_dev, x.to(dev()))
+        assert yd.shape == yr.shape and yd.dtype == torch.bfloat16
+        yd.backward(go.to(dev()).to(torch.bfloat16))
+        rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+        # the same step on the PyTorch modules under bf16 autocast (cuDNN): the bf16 error level of this layer — the
+        # conv1 gradient behind a batch-statistics BatchNorm is a difference of large sums
+        stem_amp = copy.deepcopy(stem_ref).to(dev()).train()
+        stem_amp.zero_grad()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            ya = stem_amp(x.to(dev()))
+        ya.backward(go.to(dev()).to(ya.dtype))
+        assert rel(yd.detach(), yr.detach()) < 1e-2
+        for got, amp, ref in [(stem_dev[0].weight.grad, stem_amp[0].weight.grad, stem_ref[0].weight.grad),
+                              (stem_dev[1].weight.grad, stem_amp[1].weight.grad, stem_ref[1].weight.grad),
+                              (stem_dev[1].bias.grad, stem_amp[1].bias.grad, stem_ref[1].bias.grad)]:
+            assert rel(got, ref) < max(2e-2, 1.5 * rel(amp, ref)), (rel(got, ref), rel(amp, ref))
+        assert rel(stem_dev[1].running_mean, stem_ref[1].running_mean) < 1e-2
+        assert rel(stem_dev[1].running_var, stem_ref[1].running_var) < 1e-2
+        stem_ref[1].load_state_dict(stem_dev[1].state_dict())       # keep both on the same running statistics
+    assert int(stem_dev[1].num_batches_tracked) == 2
