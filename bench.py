@@ -302,8 +302,10 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
+    eng.reset()                                   # exit statistics of the timed steps only
     dev_ms, wall_ms = timed(step_device, steps)
     launches = _lib.launch_count() - l0
+    exit_res = eng.results()                      # after the sweep's all-reduce: all ranks' images
 
     for _ in range(2):
         step_e2e()
@@ -433,7 +435,7 @@ def main():
         achieved = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         head_tf = head_fl / (head_ms * 1e-3) / 1e12 if head_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
-        res = eng.results()
+        res = exit_res
         line = {
             "metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
