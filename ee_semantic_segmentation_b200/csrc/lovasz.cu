@@ -237,7 +237,6 @@ __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(
   const int seg = blockIdx.y, tile = blockIdx.x;
   if (skip[seg]) return;
   __shared__ unsigned cnt[kRsWarps][256];     // per-warp digit counts -> exclusive prefix over warps
-  __shared__ unsigned tile_pref[256];         // exclusive prefix of the tile's digit totals
   __shared__ unsigned gl_off[256];            // global position of the tile's first element of a digit
   __shared__ unsigned wsum[8];
   __shared__ uint2 stage[kRsTile];            // 32 KB
@@ -292,24 +291,30 @@ __global__ void __launch_bounds__(kRsThreads, 3) rs_scatter_kernel(
     __syncthreads();
     unsigned off = 0;
     for (int i = 0; i < warp; ++i) off += wsum[i];
-    tile_pref[dg] = off + inc - run;
-    gl_off[dg] = digit_base[seg * 256 + dg] + hist[((int64_t)seg * 256 + dg) * d.T + tile];
+    // one table lookup per element in each of the two phases below: cnt[w][dg] becomes the position of warp w's first
+    // element of the digit inside the staged tile, gl_off[dg] the global position of staged slot 0 of the digit's run
+    const unsigned tp = off + inc - run;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) cnt[w][dg] += tp;
+    gl_off[dg] = digit_base[seg * 256 + dg] + hist[((int64_t)seg * 256 + dg) * d.T + tile] - tp;
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     if (wbase + r * 32 + lane < d.L) {
       const int dg = (int)((kv[r].x >> shift) & 255u);
-      stage[tile_pref[dg] + cnt[warp][dg] + lrank[r]] = kv[r];
+      stage[cnt[warp][dg] + lrank[r]] = kv[r];
     }
   }
   __syncthreads();
   const int64_t remaining = d.L - (int64_t)tile * kRsTile;
   const int n_valid = (int)(remaining < kRsTile ? remaining : kRsTile);
+  uint2* o = out + seg_off;
+#pragma unroll 4
   for (int i = threadIdx.x; i < n_valid; i += kRsThreads) {
     const uint2 e = stage[i];
     const int dg = (int)((e.x >> shift) & 255u);
-    out[seg_off + gl_off[dg] + ((unsigned)i - tile_pref[dg])] = e;
+    o[gl_off[dg] + (unsigned)i] = e;      // unsigned wrap-around: gl_off may be "negative" by less than the tile size
   }
 }
 

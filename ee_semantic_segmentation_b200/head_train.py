@@ -41,8 +41,9 @@ class ConvIgemmFn(torch.autograd.Function):
         from .head_plan import conv_igemm
         x = x.contiguous()
         N, h, w, Cin = x.shape
-        wt = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)     # [Cout,R,S,Cin]
-        Cout = wt.shape[0]
+        Cout, _, R, S = weight.shape
+        wt = torch.empty((Cout, R, S, Cin), dtype=torch.bfloat16, device=x.device)    # [Cout,R,S,Cin]
+        wt.copy_(weight.detach().permute(0, 2, 3, 1))                                  # layout + precision in one pass
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         out = torch.empty((N, ho, wo, Cout), dtype=torch.bfloat16, device=x.device)
         one, zero = _unit_scale_shift(x.device, Cout)

@@ -32,6 +32,12 @@ def train_epoch(net, train_iter, loss, updater, device=tch.device('cpu')):
     return last
 
 
+def _sgd_impl(net):
+    """torch's single-kernel ("fused") SGD update when every parameter lives on a GPU: the same update rule as the
+    default multi-tensor implementation in one pass over parameters, gradients and momentum buffers."""
+    return {'fused': True} if all(p.is_cuda for p in net.parameters()) else {}
+
+
 def make_optimizer(net, lr, base_lr=None, weighted_lr=False):
     """SGD(momentum 0.9, weight decay 5e-4) with the reference's parameter groups
     (deepv3_funcs.py:77-101): backbone at base_lr, branches at lr, final classifier at 1.1*lr."""
@@ -46,8 +52,8 @@ def make_optimizer(net, lr, base_lr=None, weighted_lr=False):
         else:
             params.append({'params': net.branches.parameters(), 'lr': lr})
             params.append({'params': net.classifier.parameters(), 'lr': lr * 1.1})
-        return optim.SGD(params, lr=lr, momentum=.9, weight_decay=5e-4)
-    return optim.SGD(net.parameters(), lr=lr, momentum=.9, weight_decay=5e-4)
+        return optim.SGD(params, lr=lr, momentum=.9, weight_decay=5e-4, **_sgd_impl(net))
+    return optim.SGD(net.parameters(), lr=lr, momentum=.9, weight_decay=5e-4, **_sgd_impl(net))
 
 
 def poly_scheduler(optimizer, num_epochs, lr=None, min_lr=None):

@@ -122,6 +122,13 @@ def test_engine_graphed_skipping_equals_eager_skipping(nets):
         assert torch.equal(eager.counts, graphed.counts)
         assert torch.equal(eager.exited_px, graphed.exited_px)
         assert int(graphed.counts[-1]) == 2 * 3 * N
+    # skip=1 (the first early exit is not allowed to answer: its stage passes every image on) and a single image
+    for X, y in [batches[0], (batches[2][0][:1], batches[2][1][:1])]:
+        eager = EarlyExitEngine(net, 21, taus[2], skip=1, skip_compute=True)
+        graphed = EarlyExitEngine(net, 21, taus[2], skip=1, skip_compute=True, use_graph=True)
+        a, b = eager.evaluate(X, y), graphed.evaluate(X, y)
+        assert torch.equal(a["exit"], b["exit"]) and torch.equal(a["pred"], b["pred"]) and int(b["exit"].min()) >= 1
+        assert torch.equal(eager.cm, graphed.cm) and torch.equal(eager.counts, graphed.counts)
     # inference-only entry
     graphed = EarlyExitEngine(net, 21, taus[1], skip_compute=True, use_graph=True)
     eager = EarlyExitEngine(net, 21, taus[1], skip_compute=True)
