@@ -587,6 +587,19 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   int BN = 256;
   while (BN > 16 && (Cout % BN)) BN >>= 1;
   (void)kb_total;
+  if (schedule) {
+    // grouped launch: the caller's work list fixes the number of channel tiles (eeseg_conv_group_tiles + the
+    // under-filled-grid rule below, applied by the scheduler)
+    const int spatial = N * p.tiles_x * p.tiles_y * nprob;
+    EESEG_REQUIRE(spatial > 0 && n_items % spatial == 0 && Cout % (n_items / spatial) == 0,
+                  "conv_igemm: schedule of %d items does not tile %d spatial tiles", n_items, spatial);
+    BN = Cout / (n_items / spatial);
+    EESEG_REQUIRE(BN >= 16 && BN <= 256 && (BN & (BN - 1)) == 0, "conv_igemm: schedule implies a %d-column tile", BN);
+  } else {
+    // under-filled grid (small batches: one image of 65x65 is 36 spatial tiles for 148 SMs): narrower channel tiles
+    // put more CTAs to work; a narrower tile re-reads the activation tile, so only while half the SMs would idle
+    while (BN > 64 && N * p.tiles_x * p.tiles_y * (Cout / BN) * 2 <= kNumSMs) BN >>= 1;
+  }
   if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;

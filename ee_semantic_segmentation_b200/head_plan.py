@@ -71,6 +71,10 @@ def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
     check(lib().eeseg_conv_group_tiles(h, w, cout, ctypes.byref(tx), ctypes.byref(ty), ctypes.byref(bw),
                                        ctypes.byref(bh), ctypes.byref(bn)), "eeseg_conv_group_tiles")
     tx, ty, bw, bh, bn = tx.value, ty.value, bw.value, bh.value, bn.value
+    # under-filled grid (one or two images): narrower channel tiles double the work items — twice the CTAs busy and a
+    # finer-grained balance between the cheap 1x1 tiles and the 9-tap ones; the launcher reads the tile width off the list
+    while bn > 64 and len(ksizes) * N * tx * ty * (cout // bn) <= n_ctas:
+        bn //= 2
     n_tiles = cout // bn
     y0 = np.arange(ty) * bh
     x0 = np.arange(tx) * bw
