@@ -8,7 +8,11 @@ Same constructor / call signature and result keys ('exit', 'n', 'last', 'exit_fl
 * FLOP tables are computed once per input shape on meta tensors and cached, instead of a pthflops
   trace per section per image (:64-78);
 * `compute_last=False` skips the tail the reference always executes (:91-101) when the image left
-  early — the reference behaviour (`last` always present) stays the default."""
+  early — the reference behaviour (`last` always present) stays the default;
+* `use_graph=True` (default when the metric is the eeseg `img_norm_entropy`): every backbone section and every
+  head + gate is captured once per input shape as a CUDA graph and replayed per image — the ~700 launches of an
+  image become 2(n+1) graph launches, with one 4-byte read of the score per gate (the operator is launch-bound
+  when run eagerly on one image)."""
 import numpy as np
 import torch as tch
 
@@ -46,7 +50,7 @@ class mIoU:
 
 class eval_ee_deeplabv3():
     def __init__(self, ee_model, metric, th, less_than=True, ignore=[], device=tch.device('cpu'),
-                 compute_last=True):
+                 compute_last=True, use_graph=True):
         self.model = ee_model
         self.n = self.model.n_branches
         self.ignore = ignore
@@ -57,6 +61,9 @@ class eval_ee_deeplabv3():
         self.last_br = max([i for i in range(self.n) if i not in ignore])
         self.compute_last = compute_last
         self._flops = {}
+        self.use_graph = use_graph and hasattr(metric, 'scores') and hasattr(ee_model, 'run_section') \
+            and getattr(ee_model, 'fast_inference', False)
+        self._graphs = {}
 
     def _flop_table(self, shape):
         """(main_flops per section, branch_flops per head incl. classifier) for an input shape."""
@@ -85,7 +92,100 @@ class eval_ee_deeplabv3():
         am = ops.exit_gate(up, None, want_score=False).amax
         return float(self.metric(probs)), am
 
+    # ---- CUDA-graph stages (one image): section i: xin[i] -> xin[i+1]; head i: xin[i+1] -> score, argmax map ----------
+    def _capture(self, fn):
+        dev = tch.cuda.current_device()
+        s = tch.cuda.Stream()
+        s.wait_stream(tch.cuda.current_stream())
+        with tch.cuda.stream(s):
+            for _ in range(2):
+                out = fn()
+        tch.cuda.current_stream().wait_stream(s)
+        g = tch.cuda.CUDAGraph()
+        with tch.cuda.graph(g):
+            out = fn()
+        return g, out
+
+    def _graph_state(self, X):
+        key = (tuple(X.shape), X.device)
+        st = self._graphs.get(key)
+        if st is None:
+            st = {'x': tch.zeros_like(X, dtype=tch.float32), 'sec': {}, 'head': {}}
+            self._graphs[key] = st
+        return st
+
+    def _section(self, st, i):
+        """Replays section i; its input is the image (i == 0) or the output tensor of section i-1's graph."""
+        if i not in st['sec']:
+            xin = st['x'] if i == 0 else st['sec'][i - 1][1]
+            st['sec'][i] = self._capture(lambda: self.model.run_section(i, xin))
+        st['sec'][i][0].replay()
+        return st['sec'][i][1]
+
+    def _head(self, st, i, inp_shape, gated):
+        if (i, gated) not in st['head']:
+            xin = st['sec'][i][1]
+            model = self.model
+
+            def fn():
+                low = model._plan(i).run(xin)
+                if gated:
+                    sc, res = self.metric.scores(low, kind='logits', out_hw=inp_shape, layout='NHWC', want_amax=True)
+                    return sc, res.amax
+                return None, ops.exit_gate(low, inp_shape, layout='NHWC', n_classes=model.num_classes,
+                                           want_score=False).amax
+            st['head'][(i, gated)] = self._capture(fn)
+        g, out = st['head'][(i, gated)]
+        g.replay()
+        return out
+
+    def _call_graphed(self, X):
+        output = dict()
+        inp_shape = tuple(X.shape[-2:])
+        main_all, head_all = self._flop_table(X.shape)
+        main_flops, branch_flops = [], []
+        left = False
+        if not X.is_cuda:
+            raise RuntimeError('eval_ee_deeplabv3 needs a CUDA input (no CPU fallback)')
+        X = X.unsqueeze(0)
+        with tch.no_grad(), tch.cuda.device(X.device):
+            st = self._graph_state(X)
+            st['x'].copy_(X, non_blocking=True)
+            for i in range(self.n):
+                if left and not self.compute_last:
+                    break
+                main_flops.append(main_all[i])
+                self._section(st, i)
+                if i not in self.ignore and not left:
+                    branch_flops.append(head_all[i])
+                    sc, am = self._head(st, i, inp_shape, True)
+                    t = float(sc.item())
+                    if (t < self.threshold) if self.less_than else (t > self.threshold):
+                        output['exit'] = am.squeeze(0).to(tch.int64).cpu()
+                        output['exit_flops'] = sum(branch_flops) + sum(main_flops)
+                        output['edge_flops'] = output['exit_flops']
+                        output['n'] = i + 1
+                        left = True
+                if not left and i == self.last_br:
+                    output['edge_flops'] = sum(branch_flops) + sum(main_flops)
+            if left and not self.compute_last:
+                return output
+            main_flops.append(main_all[self.n])
+            self._section(st, self.n)
+            main_flops.append(head_all[self.n])
+            _, am = self._head(st, self.n, inp_shape, False)
+            Y = am.squeeze(0).to(tch.int64).cpu()
+        output['last'] = Y
+        output['last_flops'] = sum(branch_flops) + sum(main_flops)
+        if not left:
+            output['exit'] = Y
+            output['exit_flops'] = output['last_flops']
+            output['n'] = self.n + 1
+        return output
+
     def __call__(self, X):
+        if self.use_graph and X.is_cuda:
+            return self._call_graphed(X)
         output = dict()
         inp_shape = X.shape[-2:]
         main_all, head_all = self._flop_table(X.shape)

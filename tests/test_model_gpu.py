@@ -184,6 +184,19 @@ def test_mIoU_evaluator_and_operator(nets):
     op = eval_ee_deeplabv3(net, img_norm_entropy(21), -1.0, device=dev())    # never confident
     out = op(x[0].to(dev()))
     assert out["n"] == 3 and torch.equal(out["exit"], out["last"])
+    # graph-replayed stages (default) == eagerly launched stages, for every exit pattern / option
+    sc = [eval_ee_deeplabv3(net, img_norm_entropy(21), -1.0, use_graph=False)._score(lo, (65, 81))[0]
+          for lo in net.forward_lowres(x[:1].to(dev()))[:2]]
+    for th in (2.0, -1.0, (sc[0] + sc[1]) / 2):
+        for kw in (dict(), dict(ignore=[0]), dict(compute_last=False), dict(less_than=False)):
+            a = eval_ee_deeplabv3(net, img_norm_entropy(21), th, use_graph=False, **kw)
+            b = eval_ee_deeplabv3(net, img_norm_entropy(21), th, **kw)
+            assert b.use_graph and not a.use_graph
+            for img in (x[0], x[1], x[0]):           # the third call replays graphs captured by the first
+                oa, ob = a(img.to(dev())), b(img.to(dev()))
+                assert set(oa) == set(ob), (th, kw)
+                for k in oa:
+                    assert torch.equal(oa[k], ob[k]) if torch.is_tensor(oa[k]) else oa[k] == ob[k], (th, kw, k)
 
 
 def test_engine_graph_and_pipelined_match_eager(nets):
