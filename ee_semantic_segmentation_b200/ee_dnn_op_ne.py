@@ -107,7 +107,7 @@ class eval_ee_deeplabv3():
         return g, out
 
     def _graph_state(self, X):
-        key = (tuple(X.shape), X.device)
+        key = (tuple(X.shape), X.device, getattr(self.model, 'weights_epoch', 0))
         st = self._graphs.get(key)
         if st is None:
             st = {'x': tch.zeros_like(X, dtype=tch.float32), 'sec': {}, 'head': {}}

@@ -82,7 +82,7 @@ class EarlyExitEngine:
         return g['out']
 
     def _capture(self, shape, with_targets, slot=0):
-        key = (shape, with_targets, slot)
+        key = (shape, with_targets, slot, getattr(self.net, 'weights_epoch', 0))
         if key in self._graphs:
             return self._graphs[key]
         N, _, H, W = shape
@@ -178,7 +178,7 @@ class EarlyExitEngine:
         """Static buffers of the staged step for one input shape: the input of every backbone section
         (`xin[i]`, its first n rows hold the compacted still-active images), their original batch
         positions (`act[i]`), the per-image results, and a pinned host word per gate for the count."""
-        key = ('skip', shape, with_targets, slot)
+        key = ('skip', shape, with_targets, slot, getattr(self.net, 'weights_epoch', 0))
         st = self._graphs.get(key)
         if st is not None:
             return st

@@ -130,6 +130,44 @@ class branchyDeepv3(nn.Module):
         self.fast_backbone = True      # ... including the ResNet bottlenecks of the sections
         self.fast_training_heads = True   # autograd forward: head convolutions (fwd/dgrad/wgrad) on eeseg kernels
         self.fast_training_backbone = True   # ... and the Bottleneck convolutions of the sections (bf16 activations)
+        self.graph_inference = True    # forward_lowres replays one CUDA graph per input shape (see there)
+        self._lowres_graphs = {}
+        self.weights_epoch = 0         # bumped by train() / load_state_dict(): captured graphs of older epochs are stale
+
+    _RUNTIME_DEFAULTS = dict(fast_inference=True, fast_backbone=True, fast_training_heads=True,
+                             fast_training_backbone=True, graph_inference=True, weights_epoch=0, num_classes=21)
+
+    def __getstate__(self):
+        """Pickles (tch.save(net), copy.deepcopy) carry parameters and flags, not the kernel plans / CUDA graphs."""
+        st = dict(self.__dict__)
+        st['_plans'], st['_section_plans'], st['_lowres_graphs'] = {}, {}, {}
+        return st
+
+    def __setstate__(self, st):
+        """Also accepts whole-module pickles written by the reference class (eval_br_ent.py:146): the run-time
+        attributes it does not have take their defaults."""
+        self.__dict__.update(st)
+        for k in ('_plans', '_section_plans', '_lowres_graphs'):
+            self.__dict__[k] = {}
+        for k, v in self._RUNTIME_DEFAULTS.items():
+            self.__dict__.setdefault(k, v)
+
+    def _bump_epoch(self):
+        self.weights_epoch = getattr(self, 'weights_epoch', 0) + 1
+        self._lowres_graphs = {}
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._bump_epoch()                       # load_state_dict (also through a parent module / DDP wrapper)
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        """nn.Module.train; entering training mode announces parameter updates: CUDA graphs captured from the folded
+        inference plans (here, in engine.EarlyExitEngine and ee_dnn_op_ne.eval_ee_deeplabv3) are keyed by
+        `weights_epoch` and re-captured afterwards. Parameters edited in place while in eval mode need an explicit
+        `_bump_epoch()`."""
+        if mode and hasattr(self, 'weights_epoch'):
+            self._bump_epoch()
+        return super().train(mode)
 
     # ---- construction helpers ---------------------------------------------------------------------
     @staticmethod
@@ -277,11 +315,44 @@ class branchyDeepv3(nn.Module):
         padded to the kernel's column multiple). Inference only."""
         if not X.is_cuda:
             raise RuntimeError('branchyDeepv3 fast path needs CUDA tensors (no CPU fallback)')
+        if self.graph_inference and not tch.cuda.is_current_stream_capturing():
+            return self._lowres_graph(X)
+        return self._lowres_eager(X)
+
+    def _lowres_eager(self, X):
         outs = []
         with tch.no_grad():
             for i in range(self.n_branches + 1):
                 X = self.run_section(i, X)
                 outs.append(self._plan(i).run(X))
+        return outs
+
+    def _lowres_graph(self, X):
+        """The ~700 launches of a forward replayed as one CUDA graph per (input shape, device): evaluators that feed
+        one image at a time (br_evaluator, mIoU_evaluator: batch-1 loaders as in the reference) are launch-bound
+        otherwise. The returned tensors are the graph's static outputs: valid until the next call with that shape."""
+        key = (tuple(X.shape), X.device, X.dtype)
+        ent = self._lowres_graphs.get(key)
+        with tch.cuda.device(X.device):
+            if ent is None:
+                xs = tch.zeros_like(X)
+                xs.copy_(X)
+                side = tch.cuda.Stream()
+                side.wait_stream(tch.cuda.current_stream())
+                with tch.cuda.stream(side):
+                    for _ in range(2):
+                        self._lowres_eager(xs)
+                tch.cuda.current_stream().wait_stream(side)
+                g = tch.cuda.CUDAGraph()
+                with tch.cuda.graph(g):
+                    outs = self._lowres_eager(xs)
+                ent = (g, xs, outs)
+                if len(self._lowres_graphs) >= 8:          # a few shapes at most: drop the oldest
+                    self._lowres_graphs.pop(next(iter(self._lowres_graphs)))
+                self._lowres_graphs[key] = ent
+            g, xs, outs = ent
+            xs.copy_(X, non_blocking=True)
+            g.replay()
         return outs
 
     def forward(self, X):

@@ -439,3 +439,31 @@ def test_cityscapes_shaped_full_res_sweep():
     assert [r["out_gl"] for r in res] == [1, 1, 1]
     assert res[0]["count_out"] == 1 and res[2]["b1_count"] == 1
     assert int(sweep.cm[:, -1].sum()) == 3 * 1024 * 2048       # every pixel counted once per tau
+
+
+def test_graph_replayed_forward_tracks_weights(nets):
+    """forward_lowres replays a CUDA graph per input shape: same logits as the eager launches, re-captured after
+    load_state_dict() / train() (weights_epoch), static outputs documented as overwritten by the next call."""
+    import copy
+    _, net0 = nets
+    net = copy.deepcopy(net0)
+    assert net._lowres_graphs == {} and net.graph_inference
+    g = torch.Generator().manual_seed(41)
+    x1 = torch.randn(1, 3, 65, 81, generator=g).to(dev())
+    x2 = torch.randn(1, 3, 65, 81, generator=g).to(dev())
+    with torch.no_grad():
+        ya = net(x1).clone()
+        yb = net(x2).clone()                     # replay with new contents
+        net.graph_inference = False
+        assert torch.equal(net(x1), ya) and torch.equal(net(x2), yb)
+        net.graph_inference = True
+        assert len(net._lowres_graphs) == 1
+        sd = copy.deepcopy(net.state_dict())
+        key = next(k for k in sd if k.endswith("classifier.4.weight") or k.endswith("4.weight"))
+        sd[key] = sd[key] * 1.5
+        e0 = net.weights_epoch
+        net.load_state_dict(sd)
+        assert net.weights_epoch > e0 and net._lowres_graphs == {}
+        yc = net(x1)
+        net.graph_inference = False
+        assert torch.equal(net(x1), yc) and not torch.equal(yc, ya)
