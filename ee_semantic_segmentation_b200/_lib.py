@@ -51,6 +51,7 @@ PROTOTYPES = {
     "eeseg_soft_overlap_bwd": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc_train": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc_bwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "eeseg_exit_stage_commit": (c_i, [c_p, c_f, c_i, c_i, c_i, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "eeseg_compact_rows": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i64, c_p]),
     "eeseg_focal_workspace_bytes": (c_sz, [c_i, c_i, c_i64]),
     "eeseg_focal_fwd": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -299,6 +299,48 @@ __global__ void decide_kernel(const float* __restrict__ score, int N, float tau,
   }
 }
 
+// Stage commit of the compute-skipping engine: everything that follows a gate's scores for the n images still in flight,
+// in one launch — the decision rule (eval_br_ent.py:57-64), the results of the images that leave here scattered to their
+// batch positions (score, exit index, arg-max map), the ascending list of survivors with its count, and the survivors' batch
+// positions for the next stage. grid = (chunks of the map, n); block (0,0) does the O(n) bookkeeping.
+__global__ void __launch_bounds__(256) stage_commit_kernel(const float* __restrict__ score, float tau, int less_than,
+                                                           int exit_id, int take_all, const int64_t* __restrict__ act,
+                                                           const uint8_t* __restrict__ amax, int n, int64_t HW,
+                                                           float* __restrict__ scores_row, int32_t* __restrict__ exit_out,
+                                                           uint8_t* __restrict__ pred, const int64_t* __restrict__ px_in,
+                                                           int64_t* __restrict__ px_acc, int32_t* __restrict__ keep,
+                                                           int32_t* __restrict__ count, int64_t* __restrict__ act_next) {
+  const int j = blockIdx.y;
+  const float sc = score ? score[j] : 0.f;
+  const bool took = take_all || (less_than ? (sc < tau) : (sc > tau));
+  const int64_t dst_img = act[j];
+  if (took) {
+    const uint8_t* s = amax + (int64_t)j * HW;
+    uint8_t* d = pred + dst_img * HW;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < HW; i += (int64_t)gridDim.x * 256) d[i] = s[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (scores_row) scores_row[dst_img] = sc;
+    exit_out[dst_img] = took ? exit_id : -1;
+    if (j == 0) {
+      int k = 0;
+      long long px = 0;
+      for (int q = 0; q < n; ++q) {
+        const float sq = score ? score[q] : 0.f;
+        const bool tq = take_all || (less_than ? (sq < tau) : (sq > tau));
+        if (!tq) {
+          if (keep) keep[k] = q;
+          if (act_next) act_next[k] = act[q];
+          ++k;
+        }
+        if (px_in) px += px_in[q];
+      }
+      if (count) *count = k;
+      if (px_acc && px_in) *px_acc += px;
+    }
+  }
+}
+
 // Batch compaction after a gate: dst[j] = src[active_list[j]] for j < *active_count (all n rows when the count pointer is
 // null) — the still-active images' activations moved to the front of the next backbone section's input. Rows are whole
 // images (tens of MB): 16-byte vectors, grid.y = destination row, grid-stride along the row; rows past the count cost nothing.
@@ -496,6 +538,25 @@ extern "C" int eeseg_exit_gate_decide(const double* part_sum, const int32_t* par
     return check_launch("decide_kernel");
   }
   return EESEG_OK;
+}
+
+extern "C" int eeseg_exit_stage_commit(const float* score, float tau, int less_than, int exit_id, int take_all,
+                                       const int64_t* positions, const uint8_t* amax, int n, int64_t HW, float* scores_row,
+                                       int32_t* exit_idx, uint8_t* pred, const int64_t* exited_px_in, int64_t* exited_px_acc,
+                                       int32_t* active_list, int32_t* active_count, int64_t* next_positions, void* stream) {
+  EESEG_REQUIRE(positions && amax && exit_idx && pred, "exit_stage_commit: null pointer");
+  EESEG_REQUIRE(score || take_all, "exit_stage_commit: scores are required unless every image leaves");
+  EESEG_REQUIRE(n >= 0 && n <= 65535 && HW >= 1, "exit_stage_commit: bad sizes");
+  if (n == 0) {
+    if (active_count) EESEG_CUDA(cudaMemsetAsync(active_count, 0, sizeof(int32_t), (cudaStream_t)stream));
+    return EESEG_OK;
+  }
+  int bx = (int)((HW + 4095) / 4096);
+  if (bx > 64) bx = 64;
+  stage_commit_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+      score, tau, less_than, exit_id, take_all, positions, amax, n, HW, scores_row, exit_idx, pred, exited_px_in,
+      exited_px_acc, active_list, active_count, next_positions);
+  return check_launch("stage_commit_kernel");
 }
 
 extern "C" int eeseg_compact_rows(const void* src, void* dst, const int32_t* active_list, const int32_t* active_count,

@@ -64,6 +64,7 @@ class eval_ee_deeplabv3():
         self.use_graph = use_graph and hasattr(metric, 'scores') and hasattr(ee_model, 'run_section') \
             and getattr(ee_model, 'fast_inference', False)
         self._graphs = {}
+        self._seen = {}
 
     def _flop_table(self, shape):
         """(main_flops per section, branch_flops per head incl. classifier) for an input shape."""
@@ -107,7 +108,7 @@ class eval_ee_deeplabv3():
         return g, out
 
     def _graph_state(self, X):
-        key = (tuple(X.shape), X.device, getattr(self.model, 'weights_epoch', 0))
+        key = (tuple(X.shape[1:]), X.device, getattr(self.model, 'weights_epoch', 0))
         st = self._graphs.get(key)
         if st is None:
             st = {'x': tch.zeros_like(X, dtype=tch.float32), 'sec': {}, 'head': {}}
@@ -185,7 +186,13 @@ class eval_ee_deeplabv3():
 
     def __call__(self, X):
         if self.use_graph and X.is_cuda:
-            return self._call_graphed(X)
+            # graphs are captured the second time an input shape shows up (images of varying sizes stay eager)
+            key = (tuple(X.shape), X.device, getattr(self.model, 'weights_epoch', 0))
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] >= 2:
+                return self._call_graphed(X)
+            if len(self._seen) > 64:
+                self._seen.clear()
         output = dict()
         inp_shape = X.shape[-2:]
         main_all, head_all = self._flop_table(X.shape)

@@ -217,25 +217,25 @@ class EarlyExitEngine:
         low = net._plan(i).run(Xc)
         gated = not last and i >= self.skip
         res = self._gate(low, (H, W), want_score=gated)
-        if last:
-            out['pred'].index_copy_(0, act, res.amax)
-            out['exit'].index_fill_(0, act, i)
-        elif gated:
-            out['scores'][i].index_copy_(0, act, res.score)
-            sub = torch.full((n,), -1, dtype=torch.int32, device=Xc.device)
-            al, ac = ops.gate_decide(res.score, self.tau, i, sub, want_active=True)
-            took = (sub == i).view(-1, 1, 1)
-            out['pred'].index_copy_(0, act, torch.where(took, res.amax, out['pred'].index_select(0, act)))
-            out['exit'].index_copy_(0, act, sub)
-            if res.exited_px is not None:
-                self.exited_px[i] += res.exited_px.sum()
-            keep = al.long().clamp_(0, n - 1)      # entries past the active count are don't-cares
-            ops.compact_rows(self._dense_rows(Xc), al, ac, self._dense_rows(st['xin'][i + 1][:n]))   # survivors to the front
-            torch.index_select(act, 0, keep, out=st['act'][i + 1][:n])
-            st['cnt_host'][i:i + 1].copy_(ac, non_blocking=True)
-        else:
+        if not last and not gated:                  # an exit that is not allowed to answer: everybody moves on
             st['xin'][i + 1][:n].copy_(Xc)
             st['act'][i + 1][:n].copy_(act)
+            return
+        # one launch: decision, results of the leaving images to their batch positions, survivor list + count + positions
+        al = torch.empty((n,), dtype=torch.int32, device=Xc.device)
+        ac = torch.empty((1,), dtype=torch.int32, device=Xc.device)
+        px = res.exited_px if gated else None
+        with torch.cuda.device(Xc.device):
+            ops.check(ops.lib().eeseg_exit_stage_commit(
+                res.score.data_ptr() if gated else None, self.tau, 1, i, 1 if last else 0, act.data_ptr(),
+                res.amax.data_ptr(), n, H * W, out['scores'][i].data_ptr() if gated else None, out['exit'].data_ptr(),
+                out['pred'].data_ptr(), None if px is None else px.data_ptr(),
+                None if px is None else self.exited_px[i:i + 1].data_ptr(), al.data_ptr(), ac.data_ptr(),
+                None if last else st['act'][i + 1].data_ptr(), torch.cuda.current_stream(Xc.device).cuda_stream),
+                "eeseg_exit_stage_commit")
+        if not last:
+            ops.compact_rows(self._dense_rows(Xc), al, ac, self._dense_rows(st['xin'][i + 1][:n]))   # survivors to the front
+            st['cnt_host'][i:i + 1].copy_(ac, non_blocking=True)
 
     @staticmethod
     def _dense_rows(t):

@@ -333,6 +333,14 @@ class branchyDeepv3(nn.Module):
         otherwise. The returned tensors are the graph's static outputs: valid until the next call with that shape."""
         key = (tuple(X.shape), X.device, X.dtype)
         ent = self._lowres_graphs.get(key)
+        if ent is None:
+            # capture a shape the second time it shows up: a loader of varying image sizes must not pay a capture per image
+            seen = self._lowres_graphs.setdefault('seen', {})
+            seen[key] = seen.get(key, 0) + 1
+            if seen[key] < 2:
+                if len(seen) > 64:
+                    seen.clear()
+                return self._lowres_eager(X)
         with tch.cuda.device(X.device):
             if ent is None:
                 xs = tch.zeros_like(X)
@@ -347,8 +355,9 @@ class branchyDeepv3(nn.Module):
                 with tch.cuda.graph(g):
                     outs = self._lowres_eager(xs)
                 ent = (g, xs, outs)
-                if len(self._lowres_graphs) >= 8:          # a few shapes at most: drop the oldest
-                    self._lowres_graphs.pop(next(iter(self._lowres_graphs)))
+                graphs = [k for k in self._lowres_graphs if k != 'seen']
+                if len(graphs) >= 8:                       # a few shapes at most: drop the oldest
+                    self._lowres_graphs.pop(graphs[0])
                 self._lowres_graphs[key] = ent
             g, xs, outs = ent
             xs.copy_(X, non_blocking=True)

@@ -105,6 +105,18 @@ int eeseg_exit_gate_decide(const double* part_sum, const int32_t* part_cnt, int 
                            int exit_id, int32_t* exit_idx, float* score_out, int64_t* exited_px,
                            int32_t* active_list, int32_t* active_count, void* stream);
 
+/* Stage commit of the compute-skipping engine — what follows a gate for the n images still in flight, in one launch
+ * (decision rule of eval_br_ent.py:57-64 / ee_dnn_op_ne.py:80-87):
+ *   image j (batch position positions[j]) leaves at `exit_id` iff take_all, or less_than ? score[j] < tau : score[j] > tau;
+ *   scores_row[positions[j]] = score[j] (optional);  exit_idx[positions[j]] = exit_id or -1;
+ *   pred[positions[j]][:] = amax[j][:] (u8 [HW]) for the images that leave;
+ *   active_list / active_count: ascending j of the survivors;  next_positions[k] = positions[active_list[k]];
+ *   *exited_px_acc += sum(exited_px_in[0..n)) (both optional). */
+int eeseg_exit_stage_commit(const float* score, float tau, int less_than, int exit_id, int take_all,
+                            const int64_t* positions, const uint8_t* amax, int n, int64_t HW, float* scores_row,
+                            int32_t* exit_idx, uint8_t* pred, const int64_t* exited_px_in, int64_t* exited_px_acc,
+                            int32_t* active_list, int32_t* active_count, int64_t* next_positions, void* stream);
+
 /* Batch compaction after a gate (the compute-skipping form of ee_dnn_op_ne.py:80-101, which always runs the tail):
  *   dst[j][:] = src[active_list[j]][:]  for j < *active_count (j < n_dst when active_count == NULL)
  * rows of row_bytes bytes (16-byte multiple, 16-byte aligned): the activations of the images still active after an

@@ -452,18 +452,21 @@ def test_graph_replayed_forward_tracks_weights(nets):
     x1 = torch.randn(1, 3, 65, 81, generator=g).to(dev())
     x2 = torch.randn(1, 3, 65, 81, generator=g).to(dev())
     with torch.no_grad():
-        ya = net(x1).clone()
-        yb = net(x2).clone()                     # replay with new contents
+        ya = net(x1).clone()                     # first sight of the shape: eager
+        assert [k for k in net._lowres_graphs if k != 'seen'] == []
+        yb = net(x2).clone()                     # second: captured
+        assert torch.equal(net(x1), ya)          # replay with new contents
         net.graph_inference = False
         assert torch.equal(net(x1), ya) and torch.equal(net(x2), yb)
         net.graph_inference = True
-        assert len(net._lowres_graphs) == 1
+        assert len([k for k in net._lowres_graphs if k != 'seen']) == 1
         sd = copy.deepcopy(net.state_dict())
         key = next(k for k in sd if k.endswith("classifier.4.weight") or k.endswith("4.weight"))
         sd[key] = sd[key] * 1.5
         e0 = net.weights_epoch
         net.load_state_dict(sd)
         assert net.weights_epoch > e0 and net._lowres_graphs == {}
-        yc = net(x1)
+        yc = net(x1).clone()
+        assert torch.equal(net(x1), yc)          # captured again from the new weights
         net.graph_inference = False
         assert torch.equal(net(x1), yc) and not torch.equal(yc, ya)
