@@ -109,6 +109,8 @@ class eval_ee_deeplabv3():
 
     def _graph_state(self, X):
         key = (tuple(X.shape[1:]), X.device, getattr(self.model, 'weights_epoch', 0))
+        if any(k[2] != key[2] for k in self._graphs):      # weights changed: release the graphs of the old plans
+            self._graphs.clear()
         st = self._graphs.get(key)
         if st is None:
             st = {'x': tch.zeros_like(X, dtype=tch.float32), 'sec': {}, 'head': {}}

@@ -46,6 +46,13 @@ class EarlyExitEngine:
         self.counts = torch.zeros((self.E + 1,), dtype=torch.int64, device=dev)
         self.exited_px = torch.zeros((self.E,), dtype=torch.int64, device=dev)
 
+    def _drop_stale_graphs(self):
+        """Graphs captured from an older set of weights (the model's weights_epoch moved on) are released, not kept."""
+        epoch = getattr(self.net, 'weights_epoch', 0)
+        if getattr(self, '_graph_epoch', epoch) != epoch:
+            self._graphs.clear()
+        self._graph_epoch = epoch
+
     def _side_stream(self):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -82,6 +89,7 @@ class EarlyExitEngine:
         return g['out']
 
     def _capture(self, shape, with_targets, slot=0):
+        self._drop_stale_graphs()
         key = (shape, with_targets, slot, getattr(self.net, 'weights_epoch', 0))
         if key in self._graphs:
             return self._graphs[key]
@@ -178,6 +186,7 @@ class EarlyExitEngine:
         """Static buffers of the staged step for one input shape: the input of every backbone section
         (`xin[i]`, its first n rows hold the compacted still-active images), their original batch
         positions (`act[i]`), the per-image results, and a pinned host word per gate for the count."""
+        self._drop_stale_graphs()
         key = ('skip', shape, with_targets, slot, getattr(self.net, 'weights_epoch', 0))
         st = self._graphs.get(key)
         if st is not None:

@@ -470,3 +470,30 @@ def test_graph_replayed_forward_tracks_weights(nets):
         assert torch.equal(net(x1), yc)          # captured again from the new weights
         net.graph_inference = False
         assert torch.equal(net(x1), yc) and not torch.equal(yc, ya)
+
+
+def test_engine_graphs_follow_weight_updates(nets):
+    """A graph-replaying engine kept across a training phase: train() bumps the model's weights_epoch, the engine drops
+    the graphs captured from the old folded weights and evaluates the new ones (same results as a fresh eager engine)."""
+    import copy
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine
+    _, net0 = nets
+    net = copy.deepcopy(net0).eval()
+    g = torch.Generator().manual_seed(43)
+    X = torch.randn(2, 3, 65, 81, generator=g).to(dev())
+    y = torch.randint(0, 22, (2, 1, 65, 81), generator=g).to(dev())
+    for kw in (dict(use_graph=True), dict(use_graph=True, skip_compute=True)):
+        eng = EarlyExitEngine(net, 21, 0.97, **kw)
+        before = {k: v.clone() for k, v in eng.evaluate(X, y).items()}
+        net.train()
+        with torch.no_grad():
+            for p in net.classifier[-1].parameters():
+                p.add_(torch.randn_like(p) * 0.5)
+            for p in net.branches[0][-1].parameters():
+                p.add_(torch.randn_like(p) * 0.5)
+        net.eval()
+        after = eng.evaluate(X, y)
+        ref = EarlyExitEngine(net, 21, 0.97, skip_compute=kw.get("skip_compute", False)).evaluate(X, y)
+        assert torch.equal(after["pred"], ref["pred"]) and torch.equal(after["exit"], ref["exit"])
+        assert not torch.equal(after["pred"], before["pred"])
+        assert len(eng._graphs) <= 2
