@@ -1,12 +1,19 @@
-"""Drop-in for the step-level part of the reference's training driver: `train_epoch`
-(train_funcs.py:12-33) plus the optimiser / schedule construction of `train_deepv3`
-(deepv3_funcs.py:74-101,138-156) as small helpers, with one-process-per-GPU data parallelism.
+"""Drop-in for the reference's training driver: `train_epoch` (train_funcs.py:12-33), the epoch loop `train`
+(:60-269: validation tracker, best-validation checkpoint dict, early stopping) and the optimiser / schedule
+construction of `train_deepv3` (deepv3_funcs.py:74-101,138-156) as small helpers, with one-process-per-GPU data
+parallelism.
 
-The forward/backward of the convolutions runs on the PyTorch modules (autograd through cuDNN; conv
-dgrad/wgrad kernels are future work); the multi-exit loss (forward + fused backward) runs on the
-eeseg kernels. Under `torchrun`, wrap the model with `parallel.wrap_ddp` — gradients are averaged
-by NCCL bucket all-reduces overlapped with the backward pass; BatchNorm stays per rank, as in a
-single-GPU reference run at the per-GPU batch."""
+Under net.train() the model's convolutions (forward, input and weight gradients), BatchNorm, max-pool, up-sampling
+and the multi-exit losses run on the eeseg kernels behind autograd (head_train / backbone_train / bn_train / ops);
+`GraphedTrainStep` replays the whole step as one CUDA graph. Under `torchrun`, wrap the model with
+`parallel.wrap_ddp` — gradients are averaged by NCCL bucket all-reduces overlapped with the backward pass; BatchNorm
+stays per rank, as in a single-GPU reference run at the per-GPU batch."""
+import os
+import re
+from collections import defaultdict
+from copy import deepcopy
+
+import numpy as np
 import torch as tch
 from torch import optim
 
@@ -30,6 +37,138 @@ def train_epoch(net, train_iter, loss, updater, device=tch.device('cpu')):
         last = l.detach()
         del X, y
     return last
+
+
+def train(net, train_iter, loss, num_epochs, updater, val_iter=None, metrics=None, patience=None, saveat=None,
+          start_from=None, verbose=False, device='cpu', scheduler=None, use_file=None, up_updater=False, ret_lr=False,
+          ae_train=False, transform=None, name=None, minimize=True, start_counting=0, **kwargs):
+    """The reference's epoch loop (train_funcs.py:60-269) for the segmentation path: per epoch `train_epoch`, then
+    every `(name, f)` of `metrics` on `val_iter` — 'mIoU' is called as `f(net, n_exits, kwargs['nout_channels'], val_iter,
+    device)` (eval_mIoU.mIoU_evaluator) and, for a branchy net (`n_branches=` given), its result dict lands in
+    `tracker['val_mIoU_<key>']` (b1_mIoU, ..., mIoU); the followed value is the mean of the tracker entries matching
+    `val_<metrics[0][0]>`; a better value saves `{"model_state_dict", "opt_state_dict", "epoch", ...}` to `saveat`;
+    `patience` epochs without improvement stop the loop (after `start_counting`). Returns the tracker.
+
+    Kept quirks of the reference: the loop runs epochs 1 .. num_epochs-1 (`if epoch >= num_epochs: break` after the
+    increment, :139-141); `start_from` restores model (and optionally optimiser) state and the best value; the learning
+    rate logged is the LAST param group's for a branchy net. Not carried over: the auto-encoder branch (`ae_train`) and
+    the `funcs.eval_branches / eval_results` wrappers for non-mIoU metrics (`funcs` is missing from the reference tree) —
+    other metrics are called as `f(net, val_iter, device)` and must return a dict (branchy) or a number."""
+    if ae_train:
+        raise NotImplementedError("ae_train (auto-encoder pre-training) is outside the segmentation path")
+    metrics = metrics or []
+    follow = f'val_{metrics[0][0]}' if metrics else None
+    tracker = defaultdict(list)
+    net.to(device)
+    name = name or 'unspecified'
+
+    def say(msg):
+        if not verbose:
+            return
+        if use_file:
+            with open(use_file, 'a') as f:
+                f.write(msg + '\n')
+        else:
+            print(msg)
+    counter = 0
+    best_val = np.inf if minimize else 0.
+    saveat = saveat or os.path.join('.', 'model.pth')
+    if patience:
+        say(f'<< {name} progress update >> Earlystopping will follow {follow} with patience set to {patience}.')
+    else:
+        patience = None
+        say(f'<< {name} progress update >> Earlystopping not set.')
+    if start_from:
+        save_dict = tch.load(start_from, weights_only=False)
+        net.load_state_dict(save_dict['model_state_dict'])
+        if up_updater:
+            lr_aux = updater.param_groups[0]['lr']
+            updater.load_state_dict(save_dict['opt_state_dict'])
+            updater.param_groups[0]['lr'] = lr_aux
+        if patience and follow in save_dict.keys():
+            best_val = save_dict[follow]
+    branchy = bool(kwargs.get('n_branches'))
+    epoch, last_lr = 0, 0
+    num_epochs = num_epochs or np.inf
+    tch.backends.cuda.matmul.allow_tf32 = True       # :117-118 (only the PyTorch-module fallbacks are affected)
+    tch.backends.cudnn.allow_tf32 = True
+
+    def save(cur_val, branch_val):
+        save_dict = {"model_state_dict": deepcopy(net.state_dict()), "opt_state_dict": deepcopy(updater.state_dict()),
+                     "epoch": epoch}
+        for key, _ in metrics:                         # :211-214 (the pattern is the tracker key, as in the reference)
+            for k in list(tracker.keys()):
+                if re.search(k, key):
+                    save_dict[f'val_{k}'] = tracker[f'val_{k}'][-1]
+        tch.save(save_dict, saveat)
+        msg = f'<< {name} progress update >> saved @ {epoch} epoch. Best score: {cur_val:.5g}'
+        if branchy:
+            msg += '\nFor each branch:\n\t' + '\n\t'.join(f'b{i + 1} = {v:.5g}' for i, v in enumerate(branch_val))
+        say(msg)
+
+    while True:
+        epoch += 1
+        if epoch >= num_epochs:
+            break
+        cur_lr = updater.state_dict()['param_groups'][-1 if branchy else 0]['lr']
+        say(f'<< {name} progress update >> starting #{epoch} training epoch; lr = {cur_lr}, no updates since {counter} epochs')
+        train_epoch(net, train_iter, loss, updater, device)
+        if val_iter:
+            with tch.no_grad():
+                for met, f in metrics:
+                    if met == 'mIoU':
+                        cur_res = f(net, net.n_branches + 1 if branchy else 1, kwargs['nout_channels'], val_iter, device)
+                    else:
+                        cur_res = f(net, val_iter, device)
+                    if branchy:
+                        for key, value in cur_res.items():
+                            tracker[f'val_{met}_{key}'].append(value)
+                    elif met == 'mIoU':
+                        tracker[f'val_{met}'].append(cur_res['mIoU'])
+                    else:
+                        tracker[f'val_{met}'].append(cur_res)
+        if ret_lr or scheduler:
+            tracker['lr'].append(cur_lr)
+        branch_val = []
+        if follow is None or not val_iter:
+            cur_val = np.inf if minimize else 0.
+        elif branchy:
+            branch_val = [tracker[key][-1] for key in tracker.keys() if re.search(follow, key)]
+            if kwargs.get('max2min'):
+                # the reference reads an undefined `cur_val` here (:188); the evident intent: weights 1..E, optionally flipped
+                weights = np.arange(len(branch_val)) + 1
+                w_max = np.max(weights)
+                if kwargs['max2min']:
+                    weights = np.flip(weights)
+                cur_val = np.average(branch_val, weights=weights / w_max)
+            else:
+                cur_val = np.average(branch_val)
+        else:
+            cur_val = tracker[follow][-1]
+        if scheduler:
+            scheduler.step()
+        better = best_val > cur_val if minimize else best_val < cur_val
+        if patience:
+            if counter < patience:
+                if better:
+                    save(cur_val, branch_val)
+                    best_val, counter = cur_val, 0
+                elif 'lr' in tracker and last_lr != cur_lr:
+                    counter, last_lr = 1, cur_lr
+                else:
+                    counter += 1
+            elif epoch > start_counting:
+                break
+            else:
+                if 'lr' in tracker and last_lr != cur_lr:
+                    counter, last_lr = 0, cur_lr
+                counter += 1
+        elif better:
+            save(cur_val, branch_val)
+            best_val, counter = cur_val, 0
+        else:
+            counter += 1
+    return tracker
 
 
 def _sgd_impl(net):

@@ -62,3 +62,53 @@ def test_bench_workloads():
     assert bench.img_hw() == (513, 513) and bench.METRIC == "early_exit_images_per_sec_513"
     h = (513 - 1) // 8 + 1
     assert bench.head_flops(h, h, 4, [1024, 2048, 2048]) == 1327685632000      # 3 heads, N = 4
+
+
+def test_train_driver_tracker_checkpoint_and_early_stopping(tmp_path):
+    """train_funcs.train (reference :60-269) on a toy model: epochs 1..num_epochs-1, branchy tracker keys
+    val_mIoU_<key>, the followed value = mean over the exits, best-validation checkpoint dict, patience stop, start_from."""
+    import torch
+    from ee_semantic_segmentation_b200.train_funcs import train
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.n_branches = 2
+
+        def forward(self, X):
+            return X * self.w
+
+    net = Toy()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    data = [(torch.ones(2, 1), torch.ones(2, 1))] * 3
+    seen = []
+    vals = iter([0.2, 0.5, 0.4, 0.4, 0.4, 0.9])           # mean mIoU per epoch (maximised)
+
+    def fake_miou(net_, n_exits, n_classes, loader, device):
+        assert n_exits == 3 and n_classes == 21
+        v = next(vals)
+        seen.append(v)
+        return {"b1_mIoU": v - 0.1, "b2_mIoU": v, "mIoU": v + 0.1}
+    ck = tmp_path / "best.pth"
+    tr = train(net, data, lambda a, b: ((a - b) ** 2).mean(), 20, opt, val_iter=data, metrics=[("mIoU", fake_miou)],
+               patience=2, saveat=str(ck), device="cpu", minimize=False, n_branches=2, nout_channels=21, ret_lr=True)
+    assert set(tr) == {"val_mIoU_b1_mIoU", "val_mIoU_b2_mIoU", "val_mIoU_mIoU", "lr"}
+    # best at epoch 2 (0.5); epochs 3, 4 do not improve -> counter reaches the patience, epoch 5 stops the loop
+    assert seen == [0.2, 0.5, 0.4, 0.4, 0.4] and len(tr["lr"]) == 5
+    sd = torch.load(str(ck), weights_only=False)
+    assert set(sd) == {"model_state_dict", "opt_state_dict", "epoch"} and sd["epoch"] == 2
+    w_best = sd["model_state_dict"]["w"].clone()
+    # no patience: runs epochs 1 .. num_epochs-1 and keeps the best
+    net2, seen2 = Toy(), []
+    opt2 = torch.optim.SGD(net2.parameters(), lr=0.1)
+    vals2 = iter([3.0, 1.0, 2.0])
+
+    def fake2(net_, n_exits, n_classes, loader, device):
+        seen2.append(1)
+        return {"mIoU": next(vals2)}
+    tr2 = train(net2, data, lambda a, b: ((a - b) ** 2).mean(), 4, opt2, val_iter=data, metrics=[("mIoU", fake2)],
+                saveat=str(tmp_path / "b2.pth"), start_from=str(ck), nout_channels=21)
+    assert len(seen2) == 3 and tr2["val_mIoU"] == [3.0, 1.0, 2.0]
+    assert torch.load(str(tmp_path / "b2.pth"), weights_only=False)["epoch"] == 2         # minimised: 1.0 at epoch 2
+    assert not torch.equal(net2.w.detach(), w_best)                                        # started from it, then trained on
