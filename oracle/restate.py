@@ -304,6 +304,48 @@ def tversky_loss(logits, targets, smooth=1e-6, alpha=.5, beta=.5, gamma=None):
     return loss if gamma is None else loss ** np.float32(gamma)
 
 
+def seg_overlap_loss(logits, targets, kind, smooth=1e-6, index=False, downgrad_bg=1.0, alpha=.5, beta=.5, gamma=None):
+    """Single-output family of new_seg_losses.py: kind 'dice' (:34-56), 'jaccard' (:58-88), 'tversky' (:90-111; gamma ->
+    FocalTverskyLoss :113-121, exponent 1/gamma). Labels >= C are void and dropped by dice / jaccard (:47-48); tversky's
+    one_hot(num_classes=C) raises on them (:101). Returns (_compute_loss tensor, d sum(loss) / d logits)."""
+    p, oh, t = _overlap_sums(logits, targets)
+    C = p.shape[1]
+    if (t < 0).any() or (kind == "tversky" and (t >= C).any()):
+        raise RuntimeError("Class values must be smaller than num_classes.")
+    if kind == "dice":
+        num = 2 * (p * oh).sum(axis=(1, 2)) + smooth
+        den = (p + oh).sum(axis=(1, 2)) + smooth
+        val = num / den
+        g = (2 * oh) / den[:, None, None] - (num / den ** 2)[:, None, None]          # d val / d p
+        loss, g = (val, g) if index else (1 - val, -g)
+    elif kind == "jaccard":
+        inter = (p * oh).sum(axis=-1)
+        union = (p + oh).sum(axis=-1) - inter
+        iou = (inter + smooth) / (union + smooth)
+        u = (union + smooth)[:, :, None]
+        diou = (oh * u - (inter + smooth)[:, :, None] * (1 - oh)) / u ** 2
+        if index:
+            loss, g = iou, diou
+        elif downgrad_bg:
+            scale = np.ones(C)
+            scale[0] = downgrad_bg
+            loss, g = (1 - iou) * scale, -diou * scale[None, :, None]
+        else:
+            loss, g = (1 - iou).sum(axis=-1), -diou
+    else:
+        TP = (p * oh).sum(axis=-1)
+        FP = (p * (1 - oh)).sum(axis=-1)
+        FN = ((1 - p) * oh).sum(axis=-1)
+        D = TP + alpha * FP + beta * FN + smooth
+        T = (TP + smooth) / D
+        dT = (oh * D[:, :, None] - (TP + smooth)[:, :, None] * (oh + alpha * (1 - oh) - beta * oh)) / D[:, :, None] ** 2
+        loss, g = 1 - T, -dT
+        if gamma is not None:
+            g = g * ((1 / gamma) * loss ** (1 / gamma - 1))[:, :, None]
+            loss = loss ** (1 / gamma)
+    return loss.astype(np.float32), _softmax_backward(p, g).reshape(np.asarray(logits).shape)
+
+
 def focal_loss(logits, targets, gamma=2.0, alpha=None):
     """FocalLoss._compute_loss (branchy_seg_losses.py:122-131). logits [N,C,H,W], targets [N,1,H,W] in [0,C).
     Returns the reference's loss tensor — [N,H,W], or [N,N,H,W] when alpha is given: `loss * alpha[targets]` broadcasts

@@ -664,3 +664,35 @@ def test_compact_rows(dtype, row):
     assert torch.equal(out, src[[4, 0, 2]])
     with pytest.raises(RuntimeError):
         ops.compact_rows(src.cpu(), al, ac, out)
+
+
+def test_new_seg_losses_golden(golden):
+    """new_seg_losses.DiceLoss / JaccardLoss / TverskyLoss / FocalTverskyLoss on the soft-overlap kernels against the
+    reference's demo known answers (0.0504 / 0.4033) and its values / autograd gradients (tests/golden/seg_losses.npz)."""
+    from ee_semantic_segmentation_b200 import new_seg_losses as NSL
+    G = golden("seg_losses")
+    yp, yt = torch.from_numpy(G["demo_y_pred"]).to(dev()), torch.from_numpy(G["demo_y_true"]).to(dev())
+    assert f"{NSL.JaccardLoss()(yp, yt).item():.4f}" == "0.0504"
+    assert f"{NSL.JaccardLoss(reduction='sum')(yp, yt).item():.4f}" == "0.4033"
+    np.testing.assert_allclose(NSL.DiceLoss()(yp, yt).item(), G["demo_dice_mean"], rtol=1e-5)
+    y = torch.from_numpy(G["y_pred"]).to(dev())
+    tg = {k: torch.from_numpy(G[k]).to(dev()) for k in ("targets", "targets_void")}
+    cases = {
+        "dice_mean": (NSL.DiceLoss(), "targets_void"), "dice_index_sum": (NSL.DiceLoss(reduction="sum", index=True), "targets_void"),
+        "dice_batchwise": (NSL.DiceLoss(reduction="mean_batchwise"), "targets"),
+        "jaccard_mean": (NSL.JaccardLoss(), "targets_void"),
+        "jaccard_bg": (NSL.JaccardLoss(downgrad_bg=0.25, reduction="sum"), "targets_void"),
+        "jaccard_nobg": (NSL.JaccardLoss(downgrad_bg=0.0, reduction="sum_batchwise"), "targets_void"),
+        "jaccard_index": (NSL.JaccardLoss(index=True, reduction="none"), "targets"),
+        "tversky_mean": (NSL.TverskyLoss(alpha=0.3, beta=0.7), "targets"),
+        "ftversky_sum": (NSL.FocalTverskyLoss(alpha=0.7, beta=0.3, gamma=4 / 3, reduction="sum"), "targets"),
+    }
+    for tag, (fn, tk) in cases.items():
+        yy = y.clone().requires_grad_(True)
+        l = fn(yy, tg[tk])
+        l.sum().backward()
+        np.testing.assert_allclose(l.detach().cpu().numpy(), G[f"{tag}_loss"], rtol=1e-4, err_msg=tag)
+        ref = G[f"{tag}_grad"]
+        assert np.abs(yy.grad.cpu().numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-8, tag
+    with pytest.raises(RuntimeError, match="smaller than num_classes"):
+        NSL.TverskyLoss()(y, tg["targets_void"])

@@ -224,3 +224,52 @@ def test_focal_loss_oracle_vs_reference_golden(golden):
         R.focal_loss(y[0], t[:, 0])          # [N,H,W] targets: gather() needs [N,1,H,W]
     with pytest.raises(RuntimeError):
         R.focal_loss(y[0], np.full_like(t, 7))
+
+
+SEG_LOSS_CASES = {
+    "dice_mean": ("dice", dict(), "mean", "targets_void"),
+    "dice_index_sum": ("dice", dict(index=True), "sum", "targets_void"),
+    "dice_batchwise": ("dice", dict(), "mean_batchwise", "targets"),
+    "jaccard_mean": ("jaccard", dict(), "mean", "targets_void"),
+    "jaccard_bg": ("jaccard", dict(downgrad_bg=0.25), "sum", "targets_void"),
+    "jaccard_nobg": ("jaccard", dict(downgrad_bg=0.0), "sum_batchwise", "targets_void"),
+    "jaccard_index": ("jaccard", dict(index=True), "none", "targets"),
+    "tversky_mean": ("tversky", dict(alpha=0.3, beta=0.7), "mean", "targets"),
+    "ftversky_sum": ("tversky", dict(alpha=0.7, beta=0.3, gamma=4 / 3), "sum", "targets"),
+}
+
+
+def _seg_reduce(l, reduction):
+    """SegLoss.forward (new_seg_losses.py:17-32); mean over an empty dim list reduces everything, as torch does."""
+    if reduction == "mean":
+        return l.mean(), 1.0 / l.size
+    if reduction == "sum":
+        return l.sum(), 1.0
+    if reduction in ("mean_batchwise", "sum_batchwise"):
+        dims = tuple(range(1, l.ndim))
+        if reduction == "mean_batchwise":
+            return (l.mean(axis=dims), 1.0 / np.prod(l.shape[1:])) if dims else (l.mean(), 1.0 / l.size)
+        return (l.sum(axis=dims), 1.0) if dims else (l.sum(), 1.0)
+    return l, 1.0
+
+
+def test_seg_losses_oracle_vs_reference_golden(golden):
+    """new_seg_losses.py Dice / Jaccard / Tversky / FocalTversky restatement against (1) the values the reference's own
+    __main__ demo prints (0.0504 / 0.4033, new_seg_losses.py:170-256) and (2) the unmodified reference's values and
+    autograd gradients on seeded inputs (tests/golden/seg_losses.npz, oracle/make_golden_seg_losses.py)."""
+    G = golden("seg_losses")
+    out = str(G["demo_stdout"])
+    assert "0.0504" in out and "0.4033" in out
+    l, _ = R.seg_overlap_loss(G["demo_y_pred"], G["demo_y_true"], "jaccard")
+    assert f"{l.mean():.4f}" == "0.0504" and f"{l.sum():.4f}" == "0.4033"
+    np.testing.assert_allclose(l.mean(), G["demo_jaccard_mean"], rtol=1e-5)
+    np.testing.assert_allclose(R.seg_overlap_loss(G["demo_y_pred"], G["demo_y_true"], "dice")[0].mean(), G["demo_dice_mean"],
+                               rtol=1e-5)
+    for tag, (kind, kw, red, tk) in SEG_LOSS_CASES.items():
+        l, g = R.seg_overlap_loss(G["y_pred"], G[tk], kind, **kw)
+        val, gscale = _seg_reduce(l, red)
+        np.testing.assert_allclose(val, G[f"{tag}_loss"], rtol=1e-5, err_msg=tag)
+        ref = G[f"{tag}_grad"]
+        assert np.abs(g * gscale - ref).max() < 1e-4 * np.abs(ref).max() + 1e-9, tag
+    with pytest.raises(RuntimeError):
+        R.seg_overlap_loss(G["y_pred"], G["targets_void"], "tversky")
