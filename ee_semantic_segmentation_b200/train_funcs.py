@@ -215,10 +215,27 @@ class GraphedTrainStep:
     momentum), so the first replay is the first real update. Learning-rate changes made by a scheduler are baked
     into the graph: call `recapture()` after `scheduler.step()` (the reference steps it once per epoch)."""
 
-    def __init__(self, net, loss, optimizer, X, y, warmup=3):
+    def __init__(self, net, loss, optimizer, X, y, warmup=3, data_parallel=None):
+        """data_parallel (default: torch.distributed initialised with more than one rank): every parameter's .grad is a
+        view into ONE flat fp32 buffer, which the step averages over the ranks with a single NCCL all-reduce captured in
+        the graph between backward and optimizer.step() — the reference's update at the per-GPU batch on every rank, with
+        identical parameters everywhere (ranks must start from identical weights). BatchNorm stays per rank.
+        Call `release()` (or drop the object) before `destroy_process_group()`: a live graph keeps the communicator busy."""
+        import torch.distributed as dist
         self.net, self.loss_fn, self.opt = net, loss, optimizer
         self.X, self.y = X.clone(), y.clone()
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel)
+        self.flat = None
         net.train()
+        if self.dp:
+            params = [p for g in optimizer.param_groups for p in g['params'] if p.requires_grad]
+            self.flat = tch.zeros(sum(p.numel() for p in params), dtype=tch.float32, device=self.X.device)
+            o = 0
+            for p in params:
+                assert p.dtype == tch.float32 and p.is_contiguous()
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
         saved = [t.detach().clone() for t in list(net.parameters()) + list(net.buffers())]
         cur = tch.cuda.current_stream()
         side = tch.cuda.Stream()
@@ -237,17 +254,32 @@ class GraphedTrainStep:
         self.recapture()
 
     def _step(self):
-        self.opt.zero_grad(set_to_none=True)
+        if self.flat is not None:
+            self.flat.zero_()                            # gradients accumulate in place into the flat buffer
+        else:
+            self.opt.zero_grad(set_to_none=True)
         l = self.loss_fn(self.net(self.X), self.y)
         l.mean().backward()
+        if self.flat is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)     # NCCL over NVLink: one collective per step
         self.opt.step()
         return l
 
     def recapture(self):
         self.graph = tch.cuda.CUDAGraph()
-        self.opt.zero_grad(set_to_none=True)
-        with tch.cuda.graph(self.graph):
+        if self.flat is None:
+            self.opt.zero_grad(set_to_none=True)
+        # NCCL's watchdog thread may touch the CUDA API while this thread captures
+        kw = {'capture_error_mode': 'thread_local'} if self.world > 1 else {}
+        with tch.cuda.graph(self.graph, **kw):
             self.loss = self._step().detach()
+
+    def release(self):
+        """Destroys the captured graph (it references the NCCL communicator when data parallel)."""
+        tch.cuda.synchronize()
+        self.graph.reset()
+        self.graph = None
 
     def __call__(self, X, y):
         self.X.copy_(X, non_blocking=True)

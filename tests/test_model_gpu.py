@@ -413,6 +413,19 @@ def test_graphed_train_step_matches_eager_steps(nets):
             assert torch.allclose(ba, bb, rtol=1e-2, atol=1e-3), n
         else:
             assert torch.equal(ba, bb), n          # num_batches_tracked: 2, the warm-up was rolled back
+    # the data-parallel form on one rank (gradients accumulated in place into one flat buffer, no collective): same updates
+    nc = copy.deepcopy(net).train()
+    for mod in nc.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    opt_c = make_optimizer(nc, lr=1e-2, base_lr=1e-3)
+    step_c = GraphedTrainStep(nc, loss_fn, opt_c, *batches[0], data_parallel=True)
+    l_flat = [step_c(*b).item() for b in batches]
+    assert l_flat == pytest.approx(l_graph, rel=2e-3)
+    pc = torch.cat([p.detach().flatten() for p in nc.parameters()])
+    assert ((pc - pb).norm() / pb.norm()).item() < 1e-4
+    assert all(p.grad.data_ptr() >= step_c.flat.data_ptr() for p in nc.parameters())
+    step_c.release()
     net.eval()
 
 

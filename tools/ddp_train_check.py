@@ -19,7 +19,7 @@ import bench  # noqa: E402
 from ee_semantic_segmentation_b200 import parallel  # noqa: E402
 from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3  # noqa: E402
 from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss  # noqa: E402
-from ee_semantic_segmentation_b200.train_funcs import make_optimizer  # noqa: E402
+from ee_semantic_segmentation_b200.train_funcs import GraphedTrainStep, make_optimizer  # noqa: E402
 
 
 def main():
@@ -29,7 +29,7 @@ def main():
     steps = int(os.environ.get("STEPS", "10"))
     torch.manual_seed(0)
     net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=bench.SECTIONS, pretrained=False).to(dev).train()
-    mode = os.environ.get("DDP_MODE", "ddp")
+    mode = os.environ.get("DDP_MODE", "ddp")       # "graph": GraphedTrainStep with the all-reduce captured in the graph
     if world > 1 and mode == "ddp":
         ddp = parallel.wrap_ddp(net, local)
     elif world > 1 and mode == "nobcast":
@@ -42,12 +42,19 @@ def main():
     X, y = bench.synth_batch(rank, 4)
     X, y = X.to(dev), y.to(dev)
 
-    def step():
-        l = loss_fn(ddp(X), y)
-        opt.zero_grad(set_to_none=True)
-        l.backward()
-        opt.step()
-        return l
+    gstep = None
+    if mode == "graph":
+        gstep = GraphedTrainStep(net, loss_fn, opt, X, y)
+
+        def step():
+            return gstep(X, y)
+    else:
+        def step():
+            l = loss_fn(ddp(X), y)
+            opt.zero_grad(set_to_none=True)
+            l.backward()
+            opt.step()
+            return l
     for _ in range(3):
         l = step()
     torch.cuda.synchronize()
@@ -70,8 +77,10 @@ def main():
         same = True
     if rank == 0:
         print(json.dumps({"n_gpus": world, "per_gpu_batch": 4, "ms_per_step": float(ms), "images_per_s": 4 * world / float(ms) * 1e3,
-                          "loss_rank0": float(l), "params_identical_across_ranks": bool(same)}), flush=True)
+                          "loss_rank0": float(l), "params_identical_across_ranks": bool(same), "mode": mode}), flush=True)
     assert same or mode == "none", "parameters diverged across ranks"
+    if gstep is not None:
+        gstep.release()            # the graph references the communicator: destroy it first
     if world > 1:
         dist.destroy_process_group()
 
