@@ -2,7 +2,8 @@
 twin of the entropy operator — an image leaves at exit i when metric(previous exit's argmax map,
 this exit's argmax map) crosses the threshold. The skimage similarity metrics themselves
 (sim_metrics.py) are CPU analysis code and out of scope: `metric` is any
-callable taking two int64 [H,W] CPU tensors. The reference's `sel.threshold` typo (:84) is fixed."""
+callable taking two int64 [H,W] CPU tensors. The reference's `sel.threshold` typo (:84) is fixed. Result keys as in the
+reference, including the `*_flops_2` variants that leave out the first branch (the reference image, :86-110)."""
 import torch as tch
 
 from . import ops
@@ -35,12 +36,15 @@ class eval_ee_deeplabv3(_EntropyOp):
                         if (t < self.threshold) if self.less_than else (t > self.threshold):
                             output['exit'] = cur
                             output['exit_flops'] = sum(branch_flops) + sum(main_flops)
+                            output['exit_flops_2'] = sum(branch_flops[1:]) + sum(main_flops)
                             output['edge_flops'] = output['exit_flops']
+                            output['edge_flops_2'] = output['exit_flops_2']
                             output['n'] = i + 1
                             left = True
                     prev = cur
                 if not left and i == self.last_br:
                     output['edge_flops'] = sum(branch_flops) + sum(main_flops)
+                    output['edge_flops_2'] = sum(branch_flops[1:]) + sum(main_flops)
             main_flops.append(main_all[self.n])
             X = model.run_section(self.n, X)
             main_flops.append(head_all[self.n])
@@ -49,8 +53,10 @@ class eval_ee_deeplabv3(_EntropyOp):
                               want_score=False).amax.squeeze(0).to(tch.int64).cpu()
         output['last'] = Y
         output['last_flops'] = sum(branch_flops) + sum(main_flops)
+        output['last_flops_2'] = sum(branch_flops[1:]) + sum(main_flops)
         if not left:
             output['exit'] = Y
             output['exit_flops'] = output['last_flops']
+            output['exit_flops_2'] = output['last_flops_2']
             output['n'] = self.n + 1
         return output

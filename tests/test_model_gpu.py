@@ -510,3 +510,25 @@ def test_engine_graphs_follow_weight_updates(nets):
         assert torch.equal(after["pred"], ref["pred"]) and torch.equal(after["exit"], ref["exit"])
         assert not torch.equal(after["pred"], before["pred"])
         assert len(eng._graphs) <= 2
+
+
+def test_similarity_operator_keys_and_rule(nets):
+    """ee_dnn_op.eval_ee_deeplabv3 (similarity twin, ee_dnn_op.py:40-118): the first exit is only the reference image,
+    an image leaves at the first later exit whose map is close enough to the previous one; result keys of the reference
+    including the *_flops_2 variants."""
+    from ee_semantic_segmentation_b200.ee_dnn_op import eval_ee_deeplabv3 as SimOp
+    _, net = nets
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(3, 65, 81, generator=g).to(dev())
+    diff = lambda a, b: float((a != b).float().mean())
+    out = SimOp(net, diff, 2.0, device=dev())(x)                    # always "similar": leaves at exit 2, never at exit 1
+    assert out["n"] == 2 and out["exit"].shape == (65, 81) and out["exit"].dtype == torch.int64
+    assert set(out) == {"exit", "exit_flops", "exit_flops_2", "edge_flops", "edge_flops_2", "n", "last", "last_flops",
+                        "last_flops_2"}
+    assert out["exit_flops_2"] < out["exit_flops"] < out["last_flops"] and out["edge_flops_2"] == out["exit_flops_2"]
+    out = SimOp(net, diff, -1.0, device=dev())(x)                   # never similar
+    assert out["n"] == 3 and torch.equal(out["exit"], out["last"]) and out["exit_flops_2"] == out["last_flops_2"]
+    assert "edge_flops_2" in out
+    with torch.no_grad():
+        ref = net(x.unsqueeze(0))[-1, 0].argmax(0).cpu()
+    assert (out["last"] == ref).float().mean().item() > 0.999
