@@ -153,8 +153,13 @@ class branchyDeepv3(nn.Module):
             self.__dict__.setdefault(k, v)
 
     def _bump_epoch(self):
+        """Drops everything derived from the parameters: CUDA graphs AND the folded kernel plans. The plans are keyed by
+        the parameters' version counters, which a replayed training graph (train_funcs.GraphedTrainStep) does not advance —
+        without this, an evaluation after graph-replayed training would run on the weights folded before it."""
         self.weights_epoch = getattr(self, 'weights_epoch', 0) + 1
         self._lowres_graphs = {}
+        self._plans = {}
+        self._section_plans = {}
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._bump_epoch()                       # load_state_dict (also through a parent module / DDP wrapper)
