@@ -112,3 +112,42 @@ def test_train_driver_tracker_checkpoint_and_early_stopping(tmp_path):
     assert len(seen2) == 3 and tr2["val_mIoU"] == [3.0, 1.0, 2.0]
     assert torch.load(str(tmp_path / "b2.pth"), weights_only=False)["epoch"] == 2         # minimised: 1.0 at epoch 2
     assert not torch.equal(net2.w.detach(), w_best)                                        # started from it, then trained on
+
+
+def test_train_and_load_state_dict_drop_plans_and_graphs():
+    """Everything derived from the parameters — folded kernel plans, captured CUDA graphs — is dropped when the model
+    enters training mode or loads a state dict (weights_epoch): a training step replayed as a CUDA graph does not
+    advance the parameters' version counters, so version-keyed plans alone would go stale. Also: pickles and deep
+    copies carry no plans / graphs, and reference-style pickles get the run-time defaults."""
+    import copy
+    import io
+    import torch
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 1, 65, sections=[18, 2], pretrained=False).eval()
+    e0 = net.weights_epoch
+    net._plans[0] = ("key", object())
+    net._section_plans[0] = ("key", object())
+    net._lowres_graphs["shape"] = object()
+    net.eval()
+    assert net._plans and net.weights_epoch == e0                     # eval() keeps them
+    net.train()
+    assert net._plans == {} and net._section_plans == {} and net._lowres_graphs == {} and net.weights_epoch == e0 + 1
+    net.eval()
+    net._plans[0] = ("key", object())
+    sd = copy.deepcopy(net.state_dict())
+    net.load_state_dict(sd)
+    assert net._plans == {} and net.weights_epoch > e0 + 1
+    net._plans[0] = ("key", torch.zeros(1))
+    n2 = copy.deepcopy(net)
+    assert n2._plans == {} and n2.weights_epoch == net.weights_epoch and net._plans
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    n3 = torch.load(buf, weights_only=False)
+    assert n3._plans == {} and n3.fast_inference and n3.graph_inference
+    st = n3.__getstate__()
+    for k in ("fast_inference", "fast_backbone", "graph_inference", "weights_epoch", "_plans"):
+        st.pop(k)
+    n4 = branchyDeepv3.__new__(branchyDeepv3)
+    n4.__setstate__(st)                                               # a pickle without the run-time attributes
+    assert n4.fast_inference and n4.fast_backbone and n4.graph_inference and n4.weights_epoch == 0 and n4._plans == {}
