@@ -53,3 +53,34 @@ def wrap_ddp(net, local_rank):
     BatchNorm stays per rank, as in a single-GPU reference run at the per-GPU batch."""
     from torch.nn.parallel import DistributedDataParallel as DDP
     return DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+
+
+class FlatGradients:
+    """Gradients of a set of parameters as views of ONE flat fp32 buffer, so that a data-parallel step needs a single
+    all-reduce: autograd accumulates into the views in place, `zero()` clears them with one fill, `all_reduce_mean()`
+    averages them over the ranks (NCCL: one AVG collective, capturable in a CUDA graph — train_funcs.GraphedTrainStep;
+    gloo on CPU tensors: SUM and a division, used by the CPU tests), and the optimizer reads the views as usual."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        assert all(p.dtype == torch.float32 and p.is_contiguous() and p.device == dev for p in self.params), \
+            "flat gradients need contiguous fp32 parameters on one device"
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        if self.flat.is_cuda:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(dist.get_world_size())

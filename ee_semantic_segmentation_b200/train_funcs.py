@@ -226,16 +226,12 @@ class GraphedTrainStep:
         self.X, self.y = X.clone(), y.clone()
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel)
-        self.flat = None
+        self.flat = self._fg = None
         net.train()
         if self.dp:
-            params = [p for g in optimizer.param_groups for p in g['params'] if p.requires_grad]
-            self.flat = tch.zeros(sum(p.numel() for p in params), dtype=tch.float32, device=self.X.device)
-            o = 0
-            for p in params:
-                assert p.dtype == tch.float32 and p.is_contiguous()
-                p.grad = self.flat[o:o + p.numel()].view_as(p)
-                o += p.numel()
+            from .parallel import FlatGradients
+            self._fg = FlatGradients([p for g in optimizer.param_groups for p in g['params']])
+            self.flat = self._fg.flat
         saved = [t.detach().clone() for t in list(net.parameters()) + list(net.buffers())]
         cur = tch.cuda.current_stream()
         side = tch.cuda.Stream()
@@ -260,9 +256,8 @@ class GraphedTrainStep:
             self.opt.zero_grad(set_to_none=True)
         l = self.loss_fn(self.net(self.X), self.y)
         l.mean().backward()
-        if self.flat is not None and self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)     # NCCL over NVLink: one collective per step
+        if self._fg is not None:
+            self._fg.all_reduce_mean()                   # NCCL over NVLink: one collective per step (none on one rank)
         self.opt.step()
         return l
 

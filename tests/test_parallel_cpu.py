@@ -57,3 +57,47 @@ def test_sharded_confusion_allreduce_matches_single_process(tmp_path):
     ref = (tp / (tp + fp + fn)).sum() / C
     assert float(a["miou"][-1]) == pytest.approx(ref, abs=1e-12)
     assert list(parallel.shard_range(7, 1, 2)) == [1, 3, 5]
+
+
+def _train_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from ee_semantic_segmentation_b200 import parallel
+    parallel.init_from_env("gloo")
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    fg = parallel.FlatGradients(net.parameters())
+    g = torch.Generator().manual_seed(7)
+    X, y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+    Xs, ys = X[rank::world], y[rank::world]                # this rank's shard
+    for _ in range(3):
+        fg.zero()
+        ((net(Xs) - ys) ** 2).mean().backward()            # accumulates in place into the flat buffer
+        assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in net.parameters())
+        fg.all_reduce_mean()
+        opt.step()
+    torch.save([p.detach().clone() for p in net.parameters()], os.path.join(tmp, f"p{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_training_matches_single_process(tmp_path):
+    """The data-parallel step of train_funcs.GraphedTrainStep on CPU/gloo: gradients as views of one flat buffer, one
+    all-reduce(mean) per step. Two ranks on disjoint equal shards end with identical parameters, equal to single-process
+    SGD on the whole batch (the mean of the shard means is the batch mean)."""
+    port = 29500 + ((os.getpid() + 137) % 500)
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "p0.pt"), torch.load(tmp_path / "p1.pt")
+    assert all(torch.equal(x, z) for x, z in zip(a, b))
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    g = torch.Generator().manual_seed(7)
+    X, y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+    for _ in range(3):
+        opt.zero_grad()
+        ((net(X) - y) ** 2).mean().backward()
+        opt.step()
+    for x, p in zip(a, net.parameters()):
+        assert torch.allclose(x, p.detach(), rtol=1e-5, atol=1e-6)
