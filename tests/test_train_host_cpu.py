@@ -151,3 +151,24 @@ def test_train_and_load_state_dict_drop_plans_and_graphs():
     n4 = branchyDeepv3.__new__(branchyDeepv3)
     n4.__setstate__(st)                                               # a pickle without the run-time attributes
     assert n4.fast_inference and n4.fast_backbone and n4.graph_inference and n4.weights_epoch == 0 and n4._plans == {}
+
+
+def test_grouped_conv_work_list_tile_width_rule():
+    """head_plan.group_schedule: the grouped ASPP work list (4 problems on a 65x65 map, Cout 256). With 4 images the
+    256-column tiles already cover the 148 SMs; with one image the list switches to 128-column tiles (twice the items),
+    every (problem, tile) exactly once, sorted by cost inside each round of n_ctas items (snake order)."""
+    import numpy as np
+    from ee_semantic_segmentation_b200.head_plan import group_schedule
+    ks, ds = [1, 3, 3, 3], [1, 12, 24, 36]
+    s4 = group_schedule(4, 65, 65, 2048, 256, ks, ds).numpy()
+    s1 = group_schedule(1, 65, 65, 2048, 256, ks, ds).numpy()
+    s2 = group_schedule(2, 65, 65, 2048, 256, ks, ds).numpy()
+    assert len(s4) == 4 * 4 * 36 and len(s2) == 4 * 2 * 36           # 256-column tiles: one channel tile per position
+    assert len(s1) == 4 * 1 * 36 * 2                                  # 128-column tiles
+    for s, n_items in ((s4, 4 * 36), (s1, 2 * 36), (s2, 2 * 36)):
+        assert len(set(s.tolist())) == len(s)
+        for g in range(4):
+            tiles = np.sort(s[(s >> 24) == g] & 0xffffff)
+            np.testing.assert_array_equal(tiles, np.arange(n_items))
+    # the first round holds the most expensive items: none of the cheap 1x1 tiles (problem 0)
+    assert not np.any((s4[:148] >> 24) == 0)
