@@ -446,7 +446,9 @@ def main():
                     "d2h_bytes_per_step": PER_GPU_BATCH * 4 + 2 * PER_GPU_BATCH * 4, "ms_per_step": e2e_ms / steps,
                     "h2d_ms_alone": h2d_ms,
                     "mode": "pipelined: upload of batch k+1 and read-back of batch k-1 overlap the graph replay of batch k"
-                            if eng.use_graph else "sequential"},
+                            if eng.use_graph else "sequential",
+                    "l2": "every step's inputs arrive from pinned host memory (never cache-resident); no flush between "
+                          "batches, so weights may stay in L2 as in a real stream — `value` is the flushed number"},
             "gpu_launches": int(launches) if args.no_graph else int(launches_per_step * steps),
             "launch_mode": "eager" if args.no_graph else "cuda_graph_replay (eeseg kernels captured in the graph)",
             "roofline": {"kernel": f"conv_igemm_kernel (tcgen05 implicit GEMM, {n_conv // steps} launches/step: "
