@@ -159,34 +159,68 @@ def conv_traffic():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_images=2):
-    """The reference's CPU path (oracle port: torchvision fp32 model + numpy/scipy-style entropy gate
-    + confusion matrix), all host threads, on `sample_images` images per step."""
+def cpu_reference_run(steps, warmup, sample_images=None):
+    """The reference's CPU path on all host threads, `sample_images` images per step (default: the config's per-GPU
+    batch). When the unmodified reference is staged (oracle/_ref, see oracle/build_ref.py; /root/reference in the build
+    container) and the workload is the 21-class one its constructor hard-codes: the reference's OWN
+    `from_deepv3_new.branchyDeepv3(base, 'deeplabv3_resnet50', 2, 513, count_branches=False)` (its FLOP-quantile
+    placement then gives the sections 16/3/1 of config.workload) and `eval_br_ent.br_evaluator` over a batch-1 loader
+    (the reference needs batch 1), kind = "reference". Otherwise the oracle port (oracle/model_port), kind = "port"."""
     import torch
-    from oracle import model_port
+    from oracle import ref_import
     torch.set_num_threads(os.cpu_count() or 1)
-    net = model_port.build_port(SECTIONS, seed=0, num_classes=N_CLASSES).eval()
-    X, y = synth_batch(0, sample_images)
+    n = PER_GPU_BATCH if sample_images is None else sample_images
+    X, y = synth_batch(0, n)
+    H, W = img_hw()
+    if ref_import.available() and N_CLASSES == 21 and H == W:
+        import warnings
+        import torchvision
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fd_new, ebe = ref_import.load("from_deepv3_new", "eval_br_ent")
+        base_path = os.path.join(tempfile.mkdtemp(prefix="eeseg_ref_"), "base_r50.pth")
+        torch.manual_seed(0)
+        torch.save(torchvision.models.segmentation.deeplabv3_resnet50(
+            weights=None, weights_backbone=None, num_classes=21, aux_loss=True), base_path)
+        net = fd_new.branchyDeepv3(base_path, "deeplabv3_resnet50", 2, H, count_branches=False).eval()
+        assert [len(sec) for sec in net.base_model] == SECTIONS, [len(sec) for sec in net.base_model]
+        loader = [(X[k:k + 1], y[k:k + 1]) for k in range(n)]
+        cpu = torch.device("cpu")
+
+        def step():
+            return ebe.br_evaluator(net, 3, N_CLASSES, loader, cpu, TAU)
+        kind = "reference"
+        how = ("UNMODIFIED reference (" + ("oracle/_ref" if ref_import.STAGED else ref_import.REFERENCE_DIR) +
+               "): from_deepv3_new.branchyDeepv3 + eval_br_ent.br_evaluator, batch-1 loader")
+    else:
+        from oracle import model_port
+        net = model_port.build_port(SECTIONS, seed=0, num_classes=N_CLASSES).eval()
+
+        def step():
+            return model_port.evaluate_batch_cpu(net, X, y, N_CLASSES, TAU)
+        kind = "port"
+        how = "oracle/model_port.evaluate_batch_cpu (the reference is not staged or hard-codes 21 classes)"
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        model_port.evaluate_batch_cpu(net, X, y, N_CLASSES, TAU)
+        step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     mean = sum(times) / len(times)
-    return {"value": sample_images / mean, "unit": "images/s", "cores": torch.get_num_threads(),
-            "kind": "port", "ms_per_step": mean * 1e3,
-            "sample": f"{sample_images} images of {img_hw()[0]}x{img_hw()[1]} per step x {steps} steps (+{warmup} warm-up), "
-                      f"fp32, 3 exits, oracle/model_port.evaluate_batch_cpu"}
+    return {"value": n / mean, "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": kind, "ms_per_step": mean * 1e3,
+            "sample": f"{n} images of {H}x{W} per step x {steps} steps (+{warmup} warm-up), fp32 CPU, 3 exits, {how}"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 1))
+    # the config's own batch per step; K and W as asked, bounded so the run ends within a few minutes
+    # (a step of 4 batch-1 images through the unmodified reference is ~5-10 s on 8-16 cores)
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 2))
     cb = cpu_reference_run(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
@@ -486,7 +520,7 @@ def main():
             },
         }
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_reference_run(steps=3, warmup=1)
+            cb = cpu_reference_run(steps=2, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:

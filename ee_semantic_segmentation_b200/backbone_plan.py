@@ -3,8 +3,9 @@ implicit-GEMM kernel: every torchvision ResNet `Bottleneck` becomes three (four 
 shortcut) `eeseg_conv_igemm_fwd` launches on bf16 NHWC activations with BatchNorm folded into the
 epilogue scale/shift, ReLU fused, and the residual add fused into the last 1x1 — instead of
 conv + BN + ReLU + add as separate library kernels. Stride-2 convolutions (layer2.0) use TMA element
-strides. The 7x7/stride-2 stem (3 input channels) and the max-pool stay on PyTorch (bf16,
-channels_last): their K is not a multiple of the 64-channel MMA K-block.
+strides. The 7x7/stride-2 stem (3 input channels) is a space-to-depth 4x1 implicit GEMM followed by the NHWC
+max-pool kernel (StemPlan). A section with any other unit is not `supported` (the model then warns once, or raises
+under `strict_kernels`).
 """
 import torch
 from torch import nn
@@ -117,11 +118,17 @@ class StemPlan:
 
 
 def supported(section):
-    for m in section:
-        if isinstance(m, Bottleneck):
-            for c in (m.conv1, m.conv2, m.conv3):
-                if c.in_channels % 64 or c.out_channels % 16 or c.groups != 1 or c.stride[0] not in (1, 2):
-                    return False
+    """True when EVERY unit of the section runs on the eeseg kernels: an optional ResNet stem (conv 7x7/s2 + BN + ReLU +
+    max-pool, StemPlan.matches) followed by Bottlenecks whose convolutions the implicit-GEMM kernel takes."""
+    mods = list(section)
+    if StemPlan.matches(mods):
+        mods = mods[4:]
+    for m in mods:
+        if not isinstance(m, Bottleneck):
+            return False
+        for c in (m.conv1, m.conv2, m.conv3):
+            if c.in_channels % 64 or c.out_channels % 16 or c.groups != 1 or c.stride[0] not in (1, 2):
+                return False
     return True
 
 
@@ -152,9 +159,6 @@ class SectionPlan:
                 if nhwc is None:
                     nhwc = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
                 nhwc = op.run(nhwc)
-            else:
-                if nhwc is not None:
-                    x, nhwc = nhwc.permute(0, 3, 1, 2), None
-                with torch.autocast('cuda', dtype=torch.bfloat16):
-                    x = op(x.contiguous(memory_format=torch.channels_last))
+            else:       # supported() admits stems and Bottlenecks only
+                raise RuntimeError(f'SectionPlan: {type(op).__name__} has no eeseg kernel plan')
         return nhwc.permute(0, 3, 1, 2) if nhwc is not None else x

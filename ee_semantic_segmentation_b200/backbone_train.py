@@ -154,6 +154,21 @@ def bottleneck_forward_train(blk, x):
     return bn_act(_conv(out, blk.conv3), blk.bn3, True, residual=identity)
 
 
+def section_supported(section, x):
+    """True when every unit of the section trains on the eeseg kernels (stem + Bottlenecks with supported convolutions);
+    anything else runs on the PyTorch modules inside section_forward_train."""
+    mods = list(section)
+    if stem_supported(mods, x):
+        mods = mods[4:]
+    for unit in mods:
+        if not (isinstance(unit, Bottleneck) and len(unit.downsample or [0, 0]) == 2):
+            return False
+        convs = [unit.conv1, unit.conv2, unit.conv3] + ([unit.downsample[0]] if unit.downsample is not None else [])
+        if not all(_conv_ok(c) for c in convs):
+            return False
+    return True
+
+
 def section_forward_train(section, x):
     """section(x) with autograd. x: fp32/bf16 NCHW (any memory format) -> bf16 channels_last."""
     mods = list(section)

@@ -11,8 +11,10 @@ how the work runs on a B200:
   from_deepv3_new.py:150-155).
 * `forward_lowres(X)` stops before the up-sampling and feeds the fused exit gate
   (`ee_semantic_segmentation_b200.ops.exit_gate`), which never materialises full-resolution logits.
-* training mode keeps the PyTorch modules (autograd through cuDNN) and only the loss runs on eeseg
-  kernels; conv dgrad/wgrad kernels are future work.
+* training mode runs the convolutions (forward, input and weight gradients), BatchNorm and up-sampling on the
+  eeseg kernels behind autograd (head_train.py, backbone_train.py, bn_train.py).
+* `strict_kernels = True` turns every library fall-back (a section or head layout the kernel plans do not cover)
+  into an error; by default such a module runs on the PyTorch modules with ONE warning naming it.
 
 Branch placement follows from_deepv3_new.py:75-89 literally; FLOPs are counted with
 torch.utils.flop_counter on meta tensors (the reference's `pthflops` is not installed anywhere and
@@ -133,9 +135,22 @@ class branchyDeepv3(nn.Module):
         self.graph_inference = True    # forward_lowres replays one CUDA graph per input shape (see there)
         self._lowres_graphs = {}
         self.weights_epoch = 0         # bumped by train() / load_state_dict(): captured graphs of older epochs are stale
+        self.strict_kernels = False    # True: a module the eeseg plans do not cover raises instead of running on cuDNN
 
     _RUNTIME_DEFAULTS = dict(fast_inference=True, fast_backbone=True, fast_training_heads=True,
-                             fast_training_backbone=True, graph_inference=True, weights_epoch=0, num_classes=21)
+                             fast_training_backbone=True, graph_inference=True, weights_epoch=0, num_classes=21,
+                             strict_kernels=False)
+    _warned_fallbacks = set()
+
+    def _library_fallback(self, what):
+        """A module the eeseg kernel plans do not cover: error in strict mode (bench.py and the GPU tests set it), one
+        warning per module kind otherwise. There is never a silent switch of backend."""
+        if self.strict_kernels:
+            raise RuntimeError(f'strict_kernels: {what} is not covered by the eeseg kernel plans '
+                               '(it would run on the PyTorch/cuDNN modules)')
+        if what not in branchyDeepv3._warned_fallbacks:
+            branchyDeepv3._warned_fallbacks.add(what)
+            warnings.warn(f'{what} is not covered by the eeseg kernel plans: running it on the PyTorch modules')
 
     def __getstate__(self):
         """Pickles (tch.save(net), copy.deepcopy) carry parameters and flags, not the kernel plans / CUDA graphs."""
@@ -274,6 +289,8 @@ class branchyDeepv3(nn.Module):
                 ent = (key, SectionPlan(sec))
                 self._section_plans[i] = ent
             return ent[1].run(X)
+        if self.fast_backbone:
+            self._library_fallback(f'base_model[{i}] ({type(sec[0]).__name__} ...)')
         with tch.autocast('cuda', dtype=tch.bfloat16):
             return sec(X.contiguous(memory_format=tch.channels_last))
 
@@ -281,14 +298,18 @@ class branchyDeepv3(nn.Module):
         """head(X) with autograd: the head's convolutions (forward, input and weight gradients) on the
         eeseg tcgen05 kernels when fast_training_heads is set and the head has the DeepLabHead layout,
         else the PyTorch modules (cuDNN)."""
-        if self.fast_training_heads and self.training and X.is_cuda and head_train.head_supported(head):
-            return head_train.head_forward_train(head, X)
+        if self.fast_training_heads and self.training and X.is_cuda:
+            if head_train.head_supported(head):
+                return head_train.head_forward_train(head, X)
+            self._library_fallback(f'exit head {type(head).__name__} (training)')
         return head(X)
 
     def _section_autograd(self, section, X):
         """base_model[i](X) with autograd: Bottleneck convolutions on the eeseg kernels in bf16 when
         fast_training_backbone is set (backbone_train.py), else the PyTorch modules in the input dtype."""
         if self.fast_training_backbone and self.training and X.is_cuda:
+            if not backbone_train.section_supported(section, X):
+                self._library_fallback(f'a unit of a backbone section ({type(section[0]).__name__} ...) in training')
             return backbone_train.section_forward_train(section, X)
         return section(X)
 

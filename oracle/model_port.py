@@ -86,9 +86,19 @@ def reinit_branches(branches, seed):
                 m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
 
 
-def build_port(sections, seed=0, branch_seed=None, arch='resnet50', num_classes=21):
+def sharpen_heads(branches, factors):
+    """Scales the final 1x1 classifier (weight and bias) of early-exit head i by factors[i]: larger logits = lower
+    entropy, so fixtures can order the exits' confidences (applied identically to the reference model in
+    oracle/make_golden_operator.py and to the port)."""
+    with torch.no_grad():
+        for br, f in zip(branches, factors):
+            br[-1].weight.mul_(float(f))
+            br[-1].bias.mul_(float(f))
+
+
+def build_port(sections, seed=0, branch_seed=None, arch='resnet50', num_classes=21, sharpen=None):
     """Base model: torchvision default init under manual_seed(seed) (what the reference pickles at
-    `base_name`); early-exit heads: reinit_branches(branch_seed) when given."""
+    `base_name`); early-exit heads: reinit_branches(branch_seed) when given, then sharpen_heads(sharpen)."""
     torch.manual_seed(seed)
     ctor = (torchvision.models.segmentation.deeplabv3_resnet50 if arch == 'resnet50'
             else torchvision.models.segmentation.deeplabv3_resnet101)
@@ -96,6 +106,8 @@ def build_port(sections, seed=0, branch_seed=None, arch='resnet50', num_classes=
     net = BranchyPort(base, sections, num_classes)
     if branch_seed is not None:
         reinit_branches(net.branches, branch_seed)
+    if sharpen is not None:
+        sharpen_heads(net.branches, sharpen)
     return net
 
 
@@ -118,3 +130,60 @@ def evaluate_batch_cpu(net, X, y, n_classes, tau, skip=0):
         pred = R.argmax_first(y_pred[ex, k].numpy().reshape(1, n_classes, -1), 1)
         cms.append(R.confusion_matrix(pred, y[k].numpy().reshape(1, -1), n_classes)[0])
     return np.array(exits), scores, np.stack(cms)
+
+
+def operator_entropy_cpu(net, x, n_classes, th, less_than=True, ignore=()):
+    """ee_dnn_op_ne.eval_ee_deeplabv3.__call__ (ee_dnn_op_ne.py:51-108) on CPU for one image x [3,H,W], without the
+    FLOP bookkeeping: returns {'n', 'exit', 'last'} (int64 [H,W] maps) plus 'scores' (the metric value of every
+    early exit that was evaluated, None for the others)."""
+    out, scores, left = {}, [], False
+    inp_shape = x.shape[-2:]
+    X = x.unsqueeze(0)
+    with torch.no_grad():
+        for i in range(net.n_branches):
+            X = net.base_model[i](X)
+            scores.append(None)
+            if i not in ignore and not left:
+                br = F.interpolate(net.branches[i](X), size=inp_shape, mode='bilinear', align_corners=False)
+                probs = F.softmax(br, 1).squeeze(0).numpy()
+                t = R.img_norm_entropy(probs, n_classes)
+                scores[-1] = float(t)
+                if (t < th) if less_than else (t > th):
+                    out['exit'] = br.argmax(dim=1).squeeze(0)
+                    out['n'] = i + 1
+                    left = True
+        Y = F.interpolate(net.classifier(net.base_model[-1](X)), size=inp_shape, mode='bilinear', align_corners=False)
+        Y = Y.argmax(dim=1).squeeze(0)
+    out['last'] = Y
+    if not left:
+        out['exit'] = Y
+        out['n'] = net.n_branches + 1
+    out['scores'] = scores
+    return out
+
+
+def operator_similarity_cpu(net, x, metric, th, less_than=True, ignore=()):
+    """ee_dnn_op.eval_ee_deeplabv3.__call__ (ee_dnn_op.py:51-118) on CPU for one image, without the FLOP bookkeeping:
+    the first evaluated exit only provides the reference map; a later exit answers when
+    metric(reference map, its map) crosses th, otherwise its map becomes the reference map."""
+    out, left, y_ref = {}, False, None
+    inp_shape = x.shape[-2:]
+    X = x.unsqueeze(0)
+    with torch.no_grad():
+        for i in range(net.n_branches):
+            X = net.base_model[i](X)
+            if i not in ignore and not left:
+                br = F.interpolate(net.branches[i](X), size=inp_shape, mode='bilinear', align_corners=False).argmax(dim=1)
+                if y_ref is not None and ((metric(y_ref, br) < th) if less_than else (metric(y_ref, br) > th)):
+                    out['exit'] = br.squeeze(0)
+                    out['n'] = i + 1
+                    left = True
+                else:
+                    y_ref = br
+        Y = F.interpolate(net.classifier(net.base_model[-1](X)), size=inp_shape, mode='bilinear', align_corners=False)
+        Y = Y.argmax(dim=1).squeeze(0)
+    out['last'] = Y
+    if not left:
+        out['exit'] = Y
+        out['n'] = net.n_branches + 1
+    return out

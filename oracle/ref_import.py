@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE — loader for the UNMODIFIED reference modules from /root/reference.
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU box). Used by
-``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/`` and by the
-``not gpu`` tests that pin the restatement in ``oracle/restate.py`` against the real thing.
-Nothing in the product package imports this file.
+In the build container the modules come from ``/root/reference``; on the GPU box (where that path does not exist)
+from the verbatim copy ``oracle/build_ref.py`` stages under ``oracle/_ref/`` (git-ignored). Used by
+``oracle/make_golden*.py`` to generate the fixtures under ``tests/golden/``, by the ``not gpu`` tests that pin the
+restatement in ``oracle/restate.py`` against the real thing, and by bench.py's CPU arm (``--impl reference`` /
+``cpu_baseline``), which times the reference's own model + ``br_evaluator``. Nothing in the product package imports
+this file.
 
 The stub set (``oracle/stubs``) is the one SURVEY.md §8(c) lists: ``common_header``, a shadow
 ``module_variables``, a shadow ``allocate_cuda_device``, ``pthflops`` (FlopCounterMode stand-in),
@@ -14,8 +16,15 @@ import importlib
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_DIR = os.environ.get("EESEG_REFERENCE_DIR", "/root/reference")
-STUB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+STUB_DIR = os.path.join(_HERE, "stubs")
+STAGED = False
+if not os.path.isdir(REFERENCE_DIR) and os.path.isdir(os.path.join(_HERE, "_ref", "reference")):
+    # the GPU box: the verbatim copy staged by oracle/build_ref.py (git-ignored, travels with the snapshot)
+    REFERENCE_DIR = os.path.join(_HERE, "_ref", "reference")
+    STUB_DIR = os.path.join(_HERE, "_ref", "stubs")
+    STAGED = True
 
 # module names that exist both in the reference and (as drop-in shims) in this repo
 _REF_MODULES = [

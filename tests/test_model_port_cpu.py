@@ -34,3 +34,35 @@ def test_product_model_placement_and_state_dict(golden):
     assert net.n_branches == 2 and net.count_branches is True
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net.eval()(torch.zeros(1, 3, 33, 33))
+
+
+def _operator_port(d):
+    sections = [int(s) for s in d["sections"]]
+    return model_port.build_port(sections, seed=0, branch_seed=int(d["branch_seed"]),
+                                 sharpen=[float(f) for f in d["sharpen"]]).eval()
+
+
+def test_port_operator_matches_reference_operator(golden):
+    """oracle/model_port.operator_*_cpu against the UNMODIFIED reference operators' outputs
+    (tests/golden/operator.npz from oracle/make_golden_operator.py): `n` and both maps exactly."""
+    from oracle.make_golden_operator import map_distance
+    d = golden("operator")
+    net = _operator_port(d)
+    for k in range(int(d["n_img"])):
+        x = torch.tensor(d[f"img{k}/x"])
+        for tag in [str(c) for c in d["cases"]]:
+            th = float(d[f"img{k}/{tag}/th"])
+            if tag.startswith("ne_"):
+                out = model_port.operator_entropy_cpu(net, x, 21, th, ignore=[0] if tag == "ne_ignore0" else [])
+                for i, s in enumerate(out["scores"]):
+                    if s is not None:
+                        assert abs(s - float(d[f"img{k}/scores"][i])) < 1e-5
+            else:
+                out = model_port.operator_similarity_cpu(net, x, map_distance, th)
+            assert out["n"] == int(d[f"img{k}/{tag}/n"]), (k, tag)
+            for key in ("exit", "last"):
+                ref = d[f"img{k}/{tag}/{key}"]
+                got = out[key].numpy()
+                # identical third-party calls on identical weights: the maps agree except where fp32 summation order
+                # inside the conv library flips a near-tie (none observed; bound it instead of assuming it)
+                assert (got != ref).mean() < 1e-4, (k, tag, key, (got != ref).mean())
