@@ -242,6 +242,159 @@ def workload_config(n_gpus):
             "parallelism": f"dp{n_gpus}", "l2": "flushed between timed steps (256 MiB write)"}
 
 
+def kernel_intervals(fn, reps, flush):
+    """GPU-side start/end of every kernel of `reps` calls of fn() (CUDA-graph replays included), from CUPTI's
+    activity records (torch.profiler). Returns a list (one per call) of [(name, start_us, end_us), ...]; the L2-flush
+    fill that precedes each call is the separator and is dropped."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            flush.fill_(1)
+            fn()
+        torch.cuda.synchronize()
+    path = tempfile.mktemp(prefix="eeseg_trace_", suffix=".json")
+    prof.export_chrome_trace(path)
+    with open(path) as f:
+        tr = json.load(f)
+    os.unlink(path)
+    ev = sorted(((e["ts"], e["ts"] + e["dur"], e["name"]) for e in tr["traceEvents"]
+                 if e.get("cat") == "kernel" and "dur" in e), key=lambda t: t[0])
+    calls, cur = [], None
+    for a, b, name in ev:
+        if "FillFunctor" in name and (b - a) > 20:          # the 256 MiB flush (tiny fills inside a step are ~2 us)
+            cur = []
+            calls.append(cur)
+        elif cur is not None:
+            cur.append((name, a, b))
+    return [c for c in calls if c]
+
+
+def busy_us(intervals):
+    """Length of the union of [start, end) intervals."""
+    tot, end = 0.0, None
+    for a, b in sorted(intervals):
+        if end is None or a > end:
+            tot += b - a
+            end = b
+        elif b > end:
+            tot += b - end
+            end = b
+    return tot
+
+
+def dist_max(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def leg_cityscapes_sweep(dev, rank, world, steps, warmup, barrier):
+    """BASELINE configs[4]: full-resolution Cityscapes-shaped evaluation (19 classes, 1024x2048, 2 images per GPU per
+    step), ONE forward per batch resolving a sweep of exit thresholds (engine.ThresholdSweep — what eval_br_ent.py:38-84
+    + CLI -t :96 needs one whole run per tau for), with the integer confusion-matrix all-reduce INSIDE the timed region."""
+    import torch
+    from ee_semantic_segmentation_b200.engine import ThresholdSweep
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    C, hw, B = 19, (1024, 2048), 2
+    torch.manual_seed(0)
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=SECTIONS, pretrained=False, num_classes=C).to(dev).eval()
+    net.strict_kernels = True
+    Xh, yh = synth_batch(rank, B, img=hw, n_classes=C)
+    Xh, yh = Xh.pin_memory(), yh.pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    probe = ThresholdSweep(net, C, [0.5])
+    sc = probe.update(Xd, yd)[:2].float().cpu()
+    taus = [round(0.1 * k, 1) for k in range(1, 10)] + [float(sc[0].median()), float(sc[1].median())]
+    sweep = ThresholdSweep(net, C, taus)
+    for _ in range(max(warmup, 2)):
+        sweep.update(Xd, yd)
+    out = {}
+    for name, inputs in (("value", lambda: (Xd, yd)),
+                         ("e2e", lambda: (Xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)))):
+        sweep.cm.zero_(); sweep.counts.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(steps):
+            sweep.update(*inputs())
+        sweep.all_reduce()                     # int64 [T, E+1, C+1, C] + counters, NCCL, once per sweep
+        b.record()
+        barrier()
+        (ms,) = dist_max([a.elapsed_time(b)], dev, world)
+        out[name] = (B * world * steps / (ms * 1e-3), ms / steps)
+    res = sweep.results()
+    assert all(r["out_gl"] == B * world * steps for r in res)
+    del sweep, probe, net
+    torch.cuda.empty_cache()
+    return {"metric": "tau_sweep_images_per_sec_1024x2048", "value": out["value"][0], "unit": "images/s",
+            "ms_per_step": out["value"][1], "steps": steps, "per_gpu_batch": B, "n_taus": len(taus), "n_classes": C,
+            "e2e": {"value": out["e2e"][0], "unit": "images/s", "ms_per_step": out["e2e"][1],
+                    "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 8, "mode": "sequential upload + update"},
+            "collective": "one int64 all-reduce(SUM) of cm[T,E+1,C+1,C] + counts inside the timed region (per sweep, not per batch)",
+            "exits_at_median_tau": {k: res[-2][k] for k in ("b1_count", "b2_count", "count_out")},
+            "l2": "working set of a step (50 MB of inputs, GBs of activations) exceeds the 126 MB L2; no flush"}
+
+
+def leg_train(kind, dev, rank, world, steps, warmup, barrier):
+    """BASELINE configs[2] / [3]: one training step (train_funcs.py:12-33) = forward, multi-exit loss, backward, SGD on
+    synthetic crops, replayed as one CUDA graph (train_funcs.GraphedTrainStep); data parallel: ONE flat gradient
+    all-reduce(AVG) over NCCL captured inside the step graph, i.e. inside the timed region."""
+    import torch
+    from ee_semantic_segmentation_b200.branchy_seg_losses import LovaszSoftmax
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    from ee_semantic_segmentation_b200.train_funcs import GraphedTrainStep, make_optimizer
+    C, img, B = (21, 513, 4) if kind == "ce" else (19, 768, 2)
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 2, img, sections=SECTIONS, pretrained=False, num_classes=C).to(dev).train()
+    net.strict_kernels = True
+    opt = make_optimizer(net, lr=1e-3, base_lr=1e-4)
+    loss = (BrXEntropyLoss(ignore_index=C, b_reduction="sum", n_exits=3) if kind == "ce"      # main_bradeepv3_ce.py:121
+            else LovaszSoftmax(classes="present", ignore=C, n_branches=2))                      # main_bradeepv3.py:121
+    Xh, yh = synth_batch(rank, B, img=img, n_classes=C)
+    Xh, yh = Xh.pin_memory(), yh.pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    gstep = GraphedTrainStep(net, loss, opt, Xd, yd)
+    for _ in range(max(warmup, 3)):
+        l = gstep(Xd, yd)
+    out = {}
+    for name in ("value", "e2e"):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(steps):
+            if name == "value":
+                l = gstep(Xd, yd)
+            else:
+                lv = float(gstep(Xh, yh))                  # H2D of the batch + D2H of the loss every step
+        b.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        (ms,) = dist_max([max(a.elapsed_time(b), wall - 0.5) if name == "e2e" else a.elapsed_time(b)], dev, world)
+        out[name] = (B * world * steps / (ms * 1e-3), ms / steps)
+    lv = float(l)
+    nparam = sum(p.numel() for p in net.parameters())
+    gstep.release()
+    del gstep, opt, net
+    torch.cuda.empty_cache()
+    return {"metric": f"train_{kind}_images_per_sec_{img}", "value": out["value"][0], "unit": "images/s",
+            "ms_per_step": out["value"][1], "steps": steps, "per_gpu_batch": B, "n_classes": C, "loss": lv,
+            "loss_fn": "BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3)" if kind == "ce"
+                       else "BSL.LovaszSoftmax(classes='present', ignore=19, n_branches=2)",
+            "e2e": {"value": out["e2e"][0], "unit": "images/s", "ms_per_step": out["e2e"][1],
+                    "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
+            "collective": (f"one fp32 all-reduce(AVG) of {nparam * 4 / 1e6:.0f} MB of gradients per step, captured in the step "
+                           "graph (inside the timed region)") if world > 1 else "none (1 rank)",
+            "dtype": "bf16 activations, fp32 master weights / gradients", "optimizer": "SGD momentum 0.9 wd 5e-4, 3 param groups",
+            "l2": "a step touches > 10 GB; no flush"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,10 +405,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the conv kernel")
+    ap.add_argument("--legs", default="all", help="comma list of extra workloads after the headline: cityscapes_sweep, "
+                                                  "train_ce, train_lovasz; 'all' (default) or 'none'")
     args = ap.parse_args()
     set_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
+    if args.no_pdl:
+        os.environ["EESEG_CONV_PDL"] = "0"          # read once when the library is first used
 
     import torch
     import torch.distributed as dist
@@ -275,16 +432,22 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     steps = args.steps
+    legs = ([] if args.legs == "none" else ["cityscapes_sweep", "train_ce", "train_lovasz"] if args.legs == "all"
+            else [l for l in args.legs.split(",") if l])
+    if args.workload != "voc513":
+        legs = []
 
-    if args.no_pdl:
-        _lib.lib().eeseg_conv_set_pdl(0)
     torch.manual_seed(0)
     net = branchyDeepv3(None, "deeplabv3_resnet50", 2, img_hw()[0], sections=SECTIONS, pretrained=False,
                         num_classes=N_CLASSES).to(dev).eval()
+    net.strict_kernels = True                       # a module without an eeseg kernel plan is an error, not a cuDNN call
     eng = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=not args.no_graph)
     Xh, yh = synth_batch(rank, PER_GPU_BATCH)
     Xh, yh = Xh.pin_memory(), yh.pin_memory()
     Xd, yd = Xh.to(dev), yh.to(dev)
+    # what a bf16 inference stream uploads: bf16 images (the stem rounds fp32 images to bf16 as its first step, so the
+    # results are bit-identical) and uint8 labels (void = any value >= C), prepared once like a loader worker would
+    Xh16, yh8 = Xh.to(torch.bfloat16).pin_memory(), yh.to(torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -293,7 +456,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
+    def timed(fn, k, reduce_eng=None):
         """k steps, each bracketed by CUDA events on the launching (current) stream, L2 flushed
         between steps; returns (sum of step ms, wall ms incl. flushes)."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
@@ -304,8 +467,8 @@ def main():
             a.record()
             fn()
             b.record()
-        if world > 1:
-            eng.all_reduce()           # the sweep's one integer collective (once, not per step)
+        if world > 1 and reduce_eng is not None:
+            reduce_eng.all_reduce()           # the sweep's one integer collective (once, not per step)
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
         return sum(a.elapsed_time(b) for a, b in ev), wall
@@ -313,22 +476,15 @@ def main():
     def step_device():
         eng.evaluate(Xd, yd)
 
-    def step_e2e():
-        if eng.use_graph:
-            Xs, ys = eng.static_inputs(Xh.shape)          # H2D straight into the graph's input buffers
-            Xs.copy_(Xh, non_blocking=True)
-            ys.copy_(yh, non_blocking=True)
-            out = eng.replay(Xh.shape)
-        else:
-            out = eng.evaluate(Xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
-        return out["exit"].cpu(), out["scores"].cpu()    # D2H of the per-image results (syncs)
-
-    # eeseg kernel launches of one step (counted on an eager step; a graph replay re-issues the same)
+    # eeseg kernel launches and conv FLOPs of one step (counted on an eager step; a graph replay re-issues the same)
     eng_count = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=False)
     eng_count.evaluate(Xd, yd)
+    flop_log = []
+    head_plan.FLOP_LOG = flop_log
     c0 = _lib.launch_count()
     eng_count.evaluate(Xd, yd)
     launches_per_step = _lib.launch_count() - c0
+    head_plan.FLOP_LOG = None
     del eng_count
     for _ in range(warmup):
         step_device()
@@ -337,49 +493,65 @@ def main():
         sampler.start()
     l0 = _lib.launch_count()
     eng.reset()                                   # exit statistics of the timed steps only
-    dev_ms, wall_ms = timed(step_device, steps)
+    dev_ms, wall_ms = timed(step_device, steps, eng)
     launches = _lib.launch_count() - l0
     exit_res = eng.results()                      # after the sweep's all-reduce: all ranks' images
 
-    for _ in range(2):
-        step_e2e()
-    # raw upload time of one step's inputs (pinned host -> device), for the e2e breakdown
-    h2d_ms = None
-    if eng.use_graph:
-        Xs, ys = eng.static_inputs(Xh.shape)
-        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(5):
-            Xs.copy_(Xh, non_blocking=True)
-            ys.copy_(yh, non_blocking=True)
-        b2.record()
-        torch.cuda.synchronize()
-        h2d_ms = a.elapsed_time(b2) / 5
-    if eng.use_graph:
-        # end to end through the public streaming API: pinned host batches in, per-image results out;
-        # uploads, graph replays and read-backs overlap (double-buffered inputs), all inside the timing
-        def host_batches(n):
-            for _ in range(n):
-                yield Xh, yh
-        for _ in eng.evaluate_pipelined(host_batches(3)):
+    # ---- end to end through the public streaming API: pinned host batches in, per-image results out; uploads, graph
+    # replays and read-backs overlap (double-buffered inputs), all inside the timing -------------------------------
+    def host_batches(n, X, y):
+        for _ in range(n):
+            yield X, y
+
+    def run_pipelined(engine, X, y):
+        for _ in engine.evaluate_pipelined(host_batches(3, X, y)):
             pass
         barrier()
         t0 = time.perf_counter()
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         n_out = 0
-        for ex, sc in eng.evaluate_pipelined(host_batches(steps)):
+        for ex, sc in engine.evaluate_pipelined(host_batches(steps, X, y)):
             n_out += ex.numel()
         b2.record()
         if world > 1:
-            eng.all_reduce()
+            engine.all_reduce()
         barrier()
         assert n_out == PER_GPU_BATCH * steps
-        e2e_ms = max(a.elapsed_time(b2), 0.0)
-        e2e_wall = (time.perf_counter() - t0) * 1e3
-        e2e_ms = max(e2e_ms, e2e_wall - 0.5)     # events bracket the stream work; the wall clock includes the last read-back
+        ms = max(a.elapsed_time(b2), 0.0)
+        wall = (time.perf_counter() - t0) * 1e3
+        return max(ms, wall - 0.5)     # events bracket the stream work; the wall clock includes the last read-back
+
+    def h2d_alone(engine, X, y):
+        Xs, ys = engine.static_inputs(X.shape)
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            Xs.copy_(X, non_blocking=True)
+            ys.copy_(y.view_as(ys), non_blocking=True)
+        b2.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b2) / 5
+
+    e2e32_ms = h2d32_ms = h2d_ms = None
+    if eng.use_graph:
+        e2e32_ms = run_pipelined(eng, Xh, yh)                     # the reference loader's dtypes: fp32 images, int64 labels
+        h2d32_ms = h2d_alone(eng, Xh, yh)
+        eng16 = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=True, input_dtype=torch.bfloat16, target_dtype=torch.uint8)
+        e2e_ms = run_pipelined(eng16, Xh16, yh8)
+        h2d_ms = h2d_alone(eng16, Xh16, yh8)
+        # same decisions and confusion matrices from either input format
+        eng.reset(); eng16.reset()
+        ra, rb = eng.evaluate(Xd, yd), eng16.evaluate(Xh16.to(dev), yh8.to(dev))
+        assert torch.equal(ra["exit"], rb["exit"]) and torch.equal(ra["pred"], rb["pred"]) and torch.equal(eng.cm, eng16.cm)
+        del eng16
     else:
+        def step_e2e():
+            out = eng.evaluate(Xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
+            return out["exit"].cpu(), out["scores"].cpu()
+        for _ in range(2):
+            step_e2e()
         e2e_ms, _ = timed(step_e2e, steps)
 
     # ---- an early-exit operating point: tau between the middle first-exit scores of the batch, so
@@ -403,121 +575,118 @@ def main():
     skip_px = [int(v) for v in eng_skip.exited_px.cpu()]
     skip_e2e_ms = None
     if eng_skip.use_graph:
-        for _ in eng_skip.evaluate_pipelined(host_batches(3)):
+        eng_skip16 = EarlyExitEngine(net, N_CLASSES, tau_mid, skip_compute=True, use_graph=True,
+                                     input_dtype=torch.bfloat16, target_dtype=torch.uint8)
+        for _ in eng_skip16.evaluate_pipelined(host_batches(3, Xh16, yh8)):
             pass
         barrier()
         t0 = time.perf_counter()
-        for ex, sc in eng_skip.evaluate_pipelined(host_batches(steps)):
+        for ex, sc in eng_skip16.evaluate_pipelined(host_batches(steps, Xh16, yh8)):
             pass
         torch.cuda.synchronize()
         skip_e2e_ms = (time.perf_counter() - t0) * 1e3
+        del eng_skip16
 
-    # ---- per-launch timing of the dominant kernel (conv igemm) with CUDA events, same steps ------
-    prof = []
-    eng_prof = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=False)   # same kernels, launched eagerly
-    eng_prof.overlap_gates = False     # gates and pooled branches in stream order: nothing shares the SMs with the
-    head_plan.OVERLAP_POOLED = False   # conv kernel being timed
-    eng_prof.evaluate(Xd, yd)
-    head_plan.PROFILE = prof
-    barrier()
-    prof_steps = []
-    for _ in range(steps):
-        flush.fill_(1)
-        # park the GPU for ~10 ms so the host enqueues the whole eager step ahead of it: the events
-        # then bracket back-to-back kernel executions, not host launch gaps
-        torch.cuda._sleep(int(2e7))
-        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sa.record()
-        eng_prof.evaluate(Xd, yd)
-        sb.record()
-        prof_steps.append((sa, sb))
-    torch.cuda.synchronize()
-    head_plan.PROFILE = None
-    # the same launches on the kernel's own clock (%globaltimer: first CTA start -> last CTA end of every
-    # launch, no events between the launches, so programmatic dependent launch overlaps as in the graph)
-    tcap = 512
-    tbuf = torch.zeros((tcap, 2), dtype=torch.int64, device=dev)
-    tbuf[:, 0] = torch.iinfo(torch.int64).max
-    torch.cuda.synchronize()
-    _lib.lib().eeseg_conv_timing(tbuf.data_ptr(), tcap)
-    torch.cuda._sleep(int(2e7))
-    eng_prof.evaluate(Xd, yd)
-    torch.cuda.synchronize()
-    n_t = _lib.lib().eeseg_conv_timing(None, 0)
-    tb = tbuf[:n_t].cpu()
-    inkernel_ms = float((tb[:, 1] - tb[:, 0]).sum()) / 1e6
-    head_plan.OVERLAP_POOLED = True
-    prof_step_ms = sum(a.elapsed_time(b) for a, b in prof_steps)
+    # ---- the dominant kernel inside the TIMED kind of step: GPU-side intervals of every kernel of a few more replays
+    # of the same graph (CUPTI activity records), conv-busy time = union of the conv_igemm_kernel intervals -----------
+    share = conv_busy = span = None
+    by_name = {}
+    try:
+        calls = kernel_intervals(step_device, 5, flush)
+        conv_busy = sum(busy_us([(a, b) for n, a, b in c if "conv_igemm_kernel" in n]) for c in calls) / len(calls)
+        span = sum(max(b for _, _, b in c) - min(a for _, a, _ in c) for c in calls) / len(calls)
+        share = conv_busy / span
+        for c in calls:
+            for n, a, b in c:
+                key = n.split("(")[0].split("<")[0].replace("void ", "").strip()[-60:]
+                by_name[key] = by_name.get(key, 0.0) + (b - a) / len(calls)
+    except Exception as err:                        # no CUPTI: fall back to the whole step as the denominator
+        by_name = {"error": f"{type(err).__name__}: {err}"}
     clocks = sampler.stop() if rank == 0 else {}
-    conv_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
-    head_ms = sum(p[0].elapsed_time(p[1]) for p in prof if p[3] == "head")
-    conv_fl = sum(p[2] for p in prof)
-    head_fl = sum(p[2] for p in prof if p[3] == "head")
-    n_conv = len(prof)
+    conv_fl = sum(f[0] for f in flop_log)
+    conv_fl_eff = sum(f[1] for f in flop_log)
+    head_fl = sum(f[0] for f in flop_log if f[2] == "head")
+    n_conv = len(flop_log)
 
-    t = torch.tensor([dev_ms, e2e_ms, conv_ms, head_ms, skip_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, conv_ms, head_ms, skip_ms = (float(v) for v in t.cpu())
+    dev_ms, e2e_ms, skip_ms = dist_max([dev_ms, e2e_ms, skip_ms], dev, world)
+
+    extra = {}
+    del eng_skip, eng_skip_eager
+    torch.cuda.empty_cache()
+    for leg in legs:
+        try:
+            if leg == "cityscapes_sweep":
+                extra[leg] = leg_cityscapes_sweep(dev, rank, world, max(4, steps // 2), warmup, barrier)
+            elif leg in ("train_ce", "train_lovasz"):
+                extra[leg] = leg_train(leg.split("_")[1], dev, rank, world, max(4, steps // 2), warmup, barrier)
+        except Exception as err:
+            import traceback
+            extra[leg] = {"error": f"{type(err).__name__}: {err}", "trace": traceback.format_exc()[-600:]}
 
     if rank == 0:
         peaks = measured_peaks()
         imgs = PER_GPU_BATCH * world * steps
         fh, fw = ((d - 1) // 8 + 1 for d in img_hw())
-        assert head_fl == head_flops(fh, fw, PER_GPU_BATCH, [1024, 2048, 2048]) * steps, "head FLOP model out of date"
-        fl = conv_fl
-        achieved = fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        head_tf = head_fl / (head_ms * 1e-3) / 1e12 if head_ms > 0 else 0.0
+        assert head_fl == head_flops(fh, fw, PER_GPU_BATCH, [1024, 2048, 2048]), "head FLOP model out of date"
+        ms_step = dev_ms / steps
+        conv_ms = ms_step * share if share is not None else ms_step
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+        achieved_eff = conv_fl_eff / (conv_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         res = exit_res
+        top = sorted(((v, k) for k, v in by_name.items() if isinstance(v, float)), reverse=True)[:8]
         line = {
             "metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 8,
+                    "h2d_bytes_per_step": (Xh16.numel() * 2 + yh8.numel()) if eng.use_graph else (Xh.numel() * 4 + yh.numel() * 8),
                     "d2h_bytes_per_step": PER_GPU_BATCH * 4 + 2 * PER_GPU_BATCH * 4, "ms_per_step": e2e_ms / steps,
                     "h2d_ms_alone": h2d_ms,
+                    "inputs": "pinned host batches: bf16 images [N,3,H,W] + uint8 labels (bit-identical exits, maps and "
+                              "confusion matrices to the fp32 / int64 upload: checked in this run)" if eng.use_graph else "fp32 / int64",
+                    "fp32_int64_inputs": {"value": imgs / (max(e2e32_ms, 1e-9) * 1e-3) if e2e32_ms else None,
+                                          "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 8, "h2d_ms_alone": h2d32_ms,
+                                          "note": "rank 0 timing"},
                     "mode": "pipelined: upload of batch k+1 and read-back of batch k-1 overlap the graph replay of batch k"
                             if eng.use_graph else "sequential",
                     "l2": "every step's inputs arrive from pinned host memory (never cache-resident); no flush between "
                           "batches, so weights may stay in L2 as in a real stream — `value` is the flushed number"},
             "gpu_launches": int(launches) if args.no_graph else int(launches_per_step * steps),
             "launch_mode": "eager" if args.no_graph else "cuda_graph_replay (eeseg kernels captured in the graph)",
-            "roofline": {"kernel": f"conv_igemm_kernel (tcgen05 implicit GEMM, {n_conv // steps} launches/step: "
-                                   "exit heads + ResNet bottlenecks)",
+            "roofline": {"kernel": f"conv_igemm_kernel (tcgen05 implicit GEMM, {n_conv} launches/step: "
+                                   "exit heads + ResNet stem / bottlenecks)",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": conv_traffic(),
-                         "exit_heads_only": {"achieved": head_tf, "frac": head_tf / peak,
-                                             "ms_per_step": head_ms / steps, "flops_per_step": head_fl / steps},
+                         "frac": achieved / peak, "frac_nominal": achieved / peak, "frac_effective": achieved_eff / peak,
+                         "achieved_effective": achieved_eff, "traffic": conv_traffic(),
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                         "launches_timed": n_conv, "conv_ms_per_step": conv_ms / steps,
-                         "conv_share_of_step": conv_ms / prof_step_ms if prof_step_ms else None,
-                         "timing": "CUDA events around every conv launch of an eagerly launched step (GPU parked first so "
-                                   "launches are back to back); the per-launch events cost ~15 % over the graph replay",
-                         "eager_event_step_ms": prof_step_ms / steps,
-                         "in_kernel_clock": {"conv_ms_per_step": inkernel_ms,
-                                             "achieved": (fl / steps) / (inkernel_ms * 1e-3) / 1e12 if inkernel_ms > 0 else None,
-                                             "frac": (fl / steps) / (inkernel_ms * 1e-3) / 1e12 / peak if inkernel_ms > 0 else None,
-                                             "how": "sum over one step's conv launches of (last CTA end - first CTA start) on "
-                                                    "%globaltimer, launches not separated by events"},
-                         "flops_per_step": fl / steps},
+                         "conv_ms_per_step": conv_ms, "conv_share_of_step": share,
+                         "flops_per_step": conv_fl, "flops_per_step_effective": conv_fl_eff,
+                         "flops_exit_heads": head_fl,
+                         "timing": "conv_ms_per_step = ms_per_step (CUDA events around the graph replays of the timed region) x "
+                                   "conv share; share = union of the conv_igemm_kernel intervals / span of the step, from the "
+                                   "GPU-side kernel timestamps (CUPTI activity records via torch.profiler) of 5 further replays of "
+                                   "the SAME graph with the same L2 flush; nominal FLOPs count padding taps the kernel skips, "
+                                   "effective FLOPs do not",
+                         "step_span_us_profiled": span, "conv_busy_us_profiled": conv_busy,
+                         "kernel_us_per_step_top": [{"kernel": k, "us": round(v, 1)} for v, k in top]},
             "clocks": clocks,
             "wall_ms_timed_region": wall_ms,
             "exit_stats": {k: res[k] for k in ("b1_count", "b2_count", "count_out", "out_gl")},
             "early_exit_operating_point": {
                 "tau": tau_mid, "value": imgs / (skip_ms * 1e-3), "unit": "images/s", "ms_per_step": skip_ms / steps,
                 "mode": "skip_compute engine, one CUDA graph per (exit stage, active image count), one 4-byte D2H per gate "
-                        "for the active count; rank 0 counters" if eng_skip.use_graph else "skip_compute engine, eager launches",
+                        "for the active count; rank 0 counters" if eng_skip_use_graph(args) else "skip_compute engine, eager launches",
                 "e2e": {"value": imgs / (skip_e2e_ms * 1e-3), "unit": "images/s",
-                        "how": "pinned host batches through evaluate_pipelined, rank 0 wall clock (x world size)"} if skip_e2e_ms else None,
+                        "how": "pinned host batches (bf16 images, uint8 labels) through evaluate_pipelined, rank 0 wall clock (x world size)"} if skip_e2e_ms else None,
                 "eager_launch_value": imgs / (skip_eager_ms * 1e-3),
                 "images_per_exit": skip_counts[:-1],
                 "pct_images_exited_early": 100.0 * sum(skip_counts[:-2]) / max(1, skip_counts[-1]),
                 "pct_pixels_below_tau_per_gate": [100.0 * px / max(1, PER_GPU_BATCH * steps * img_hw()[0] * img_hw()[1])
                                                   for px in skip_px[:-1]],
             },
+            "extra_workloads": extra,
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_reference_run(steps=2, warmup=1)
@@ -526,6 +695,10 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def eng_skip_use_graph(args):
+    return not args.no_graph
 
 
 if __name__ == "__main__":

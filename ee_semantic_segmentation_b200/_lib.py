@@ -10,7 +10,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "eeseg.h")
 
 _lib = None
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 
 c_i, c_i64, c_f, c_p, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
@@ -21,6 +21,7 @@ PROTOTYPES = {
     "eeseg_launch_count": (c_i64, []),
     "eeseg_confusion_hist": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
     "eeseg_exit_accumulate": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p, c_p]),
+    "eeseg_exit_accumulate_u8": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p, c_p]),
     "eeseg_exit_gate_num_partials": (c_i, [c_i, c_i]),
     "eeseg_exit_gate_pixels": (c_i, [c_p, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i,
                                      c_i, c_i, c_f, c_p, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -62,13 +63,18 @@ PROTOTYPES = {
     "eeseg_conv_igemm_grouped": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i,
                                        c_p, c_i64, c_i, c_p, c_i, c_p]),
     "eeseg_stem_space_to_depth": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
+    "eeseg_stem_space_to_depth_any": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_dense_bn_act": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
-    "eeseg_conv_debug_stats": (c_i, [c_p]),
-    "eeseg_conv_set_pdl": (c_i, [c_i]),
-    "eeseg_conv_timing": (c_i, [c_p, c_i]),
     "eeseg_global_avgpool_workspace_bytes": (c_sz, [c_i, c_i]),
     "eeseg_global_avgpool_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_p, c_p, c_p]),
+}
+
+
+# present only in the -DEESEG_TUNING build (include/eeseg_tuning.h); bound when the loaded library has them
+TUNING_PROTOTYPES = {
+    "eeseg_conv_debug_stats": (c_i, [c_p]),
+    "eeseg_conv_timing": (c_i, [c_p, c_i]),
 }
 
 
@@ -90,6 +96,10 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        for name, (res, args) in TUNING_PROTOTYPES.items():
+            if hasattr(l, name):
+                fn = getattr(l, name)
+                fn.restype, fn.argtypes = res, args
         if l.eeseg_abi_version() != 1:
             raise RuntimeError("libeeseg_b200.so ABI version mismatch")
         _lib = l

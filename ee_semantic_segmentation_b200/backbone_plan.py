@@ -97,17 +97,28 @@ class StemPlan:
                 and m.kernel_size in (3, (3, 3)) and m.stride in (2, (2, 2)) and m.padding in (1, (1, 1))
                 and m.dilation in (1, (1, 1)) and not m.ceil_mode)
 
-    def run(self, x):
-        """x fp32 NCHW [N,3,H,W] -> bf16 NHWC [N, H/4-ish, W/4-ish, 64]."""
+    def run(self, x, norm=None):
+        """x NCHW [N,3,H,W] fp32, bf16 or uint8 -> bf16 NHWC [N, H/4-ish, W/4-ish, 64]. The kernel's first step rounds
+        the image to bf16, so a bf16 upload gives bit-identical results at half the bytes; uint8 pixels are normalised
+        inside the kernel, (u/255 - mean[c]) / std[c] with norm = (mean, std) (3 floats each; None: mean 0, std 1) —
+        what the reference's loader does on the CPU (get_seg_datasets.py:62-70)."""
+        import ctypes
         N, _, H, W = x.shape
         dev = x.device
-        x = x.float().contiguous()
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+            x = x.float()
+        x = x.contiguous()
+        kind = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.uint8: _lib.U8}[x.dtype]
+        mean = std = None
+        if norm is not None and x.dtype == torch.uint8:
+            mean = (ctypes.c_float * 3)(*[float(v) for v in norm[0]])
+            std = (ctypes.c_float * 3)(*[float(v) for v in norm[1]])
         H2, W2 = (H + 1) // 2, (W + 1) // 2
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             s2d = torch.empty((N, H2, W2, 64), dtype=torch.bfloat16, device=dev)
-            _lib.check(_lib.lib().eeseg_stem_space_to_depth(x.data_ptr(), N, H, W, s2d.data_ptr(), stream),
-                       "eeseg_stem_space_to_depth")
+            _lib.check(_lib.lib().eeseg_stem_space_to_depth_any(x.data_ptr(), kind, mean, std, N, H, W, s2d.data_ptr(),
+                                                                stream), "eeseg_stem_space_to_depth_any")
             y = torch.empty((N, H2, W2, self.cout), dtype=torch.bfloat16, device=dev)
             conv_igemm(s2d, self.w, self.s, self.b, 1, True, y, _lib.BF16, self.cout, pad=2)
             ho, wo = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
@@ -141,20 +152,20 @@ class SectionPlan:
             mods = mods[4:]
         self.ops += [BottleneckPlan(m) if isinstance(m, Bottleneck) else m for m in mods]
 
-    def run(self, x):
-        """x: [N,C,h,w] tensor (any float dtype / memory format). Returns a bf16 [N,C',h',w'] tensor
-        in channels_last memory format (an NHWC buffer viewed as NCHW)."""
+    def run(self, x, norm=None):
+        """x: [N,C,h,w] tensor (any float dtype / memory format; uint8 images for a section that starts with the stem).
+        Returns a bf16 [N,C',h',w'] tensor in channels_last memory format (an NHWC buffer viewed as NCHW)."""
         nhwc = None
         head_plan.PROFILE_TAG = "backbone"
         try:
-            return self._run(x, nhwc)
+            return self._run(x, nhwc, norm)
         finally:
             head_plan.PROFILE_TAG = "head"
 
-    def _run(self, x, nhwc):
+    def _run(self, x, nhwc, norm=None):
         for op in self.ops:
             if isinstance(op, StemPlan):
-                nhwc = op.run(x)
+                nhwc = op.run(x, norm)
             elif isinstance(op, BottleneckPlan):
                 if nhwc is None:
                     nhwc = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()

@@ -48,7 +48,10 @@ class BrSegLoss(SegLoss):
 
 def _no_void(s_t, n_pixels):
     """F.one_hot(targets, num_classes=C) of the reference raises on labels outside [0,C) (branchy_seg_losses.py:44,92)."""
-    if float(s_t.sum()) != float(n_pixels):
+    # the per-class counts are fp32 (exact per class up to 2^24 pixels); summed in fp64 so the total stays exact for
+    # any batch (an fp32 sum of an odd total above 2^24 rounds and raised spuriously). One host read: these losses
+    # cannot be captured in a CUDA graph (train_funcs.GraphedTrainStep takes the CE, Lovasz and Jaccard losses).
+    if int(s_t.double().sum().round().item()) != int(n_pixels):
         raise RuntimeError("Class values must be smaller than num_classes.")
 
 

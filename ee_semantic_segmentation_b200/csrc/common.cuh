@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/eeseg.h"
 
@@ -42,6 +43,20 @@ inline int check_launch(const char* what) {
       return EESEG_ERR_CUDA;                                                   \
     }                                                                          \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and kernel, race-free (the attribute is per
+// device; callers may launch from several host threads)
+template <typename K>
+inline cudaError_t ensure_max_smem(K kernel, int bytes) {
+  static std::once_flag once[64];
+  static cudaError_t result[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  std::call_once(once[dev], [&] { result[dev] = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+  return result[dev];
+}
 
 // ---- typed scalar access ------------------------------------------------------------------------
 __device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }

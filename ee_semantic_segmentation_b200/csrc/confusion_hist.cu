@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(256) cm_from_map_kernel(const P* __restrict__ 
 // argmax map of the exit it took (amax_all[exit][n]) is histogrammed against the target and added to
 // the accumulators of that exit and of the global slot E; exit counters are bumped; still-active
 // images (exit_idx < 0) are assigned the final exit. One launch instead of a dozen tiny library ops.
-template <int PIX>
+template <int PIX, typename TG>
 __global__ void __launch_bounds__(256) exit_accumulate_kernel(
-    const uint8_t* __restrict__ amax_all, const int64_t* __restrict__ targets, int32_t* __restrict__ exit_idx,
+    const uint8_t* __restrict__ amax_all, const TG* __restrict__ targets, int32_t* __restrict__ exit_idx,
     int E, int N, int C, int64_t HW, int copies, unsigned long long* __restrict__ cm_acc,
     unsigned long long* __restrict__ counts, uint8_t* __restrict__ pred) {
   extern __shared__ unsigned hist[];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) exit_accumulate_kernel(
   int e = exit_idx[n];
   if (e < 0 || e >= E) e = E - 1;
   const uint8_t* pr = amax_all + ((int64_t)e * N + n) * HW;
-  const int64_t* tg = targets + (int64_t)n * HW;
+  const TG* tg = targets + (int64_t)n * HW;
   const int64_t step = (int64_t)gridDim.x * blockDim.x * PIX;
   for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x * PIX + (threadIdx.x & ~31); p0 < HW; p0 += step) {
 #pragma unroll
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) exit_accumulate_kernel(
       int key = -1;
       if (pp < HW) {
         const int a = (int)__ldg(pr + pp);
-        const int64_t t = __ldg(tg + pp);
+        const int64_t t = (int64_t)__ldg(tg + pp);     // uint8 labels widen here: 0..C-1 classes, >= C void
         if (pred) pred[(int64_t)n * HW + pp] = (uint8_t)a;
         if (a < C) key = ((t >= 0 && t < C) ? (int)t : C) * C + a;
       }
@@ -328,6 +328,27 @@ extern "C" int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype,
   return check_launch("cm_from_map_kernel");
 }
 
+extern "C" int eeseg_exit_accumulate_u8(const uint8_t* amax_all, const uint8_t* targets, int32_t* exit_idx, int E,
+                                        int N, int C, int64_t HW, int64_t* cm_acc, int64_t* counts, uint8_t* pred,
+                                        void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EESEG_REQUIRE(amax_all && targets && exit_idx && cm_acc && counts, "exit_accumulate: null pointer");
+  EESEG_REQUIRE(E >= 1 && C >= 1 && C <= 255 && HW >= 1, "exit_accumulate: bad sizes (uint8 labels: C <= 255)");
+  if (N <= 0) return EESEG_OK;
+  const size_t bytes1 = (size_t)(C + 1) * C * sizeof(unsigned);
+  int copies = (int)((48 * 1024) / bytes1);
+  EESEG_REQUIRE(copies > 0, "exit_accumulate: C=%d too large", C);
+  if (copies > 8) copies = 8;
+  constexpr int kPix = 4;
+  int64_t want = (HW + 256 * kPix - 1) / (256 * kPix);
+  int64_t cap = (kNumSMs * 8 + N - 1) / N;
+  dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)N);
+  exit_accumulate_kernel<kPix, uint8_t><<<grid, 256, copies * bytes1, stream>>>(
+      amax_all, targets, exit_idx, E, N, C, HW, copies, reinterpret_cast<unsigned long long*>(cm_acc),
+      reinterpret_cast<unsigned long long*>(counts), pred);
+  return check_launch("exit_accumulate_kernel");
+}
+
 extern "C" int eeseg_exit_accumulate(const uint8_t* amax_all, const int64_t* targets, int32_t* exit_idx, int E,
                                      int N, int C, int64_t HW, int64_t* cm_acc, int64_t* counts, uint8_t* pred,
                                      void* stream_) {
@@ -343,7 +364,7 @@ extern "C" int eeseg_exit_accumulate(const uint8_t* amax_all, const int64_t* tar
   int64_t want = (HW + 256 * kPix - 1) / (256 * kPix);
   int64_t cap = (kNumSMs * 8 + N - 1) / N;
   dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)N);
-  exit_accumulate_kernel<kPix><<<grid, 256, copies * bytes1, stream>>>(
+  exit_accumulate_kernel<kPix, int64_t><<<grid, 256, copies * bytes1, stream>>>(
       amax_all, targets, exit_idx, E, N, C, HW, copies, reinterpret_cast<unsigned long long*>(cm_acc),
       reinterpret_cast<unsigned long long*>(counts), pred);
   return check_launch("exit_accumulate_kernel");

@@ -19,6 +19,8 @@
 //   64-channel block — full 128 B lines to L2, image-edge rows clipped by the tensor map.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -72,10 +74,16 @@ struct ConvParams {
   unsigned long long* tslot; // optional {min start, max end} wall-clock ns of this launch (eeseg_conv_timing)
 };
 
-// cycle accounting for tuning: DBG_T(slot, stmt) adds the cycles `stmt` takes to counter `slot`
+// Tuning instrumentation (cycle accounting per role, %globaltimer launch brackets) exists only in builds with
+// -DEESEG_TUNING (`python -m ee_semantic_segmentation_b200.build --tuning` -> libeeseg_b200_tuning.so, used by
+// tools/conv_debug.py and tools/conv_step_times.py): the shipped library has neither the code nor the hooks.
+#ifdef EESEG_TUNING
+#define DBG_ON(p) ((p).dbg != nullptr)
+#define TS_ON(p) ((p).tslot != nullptr)
+// DBG_T(slot, stmt) adds the cycles `stmt` takes to counter `slot`
 #define DBG_T(slot, stmt)                                   \
   do {                                                      \
-    if (p.dbg) {                                            \
+    if (DBG_ON(p)) {                                            \
       const long long t0__ = clock64();                     \
       stmt;                                                 \
       dbg_acc[slot] += (unsigned long long)(clock64() - t0__); \
@@ -83,6 +91,14 @@ struct ConvParams {
       stmt;                                                 \
     }                                                       \
   } while (0)
+#else
+#define DBG_ON(p) false
+#define TS_ON(p) false
+#define DBG_T(slot, stmt) \
+  do {                    \
+    stmt;                 \
+  } while (0)
+#endif
 
 __host__ __device__ inline uint32_t tmem_cols_for(int bn) {
   return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : bn <= 256 ? 256u : 512u;
@@ -136,11 +152,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* s_shift = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((p.dbg || p.tslot) && threadIdx.x == 0) {   // kernel-entry wall clock (ns) of this CTA
+  if ((DBG_ON(p) || TS_ON(p)) && threadIdx.x == 0) {   // kernel-entry wall clock (ns) of this CTA
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    if (p.dbg) p.dbg[(size_t)blockIdx.x * 32 + 16] = g;
-    if (p.tslot) atomicMin(p.tslot, g);
+    if (DBG_ON(p)) p.dbg[(size_t)blockIdx.x * 32 + 16] = g;
+    if (TS_ON(p)) atomicMin(p.tslot, g);
   }
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.Cout / p.BN;
@@ -235,7 +251,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (p.dbg) {
+      if (DBG_ON(p)) {
         unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32;
         d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = (unsigned long long)(clock64() - dbg_t0); d[3] = (unsigned long long)it;
       }
@@ -287,7 +303,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         umma_commit(tmem_full_bar + a);   // accumulator complete
       }
-      if (p.dbg) {
+      if (DBG_ON(p)) {
         unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32 + 4;
         d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = (unsigned long long)(clock64() - dbg_t0);
       }
@@ -305,7 +321,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long dbg_t0 = clock64();
     unsigned long long dbg_g0 = 0;
-    if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+    if (DBG_ON(p)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
     long long dbg_t1 = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -315,19 +331,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int a = it & 1;
       const uint32_t aph = ((uint32_t)it >> 1) & 1u;
       // every epilogue thread passed the last barrier of the previous tile: scale/shift can change
-      if (p.dbg) dbg_t1 = clock64();
+      if (DBG_ON(p)) dbg_t1 = clock64();
       for (int i = et; i < p.BN; i += kEpiThreads) {
         s_scale[i] = q.scale[n0 + i];
         s_shift[i] = q.shift[(int64_t)n_img * p.shift_sn + n0 + i];
       }
-      if (p.dbg) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
+      if (DBG_ON(p)) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
       // the staging tile is reused every tile: the previous TMA stores must have read it out
       if (et == 0 && !p.direct) DBG_T(2, bulk_wait_read(0));
       DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
-      if (p.dbg) dbg_t1 = clock64();
+      if (DBG_ON(p)) dbg_t1 = clock64();
       for (int col = col_lo; col < col_hi; col += 16) {
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)col, v);
@@ -405,7 +421,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (p.dbg) { dbg_acc[5] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
+      if (DBG_ON(p)) { dbg_acc[5] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
       // all TMEM reads of this tile are done: hand the accumulator buffer back
       tcgen05_fence_before();
       __syncwarp();
@@ -415,16 +431,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
       fence_proxy_async();
       asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (p.dbg) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
+      if (DBG_ON(p)) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
       if (et == 0 && !p.direct) {
         for (int blk = 0; blk < p.nblk; ++blk)
           tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, q.ch_off + n0 + blk * p.blk_cols, x0, y0, n_img);
         bulk_commit();
       }
-      if (p.dbg) dbg_acc[7] += (unsigned long long)(clock64() - dbg_t1);
+      if (DBG_ON(p)) dbg_acc[7] += (unsigned long long)(clock64() - dbg_t1);
     }
     if (et == 0) bulk_wait_read(0);   // shared memory must outlive the stores' reads
-    if (p.dbg && et == 0) {
+    if (DBG_ON(p) && et == 0) {
       unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32 + 8;
       d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3];
       d[4] = (unsigned long long)(clock64() - dbg_t0);
@@ -441,11 +457,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
                  : "memory");
   }
-  if ((p.dbg || p.tslot) && threadIdx.x == 0) {   // kernel-exit wall clock (ns)
+  if ((DBG_ON(p) || TS_ON(p)) && threadIdx.x == 0) {   // kernel-exit wall clock (ns)
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    if (p.dbg) p.dbg[(size_t)blockIdx.x * 32 + 17] = g;
-    if (p.tslot) atomicMax(p.tslot + 1, g);
+    if (DBG_ON(p)) p.dbg[(size_t)blockIdx.x * 32 + 17] = g;
+    if (TS_ON(p)) atomicMax(p.tslot + 1, g);
   }
 }
 
@@ -501,12 +517,12 @@ __global__ void avgpool_final_kernel(const float* __restrict__ part, int64_t hw,
 
 using namespace eeseg;
 
+#ifdef EESEG_TUNING
 static unsigned long long* g_conv_dbg = nullptr;
-static int g_conv_pdl = 1;
 static unsigned long long* g_conv_tbuf = nullptr;
 static int g_conv_tcap = 0, g_conv_tnext = 0;
-// Measurement hook: every following conv launch i records {first CTA start, last CTA end} in wall-clock
-// nanoseconds (%globaltimer) at buffer[2*i], buffer[2*i+1] (i < capacity; the caller initialises starts
+// Measurement hook (tuning builds only): every following conv launch i records {first CTA start, last CTA end} in
+// wall-clock nanoseconds (%globaltimer) at buffer[2*i], buffer[2*i+1] (i < capacity; the caller initialises starts
 // to UINT64_MAX and ends to 0). NULL switches it off. Returns the number of launches recorded so far.
 extern "C" int eeseg_conv_timing(void* device_buffer, int capacity) {
   const int n = g_conv_tnext;
@@ -515,17 +531,22 @@ extern "C" int eeseg_conv_timing(void* device_buffer, int capacity) {
   g_conv_tnext = 0;
   return n;
 }
-// Programmatic dependent launch of the conv kernel on/off (default on); returns the previous setting.
-extern "C" int eeseg_conv_set_pdl(int enable) {
-  const int old = g_conv_pdl;
-  g_conv_pdl = enable ? 1 : 0;
-  return old;
-}
-// Tuning hook (not part of the product path): device buffer of [148][32] uint64 cycle counters that
-// the next conv launches fill (producer / MMA / epilogue wait times); NULL switches it off.
+// Tuning hook: device buffer of [148][32] uint64 cycle counters that the next conv launches fill (producer / MMA /
+// epilogue wait times); NULL switches it off.
 extern "C" int eeseg_conv_debug_stats(void* device_buffer) {
   g_conv_dbg = reinterpret_cast<unsigned long long*>(device_buffer);
   return EESEG_OK;
+}
+#endif
+
+// Programmatic dependent launch of the conv kernels: on unless the environment says EESEG_CONV_PDL=0 when the library
+// is first used (read once; there is no mutable process-wide switch).
+static bool conv_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EESEG_CONV_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 struct HostProblem {
@@ -603,8 +624,13 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   if (residual && BN < 64) { set_error("conv_igemm: residual needs a 64-column tile"); return EESEG_ERR_UNSUPPORTED; }
   p.BN = BN;
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
+#ifdef EESEG_TUNING
   p.dbg = g_conv_dbg;
   p.tslot = (g_conv_tbuf && g_conv_tnext < g_conv_tcap) ? g_conv_tbuf + 2 * (size_t)(g_conv_tnext++) : nullptr;
+#else
+  p.dbg = nullptr;
+  p.tslot = nullptr;
+#endif
   // epilogue blocks: 128 B of output per pixel row (64 bf16 / 32 fp32 channels), swizzled; narrower
   // tiles use one dense block
   const int full_cols = 128 / oes;
@@ -673,11 +699,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_igemm: cuTensorMapEncodeTiled(w) failed: %d", (int)r); return EESEG_ERR_CUDA; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    EESEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  EESEG_CUDA(ensure_max_smem(conv_igemm_kernel, 227 * 1024));
   dim3 grid((unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs));   // persistent: one CTA per SM
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -686,7 +708,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
-  attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = conv_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmx, wm, tmo, tmr, p));

@@ -292,11 +292,7 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   if (rc) return rc;
   rc = encode_act_map(encode, &tmx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cin, w, h, N, Cin, 64, p.BW, p.BH, 1, true, "x");
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EESEG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  EESEG_CUDA(ensure_max_smem(conv_wgrad_kernel, 227 * 1024));
   conv_wgrad_kernel<<<base_items * p.ksplit, kWgThreads, smem_bytes, stream>>>(tmdy, tmx, p);
   rc = check_launch("conv_wgrad_kernel");
   if (rc || p.ksplit == 1) return rc;

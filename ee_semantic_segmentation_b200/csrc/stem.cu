@@ -6,8 +6,20 @@
 
 namespace eeseg {
 
-__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, int N, int H, int W,
-                                                        int H2, int W2, __nv_bfloat16* __restrict__ out) {
+// image element -> float: fp32 / bf16 as stored; uint8 as ToTensor + Normalize would produce it,
+// (u/255 - mean[c]) / std[c] = u * a[c] + b[c] (a, b folded on the host side of the launcher)
+__device__ __forceinline__ float img_ld(const float* p, float, float) { return __ldg(p); }
+__device__ __forceinline__ float img_ld(const __nv_bfloat16* p, float, float) { return __bfloat162float(__ldg(p)); }
+__device__ __forceinline__ float img_ld(const uint8_t* p, float a, float b) { return fmaf((float)__ldg(p), a, b); }
+
+struct StemNorm {
+  float a[3], b[3];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const T* __restrict__ x, int N, int H, int W,
+                                                        int H2, int W2, const StemNorm nm,
+                                                        __nv_bfloat16* __restrict__ out) {
   // one thread per output pixel (n, Y, X): 4 horizontal taps x (2x2 space-to-depth x 3 channels) = 48
   // values from input rows 2Y, 2Y+1 and columns 2(X-2) .. 2(X+1)+1, then 16 zero channels
   const int64_t total = (int64_t)N * H2 * W2;
@@ -28,7 +40,7 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__
           for (int c = 0; c < 3; ++c) {
             const int yy = 2 * Y + a, xx = 2 * (X + u - 2) + b;
             v[(a * 2 + b) * 3 + c] =
-                (yy < H && xx >= 0 && xx < W) ? __ldg(x + (((int64_t)n * 3 + c) * H + yy) * W + xx) : 0.f;
+                (yy < H && xx >= 0 && xx < W) ? img_ld(x + (((int64_t)n * 3 + c) * H + yy) * W + xx, nm.a[c], nm.b[c]) : 0.f;
           }
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
@@ -206,15 +218,34 @@ extern "C" int eeseg_maxpool3x3s2_nhwc_bwd(const void* dout, const void* idx, in
   return check_launch("maxpool3x3s2_bwd_kernel");
 }
 
-extern "C" int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream) {
+extern "C" int eeseg_stem_space_to_depth_any(const void* x, int x_kind, const float* mean, const float* std_, int N, int H,
+                                             int W, void* out, void* stream) {
   EESEG_REQUIRE(x && out, "stem_space_to_depth: null pointer");
   EESEG_REQUIRE(((uintptr_t)out & 15) == 0, "stem_space_to_depth: output must be 16-byte aligned");
+  EESEG_REQUIRE(x_kind == EESEG_F32 || x_kind == EESEG_BF16 || x_kind == EESEG_U8, "stem_space_to_depth: image dtype %d", x_kind);
   if (N <= 0) return EESEG_OK;
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
   const int64_t total = (int64_t)N * H2 * W2;
   const int blocks = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
-  stem_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, H2, W2, (__nv_bfloat16*)out);
+  StemNorm nm;
+  for (int c = 0; c < 3; ++c) {   // host arrays (3 floats each); NULL = plain u/255
+    const float m = mean ? mean[c] : 0.f, sd = std_ ? std_[c] : 1.f;
+    EESEG_REQUIRE(sd != 0.f, "stem_space_to_depth: zero std");
+    nm.a[c] = 1.f / (255.f * sd);
+    nm.b[c] = -m / sd;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_kind == EESEG_F32)
+    stem_s2d_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, N, H, W, H2, W2, nm, (__nv_bfloat16*)out);
+  else if (x_kind == EESEG_BF16)
+    stem_s2d_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, N, H, W, H2, W2, nm, (__nv_bfloat16*)out);
+  else
+    stem_s2d_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)x, N, H, W, H2, W2, nm, (__nv_bfloat16*)out);
   return check_launch("stem_s2d_kernel");
+}
+
+extern "C" int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream) {
+  return eeseg_stem_space_to_depth_any(x, EESEG_F32, nullptr, nullptr, N, H, W, out, stream);
 }
 
 extern "C" int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream) {

@@ -31,7 +31,7 @@ class mIoU:
         Gt = tch.as_tensor(Gt).reshape(1, -1).to(tch.int64)
         C = self.n_classes
         if Img.is_cuda:
-            cm = ops.confusion_hist(Img.clamp(0, C - 1), Gt.to(Img.device), C)[0].cpu().numpy()
+            cm = ops.confusion_hist(Img, Gt.to(Img.device), C)[0].cpu().numpy()   # out-of-range predictions are dropped, as on CPU
         else:
             g = np.where((Gt.numpy() >= 0) & (Gt.numpy() < C), Gt.numpy(), C)[0]
             p = Img.numpy()[0]
@@ -65,6 +65,10 @@ class eval_ee_deeplabv3():
             and getattr(ee_model, 'fast_inference', False)
         self._graphs = {}
         self._seen = {}
+
+    def _weights_token(self):
+        f = getattr(self.model, 'weights_token', None)
+        return f() if f is not None else getattr(self.model, 'weights_epoch', 0)
 
     def _flop_table(self, shape):
         """(main_flops per section, branch_flops per head incl. classifier) for an input shape."""
@@ -108,7 +112,7 @@ class eval_ee_deeplabv3():
         return g, out
 
     def _graph_state(self, X):
-        key = (tuple(X.shape[1:]), X.device, getattr(self.model, 'weights_epoch', 0))
+        key = (tuple(X.shape[1:]), X.device, self._weights_token())
         if any(k[2] != key[2] for k in self._graphs):      # weights changed: release the graphs of the old plans
             self._graphs.clear()
         st = self._graphs.get(key)
@@ -122,6 +126,7 @@ class eval_ee_deeplabv3():
         if i not in st['sec']:
             xin = st['x'] if i == 0 else st['sec'][i - 1][1]
             st['sec'][i] = self._capture(lambda: self.model.run_section(i, xin))
+            st.setdefault('plans', []).append(dict(getattr(self.model, '_section_plans', {})))   # kept alive with the graph
         st['sec'][i][0].replay()
         return st['sec'][i][1]
 
@@ -138,6 +143,7 @@ class eval_ee_deeplabv3():
                 return None, ops.exit_gate(low, inp_shape, layout='NHWC', n_classes=model.num_classes,
                                            want_score=False).amax
             st['head'][(i, gated)] = self._capture(fn)
+            st.setdefault('plans', []).append(dict(getattr(self.model, '_plans', {})))
         g, out = st['head'][(i, gated)]
         g.replay()
         return out
@@ -189,7 +195,7 @@ class eval_ee_deeplabv3():
     def __call__(self, X):
         if self.use_graph and X.is_cuda:
             # graphs are captured the second time an input shape shows up (images of varying sizes stay eager)
-            key = (tuple(X.shape), X.device, getattr(self.model, 'weights_epoch', 0))
+            key = (tuple(X.shape), X.device)
             self._seen[key] = self._seen.get(key, 0) + 1
             if self._seen[key] >= 2:
                 return self._call_graphed(X)

@@ -20,12 +20,17 @@ from . import ops
 
 class EarlyExitEngine:
     def __init__(self, net, n_classes, tau, metric='ent', size=1, skip=0, skip_compute=False,
-                 use_graph=False):
+                 use_graph=False, input_dtype=torch.float32, target_dtype=torch.int64):
         """use_graph: capture the whole (static) step — backbone sections, heads, gates, decision,
         histogram — into one CUDA graph per input shape and replay it; removes the per-launch host
         overhead of the ~700 launches of a step. With skip_compute the step is captured as one
         graph per (exit stage, number of still-active images) instead: after each gate the host reads
         the 4-byte active count and replays the next stage's graph of that size (_skip_state)."""
+        # dtypes of the graph-mode input buffers = what crosses PCIe in evaluate_pipelined: images fp32 (the reference's
+        # loader output), bf16 (bit-identical results: the stem rounds to bf16 first; half the bytes) or uint8 (raw
+        # pixels, normalised inside the stem kernel with net.input_norm); labels int64 (reference) or uint8 (>= C void)
+        assert input_dtype in (torch.float32, torch.bfloat16, torch.uint8) and target_dtype in (torch.int64, torch.uint8)
+        self.input_dtype, self.target_dtype = input_dtype, target_dtype
         self.use_graph = use_graph
         self.overlap_gates = True      # early-exit gates on a side stream, overlapping the next section
         self._side = None
@@ -46,12 +51,18 @@ class EarlyExitEngine:
         self.counts = torch.zeros((self.E + 1,), dtype=torch.int64, device=dev)
         self.exited_px = torch.zeros((self.E,), dtype=torch.int64, device=dev)
 
+    def _weights_token(self):
+        f = getattr(self.net, 'weights_token', None)
+        return f() if f is not None else getattr(self.net, 'weights_epoch', 0)
+
     def _drop_stale_graphs(self):
-        """Graphs captured from an older set of weights (the model's weights_epoch moved on) are released, not kept."""
-        epoch = getattr(self.net, 'weights_epoch', 0)
-        if getattr(self, '_graph_epoch', epoch) != epoch:
+        """Graphs captured from an older set of weights are released, not kept: the model's weights_token() (epoch +
+        version counters of every parameter and buffer) is compared before every capture lookup AND every replay."""
+        token = self._weights_token()
+        if getattr(self, '_graph_token', token) != token:
             self._graphs.clear()
-        self._graph_epoch = epoch
+        self._graph_token = token
+        return token
 
     def _side_stream(self):
         if self._side is None:
@@ -89,14 +100,14 @@ class EarlyExitEngine:
         return g['out']
 
     def _capture(self, shape, with_targets, slot=0):
-        self._drop_stale_graphs()
-        key = (shape, with_targets, slot, getattr(self.net, 'weights_epoch', 0))
+        token = self._drop_stale_graphs()
+        key = (shape, with_targets, slot, token)
         if key in self._graphs:
             return self._graphs[key]
         N, _, H, W = shape
         dev = self.device
-        Xs = torch.zeros(shape, dtype=torch.float32, device=dev)
-        ys = torch.full((N, 1, H, W), self.C, dtype=torch.int64, device=dev) if with_targets else None
+        Xs = torch.zeros(shape, dtype=self.input_dtype, device=dev)
+        ys = torch.full((N, 1, H, W), self.C, dtype=self.target_dtype, device=dev) if with_targets else None
         fn = (lambda: self._evaluate(Xs, ys)) if with_targets else (lambda: self._infer(Xs))
         saved = (self.cm.clone(), self.counts.clone(), self.exited_px.clone())
         s = torch.cuda.Stream(device=dev)
@@ -110,7 +121,9 @@ class EarlyExitEngine:
             out = fn()
         # the warm-up / capture runs must not count
         self.cm.copy_(saved[0]); self.counts.copy_(saved[1]); self.exited_px.copy_(saved[2])
-        g = {'graph': graph, 'X': Xs, 'y': ys, 'out': out}
+        # the folded plans the graph reads live outside its memory pool: keep them referenced next to it
+        g = {'graph': graph, 'X': Xs, 'y': ys, 'out': out,
+             'plans': (dict(getattr(self.net, '_plans', {})), dict(getattr(self.net, '_section_plans', {})))}
         self._graphs[key] = g
         return g
 
@@ -186,21 +199,21 @@ class EarlyExitEngine:
         """Static buffers of the staged step for one input shape: the input of every backbone section
         (`xin[i]`, its first n rows hold the compacted still-active images), their original batch
         positions (`act[i]`), the per-image results, and a pinned host word per gate for the count."""
-        self._drop_stale_graphs()
-        key = ('skip', shape, with_targets, slot, getattr(self.net, 'weights_epoch', 0))
+        token = self._drop_stale_graphs()
+        key = ('skip', shape, with_targets, slot, token)
         st = self._graphs.get(key)
         if st is not None:
             return st
         N, _, H, W = shape
         dev, E = self.device, self.E
-        X = torch.zeros(shape, dtype=torch.float32, device=dev)
+        X = torch.zeros(shape, dtype=self.input_dtype, device=dev)
         xin, Xc = [X], X
         for i in range(E - 1):                 # one eager pass: shapes of the section boundaries (+ plan warm-up)
             Xc = self.net.run_section(i, Xc)
             xin.append(torch.empty_like(Xc))
         st = {
             'X': X, 'xin': xin,
-            'y': torch.full((N, 1, H, W), self.C, dtype=torch.int64, device=dev) if with_targets else None,
+            'y': torch.full((N, 1, H, W), self.C, dtype=self.target_dtype, device=dev) if with_targets else None,
             'act': [torch.arange(N, dtype=torch.int64, device=dev)] +
                    [torch.zeros((N,), dtype=torch.int64, device=dev) for _ in range(E - 1)],
             'cnt_host': torch.zeros((E,), dtype=torch.int32).pin_memory(),
@@ -278,6 +291,7 @@ class EarlyExitEngine:
                 fn()
             self.cm.copy_(saved[0]); self.counts.copy_(saved[1]); self.exited_px.copy_(saved[2])
             st['stages'][key] = g
+            st.setdefault('plans', []).append((dict(getattr(self.net, '_plans', {})), dict(getattr(self.net, '_section_plans', {}))))
         return g
 
     def _run_skip_graphs(self, st):
@@ -361,9 +375,10 @@ class EarlyExitEngine:
             # one kernel: final-exit assignment, histogram of the map each image took, accumulators, pred
             pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
             tg = targets.reshape(N, -1)
-            tg = (tg if tg.dtype == torch.int64 else tg.to(torch.int64)).contiguous()
+            tg = (tg if tg.dtype in (torch.int64, torch.uint8) else tg.to(torch.int64)).contiguous()
+            accumulate = ops.lib().eeseg_exit_accumulate_u8 if tg.dtype == torch.uint8 else ops.lib().eeseg_exit_accumulate
             with torch.cuda.device(dev):
-                ops.check(ops.lib().eeseg_exit_accumulate(
+                ops.check(accumulate(
                     amax_all.data_ptr(), tg.data_ptr(), exit_idx.data_ptr(), E, N, self.C, H * W,
                     self.cm.data_ptr(), self.counts.data_ptr(), pred.data_ptr(),
                     torch.cuda.current_stream(dev).cuda_stream), "eeseg_exit_accumulate")

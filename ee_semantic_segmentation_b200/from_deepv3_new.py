@@ -134,12 +134,14 @@ class branchyDeepv3(nn.Module):
         self.fast_training_backbone = True   # ... and the Bottleneck convolutions of the sections (bf16 activations)
         self.graph_inference = True    # forward_lowres replays one CUDA graph per input shape (see there)
         self._lowres_graphs = {}
+        self._token_tensors = None
         self.weights_epoch = 0         # bumped by train() / load_state_dict(): captured graphs of older epochs are stale
+        self.input_norm = None         # (mean[3], std[3]) applied inside the stem kernel to uint8 images (0..255)
         self.strict_kernels = False    # True: a module the eeseg plans do not cover raises instead of running on cuDNN
 
     _RUNTIME_DEFAULTS = dict(fast_inference=True, fast_backbone=True, fast_training_heads=True,
                              fast_training_backbone=True, graph_inference=True, weights_epoch=0, num_classes=21,
-                             strict_kernels=False)
+                             strict_kernels=False, input_norm=None)
     _warned_fallbacks = set()
 
     def _library_fallback(self, what):
@@ -156,25 +158,50 @@ class branchyDeepv3(nn.Module):
         """Pickles (tch.save(net), copy.deepcopy) carry parameters and flags, not the kernel plans / CUDA graphs."""
         st = dict(self.__dict__)
         st['_plans'], st['_section_plans'], st['_lowres_graphs'] = {}, {}, {}
+        st['_token_tensors'] = None
         return st
 
     def __setstate__(self, st):
-        """Also accepts whole-module pickles written by the reference class (eval_br_ent.py:146): the run-time
-        attributes it does not have take their defaults."""
-        self.__dict__.update(st)
+        """Also accepts whole-module pickles written by the reference class (eval_br_ent.py:146) or by an older torch:
+        nn.Module.__setstate__ restores the hook dictionaries such pickles lack; the run-time attributes the reference
+        class does not have take their defaults."""
+        super().__setstate__(st)
         for k in ('_plans', '_section_plans', '_lowres_graphs'):
             self.__dict__[k] = {}
+        self.__dict__['_token_tensors'] = None
         for k, v in self._RUNTIME_DEFAULTS.items():
             self.__dict__.setdefault(k, v)
 
     def _bump_epoch(self):
         """Drops everything derived from the parameters: CUDA graphs AND the folded kernel plans. The plans are keyed by
         the parameters' version counters, which a replayed training graph (train_funcs.GraphedTrainStep) does not advance —
-        without this, an evaluation after graph-replayed training would run on the weights folded before it."""
+        GraphedTrainStep therefore calls this after every replay, as do train(), load_state_dict() and .to()/.cuda()."""
         self.weights_epoch = getattr(self, 'weights_epoch', 0) + 1
         self._lowres_graphs = {}
         self._plans = {}
         self._section_plans = {}
+        self._token_tensors = None
+
+    def weights_token(self):
+        """Cheap fingerprint of the weights every captured CUDA graph is tagged with (here, engine.EarlyExitEngine,
+        ee_dnn_op_ne.eval_ee_deeplabv3) and compares before EACH replay: (weights_epoch, sum of the version counters of
+        all parameters and buffers). The version counters catch what never reaches this class — a sub-module
+        load_state_dict (net.branches.load_state_dict(...)), an optimizer step or any in-place edit in eval mode;
+        weights_epoch catches what leaves the counters alone (graph-replayed training, .to()). ~30 us of host time."""
+        ts = self.__dict__.get('_token_tensors')
+        if ts is None:
+            ts = list(self.parameters()) + list(self.buffers())
+            self.__dict__['_token_tensors'] = ts
+        v = 0
+        for t in ts:
+            v += t._version
+        return (self.weights_epoch, v)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)        # .to() / .cuda() / .float(): new storages
+        if hasattr(self, 'weights_epoch'):
+            self._bump_epoch()
+        return out
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._bump_epoch()                       # load_state_dict (also through a parent module / DDP wrapper)
@@ -288,7 +315,7 @@ class branchyDeepv3(nn.Module):
             if ent is None or ent[0] != key:
                 ent = (key, SectionPlan(sec))
                 self._section_plans[i] = ent
-            return ent[1].run(X)
+            return ent[1].run(X, getattr(self, 'input_norm', None))
         if self.fast_backbone:
             self._library_fallback(f'base_model[{i}] ({type(sec[0]).__name__} ...)')
         with tch.autocast('cuda', dtype=tch.bfloat16):
@@ -359,6 +386,13 @@ class branchyDeepv3(nn.Module):
         otherwise. The returned tensors are the graph's static outputs: valid until the next call with that shape."""
         key = (tuple(X.shape), X.device, X.dtype)
         ent = self._lowres_graphs.get(key)
+        token = self.weights_token()
+        if ent is not None and ent[3] != token:
+            # the weights moved since capture (sub-module load, in-place edit, optimizer step): the graph replays plans
+            # folded from the old values — drop it and capture again from the current ones
+            self._lowres_graphs.pop(key)
+            ent = None
+            self._lowres_graphs.setdefault('seen', {})[key] = 2
         if ent is None:
             # capture a shape the second time it shows up: a loader of varying image sizes must not pay a capture per image
             seen = self._lowres_graphs.setdefault('seen', {})
@@ -380,12 +414,14 @@ class branchyDeepv3(nn.Module):
                 g = tch.cuda.CUDAGraph()
                 with tch.cuda.graph(g):
                     outs = self._lowres_eager(xs)
-                ent = (g, xs, outs)
+                # the plans' folded weights are allocated outside the graph pool: the entry keeps them alive as long as
+                # the graph can replay (a later _plan(i) may re-key and drop them from self._plans)
+                ent = (g, xs, outs, token, (dict(self._plans), dict(self._section_plans)))
                 graphs = [k for k in self._lowres_graphs if k != 'seen']
                 if len(graphs) >= 8:                       # a few shapes at most: drop the oldest
                     self._lowres_graphs.pop(graphs[0])
                 self._lowres_graphs[key] = ent
-            g, xs, outs = ent
+            g, xs, outs = ent[:3]
             xs.copy_(X, non_blocking=True)
             g.replay()
         return outs

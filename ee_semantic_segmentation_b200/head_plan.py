@@ -18,7 +18,7 @@ import torch
 from torch import nn
 from torchvision.models.segmentation.deeplabv3 import ASPP
 
-from . import _lib
+from . import _lib, torch_ops  # noqa: F401  (torch_ops registers torch.ops.eeseg.*)
 from ._lib import check, lib
 
 
@@ -34,8 +34,36 @@ def _krsc(conv):
     return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
 
 
-PROFILE = None   # bench.py sets this to a list: (start event, end event, nominal FLOPs, tag) per conv launch
+PROFILE = None   # tools set this to a list: (start event, end event, nominal FLOPs, tag) per conv launch
 PROFILE_TAG = "head"
+FLOP_LOG = None  # bench.py sets this to a list: (nominal FLOPs, effective FLOPs, tag) per conv launch, no events
+_LIVE_FRAC = {}
+
+
+def live_tap_fraction(h, w, k, dil, stride=1, pad=None):
+    """Fraction of the (output pixel, tap) pairs of a k x k convolution the kernel actually multiplies: taps that fall
+    entirely into the zero padding for a whole tile are skipped (conv_igemm.cu live_taps; common for the ASPP dilations
+    12/24/36 on a 65x65 map, never for 3x3 d <= 4). h, w: OUTPUT size. effective FLOPs = nominal x this."""
+    import ctypes
+    import numpy as np
+    if k == 1:
+        return 1.0
+    key = (h, w, k, dil, stride, pad)
+    if key not in _LIVE_FRAC:
+        tx, ty, bw, bh, bn = (ctypes.c_int() for _ in range(5))
+        check(lib().eeseg_conv_group_tiles(h, w, 256, ctypes.byref(tx), ctypes.byref(ty), ctypes.byref(bw),
+                                           ctypes.byref(bh), ctypes.byref(bn)), "eeseg_conv_group_tiles")
+        bw, bh = bw.value, bh.value
+        p = dil * (k // 2) if pad is None or pad < 0 else pad
+        hin, win = (h - 1) * stride + 1, (w - 1) * stride + 1       # smallest input that gives this output ('same' convs: equal)
+        off = np.arange(k) * dil - p
+        y0, x0 = np.arange(0, h, bh), np.arange(0, w, bw)
+        y_hi, x_hi = np.minimum(y0 + bh, h), np.minimum(x0 + bw, w)
+        live_y = (((y_hi[:, None] - 1) * stride + off[None, :] >= 0) & (y0[:, None] * stride + off[None, :] < hin)).sum(1)
+        live_x = (((x_hi[:, None] - 1) * stride + off[None, :] >= 0) & (x0[:, None] * stride + off[None, :] < win)).sum(1)
+        px = (y_hi - y0)[:, None] * (x_hi - x0)[None, :]
+        _LIVE_FRAC[key] = float((live_y[:, None] * live_x[None, :] * px).sum() / (k * k * px.sum()))
+    return _LIVE_FRAC[key]
 
 
 def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, shift_sn=0, stride=1,
@@ -49,16 +77,16 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
         if PROFILE is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        check(lib().eeseg_conv_igemm_fwd(
-            x.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), shift_sn, N, h, w, Cin,
-            Cout, R, S, dilation, stride, pad, 1 if relu else 0,
-            None if residual is None else residual.data_ptr(),
-            0 if residual is None else residual.stride(2), out.data_ptr(), out_dtype_code, ldo,
-            torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_fwd")
+        assert out_dtype_code == (_lib.F32 if out.dtype == torch.float32 else _lib.BF16)
+        torch.ops.eeseg.conv_igemm_fwd(x, wt, scale, shift, shift_sn, dilation, stride, pad, bool(relu), residual, out, ldo)
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         if PROFILE is not None:
             b.record()
-            ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
             PROFILE.append((a, b, 2 * N * ho * wo * Cout * R * S * Cin, PROFILE_TAG))
+        if FLOP_LOG is not None:
+            nominal = 2 * N * ho * wo * Cout * R * S * Cin
+            frac = live_tap_fraction(ho, wo, R, dilation, stride, pad) if R == S else 1.0
+            FLOP_LOG.append((nominal, nominal * frac, PROFILE_TAG))
 
 
 def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
@@ -118,14 +146,15 @@ def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out,
         if PROFILE is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        check(lib().eeseg_conv_igemm_grouped(
-            x.data_ptr(), n, PA(*[t.data_ptr() for t in wts]), PA(*[t.data_ptr() for t in scales]),
-            PA(*[t.data_ptr() for t in shifts]), IA(*ksizes), IA(*dils), IA(*ch_offs), N, h, w, Cin, Cout,
-            1 if relu else 0, out.data_ptr(), ldo, out_channels, schedule.data_ptr(), schedule.numel(),
-            torch.cuda.current_stream(x.device).cuda_stream), "eeseg_conv_igemm_grouped")
+        torch.ops.eeseg.conv_igemm_grouped(x, list(wts), list(scales), list(shifts), list(ksizes), list(dils),
+                                           list(ch_offs), bool(relu), out, ldo, out_channels, schedule)
         if PROFILE is not None:
             b.record()
             PROFILE.append((a, b, sum(2 * N * h * w * Cout * k * k * Cin for k in ksizes), PROFILE_TAG))
+        if FLOP_LOG is not None:
+            noms = [2 * N * h * w * Cout * k * k * Cin for k in ksizes]
+            FLOP_LOG.append((sum(noms), sum(f * live_tap_fraction(h, w, k, d) for f, k, d in zip(noms, ksizes, dils)),
+                             PROFILE_TAG))
 
 
 def dense_bn_act(x, W, scale, shift, relu):

@@ -72,14 +72,12 @@ class ConvIgemmFn(torch.autograd.Function):
                 ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, S),), dtype=torch.uint8,
                                  device=x.device)
                 dx = torch.empty_like(x)
-                check(lib().eeseg_conv_igemm_dgrad(dy.data_ptr(), wt.data_ptr(), N, h, w, Cin, Cout, R, S, ctx.dilation,
-                                                   dx.data_ptr(), _lib.BF16, Cin, ws.data_ptr(), st), "eeseg_conv_igemm_dgrad")
+                torch.ops.eeseg.conv_igemm_dgrad(dy, wt, ctx.dilation, dx, ws)
             if ctx.needs_input_grad[1]:
                 dwk = torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
                 wws = torch.empty((lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, Cin, Cout, R, S),), dtype=torch.uint8,
                                   device=x.device)
-                check(lib().eeseg_conv_igemm_wgrad(x.data_ptr(), dy.data_ptr(), Cout, Cout, 0, N, h, w, Cin, Cout, R, S,
-                                                   ctx.dilation, dwk.data_ptr(), wws.data_ptr(), st), "eeseg_conv_igemm_wgrad")
+                torch.ops.eeseg.conv_igemm_wgrad(x, dy, ctx.dilation, dwk, wws)
                 dw = dwk.permute(0, 3, 1, 2)                                             # the parameter's layout
         return dx, dw, None, None
 

@@ -1,12 +1,15 @@
-"""Tensor-level wrappers over the C ABI (include/eeseg.h): argument checks, output allocation and
-autograd glue. torch is used for device memory and streams only; every op here raises on CPU
-tensors — there is no fallback path."""
+"""Tensor-level wrappers: argument checks, output allocation and autograd glue around the registered torch operators
+`torch.ops.eeseg.*` (torch_ops.py), each of which forwards to the `extern "C"` launcher of the same name in
+libeeseg_b200.so (include/eeseg.h). torch is used for device memory and streams only; every op here raises on CPU
+tensors — there is no fallback path (the operators have a CUDA implementation only)."""
 import math
 
 import torch
 
-from . import _lib
+from . import _lib, torch_ops  # noqa: F401  (torch_ops registers torch.ops.eeseg.*)
 from ._lib import BF16, F32, check, lib
+
+_ops = torch.ops.eeseg
 
 
 def _dt(t):
@@ -64,9 +67,7 @@ def confusion_hist(pred, targets, n_classes, out=None, accumulate=False):
         if out is None:
             out = torch.empty((N, C + 1, C), dtype=torch.int64, device=pred.device)
             accumulate = False
-        check(lib().eeseg_confusion_hist(pr.data_ptr(), kind, dt, tg.data_ptr(), N, C, HW,
-                                         out.data_ptr(), 1 if accumulate else 0, _stream(pred)),
-              "eeseg_confusion_hist")
+        _ops.confusion_hist(pr, kind, tg, C, out, bool(accumulate))
     return out
 
 
@@ -132,18 +133,14 @@ def exit_gate(x, out_hw=None, *, layout="NCHW", kind="logits", tau=0.0, n_classe
         if want_score:
             res.part_sum = torch.empty((N, npart), dtype=torch.float64, device=dev)
             res.part_cnt = torch.empty((N, npart), dtype=torch.int32, device=dev)
-        check(lib().eeseg_exit_gate_pixels(
-            x.data_ptr(), _dt(x), 0 if kind == "logits" else 1, sn, sc, sy, sx, N, C, h, w, H, W,
-            float(tau), _p(up_out), _dt(up_out) if up_out is not None else 0, up_sn,
-            _p(res.ent), _p(res.amax), _p(res.mask), _p(res.part_sum), _p(res.part_cnt),
-            _stream(x)), "eeseg_exit_gate_pixels")
+        _dt(x)
+        _ops.exit_gate_pixels(x, 0 if kind == "logits" else 1, sn, sc, sy, sx, N, C, h, w, H, W, float(tau), up_out,
+                              up_sn, res.ent, res.amax, res.mask, res.part_sum, res.part_cnt)
         if want_score:
             res.score = score_out if score_out is not None else torch.empty((N,), dtype=torch.float32, device=dev)
             res.exited_px = torch.empty((N,), dtype=torch.int64, device=dev)
-            check(lib().eeseg_exit_gate_decide(
-                res.part_sum.data_ptr(), res.part_cnt.data_ptr(), npart, None, N, H * W, float(tau),
-                1, 0, None, res.score.data_ptr(), res.exited_px.data_ptr(), None, None, _stream(x)),
-                "eeseg_exit_gate_decide")
+            _ops.exit_gate_decide(res.part_sum, res.part_cnt, npart, None, N, H * W, float(tau), True, 0, None,
+                                  res.score, res.exited_px, None, None)
     return res
 
 
@@ -170,10 +167,8 @@ def gate_decide(score, tau, exit_id, exit_idx, less_than=True, want_active=True)
         if want_active:
             al = torch.empty((N,), dtype=torch.int32, device=dev)
             ac = torch.empty((1,), dtype=torch.int32, device=dev)
-        check(lib().eeseg_exit_gate_decide(None, None, 0, score.data_ptr(), N, 1, float(tau),
-                                           1 if less_than else 0, int(exit_id), exit_idx.data_ptr(),
-                                           None, None, _p(al), _p(ac), _stream(score)),
-              "eeseg_exit_gate_decide")
+        _ops.exit_gate_decide(None, None, 0, score, N, 1, float(tau), bool(less_than), int(exit_id), exit_idx,
+                              None, None, al, ac)
     return al, ac
 
 
@@ -217,9 +212,8 @@ class _UpsampleBilinear(torch.autograd.Function):
         h, w = ctx.in_hw
         H, W = ctx.out_hw
         dx = torch.empty((N, C, h, w), dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
-            check(lib().eeseg_upsample_bilinear_bwd(g.data_ptr(), _dt(g), N * C, h, w, H, W, dx.data_ptr(), _stream(g)),
-                  "eeseg_upsample_bilinear_bwd")
+        _dt(g)
+        _ops.upsample_bilinear_bwd(g, N * C, h, w, H, W, dx)
         return dx, None
 
 
@@ -250,10 +244,8 @@ class _MultiExitCE(torch.autograd.Function):
             valid = torch.empty((1,), dtype=torch.int64, device=dev)
             ws = torch.empty((lib().eeseg_multi_exit_ce_workspace_bytes(E, N, HW),), dtype=torch.uint8, device=dev)
             dy = torch.empty_like(y) if need_grad else None
-            check(lib().eeseg_multi_exit_ce_fwd(
-                y.data_ptr(), _dt(y), y.stride(0), targets.data_ptr(), E, N, C, HW, int(ignore_index),
-                coef.data_ptr(), per_exit.data_ptr(), valid.data_ptr(), _p(dy), ws.data_ptr(),
-                _stream(y)), "eeseg_multi_exit_ce_fwd")
+            _dt(y)
+            _ops.multi_exit_ce_fwd(y, targets, int(ignore_index), coef, per_exit, valid, dy, ws)
         ctx.dy = dy
         ctx.save_for_backward(coef)
         ctx.mark_non_differentiable(valid)
@@ -264,12 +256,12 @@ class _MultiExitCE(torch.autograd.Function):
         dy = ctx.dy
         (coef,) = ctx.saved_tensors
         if dy is None:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("multi_exit_ce: the fused gradient was consumed by an earlier backward (the forward "
+                                   "kernel writes it once); call the loss again instead of retain_graph=True")
             return None, None, None, None
         g = g.contiguous().float()
-        with torch.cuda.device(dy.device):
-            check(lib().eeseg_scale_exits(dy.data_ptr(), _dt(dy), dy.stride(0), dy.shape[0],
-                                          dy[0].numel(), g.data_ptr(), coef.data_ptr(), _stream(dy)),
-                  "eeseg_scale_exits")
+        _ops.scale_exits(dy, g, coef)
         ctx.dy = None
         return dy, None, None, None
 
@@ -302,11 +294,8 @@ def multi_exit_ce_backward_unfused(y, targets, ignore_index, g, valid):
     HW = y[0, 0, 0].numel()
     dy = torch.empty_like(y)
     tg = targets.reshape(N, -1).to(torch.int64).contiguous()
-    with torch.cuda.device(y.device):
-        check(lib().eeseg_multi_exit_ce_bwd(y.data_ptr(), _dt(y), y.stride(0), tg.data_ptr(), E, N, C,
-                                            HW, int(ignore_index), g.float().contiguous().data_ptr(),
-                                            valid.data_ptr(), dy.data_ptr(), _stream(y)),
-              "eeseg_multi_exit_ce_bwd")
+    _dt(y)
+    _ops.multi_exit_ce_bwd(y, tg, int(ignore_index), g.float().contiguous(), valid, dy)
     return dy
 
 
@@ -406,11 +395,12 @@ class _FocalSum(torch.autograd.Function):
         dy = ctx.dy
         (coef,) = ctx.saved_tensors
         if dy is None:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("focal_sums: the fused gradient was consumed by an earlier backward; call the loss again "
+                                   "instead of retain_graph=True")
             return None, None, None, None, None, None
         g = g.contiguous().float()
-        with torch.cuda.device(dy.device):
-            check(lib().eeseg_scale_exits(dy.data_ptr(), _dt(dy), dy.stride(0), dy.shape[0], dy[0].numel(),
-                                          g.data_ptr(), coef.data_ptr(), _stream(dy)), "eeseg_scale_exits")
+        _ops.scale_exits(dy, g, coef)
         ctx.dy = None
         return dy, None, None, None, None, None
 
@@ -485,10 +475,9 @@ class _Lovasz(torch.autograd.Function):
             nbytes = lib().eeseg_lovasz_workspace_bytes(E, N, C, HW)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
             dy = torch.empty_like(y) if need_grad else None
-            check(lib().eeseg_lovasz_fwd_bwd(
-                y.data_ptr(), _dt(y), y.stride(0), labels.data_ptr(), E, N, C, HW, int(has_ignore),
-                int(ignore), int(classes_mode), int(per_image), per_exit.data_ptr(), _p(dy),
-                ws.data_ptr(), nbytes, _stream(y)), "eeseg_lovasz_fwd_bwd")
+            _dt(y)
+            _ops.lovasz_fwd_bwd(y, labels, bool(has_ignore), int(ignore), int(classes_mode), bool(per_image), per_exit,
+                                dy, ws)
         ctx.dy = dy
         return per_exit
 
@@ -496,12 +485,13 @@ class _Lovasz(torch.autograd.Function):
     def backward(ctx, g):
         dy = ctx.dy
         if dy is None:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("lovasz_multi_exit: the fused gradient was consumed by an earlier backward; call the loss "
+                                   "again instead of retain_graph=True")
             return (None,) * 6
         ctx.dy = None
         g = g.contiguous().float()
-        with torch.cuda.device(dy.device):   # dy[e] *= g[e]; a no-op on the device when g == 1
-            check(lib().eeseg_scale_exits(dy.data_ptr(), _dt(dy), dy.stride(0), dy.shape[0], dy[0].numel(),
-                                          g.data_ptr(), None, _stream(dy)), "eeseg_scale_exits")
+        _ops.scale_exits(dy, g, None)   # dy[e] *= g[e]; a no-op on the device when g == 1
         return dy, None, None, None, None, None
 
 

@@ -280,4 +280,9 @@ class GraphedTrainStep:
         self.X.copy_(X, non_blocking=True)
         self.y.copy_(y.view_as(self.y), non_blocking=True)
         self.graph.replay()
+        # a replay updates the parameters without touching their version counters: announce it, so that inference plans
+        # and graphs derived from the old values (model, engines, operators) are dropped
+        bump = getattr(getattr(self.net, 'module', self.net), '_bump_epoch', None)
+        if bump is not None:
+            bump()
         return self.loss

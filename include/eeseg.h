@@ -30,7 +30,7 @@ extern "C" {
 
 #define EESEG_ABI_VERSION 1
 
-enum { EESEG_F32 = 0, EESEG_BF16 = 1 };
+enum { EESEG_F32 = 0, EESEG_BF16 = 1, EESEG_U8 = 2 };
 enum { EESEG_OK = 0, EESEG_ERR_ARG = 1, EESEG_ERR_CUDA = 2, EESEG_ERR_UNSUPPORTED = 3 };
 
 int eeseg_abi_version(void);
@@ -59,6 +59,10 @@ int eeseg_confusion_hist(const void* pred, int pred_kind, int dtype, const int64
  * are incremented; pred (optional uint8 [N][HW]) receives the map of the exit taken. */
 int eeseg_exit_accumulate(const uint8_t* amax_all, const int64_t* targets, int32_t* exit_idx, int E, int N,
                           int C, int64_t HW, int64_t* cm_acc, int64_t* counts, uint8_t* pred, void* stream);
+/* The same with uint8 labels [N][HW] (classes 0..C-1, any value >= C is void — VOC's 255 or the reference's C;
+ * C <= 255): the label map crosses PCIe at 1 byte per pixel instead of 8 and is widened inside the kernel. */
+int eeseg_exit_accumulate_u8(const uint8_t* amax_all, const uint8_t* targets, int32_t* exit_idx, int E, int N,
+                             int C, int64_t HW, int64_t* cm_acc, int64_t* counts, uint8_t* pred, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Exit gate, stage 1 (per pixel).
@@ -292,6 +296,13 @@ int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, int64_t P, 
  * out bf16 NHWC [N][(H+1)/2][(W+1)/2][64], channel u*12 + (a*2+b)*3 + c = x[n][c][2Y+a][2(X+u-2)+b]
  * for u in 0..3 (zero outside the image and for channels >= 48). */
 int eeseg_stem_space_to_depth(const float* x, int N, int H, int W, void* out, void* stream);
+/* The same for an image tensor of dtype x_kind: EESEG_F32, EESEG_BF16 (what a bf16 inference stream uploads: the
+ * kernel rounds fp32 images to bf16 as its first step anyway, so the result is bit-identical at half the host->device
+ * bytes) or EESEG_U8 (raw 0..255 pixels, a quarter of the bytes): for uint8 the kernel applies what the reference's loader does
+ * on the CPU (get_seg_datasets.py:62-70, ToTensor + Normalize): v = (u / 255 - mean[c]) / std[c], mean / std HOST
+ * arrays of 3 floats (NULL: mean 0, std 1). */
+int eeseg_stem_space_to_depth_any(const void* x, int x_kind, const float* mean, const float* std_, int N, int H, int W,
+                                  void* out, void* stream);
 /* 3x3 / stride-2 / pad-1 max pooling of a bf16 NHWC tensor (C % 8 == 0). */
 int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C, void* out, void* stream);
 
@@ -319,24 +330,16 @@ int eeseg_conv_igemm_grouped(const void* x, int nprob, const void* const* wt, co
                              void* out, int64_t ldo, int out_channels, const int32_t* schedule, int n_items,
                              void* stream);
 
-/* Programmatic dependent launch for eeseg_conv_igemm_fwd (prologue of launch i+1 overlaps the tail of
- * launch i; the kernel executes griddepcontrol.wait before touching its inputs). Default on; returns
- * the previous setting. */
-int eeseg_conv_set_pdl(int enable);
+/* Programmatic dependent launch (the prologue of conv launch i+1 overlaps the tail of launch i; the kernel executes
+ * griddepcontrol.wait before touching its inputs) is on unless the environment holds EESEG_CONV_PDL=0 when the library
+ * is first used. The library keeps no mutable process-wide state: every entry point is re-entrant per stream; the
+ * cycle-counter / %globaltimer instrumentation used while tuning exists only in -DEESEG_TUNING builds
+ * (include/eeseg_tuning.h). */
 
 /* Small fp32 dense layer y[n][o] = act((x[n] . W[o]) * scale[o] + shift[o]) (scale/shift optional) for the
  * ASPP pooled branch (torchvision deeplabv3.py:70-83) and its share of the ASPP projection. */
 int eeseg_dense_bn_act(const float* x, const float* W, const float* scale, const float* shift, int N, int K,
                        int O, int relu, float* y, void* stream);
-
-/* Measurement hook: following eeseg_conv_igemm_* launches record {first CTA start, last CTA end} in
- * wall-clock ns (%globaltimer) at buffer[2*i], buffer[2*i+1] (uint64, i < capacity; initialise starts to
- * UINT64_MAX and ends to 0). NULL switches it off; returns how many launches were recorded. */
-int eeseg_conv_timing(void* device_buffer, int capacity);
-
-/* Tuning hook: device buffer of [148][32] uint64 cycle counters (per-CTA wait times of the producer,
- * MMA and epilogue roles) filled by subsequent eeseg_conv_igemm_fwd launches; NULL switches it off. */
-int eeseg_conv_debug_stats(void* device_buffer);
 
 /* Global average pool of an NHWC bf16 tensor: [N][h][w][C] -> f32 [N][C] (ASPPPooling's
  * AdaptiveAvgPool2d(1), torchvision deeplabv3.py:70-83). Two ordered stages (deterministic);

@@ -116,7 +116,8 @@ def bench_nets():
     return port, _product(port, SECTIONS)
 
 
-# relative L2 error of the logits per exit (depth 40 / 49 / 52 bf16 convolutions + head); measured 0.8 / 1.0 / 1.1e-2
+# relative L2 error of the logits per exit (depth 40 / 49 / 52 bf16 convolutions + head); measured 6.9e-3 / 6.3e-3 /
+# 1.09e-2 (torch's own bf16 path: 8.1e-3 / 7.7e-3 / 1.15e-2)
 L2_TOL = (1e-2, 1.25e-2, 1.25e-2)
 
 
@@ -178,8 +179,8 @@ def test_bench_config_logits(bench_nets):
 # DELTA from tau at every gate it reaches must take the oracle's exit. north_star's 1e-4 band applies to the gate
 # arithmetic on IDENTICAL logits (tests/test_kernels_gpu.py checks the gate kernel against the oracle at 1e-4 / mask
 # identical outside 1e-4 of tau); DELTA is that plus the bf16 network's effect on the score.
-SCORE_TOL = 4e-3
-DELTA = 4e-3
+SCORE_TOL = 1.5e-3     # measured 8.7e-4 over 32 images x 2 gates
+DELTA = 1.5e-3
 
 
 def test_bench_config_exit_decisions_vs_oracle(bench_nets):

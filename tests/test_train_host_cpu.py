@@ -172,3 +172,43 @@ def test_grouped_conv_work_list_tile_width_rule():
             np.testing.assert_array_equal(tiles, np.arange(n_items))
     # the first round holds the most expensive items: none of the cheap 1x1 tiles (problem 0)
     assert not np.any((s4[:148] >> 24) == 0)
+
+
+def test_old_pickles_and_weights_token():
+    """(1) a whole-module pickle written by an older torch lacks the newer hook dictionaries: __setstate__ goes through
+    nn.Module.__setstate__, which restores them (the reference's checkpoint format is tch.save(net), eval_br_ent.py:146).
+    (2) weights_token() — what every captured CUDA graph is tagged with and compares before each replay — moves on a
+    SUB-module load_state_dict, an in-place edit in eval mode and an explicit _bump_epoch (graph-replayed training),
+    and stays put otherwise."""
+    import copy
+    import torch
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    net = branchyDeepv3(None, "deeplabv3_resnet50", 1, 65, sections=[18, 2], pretrained=False).eval()
+    st = net.__getstate__()
+    for k in ("_forward_pre_hooks_with_kwargs", "_forward_hooks_with_kwargs", "_forward_hooks_always_called",
+              "_state_dict_pre_hooks", "_load_state_dict_post_hooks", "_backward_pre_hooks"):
+        st.pop(k, None)
+    old = branchyDeepv3.__new__(branchyDeepv3)
+    old.__setstate__(st)
+    for k in ("_forward_pre_hooks_with_kwargs", "_forward_hooks_always_called", "_backward_pre_hooks"):
+        assert hasattr(old, k), k
+    old.state_dict()                                   # walks _state_dict_pre_hooks: raised AttributeError before
+    with torch.no_grad():
+        try:
+            old(torch.zeros(1, 3, 33, 33))              # __call__ reads the hook dicts before reaching forward()
+        except RuntimeError as e:
+            assert "no CPU fallback" in str(e)
+
+    t0 = net.weights_token()
+    assert net.weights_token() == t0
+    net.branches.load_state_dict(copy.deepcopy(net.branches.state_dict()))      # never reaches branchyDeepv3's hooks
+    t1 = net.weights_token()
+    assert t1 != t0 and t1[0] == t0[0]
+    with torch.no_grad():
+        net.classifier[-1].bias.add_(1.0)                                        # in-place edit in eval mode
+    t2 = net.weights_token()
+    assert t2 != t1
+    net._bump_epoch()
+    assert net.weights_token()[0] == t2[0] + 1
+    net.float()                                                                  # _apply: storages may have moved
+    assert net.weights_token()[0] == t2[0] + 2
