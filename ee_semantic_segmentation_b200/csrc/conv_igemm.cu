@@ -59,6 +59,12 @@ struct ConvParams {
                                        // D[:, 64j:64j+64] += R[:, 64j:64j+64] x I64 before the main loop (scale must be 1)
   int blk_cols, nblk, row_bytes, swz;  // epilogue: output column blocks of row_bytes (<= 128 B) per pixel
   int main_bytes;                      // shared memory of the operand ring
+  int cs;                              // 1, or 2 = CTA pair (cta_group::2): the two CTAs of a cluster (one TPC) run two
+                                       // m-tiles of ONE (problem, n-tile) as a single 256-row MMA issued by rank 0; each
+                                       // CTA stages its own A tile and HALF of the weight tile's rows, so an SM ingests
+                                       // 32 KB instead of 48 KB per 128x256x64 MMA block (the L2->SM port, ~64 B/clk,
+                                       // is what bounds the single-CTA kernel at ~62 % of the tensor peak)
+  int m_tiles;                         // N * tiles_x * tiles_y
   int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
   int direct;                          // deep-K launches: epilogue stores straight from registers (no staging
                                        // tile), so the operand ring gets all the shared memory
@@ -126,6 +132,9 @@ __device__ __forceinline__ uint32_t live_taps(const ConvParams& p, const ConvPro
 //   accumulators   tmem_full[a]/tmem_empty[a] MMA issuer   <-> epilogue     (two TMEM buffers: the
 //                                             epilogue of tile i overlaps the main loop of tile i+1)
 //   residual tile  res_full[a]/res_empty[a]  TMA producer  <-> epilogue     (double buffered)
+// kPair: the CTA-pair (cta_group::2) variant, launched as clusters of two (ConvParams::cs == 2). A separate
+// instantiation: a kernel that contains cta_group::2 instructions cannot be launched without a cluster.
+template <bool kPair>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ WeightMaps wmaps,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -135,7 +144,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   //        residual tiles [2][BN/64][128 x 128 B] | barriers | tmem ptr | scale/shift
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = kBlockM * kBlockK * 2;
-  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
+  const uint32_t b_bytes = (uint32_t)(p.BN / p.cs) * kBlockK * 2;   // this CTA's rows of the weight tile
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
   const int nblk_res = p.has_res ? p.BN / 64 : 0;             // residual K blocks per tile (64 channels each)
@@ -170,28 +179,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     prefetch_tmap(&tmap_out);
     if (p.has_res) prefetch_tmap(&tmap_res);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar + s, 1);
+      mbar_init(full_bar + s, 1);     // pair: only the leader's is used (both CTAs' loads complete on it)
       mbar_init(empty_bar + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + a, 1);
-      mbar_init(tmem_empty_bar + a, kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar + a, kEpiWarps * p.cs);   // one arrival per epilogue warp (pair: of both CTAs, on the leader's)
     }
     fence_barrier_init();
   }
+  constexpr bool pair = kPair;
+  uint32_t crank = 0u;
+  if constexpr (pair) crank = cluster_ctarank();
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (pair) {   // both CTAs of the pair allocate (same columns in both TMEMs)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (p.has_res) {
-    // identity tile: element (n, k) of the K-major SW128 layout lives at n*128 + ((k/8) ^ (n%8))*16 + (k%8)*2
+    // identity tile [n][k], K-major SW128: element (row i, k) lives at i*128 + ((k/8) ^ (i%8))*16 + (k%8)*2. A pair splits
+    // B's 64 rows: this CTA holds rows n = crank*32 + i at local row i (i < 32)
     for (int i = threadIdx.x; i < 512; i += kConvThreads) reinterpret_cast<uint4*>(eye_smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    if (threadIdx.x < 64) {
-      const int n = threadIdx.x;
-      *reinterpret_cast<unsigned short*>(eye_smem + n * 128 + (((n >> 3) ^ (n & 7)) << 4) + (n & 7) * 2) = 0x3f80;  // bf16 1.0
+    if (threadIdx.x < (pair ? 32 : 64)) {
+      const int i = threadIdx.x;
+      const int k = (int)crank * 32 + i;     // the 1.0 of row n sits in column k = n
+      *reinterpret_cast<unsigned short*>(eye_smem + i * 128 + (((k >> 3) ^ (i & 7)) << 4) + (k & 7) * 2) = 0x3f80;  // bf16 1.0
     }
     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
   }
@@ -199,23 +218,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int cs = p.cs;
+  if constexpr (pair) cluster_sync_all();   // the peer's barriers / TMEM are set up before anything is sent to them
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map
   // prefetch) overlapped the tail of the previous kernel in the stream; from here on we touch its
   // outputs, so wait for it to complete. Our own dependents may start their prologue right away.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  // tile -> (image, y0, x0, n0); identical in every role
-  auto tile_coords = [&](int item_idx, int& prob, int& n_img, int& y0, int& x0, int& n0) {
-    const int item = p.schedule ? __ldg(p.schedule + item_idx) : item_idx;
-    prob = item >> 24;
-    const int t = item & 0xffffff;
-    const int nt = t % n_tiles, mt = t / n_tiles;
+  // item -> (problem, n-tile) + the m-tile of cluster rank r; tile -> (image, y0, x0, n0); identical in every role.
+  // Pair mode: an item is two m-tiles of one (problem, n-tile); without a work list these are the consecutive tiles
+  // 2g, 2g+1 (an odd last tile is repeated: same values written twice), with a work list entry 2*item + r names rank r's
+  // tile (the host pairs tiles with equal live taps).
+  const int first_item = (int)(blockIdx.x / (unsigned)cs);
+  const int item_step = (int)(gridDim.x / (unsigned)cs);
+  auto item_tile = [&](int item_idx, int rank, int& prob, int& nt) -> int {
+    if (p.schedule) {
+      const int item = __ldg(p.schedule + item_idx * cs + rank);
+      prob = item >> 24;
+      const int t = item & 0xffffff;
+      nt = t % n_tiles;
+      return t / n_tiles;
+    }
+    prob = 0;
+    nt = item_idx % n_tiles;
+    return min((item_idx / n_tiles) * cs + rank, p.m_tiles - 1);
+  };
+  auto mt_origin = [&](int mt, int& n_img, int& y0, int& x0) {
     n_img = mt / tiles_img;
     const int trem = mt % tiles_img;
     y0 = (trem / p.tiles_x) * p.BH;
     x0 = (trem % p.tiles_x) * p.BW;
+  };
+  auto tile_coords = [&](int item_idx, int& prob, int& n_img, int& y0, int& x0, int& n0) {
+    int nt;
+    mt_origin(item_tile(item_idx, (int)crank, prob, nt), n_img, y0, x0);
     n0 = nt * p.BN;
+  };
+  // taps a pair runs for an item: the union of the two tiles' live taps (one K-block list for the joint MMA; a tap dead
+  // for one of the tiles reads zeros there)
+  auto item_taps = [&](int item_idx, const ConvProblem& q, int y0, int x0) -> uint32_t {
+    uint32_t m = live_taps(p, q, y0, x0);
+    for (int r = 0; r < cs; ++r) {
+      if (r == (int)crank) continue;
+      int prob2, nt2, n2, y2, x2;
+      mt_origin(item_tile(item_idx, r, prob2, nt2), n2, y2, x2);
+      m |= live_taps(p, q, y2, x2);
+    }
+    return m;
   };
 
   if (warp == 0) {
@@ -226,15 +276,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       int s = 0;          // ring position runs across tiles; ph = parity of the number of wraps
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = first_item; t < total_tiles; t += item_step, ++it) {
         int prob, n_img, y0, x0, n0;
         tile_coords(t, prob, n_img, y0, x0, n0);
         const ConvProblem& q = p.pr[prob];
-        const uint32_t taps = live_taps(p, q, y0, x0);
+        const uint32_t taps = item_taps(t, q, y0, x0);
+        const uint32_t a_box = (uint32_t)(p.BW * p.BH * kBlockK * 2);
         for (int j = 0; j < nblk_res; ++j) {   // residual K blocks: A = 64 residual channels of the tile's pixels
           DBG_T(0, mbar_wait(empty_bar + s, ph ^ 1u));
-          mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2));
-          tma_load_4d(smem + (size_t)s * stage_bytes, &tmap_res, full_bar + s, q.ch_off + n0 + j * 64, x0, y0, n_img);
+          if constexpr (pair) {   // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both
+            if (crank == 0) mbar_expect_tx(full_bar + s, 2 * a_box);
+            tma_load_4d_pair(smem + (size_t)s * stage_bytes, &tmap_res, mapa_u32(smem_u32(full_bar + s), 0),
+                             q.ch_off + n0 + j * 64, x0, y0, n_img);
+          } else {
+            mbar_expect_tx(full_bar + s, a_box);
+            tma_load_4d(smem + (size_t)s * stage_bytes, &tmap_res, full_bar + s, q.ch_off + n0 + j * 64, x0, y0, n_img);
+          }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         for (int tp = 0; tp < q.R * q.S; ++tp) {
@@ -244,9 +301,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             DBG_T(1, mbar_wait(empty_bar + s, ph ^ 1u));
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             uint8_t* sb = sa + a_bytes;
-            mbar_expect_tx(full_bar + s, (uint32_t)(p.BW * p.BH * kBlockK * 2) + b_bytes);
-            tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
-            tma_load_2d(sb, &wmaps.m[prob], full_bar + s, tp * p.Cin + cb * kBlockK, n0);
+            if constexpr (pair) {   // own A tile + rows [crank*BN/2, +BN/2) of the weight tile
+              if (crank == 0) mbar_expect_tx(full_bar + s, 2 * (a_box + b_bytes));
+              const uint32_t fb = mapa_u32(smem_u32(full_bar + s), 0);
+              tma_load_4d_pair(sa, &tmap_x, fb, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
+              tma_load_2d_pair(sb, &wmaps.m[prob], fb, tp * p.Cin + cb * kBlockK, n0 + (int)crank * (p.BN >> 1));
+            } else {
+              mbar_expect_tx(full_bar + s, a_box + b_bytes);
+              tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
+              tma_load_2d(sb, &wmaps.m[prob], full_bar + s, tp * p.Cin + cb * kBlockK, n0);
+            }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -258,22 +322,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                           ((uint32_t)(kBlockM >> 4) << 24);
-    const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) |
-                             ((uint32_t)(kBlockM >> 4) << 24);   // N = 64: the identity blocks of the residual
-    if (elect_one()) {
+    // instruction descriptors: bf16 x bf16 -> fp32, K-major A and B, N = BN (64 for the residual's identity blocks),
+    // M = 128 per CTA (256 for a pair)
+    const uint32_t mfield = (uint32_t)((kBlockM * cs) >> 4) << 24;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | mfield;
+    const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | mfield;
+    if (crank == 0 && elect_one()) {          // pair: the leader issues for both CTAs
       unsigned long long dbg_acc[4] = {0, 0, 0, 0};
       const long long dbg_t0 = clock64();
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = first_item; t < total_tiles; t += item_step, ++it) {
         int prob, n_img, y0, x0, n0;
         tile_coords(t, prob, n_img, y0, x0, n0);
-        const int num_kb = __popc(live_taps(p, p.pr[prob], y0, x0)) * cblocks;
+        const int num_kb = __popc(item_taps(t, p.pr[prob], y0, x0)) * cblocks;
         const int a = it & 1;
-        DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue drained this buffer
+        DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue(s) drained this buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * p.BN);
         for (int j = 0; j < nblk_res; ++j) {   // D[:, 64j..64j+63] = R_j x I64 (overwrites: first MMAs of the tile)
@@ -282,9 +347,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           const uint64_t adesc = make_sw128_desc(smem_u32(smem + (size_t)s * stage_bytes));
           const uint64_t edesc = make_sw128_desc(smem_u32(eye_smem));
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16(tacc + (uint32_t)(j * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
-          umma_commit(empty_bar + s);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            if constexpr (pair)
+              umma_bf16_pair(tacc + (uint32_t)(j * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
+            else
+              umma_bf16(tacc + (uint32_t)(j * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
+          }
+          if constexpr (pair) umma_commit_pair(empty_bar + s, 3); else umma_commit(empty_bar + s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -295,13 +364,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 B per K step inside the 128 B swizzle span (start-address field is in 16 B units)
-            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (nblk_res > 0 || kb > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (nblk_res > 0 || kb > 0 || k > 0) ? 1u : 0u;
+            if constexpr (pair)
+              umma_bf16_pair(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+            else
+              umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
           }
-          umma_commit(empty_bar + s);     // frees the smem stage when these MMAs retire
+          // frees the smem stage when these MMAs retire (in both CTAs of a pair)
+          if constexpr (pair) umma_commit_pair(empty_bar + s, 3); else umma_commit(empty_bar + s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tmem_full_bar + a);   // accumulator complete
+        // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's; both epilogues are told)
+        if constexpr (pair) umma_commit_pair(tmem_full_bar + a, 3); else umma_commit(tmem_full_bar + a);
       }
       if (DBG_ON(p)) {
         unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32 + 4;
@@ -324,7 +398,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (DBG_ON(p)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
     long long dbg_t1 = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = first_item; t < total_tiles; t += item_step, ++it) {
       int prob, n_img, y0, x0, n0;
       tile_coords(t, prob, n_img, y0, x0, n0);
       const ConvProblem& q = p.pr[prob];
@@ -426,7 +500,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(tmem_empty_bar + a);
+        if constexpr (pair) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty_bar + a), 0));   // the leader's MMA warp waits for both
+        else mbar_arrive(tmem_empty_bar + a);
       }
       // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
       fence_proxy_async();
@@ -452,10 +527,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     tcgen05_fence_before();
   }
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // nobody leaves while the peer may still signal barriers here or read this smem
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
-                 : "memory");
+    if constexpr (pair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
   if ((DBG_ON(p) || TS_ON(p)) && threadIdx.x == 0) {   // kernel-exit wall clock (ns)
     unsigned long long g;
@@ -549,12 +627,52 @@ static bool conv_pdl_enabled() {
   return on;
 }
 
+// CTA-pair mode of the conv launches (see ConvParams::cs): EESEG_CONV_CLUSTER=1|2 overrides the per-launch choice
+// (read once).
+static int conv_cluster_override() {
+  static const int v = [] {
+    const char* e = getenv("EESEG_CONV_CLUSTER");
+    const int c = e ? atoi(e) : 0;
+    return (c == 1 || c == 2) ? c : 0;
+  }();
+  return v;
+}
+
 struct HostProblem {
   const void* wt;
   const float* scale;
   const float* shift;
   int R, S, dil, pad, ch_off;
 };
+
+// How many clusters of `cs` conv CTAs (one CTA per SM: the kernel takes all of an SM's shared memory) the device runs
+// at once; depends on the GPC layout only. Cached per cluster size.
+static int max_active_clusters(int cs) {
+  static int cached[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached[cs] == 0) {
+    if (ensure_max_smem(conv_igemm_kernel<true>, 227 * 1024) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(kNumSMs / cs * cs));
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_igemm_kernel<true>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = kNumSMs / cs / 2;     // conservative fallback
+    }
+    cached[cs] = n;
+  }
+  return cached[cs];
+}
 
 // Common launcher: `nprob` convolutions over the same input (same Cin, Cout, stride, output tensor)
 static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t shift_sn, int N, int hin,
@@ -640,18 +758,31 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.swz = p.row_bytes == 128 ? 1 : 0;
   const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
   const size_t res_bytes = residual ? 8192 : 0;   // the 64x64 identity tile
-  const size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
+  size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
   const size_t tail_bytes = 256 + 2 * 256 * 4;   // barriers + tmem pointer (< 256 B), scale, shift
   const int tiles_per_problem = N * p.tiles_x * p.tiles_y * (Cout / BN);
-  const int total_tiles = tiles_per_problem * nprob;
   EESEG_REQUIRE(tiles_per_problem < (1 << 24), "conv_igemm: too many tiles");
-  EESEG_REQUIRE(!schedule || n_items == total_tiles, "conv_igemm: schedule has %d items, expected %d", n_items, total_tiles);
+  EESEG_REQUIRE(!schedule || n_items == tiles_per_problem * nprob, "conv_igemm: schedule has %d items, expected %d", n_items,
+                tiles_per_problem * nprob);
   EESEG_REQUIRE(schedule || nprob == 1, "conv_igemm: a grouped launch needs a schedule");
   p.schedule = schedule;
+  p.m_tiles = N * p.tiles_x * p.tiles_y;
+  // CTA pairs (cta_group::2): two m-tiles per work item, each CTA stages half of the weight tile's rows
+  int cs = 1;
+  if (!schedule) {
+    cs = conv_cluster_override();
+    if (cs == 0) cs = 1;
+    if (cs == 2 && (BN < 32 || p.m_tiles < 2)) cs = 1;
+  }
+  p.cs = cs;
+  stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)(BN / cs) * kBlockK * 2;
+  const int total_tiles = schedule ? n_items : ((p.m_tiles + cs - 1) / cs) * (Cout / BN);   // work items (clusters' worth)
   p.n_items = total_tiles;
+  const int max_clusters = cs == 1 ? kNumSMs : max_active_clusters(cs);
+  EESEG_REQUIRE(max_clusters > 0, "conv_igemm: no cluster of %d CTAs fits", cs);
   // with at most one tile per CTA the ring is idle when the epilogue runs: the staging tile overlays
   // it and the ring gets the shared memory (deep-K ASPP convs: 4 stages instead of 3)
-  p.overlay = total_tiles <= kNumSMs ? 1 : 0;
+  p.overlay = total_tiles <= max_clusters ? 1 : 0;
   // multi-tile deep-K launches (every tile runs >= 16 K blocks): no staging tile, a deeper ring
   int kb_min = 1 << 30;
   for (int g = 0; g < nprob; ++g) {
@@ -692,26 +823,36 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
     const cuuint64_t Kt = (cuuint64_t)q.R * q.S * Cin;
     cuuint64_t dims[2] = {Kt, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {Kt * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(BN / cs)};   // one CTA's part of the weight tile
     cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&wm.m[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q.wt), dims, strides, box,
                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_igemm: cuTensorMapEncodeTiled(w) failed: %d", (int)r); return EESEG_ERR_CUDA; }
   }
-  EESEG_CUDA(ensure_max_smem(conv_igemm_kernel, 227 * 1024));
-  dim3 grid((unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs));   // persistent: one CTA per SM
+  if (cs == 2) EESEG_CUDA(ensure_max_smem(conv_igemm_kernel<true>, 227 * 1024));
+  else EESEG_CUDA(ensure_max_smem(conv_igemm_kernel<false>, 227 * 1024));
+  // persistent: one CTA per SM (one cluster per cs SMs of a GPC)
+  dim3 grid((unsigned)((total_tiles < max_clusters ? total_tiles : max_clusters) * cs));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
   attr[0].val.programmaticStreamSerializationAllowed = conv_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmx, wm, tmo, tmr, p));
+  if (cs > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cs;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  if (cs == 2) EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmx, wm, tmo, tmr, p));
+  else EESEG_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmx, wm, tmo, tmr, p));
   return check_launch("conv_igemm_kernel");
 }
 
