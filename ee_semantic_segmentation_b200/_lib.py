@@ -66,6 +66,14 @@ PROTOTYPES = {
     "eeseg_stem_space_to_depth_any": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_dense_bn_act": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "eeseg_dropout_fwd": (c_i, [c_p, c_i64, c_f, c_p, c_p, c_p, c_p]),
+    "eeseg_dropout_bwd": (c_i, [c_p, c_p, c_i64, c_f, c_p, c_p]),
+    "eeseg_sgd_chunk_bytes": (c_sz, []),
+    "eeseg_sgd_multi": (c_i, [c_p, c_i, c_p, c_f, c_f, c_p]),
+    "eeseg_dense_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "eeseg_bn_rows_fwd": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p, c_p]),
+    "eeseg_bn_rows_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
+    "eeseg_broadcast_rows_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_f, c_p, c_p]),
     "eeseg_global_avgpool_workspace_bytes": (c_sz, [c_i, c_i]),
     "eeseg_global_avgpool_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_p, c_p, c_p]),
 }

@@ -56,31 +56,101 @@ def wrap_ddp(net, local_rank):
 
 
 class FlatGradients:
-    """Gradients of a set of parameters as views of ONE flat fp32 buffer, so that a data-parallel step needs a single
-    all-reduce: autograd accumulates into the views in place, `zero()` clears them with one fill, `all_reduce_mean()`
-    averages them over the ranks (NCCL: one AVG collective, capturable in a CUDA graph — train_funcs.GraphedTrainStep;
-    gloo on CPU tensors: SUM and a division, used by the CPU tests), and the optimizer reads the views as usual."""
+    """Gradients of a set of parameters as views of ONE flat fp32 buffer: autograd accumulates into the views in place,
+    `zero()` clears them with one fill, and a data-parallel step averages them over the ranks with a few large
+    collectives instead of one per tensor (NCCL: AVG all-reduces, capturable in a CUDA graph —
+    train_funcs.GraphedTrainStep; gloo on CPU tensors: SUM and a division, used by the CPU tests). The optimizer reads
+    the views as usual.
 
-    def __init__(self, params):
+    `buckets` > 1 overlaps the exchange with the backward pass: the buffer is laid out in REVERSE parameter order (the
+    last layers' gradients are complete first) and cut into `buckets` contiguous ranges of about equal size; a
+    post-accumulate hook on every parameter counts its bucket down, and the bucket's all-reduce is issued on a side
+    stream the moment its last gradient has been written, while the rest of the backward keeps the main stream busy
+    (`begin()` before the backward, `finish()` before the optimizer). With one bucket, or without hooks, `all_reduce_mean()`
+    reduces everything after the backward."""
+
+    def __init__(self, params, buckets=1):
         self.params = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters"
         dev = self.params[0].device
         assert all(p.dtype == torch.float32 and p.is_contiguous() and p.device == dev for p in self.params), \
             "flat gradients need contiguous fp32 parameters on one device"
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
-        o = 0
-        for p in self.params:
+        total = sum((p.numel() + 3) // 4 * 4 for p in self.params)     # every view starts 16-byte aligned
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        order = list(reversed(self.params))
+        self.buckets = []          # [start, end) element ranges, in the order their gradients complete
+        self._bucket_of = {}
+        n_b = max(1, int(buckets))
+        o, start, cur = 0, 0, 0
+        for p in order:
+            size = (p.numel() + 3) // 4 * 4
+            if cur < n_b - 1 and o > start and (o - start) + size / 2 > total / n_b:
+                self.buckets.append((start, o))          # close the bucket before a tensor that would overshoot its share
+                start, cur = o, cur + 1
             p.grad = self.flat[o:o + p.numel()].view_as(p)
-            o += p.numel()
+            self._bucket_of[id(p)] = cur
+            o += size
+        self.buckets.append((start, o))
+        self._need = [0] * len(self.buckets)
+        for p in order:
+            self._need[self._bucket_of[id(p)]] += 1
+        self._left = list(self._need)
+        self._hooks = []
+        self._side = None
+        self._armed = False
+        if len(self.buckets) > 1 and hasattr(self.params[0], "register_post_accumulate_grad_hook"):
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # ---- exchange -------------------------------------------------------------------------------------------------
+    def _world(self):
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _reduce_range(self, a, b):
+        t = self.flat[a:b]
+        if t.is_cuda:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.div_(dist.get_world_size())
+
+    def _on_grad(self, p):
+        if not self._armed:
+            return
+        b = self._bucket_of[id(p)]
+        self._left[b] -= 1
+        if self._left[b] == 0 and self._world() > 1:
+            a, e = self.buckets[b]
+            if self.flat.is_cuda:
+                main = torch.cuda.current_stream(self.flat.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.flat.device)
+                self._side.wait_stream(main)           # the bucket's gradients are complete on the main stream
+                with torch.cuda.stream(self._side):
+                    self._reduce_range(a, e)
+            else:
+                self._reduce_range(a, e)
+            self._left[b] = -1                          # reduced
+
+    def begin(self):
+        """Call before backward(): arms the per-bucket countdown (overlapped exchange)."""
+        self._left = list(self._need)
+        self._armed = bool(self._hooks)
+
+    def finish(self):
+        """Call after backward(), before the optimizer: reduces whatever the hooks did not, joins the side stream."""
+        if self._world() > 1:
+            for b, (a, e) in enumerate(self.buckets):
+                if not self._armed or self._left[b] != -1:
+                    self._reduce_range(a, e)
+            if self._side is not None and self.flat.is_cuda:
+                torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+        self._armed = False
 
     def zero(self):
         self.flat.zero_()
 
     def all_reduce_mean(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        if self.flat.is_cuda:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+        """Everything in one go after the backward (no overlap)."""
+        self._armed = False
+        self.finish()

@@ -171,28 +171,113 @@ def train(net, train_iter, loss, num_epochs, updater, val_iter=None, metrics=Non
     return tracker
 
 
-def _sgd_impl(net):
-    """torch's single-kernel ("fused") SGD update when every parameter lives on a GPU: the same update rule as the
-    default multi-tensor implementation in one pass over parameters, gradients and momentum buffers."""
-    return {'fused': True} if all(p.is_cuda for p in net.parameters()) else {}
+class SGD(optim.Optimizer):
+    """torch.optim.SGD's update (momentum, weight decay, one learning rate per parameter group; dampening 0, no
+    nesterov — what deepv3_funcs.py:74-101 constructs) on ONE eeseg launch per step (eeseg_sgd_multi): a device table
+    of 64 K-element chunks over all parameters, gradients and momentum buffers, the groups' learning rates read from a
+    small device array that `step()` refreshes — so a scheduler's `param_groups[i]['lr']` changes reach a CAPTURED step
+    without re-capturing it (GraphedTrainStep refreshes the array before every replay).
+
+    Gradients are views of one flat buffer (parallel.FlatGradients; `buckets` > 1 = the overlapped data-parallel
+    exchange), momentum buffers views of another: pointers never change, `zero_grad()` is one fill. `state_dict()` /
+    `load_state_dict()` use torch.optim.SGD's layout ('momentum_buffer' per parameter), so the reference's checkpoint
+    dict ("opt_state_dict", train_funcs.py:208-216) round-trips with torch's optimizer. CUDA parameters only."""
+
+    CHUNK = 65536
+
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, buckets=1):
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        from . import _lib
+        from .parallel import FlatGradients
+        ps = [p for g in self.param_groups for p in g['params']]
+        if not ps or not all(p.is_cuda and p.dtype == tch.float32 for p in ps):
+            raise RuntimeError('eeseg SGD needs fp32 CUDA parameters (no CPU fallback)')
+        m0, w0 = self.param_groups[0]['momentum'], self.param_groups[0]['weight_decay']
+        if any(g['momentum'] != m0 or g['weight_decay'] != w0 for g in self.param_groups):
+            raise ValueError('eeseg SGD takes one momentum / weight decay for all groups (per-group learning rates)')
+        self._lib = _lib
+        self.flat_grads = FlatGradients(ps, buckets=buckets)
+        dev = ps[0].device
+        self._mom = tch.zeros_like(self.flat_grads.flat)
+        recs = []
+        for gi, g in enumerate(self.param_groups):
+            for p in g['params']:
+                if not p.requires_grad:
+                    continue
+                off = (p.grad.data_ptr() - self.flat_grads.flat.data_ptr()) // 4
+                buf = self._mom[off:off + p.numel()].view_as(p)
+                self.state[p]['momentum_buffer'] = buf
+                for c0 in range(0, p.numel(), self.CHUNK):
+                    n = min(self.CHUNK, p.numel() - c0)
+                    recs.append((p.data_ptr() + 4 * c0, p.grad.data_ptr() + 4 * c0, buf.data_ptr() + 4 * c0, n, gi))
+        assert _lib.lib().eeseg_sgd_chunk_bytes() == 32
+        table = np.zeros(len(recs), dtype=np.dtype([('p', '<u8'), ('g', '<u8'), ('b', '<u8'), ('n', '<i4'), ('grp', '<i4')]))
+        for i, r in enumerate(recs):
+            table[i] = r
+        self._table = tch.from_numpy(table.view(np.uint8).copy()).to(dev)
+        self._n_chunks = len(recs)
+        self._lrs = tch.zeros(len(self.param_groups), dtype=tch.float32, device=dev)
+        self._lrs_host = tch.zeros(len(self.param_groups), dtype=tch.float32).pin_memory()
+        self._ptrs = [p.data_ptr() for p in ps]
+        self.sync_lrs()
+
+    def sync_lrs(self):
+        """Host learning rates -> the device array the kernel reads (async copy from pinned memory)."""
+        for i, g in enumerate(self.param_groups):
+            self._lrs_host[i] = float(g['lr'])
+        self._lrs.copy_(self._lrs_host, non_blocking=True)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grads.zero()          # the views stay: the chunk table holds their addresses
+
+    @tch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        if not tch.cuda.is_current_stream_capturing():
+            self.sync_lrs()
+        g0 = self.param_groups[0]
+        dev = self._table.device
+        with tch.cuda.device(dev):
+            self._lib.check(self._lib.lib().eeseg_sgd_multi(
+                self._table.data_ptr(), self._n_chunks, self._lrs.data_ptr(), float(g0['momentum']),
+                float(g0['weight_decay']), tch.cuda.current_stream(dev).cuda_stream), 'eeseg_sgd_multi')
+        return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for g in self.param_groups:                     # loaded buffers are fresh tensors: copy them into the flat views
+            for p in g['params']:
+                if not p.requires_grad:
+                    continue
+                off = (p.grad.data_ptr() - self.flat_grads.flat.data_ptr()) // 4
+                view = self._mom[off:off + p.numel()].view_as(p)
+                loaded = self.state[p].get('momentum_buffer')
+                if loaded is not None and loaded.data_ptr() != view.data_ptr():
+                    view.copy_(loaded)
+                elif loaded is None:
+                    view.zero_()
+                self.state[p]['momentum_buffer'] = view
+        self.sync_lrs()
 
 
-def make_optimizer(net, lr, base_lr=None, weighted_lr=False):
+def make_optimizer(net, lr, base_lr=None, weighted_lr=False, buckets=1):
     """SGD(momentum 0.9, weight decay 5e-4) with the reference's parameter groups
-    (deepv3_funcs.py:77-101): backbone at base_lr, branches at lr, final classifier at 1.1*lr."""
+    (deepv3_funcs.py:77-101): backbone at base_lr, branches at lr, final classifier at 1.1*lr. CUDA parameters get the
+    eeseg single-launch optimizer (`SGD` above), CPU parameters (host-side tests) torch.optim.SGD."""
     net = getattr(net, 'module', net)      # DDP
+    on_gpu = all(p.is_cuda for p in net.parameters())
+    ctor = (lambda params, **kw: SGD(params, buckets=buckets, **kw)) if on_gpu else optim.SGD
     if base_lr and getattr(net, 'n_branches', 0):
-        params = [{'params': net.base_model.parameters(), 'lr': base_lr}]
+        params = [{'params': list(net.base_model.parameters()), 'lr': base_lr}]
         if weighted_lr:
-            import numpy as np
             w = np.linspace(1, 1.2, num=net.n_branches + 1)
-            params += [{'params': net.branches[i].parameters(), 'lr': lr * w[i]} for i in range(net.n_branches)]
-            params.append({'params': net.classifier.parameters(), 'lr': lr * w[-1]})
+            params += [{'params': list(net.branches[i].parameters()), 'lr': lr * w[i]} for i in range(net.n_branches)]
+            params.append({'params': list(net.classifier.parameters()), 'lr': lr * w[-1]})
         else:
-            params.append({'params': net.branches.parameters(), 'lr': lr})
-            params.append({'params': net.classifier.parameters(), 'lr': lr * 1.1})
-        return optim.SGD(params, lr=lr, momentum=.9, weight_decay=5e-4, **_sgd_impl(net))
-    return optim.SGD(net.parameters(), lr=lr, momentum=.9, weight_decay=5e-4, **_sgd_impl(net))
+            params.append({'params': list(net.branches.parameters()), 'lr': lr})
+            params.append({'params': list(net.classifier.parameters()), 'lr': lr * 1.1})
+        return ctor(params, lr=lr, momentum=.9, weight_decay=5e-4)
+    return ctor(list(net.parameters()), lr=lr, momentum=.9, weight_decay=5e-4)
 
 
 def poly_scheduler(optimizer, num_epochs, lr=None, min_lr=None):
@@ -212,8 +297,9 @@ class GraphedTrainStep:
 
     Same arithmetic as the body of `train_epoch` (train_funcs.py:22-27) for a fixed batch shape. The warm-up
     steps needed before capture run on the example batch and are rolled back (parameters, BatchNorm buffers,
-    momentum), so the first replay is the first real update. Learning-rate changes made by a scheduler are baked
-    into the graph: call `recapture()` after `scheduler.step()` (the reference steps it once per epoch)."""
+    momentum), so the first replay is the first real update. With the eeseg `SGD` (make_optimizer on CUDA) the
+    learning rates are read from device memory at run time, so `scheduler.step()` needs nothing; torch's optimizers
+    bake them into the graph: call `recapture()` after `scheduler.step()` (the reference steps it once per epoch)."""
 
     def __init__(self, net, loss, optimizer, X, y, warmup=3, data_parallel=None):
         """data_parallel (default: torch.distributed initialised with more than one rank): every parameter's .grad is a
@@ -228,7 +314,10 @@ class GraphedTrainStep:
         self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel)
         self.flat = self._fg = None
         net.train()
-        if self.dp:
+        if getattr(optimizer, 'flat_grads', None) is not None:      # the eeseg SGD owns the flat gradient buffer
+            self._fg = optimizer.flat_grads
+            self.flat = self._fg.flat
+        elif self.dp:
             from .parallel import FlatGradients
             self._fg = FlatGradients([p for g in optimizer.param_groups for p in g['params']])
             self.flat = self._fg.flat
@@ -255,9 +344,11 @@ class GraphedTrainStep:
         else:
             self.opt.zero_grad(set_to_none=True)
         l = self.loss_fn(self.net(self.X), self.y)
-        l.mean().backward()
-        if self._fg is not None:
-            self._fg.all_reduce_mean()                   # NCCL over NVLink: one collective per step (none on one rank)
+        if self._fg is not None and self.dp:
+            self._fg.begin()                             # bucketed exchange: each bucket's NCCL all-reduce starts on a side
+        l.mean().backward()                              # stream as soon as its gradients are complete, under the backward
+        if self._fg is not None and self.dp:
+            self._fg.finish()                            # joins the side stream (none of this on one rank)
         self.opt.step()
         return l
 
@@ -279,6 +370,8 @@ class GraphedTrainStep:
     def __call__(self, X, y):
         self.X.copy_(X, non_blocking=True)
         self.y.copy_(y.view_as(self.y), non_blocking=True)
+        if hasattr(self.opt, 'sync_lrs'):
+            self.opt.sync_lrs()                          # a scheduler's new learning rates reach the captured update
         self.graph.replay()
         # a replay updates the parameters without touching their version counters: announce it, so that inference plans
         # and graphs derived from the old values (model, engines, operators) are dropped

@@ -348,6 +348,42 @@ size_t eeseg_global_avgpool_workspace_bytes(int N, int C);
 int eeseg_global_avgpool_nhwc(const void* x, int N, int64_t hw, int C, float* out, void* workspace,
                               void* stream);
 
+/* ---- training-step helpers (csrc/train_misc.cu) ---------------------------------------------------------------
+ * Dropout of ASPP.project (torchvision deeplabv3.py:101, active under net.train(): from_deepv3_new.py:147 inside
+ * train_funcs.py:22): y = x * keep / (1 - p) on bf16 tensors of n elements (n % 8 == 0), keep ~ Bernoulli(1 - p) from a
+ * counter-based generator; rng_state: DEVICE uint64[2] = {seed, offset}, the offset advances by n/8 per call ON THE
+ * DEVICE, so a captured CUDA graph draws a fresh mask on every replay. mask: uint8[n/8] (bit k = element 8i+k kept),
+ * consumed by the backward dx = dy * keep / (1 - p). p is realised in 1/256 steps (0.5 exactly). */
+int eeseg_dropout_fwd(const void* x, int64_t n, float p, void* rng_state, void* y, void* mask, void* stream);
+int eeseg_dropout_bwd(const void* dy, const void* mask, int64_t n, float p, void* dx, void* stream);
+
+/* torch.optim.SGD's update (deepv3_funcs.py:74-101: momentum 0.9, weight decay 5e-4, one learning rate per parameter
+ * group) for MANY tensors in one launch: d = g + wd * p; buf = momentum * buf + d; p -= lr[group] * buf. `chunks`: DEVICE
+ * array of n_chunks records {float* p; const float* g; float* buf; int32 count; int32 group} (eeseg_sgd_chunk_bytes()
+ * bytes each; one thread block per record); lrs: DEVICE float array indexed by group — read at run time, so a
+ * learning-rate schedule does not invalidate a captured graph. Zero-initialised momentum buffers give torch's first step. */
+size_t eeseg_sgd_chunk_bytes(void);
+int eeseg_sgd_multi(const void* chunks, int n_chunks, const float* lrs, float momentum, float weight_decay, void* stream);
+
+/* Backward of the small dense layer y[n][o] = x[n] . W[o] (eeseg_dense_bn_act without scale/shift; the pooled ASPP
+ * branch's 1x1 convolution on one pixel per image): dW[o][k] = sum_n dy[n][o] x[n][k], dx[n][k] = sum_o dy[n][o] W[o][k]
+ * (either output may be NULL). fp32, fixed summation order. */
+int eeseg_dense_bwd(const float* dy, const float* x, const float* W, int N, int K, int O, float* dW, float* dx, void* stream);
+
+/* BatchNorm (batch statistics over the N rows, biased variance for the normalisation, unbiased for the running estimate,
+ * as nn.BatchNorm2d on an [N,C,1,1] tensor) + optional ReLU on fp32 row vectors [N][C] — the pooled ASPP branch
+ * (deeplabv3.py:70-83); forward saves mean / invstd for the backward, which returns dx, dgamma, dbeta. */
+int eeseg_bn_rows_fwd(const float* x, int N, int C, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float momentum, float eps, int relu, float* y, float* save_mean,
+                      float* save_invstd, void* stream);
+int eeseg_bn_rows_bwd(const float* dy, const float* x, const float* y, int N, int C, const float* gamma,
+                      const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
+                      void* stream);
+
+/* out[n][p][c] = bf16(v[n][c] * scale) for p < hw: a per-image vector broadcast over the map (ASPPPooling's up-sampling of
+ * a 1x1 map, deeplabv3.py:83; with scale = 1/hw the backward of the global average pool). C % 8 == 0. */
+int eeseg_broadcast_rows_nhwc(const float* v, int N, int64_t hw, int C, float scale, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

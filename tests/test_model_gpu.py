@@ -260,7 +260,8 @@ def test_training_step_matches_torch_losses(nets):
     opt_a = make_optimizer(net_a, lr=1e-2, base_lr=1e-3)
     assert [grp['lr'] for grp in opt_a.param_groups] == pytest.approx([1e-3, 1e-2, 1.1e-2])
     sched = poly_scheduler(opt_a, 10)
-    torch.manual_seed(123)      # same Dropout(0.5) masks in both runs (ASPP.project is active in train mode)
+    from ee_semantic_segmentation_b200.head_train import dropout_state
+    dropout_state(dev(), seed=123)   # same Dropout(0.5) masks in both runs (ASPP.project is active in train mode)
     l_a = train_epoch(net_a, [(X, y)], BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=3), opt_a, dev())
     sched.step()
     assert opt_a.param_groups[1]['lr'] == pytest.approx(1e-2 * (1 - 1 / 10) ** .9)
@@ -270,7 +271,7 @@ def test_training_step_matches_torch_losses(nets):
             ce = torch.nn.CrossEntropyLoss(ignore_index=21)
             return sum(ce(y_pred[i], t.squeeze(1)) for i in range(3))
     opt_b = make_optimizer(net_b, lr=1e-2, base_lr=1e-3)
-    torch.manual_seed(123)
+    dropout_state(dev(), seed=123)
     l_b = train_epoch(net_b, [(X, y)], RefLoss(), opt_b, dev())
     assert l_a.item() == pytest.approx(l_b.item(), rel=1e-4)
     pa = torch.cat([p.detach().flatten() for p in net_a.branches.parameters()])

@@ -59,7 +59,7 @@ def test_sharded_confusion_allreduce_matches_single_process(tmp_path):
     assert list(parallel.shard_range(7, 1, 2)) == [1, 3, 5]
 
 
-def _train_worker(rank, world, port, tmp):
+def _train_worker(rank, world, port, tmp, buckets=1):
     sys.path.insert(0, ROOT)
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -68,26 +68,34 @@ def _train_worker(rank, world, port, tmp):
     torch.manual_seed(0)                                   # identical initial weights on every rank
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
-    fg = parallel.FlatGradients(net.parameters())
+    fg = parallel.FlatGradients(net.parameters(), buckets=buckets)
+    assert len(fg.buckets) == buckets
     g = torch.Generator().manual_seed(7)
     X, y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
     Xs, ys = X[rank::world], y[rank::world]                # this rank's shard
     for _ in range(3):
         fg.zero()
+        if buckets > 1:
+            fg.begin()                                     # per-bucket exchange from the gradient hooks, during backward
         ((net(Xs) - ys) ** 2).mean().backward()            # accumulates in place into the flat buffer
         assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in net.parameters())
-        fg.all_reduce_mean()
+        if buckets > 1:
+            assert all(v == -1 for v in fg._left)          # every bucket was reduced by its last gradient's hook
+            fg.finish()
+        else:
+            fg.all_reduce_mean()
         opt.step()
     torch.save([p.detach().clone() for p in net.parameters()], os.path.join(tmp, f"p{rank}.pt"))
     torch.distributed.destroy_process_group()
 
 
-def test_flat_gradient_allreduce_training_matches_single_process(tmp_path):
+@pytest.mark.parametrize("buckets", [1, 2])
+def test_flat_gradient_allreduce_training_matches_single_process(tmp_path, buckets):
     """The data-parallel step of train_funcs.GraphedTrainStep on CPU/gloo: gradients as views of one flat buffer, one
     all-reduce(mean) per step. Two ranks on disjoint equal shards end with identical parameters, equal to single-process
     SGD on the whole batch (the mean of the shard means is the batch mean)."""
     port = 29500 + ((os.getpid() + 137) % 500)
-    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path), buckets), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "p0.pt"), torch.load(tmp_path / "p1.pt")
     assert all(torch.equal(x, z) for x, z in zip(a, b))
     torch.manual_seed(0)
