@@ -148,7 +148,7 @@ def measured_peaks():
 
 def conv_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per conv launch from the committed ncu capture of one
-    step of the default workload (profiles/r01_conv_traffic.json); None for other workloads."""
+    step of the default workload (profiles/r02_conv_traffic.json); None for other workloads."""
     if METRIC != "early_exit_images_per_sec_513":
         return None
     try:
@@ -463,11 +463,13 @@ def main():
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
         barrier()
         t0 = time.perf_counter()
+        torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" profiles these launches only
         for a, b in ev:
             flush.fill_(1)
             a.record()
             fn()
             b.record()
+        torch.cuda.nvtx.range_pop()
         if world > 1 and reduce_eng is not None:
             reduce_eng.all_reduce()           # the sweep's one integer collective (once, not per step)
         barrier()
