@@ -152,7 +152,7 @@ def conv_traffic():
     if METRIC != "early_exit_images_per_sec_513":
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) as f:
             return json.load(f)["traffic_bytes_per_launch"]
     except Exception:
         return None
