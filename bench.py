@@ -406,6 +406,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the conv kernel")
+    ap.add_argument("--no-overlap-heads", action="store_true", help="early-exit heads in stream order (A/B of the side-stream overlap)")
     ap.add_argument("--legs", default="all", help="comma list of extra workloads after the headline: cityscapes_sweep, "
                                                   "train_ce, train_lovasz; 'all' (default) or 'none'")
     args = ap.parse_args()
@@ -443,6 +444,7 @@ def main():
                         num_classes=N_CLASSES).to(dev).eval()
     net.strict_kernels = True                       # a module without an eeseg kernel plan is an error, not a cuDNN call
     eng = EarlyExitEngine(net, N_CLASSES, TAU, use_graph=not args.no_graph)
+    eng.overlap_heads = not args.no_overlap_heads
     Xh, yh = synth_batch(rank, PER_GPU_BATCH)
     Xh, yh = Xh.pin_memory(), yh.pin_memory()
     Xd, yd = Xh.to(dev), yh.to(dev)

@@ -33,6 +33,7 @@ class EarlyExitEngine:
         self.input_dtype, self.target_dtype = input_dtype, target_dtype
         self.use_graph = use_graph
         self.overlap_gates = True      # early-exit gates on a side stream, overlapping the next section
+        self.overlap_heads = True      # ... and the early exits' heads with them (tails of one stream's launches fill with the other's)
         self._side = None
         self._graphs = {}
         self.net = net
@@ -338,26 +339,35 @@ class EarlyExitEngine:
         amax_all = torch.empty((E, N, H, W), dtype=torch.uint8, device=dev)
         scores = torch.full((max(E - 1, 1), N), float('inf'), dtype=torch.float32, device=dev)
         pool = self.metric != 'ent'
-        # The gate of an early exit (up-sample + entropy + decision, ~35 us of small kernels) does not feed
-        # the next backbone section: it runs on a side stream, forked when the head's low-res logits are
-        # ready and joined before the final accumulation, so it overlaps the next section's convolutions
-        # (the gate CTAs need no shared memory and fit next to the persistent conv CTAs). Captured into the
-        # CUDA graph as a parallel branch; all gates share the one side stream, so decisions stay ordered.
+        # An early exit's head and gate (ASPP convolutions, up-sample + entropy + decision) do not feed the next backbone
+        # section: they run on a side stream, forked when the section's output is ready and joined before the final
+        # accumulation. Every conv launch is a persistent grid sized to the whole GPU, so two of them never share an SM —
+        # but the tail of one (a 144-tile wave on 148 SMs, CTAs draining their epilogues) frees SMs that the other
+        # stream's next launch fills, which a single in-order stream leaves idle. Captured into the CUDA graph as a
+        # parallel branch; all early exits share the one side stream, so decisions stay ordered.
+        # (overlap_gates without overlap_heads: only the gate runs aside, as in round 1.)
         main = torch.cuda.current_stream(dev)
         side = self._side_stream()
-        keep = []          # tensors produced on `main` and read on `side` stay referenced until the join
+        keep = []          # tensors produced on one stream and read on the other stay referenced until the join
         forked = False
         Xc = X
         for i in range(E):
             Xc = net.run_section(i, Xc)
-            low = net._plan(i).run(Xc)
             gated = i < E - 1 and i >= self.skip
-            on_side = self.overlap_gates and i < E - 1
-            if on_side:
+            head_aside = self.overlap_heads and self.overlap_gates and i < E - 1
+            gate_aside = self.overlap_gates and i < E - 1
+            if head_aside:
                 side.wait_stream(main)
-                keep.append(low)
+                keep.append(Xc)
                 forked = True
-            with torch.cuda.stream(side if on_side else main):
+            with torch.cuda.stream(side if head_aside else main):
+                low = net._plan(i).run(Xc)
+            if gate_aside and not head_aside:
+                side.wait_stream(main)
+                forked = True
+            if gate_aside:
+                keep.append(low)
+            with torch.cuda.stream(side if gate_aside else main):
                 res = ops.exit_gate(low, (H, W), layout='NHWC', n_classes=self.C, tau=self.tau,
                                     want_ent=pool and gated, want_amax=True, want_score=gated and not pool,
                                     amax_out=amax_all[i], score_out=scores[i] if gated and not pool else None)
@@ -367,7 +377,7 @@ class EarlyExitEngine:
                     else:
                         self.exited_px[i] += res.exited_px.sum()
                     ops.gate_decide(scores[i], self.tau, i, exit_idx, want_active=False)
-                if on_side:
+                if gate_aside:
                     keep.append(res)
         if forked:
             main.wait_stream(side)
