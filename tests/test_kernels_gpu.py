@@ -696,3 +696,35 @@ def test_new_seg_losses_golden(golden):
         assert np.abs(yy.grad.cpu().numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-8, tag
     with pytest.raises(RuntimeError, match="smaller than num_classes"):
         NSL.TverskyLoss()(y, tg["targets_void"])
+
+
+@pytest.mark.parametrize("E,N,C,H,W", [(3, 2, 21, 97, 113), (3, 1, 21, 513, 513), (2, 3, 19, 64, 64), (1, 2, 7, 1, 1),
+                                        (2, 2, 21, 1, 3), (3, 2, 21, 5, 13), (1, 1, 40, 33, 31)])
+def test_ce_bf16_does_not_depend_on_the_tensor_alignment(E, N, C, H, W):
+    """bf16 logits in a tensor that starts 2 bytes off a 4-byte boundary (a view into a larger buffer) against the same
+    values in an aligned tensor, odd-sized planes included: per-exit losses equal, the gradient BIT-identical. (Written
+    for the pixel-pair variant of the kernel, which was measured slower and dropped — profiles/r02_hbm_kernel_experiments.md;
+    kept as an alignment-robustness test of the element-wise kernel.)"""
+    from ee_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(E * 1000 + C * 10 + H)
+    vals = (torch.randn(E, N, C, H, W, generator=g) * 3).to(torch.bfloat16)
+    tgt = torch.randint(0, C + 1, (N, H, W), generator=g)
+    if H * W > 4:
+        tgt.view(-1)[::7] = C                                  # void pixels
+    tgt = tgt.to(dev())
+    coef = torch.tensor([0.5, 1.0, 2.0][:E], device=dev())
+    aligned = vals.to(dev()).contiguous()
+    buf = torch.empty(vals.numel() + 1, dtype=torch.bfloat16, device=dev())
+    shifted = buf[1:].view_as(vals)
+    shifted.copy_(vals)
+    assert aligned.data_ptr() % 4 == 0 and shifted.data_ptr() % 4 == 2
+    outs = []
+    for y in (aligned, shifted):
+        yy = y.detach().requires_grad_(True)
+        per_exit, valid = ops.multi_exit_ce(yy, tgt, ignore_index=C, coef=coef)
+        (per_exit * coef).sum().backward()
+        outs.append((per_exit.detach().clone(), int(valid), yy.grad.detach().clone()))
+    (la, va, ga), (lb, vb, gb) = outs
+    assert va == vb
+    assert torch.allclose(la, lb, rtol=1e-6, atol=0, equal_nan=True)
+    assert torch.equal(ga.view(torch.int16), gb.view(torch.int16))
