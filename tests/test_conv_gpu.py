@@ -141,7 +141,8 @@ def test_section_plan_vs_torchvision():
     assert (ga.float().cpu() - ra).abs().max().item() < 2e-2 * ra.abs().max().item()
     gb = SectionPlan(sec_b.to(dev())).run(ga)
     assert gb.shape == rb.shape
-    assert (gb.float().cpu() - rb).abs().max().item() < 3e-2 * rb.abs().max().item()
+    from conftest import assert_bf16_model_close
+    assert_bf16_model_close(gb.float().cpu(), rb)      # a whole section (up to 16 Bottlenecks) in bf16: DESIGN §2
 
 
 def test_stem_plan_vs_torch():
