@@ -44,18 +44,29 @@ inline int check_launch(const char* what) {
     }                                                                          \
   } while (0)
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and kernel, race-free (the attribute is per
-// device; callers may launch from several host threads)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device), race-free (the attribute is per device;
+// callers may launch from several host threads). Keyed by the kernel's ADDRESS: two instantiations of one template share
+// their function type.
 template <typename K>
 inline cudaError_t ensure_max_smem(K kernel, int bytes) {
-  static std::once_flag once[64];
-  static cudaError_t result[64];
+  static std::mutex mu;
+  static const void* done_fn[64];
+  static int done_dev[64];
+  static int n_done = 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  std::call_once(once[dev], [&] { result[dev] = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
-  return result[dev];
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_done; ++i)
+    if (done_fn[i] == fn && done_dev[i] == dev) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && n_done < 64) {
+    done_fn[n_done] = fn;
+    done_dev[n_done] = dev;
+    ++n_done;
+  }
+  return e;
 }
 
 // ---- typed scalar access ------------------------------------------------------------------------

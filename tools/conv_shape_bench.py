@@ -47,11 +47,14 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--only", default="", help="substring of the shape name")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
     for name, N, h, w, Cin, Cout, k, dil, stride, res in SHAPES:
+        if args.only and args.only not in name:
+            continue
         g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xffff)
         x = torch.randn(N, h, w, Cin, generator=g).to(dev).to(torch.bfloat16)
         wt = (torch.randn(Cout, k, k, Cin, generator=g) / (k * k * Cin) ** 0.5).to(dev).to(torch.bfloat16)
