@@ -44,6 +44,8 @@ PROTOTYPES = {
                                    c_i, c_i, c_i, c_i, c_p, c_i64, c_p, c_i, c_i64, c_p]),
     "eeseg_conv_igemm_wgrad_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
     "eeseg_conv_igemm_wgrad": (c_i, [c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "eeseg_conv_igemm_wgrad_to_param_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
+    "eeseg_conv_igemm_wgrad_to_param": (c_i, [c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p]),
     "eeseg_conv_igemm_dgrad_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "eeseg_conv_igemm_dgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i64, c_p, c_p]),
     "eeseg_conv_weight_rot180_t": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
@@ -59,6 +61,7 @@ PROTOTYPES = {
     "eeseg_bn_train_workspace_bytes": (c_sz, [c_i]),
     "eeseg_bn_train_fwd": (c_i, [c_p, c_i64, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "eeseg_bn_train_bwd": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "eeseg_bn_train_bwd_acc": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "eeseg_conv_group_tiles": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "eeseg_conv_igemm_grouped": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i,
                                        c_p, c_i64, c_i, c_p, c_i, c_p]),

@@ -31,6 +31,7 @@ class BnActFn(torch.autograd.Function):
                 None if res is None else res.data_ptr(), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(),
                 torch.cuda.current_stream(dev).cuda_stream), "eeseg_bn_train_fwd")
         ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+        ctx.params = (weight, bias) if isinstance(weight, nn.Parameter) and isinstance(bias, nn.Parameter) else None
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
         return y
@@ -46,9 +47,24 @@ class BnActFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        ws = torch.empty((lib().eeseg_bn_train_workspace_bytes(C),), dtype=torch.uint8, device=dev)
+        from .parallel import direct_grad
+        gw = gb = None
+        if ctx.params is not None and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            gw, gb = direct_grad(ctx.params[0]), direct_grad(ctx.params[1])
+        if gw is not None and gb is not None:
+            # dgamma / dbeta added straight into the parameters' .grad: two AccumulateGrad launches less per BatchNorm
+            with torch.cuda.device(dev):
+                check(lib().eeseg_bn_train_bwd_acc(
+                    dy.data_ptr(), x.data_ptr(), None if y is None else y.data_ptr(), P, C, weight.data_ptr(), mean.data_ptr(),
+                    invstd.data_ptr(), 1 if ctx.relu else 0, dx.data_ptr(), None if dres is None else dres.data_ptr(),
+                    gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                    "eeseg_bn_train_bwd_acc")
+            for p in ctx.params:
+                p._eeseg_flat.written(p)
+            return dx, None, None, dres, None, None, None, None, None
         dgamma = torch.empty((C,), dtype=torch.float32, device=dev)
         dbeta = torch.empty((C,), dtype=torch.float32, device=dev)
-        ws = torch.empty((lib().eeseg_bn_train_workspace_bytes(C),), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(lib().eeseg_bn_train_bwd(
                 dy.data_ptr(), x.data_ptr(), None if y is None else y.data_ptr(), P, C, weight.data_ptr(), mean.data_ptr(),

@@ -161,13 +161,14 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int splits, int C, int64_t P,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
-                                       float* __restrict__ c2, float* __restrict__ fa) {
+                                       float* __restrict__ c2, float* __restrict__ fa, int accumulate) {
   const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (c >= C) return;
   const double s = bn_warp_total(partial, splits, C, c, 0), ss = bn_warp_total(partial, splits, C, c, 1);
   if ((threadIdx.x & 31) != 0) return;
-  if (dbeta) dbeta[c] = (float)s;
-  if (dgamma) dgamma[c] = (float)ss;
+  // accumulate: dgamma / dbeta ARE the parameters' .grad tensors (one launch less per BatchNorm than AccumulateGrad's add_)
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)ss;
   // dx = a*(dy' - s/P - xhat*ss/P) = a*dy' + k1 + k2*x with xhat = (x - mean)*invstd
   const double a = (double)(gamma ? gamma[c] : 1.f) * (double)invstd[c];
   const double k2 = -a * (ss / (double)P) * (double)invstd[c];
@@ -270,9 +271,9 @@ extern "C" int eeseg_bn_train_fwd(const void* x, int64_t P, int C, const float* 
   return check_launch("bn_apply_kernel");
 }
 
-extern "C" int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
-                                  const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres,
-                                  float* dgamma, float* dbeta, void* workspace, void* stream_) {
+static int bn_bwd_launch(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
+                         const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres, float* dgamma,
+                         float* dbeta, int accumulate, void* workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EESEG_REQUIRE(dy && x && save_mean && save_invstd && dx && workspace, "bn_train_bwd: null pointer");
   EESEG_REQUIRE(P >= 1 && C >= 64 && C % 64 == 0, "bn_train_bwd: C=%d must be a positive multiple of 64", C);
@@ -288,7 +289,7 @@ extern "C" int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, 
   int rc = check_launch("bn_reduce_kernel<bwd>");
   if (rc) return rc;
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partial, splits, C, P, gamma, save_mean, save_invstd, dgamma, dbeta,
-                                                              c1, c2, fa);
+                                                              c1, c2, fa, accumulate);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
   const int64_t total8 = P * C / 8;
@@ -296,4 +297,17 @@ extern "C" int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, 
                                                            (const __nv_bfloat16*)y, total8, C, fa, c1, c2, relu,
                                                            (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
   return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
+                                  const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres,
+                                  float* dgamma, float* dbeta, void* workspace, void* stream_) {
+  return bn_bwd_launch(dy, x, y, P, C, gamma, save_mean, save_invstd, relu, dx, dres, dgamma, dbeta, 0, workspace, stream_);
+}
+
+extern "C" int eeseg_bn_train_bwd_acc(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
+                                      const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres,
+                                      float* gamma_grad, float* beta_grad, void* workspace, void* stream_) {
+  EESEG_REQUIRE(gamma_grad && beta_grad, "bn_train_bwd_acc: null gradient tensors");
+  return bn_bwd_launch(dy, x, y, P, C, gamma, save_mean, save_invstd, relu, dx, dres, gamma_grad, beta_grad, 1, workspace, stream_);
 }

@@ -210,14 +210,47 @@ __global__ void weight_rot180_t_kernel(const __nv_bfloat16* __restrict__ w, int 
 }
 
 // dW = sum over K splits of the partial buffers, fixed order (deterministic)
-__global__ void wgrad_reduce_kernel(const float4* __restrict__ part, int ksplit, int64_t n4, float4* __restrict__ dw) {
+__global__ void wgrad_reduce_kernel(const float4* __restrict__ part, int ksplit, int64_t n4, float4* __restrict__ dw,
+                                    int accumulate) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = part[i];
     for (int k = 1; k < ksplit; ++k) {
       const float4 b = part[(int64_t)k * n4 + i];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
+    if (accumulate) {
+      const float4 o = dw[i];
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
     dw[i] = a;
+  }
+}
+
+// The same sum written straight into the PARAMETER's gradient, which lives in the parameter's own layout
+// [Cout][Cin][R][S] (nn.Conv2d.weight): grad[co][ci][rs] (+)= sum_k part[k][co][rs][ci]. For 1x1 kernels the two layouts
+// coincide (wgrad_reduce_kernel with the accumulate flag); otherwise one block per (co, chunk of up to 256 ci): RS coalesced
+// rows in, transposed through shared memory, chunk*RS contiguous floats out. Replaces, per layer, autograd's AccumulateGrad
+// `grad.add_(dW.permute(...))` (a strided read-modify-write launch).
+__global__ void __launch_bounds__(256) wgrad_reduce_to_param_kernel(const float* __restrict__ part, int ksplit, int64_t part_stride,
+                                                                     int Cout, int RS, int Cin, int accumulate,
+                                                                     float* __restrict__ grad) {
+  extern __shared__ float tile[];            // [RS][257]
+  const int co = blockIdx.y, ci0 = blockIdx.x * 256, t = threadIdx.x;
+  const int nci = min(256, Cin - ci0);
+  if (t < nci) {
+    for (int rs = 0; rs < RS; ++rs) {
+      const int64_t src = ((int64_t)co * RS + rs) * Cin + ci0 + t;
+      float a = part[src];
+      for (int k = 1; k < ksplit; ++k) a += part[(int64_t)k * part_stride + src];   // fixed order
+      tile[rs * 257 + t] = a;
+    }
+  }
+  __syncthreads();
+  float* dst = grad + ((int64_t)co * Cin + ci0) * RS;
+  for (int i = t; i < nci * RS; i += 256) {
+    const int ci = i / RS, rs = i - ci * RS;
+    const float v = tile[rs * 257 + ci];
+    dst[i] = accumulate ? dst[i] + v : v;
   }
 }
 
@@ -254,9 +287,10 @@ extern "C" size_t eeseg_conv_igemm_wgrad_workspace_bytes(int N, int h, int w, in
   return (p.ksplit > 1 ? (size_t)p.ksplit * Cout * R * S * Cin * sizeof(float) : 0) + 256;
 }
 
-extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
-                                      int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* workspace,
-                                      void* stream_) {
+// to_param: 0 = dw is fp32 [Cout][R][S][Cin], overwritten; 1 / 2 = dw is the parameter's gradient [Cout][Cin][R][S],
+// overwritten / accumulated into (always through the partial buffers: the workspace holds max(ksplit, 1) of them)
+static int wgrad_launch(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h, int w, int Cin,
+                        int Cout, int R, int S, int dilation, float* dw, void* workspace, int to_param, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EESEG_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
   EESEG_REQUIRE(N >= 1 && h >= 1 && w >= 1, "conv_wgrad: bad sizes");
@@ -276,9 +310,9 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   p.pad = dilation * (R / 2);   // 'same'
   const int base_items = wgrad_geometry(N, h, w, Cin, Cout, R, S, p);
   const int64_t dw_elems = (int64_t)Cout * R * S * Cin;
-  EESEG_REQUIRE(p.ksplit == 1 || workspace, "conv_wgrad: this shape splits the pixels over %d CTAs and needs the workspace", p.ksplit);
+  EESEG_REQUIRE((p.ksplit == 1 && !to_param) || workspace, "conv_wgrad: this shape splits the pixels over %d CTAs and needs the workspace", p.ksplit);
   p.co_off = co_off;
-  p.dw = p.ksplit > 1 ? reinterpret_cast<float*>(workspace) : dw;
+  p.dw = (p.ksplit > 1 || to_param) ? reinterpret_cast<float*>(workspace) : dw;
   p.part_stride = p.ksplit > 1 ? dw_elems : 0;
   const size_t stage_bytes = (size_t)(2 + p.BN / 64) * kWgBox;
   int stages = (int)((227 * 1024 - 1024 - 256) / stage_bytes);
@@ -295,13 +329,42 @@ extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy
   EESEG_CUDA(ensure_max_smem(conv_wgrad_kernel, 227 * 1024));
   conv_wgrad_kernel<<<base_items * p.ksplit, kWgThreads, smem_bytes, stream>>>(tmdy, tmx, p);
   rc = check_launch("conv_wgrad_kernel");
-  if (rc || p.ksplit == 1) return rc;
+  if (rc) return rc;
+  if (to_param && R * S > 1) {
+    wgrad_reduce_to_param_kernel<<<dim3((unsigned)((Cin + 255) / 256), (unsigned)Cout), 256, (size_t)R * S * 257 * sizeof(float),
+                                   stream>>>(reinterpret_cast<const float*>(workspace), p.ksplit, dw_elems, Cout, R * S, Cin,
+                                             to_param == 2 ? 1 : 0, dw);
+    return check_launch("wgrad_reduce_to_param_kernel");
+  }
+  if (p.ksplit == 1 && !to_param) return rc;
   const int64_t n4 = dw_elems / 4;
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  // 1x1 kernels: [Cout][1][1][Cin] is the parameter's layout already
   wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), p.ksplit, n4,
-                                                           reinterpret_cast<float4*>(dw));
+                                                           reinterpret_cast<float4*>(dw), to_param == 2 ? 1 : 0);
   return check_launch("wgrad_reduce_kernel");
+}
+
+extern "C" int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
+                                      int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* workspace,
+                                      void* stream_) {
+  return wgrad_launch(x, dy, ldy, dy_channels, co_off, N, h, w, Cin, Cout, R, S, dilation, dw, workspace, 0, stream_);
+}
+
+extern "C" size_t eeseg_conv_igemm_wgrad_to_param_workspace_bytes(int N, int h, int w, int Cin, int Cout, int R, int S) {
+  if (N < 1 || h < 1 || w < 1 || Cin < 64 || Cout < 64 || R < 1 || S < 1) return 256;
+  WgradParams p;
+  wgrad_geometry(N, h, w, Cin, Cout, R, S, p);
+  return (size_t)(p.ksplit > 1 ? p.ksplit : 1) * Cout * R * S * Cin * sizeof(float) + 256;
+}
+
+extern "C" int eeseg_conv_igemm_wgrad_to_param(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N,
+                                               int h, int w, int Cin, int Cout, int R, int S, int dilation, float* grad,
+                                               int accumulate, void* workspace, void* stream_) {
+  EESEG_REQUIRE(workspace, "conv_wgrad_to_param: null workspace");
+  return wgrad_launch(x, dy, ldy, dy_channels, co_off, N, h, w, Cin, Cout, R, S, dilation, grad, workspace, accumulate ? 2 : 1,
+                      stream_);
 }
 
 extern "C" int eeseg_conv_weight_rot180_t(const void* w, int Cout, int R, int S, int Cin, void* out, void* stream_) {

@@ -78,7 +78,7 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
         assert out_dtype_code == (_lib.F32 if out.dtype == torch.float32 else _lib.BF16)
-        torch.ops.eeseg.conv_igemm_fwd(x, wt, scale, shift, shift_sn, dilation, stride, pad, bool(relu), residual, out, ldo)
+        torch_ops.fast.conv_igemm_fwd(x, wt, scale, shift, shift_sn, dilation, stride, pad, bool(relu), residual, out, ldo)
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         if PROFILE is not None:
             b.record()
@@ -146,7 +146,7 @@ def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out,
         if PROFILE is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        torch.ops.eeseg.conv_igemm_grouped(x, list(wts), list(scales), list(shifts), list(ksizes), list(dils),
+        torch_ops.fast.conv_igemm_grouped(x, list(wts), list(scales), list(shifts), list(ksizes), list(dils),
                                            list(ch_offs), bool(relu), out, ldo, out_channels, schedule)
         if PROFILE is not None:
             b.record()

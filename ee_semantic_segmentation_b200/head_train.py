@@ -18,7 +18,7 @@ import torch
 from torch import nn
 from torchvision.models.segmentation.deeplabv3 import ASPP
 
-from . import _lib
+from . import _lib, torch_ops
 from ._lib import check, lib
 
 _UNIT = {}
@@ -55,6 +55,7 @@ class ConvIgemmFn(torch.autograd.Function):
         ctx.save_for_backward(x, wt)
         ctx.dilation = dilation
         ctx.stride = stride
+        ctx.weight = weight if isinstance(weight, nn.Parameter) else None   # for the direct-to-.grad weight gradient
         return out
 
     @staticmethod
@@ -76,13 +77,24 @@ class ConvIgemmFn(torch.autograd.Function):
                 ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, S),), dtype=torch.uint8,
                                  device=x.device)
                 dx = torch.empty_like(x)
-                torch.ops.eeseg.conv_igemm_dgrad(dy, wt, ctx.dilation, dx, ws)
+                torch_ops.fast.conv_igemm_dgrad(dy, wt, ctx.dilation, dx, ws)
             if ctx.needs_input_grad[1]:
-                dwk = torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
-                wws = torch.empty((lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, Cin, Cout, R, S),), dtype=torch.uint8,
-                                  device=x.device)
-                torch.ops.eeseg.conv_igemm_wgrad(x, dy, ctx.dilation, dwk, wws)
-                dw = dwk.permute(0, 3, 1, 2)                                             # the parameter's layout
+                from .parallel import direct_grad
+                g = direct_grad(ctx.weight) if ctx.weight is not None else None
+                if g is not None and tuple(g.shape) == (Cout, Cin, R, S):
+                    # straight into the parameter's .grad (its own [Cout,Cin,R,S] layout): no AccumulateGrad launch
+                    wws = torch.empty((lib().eeseg_conv_igemm_wgrad_to_param_workspace_bytes(N, h, w, Cin, Cout, R, S),),
+                                      dtype=torch.uint8, device=x.device)
+                    check(lib().eeseg_conv_igemm_wgrad_to_param(x.data_ptr(), dy.data_ptr(), Cout, Cout, 0, N, h, w, Cin, Cout,
+                                                                R, S, ctx.dilation, g.data_ptr(), 1, wws.data_ptr(), st),
+                          "eeseg_conv_igemm_wgrad_to_param")
+                    ctx.weight._eeseg_flat.written(ctx.weight)
+                else:
+                    dwk = torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
+                    wws = torch.empty((lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, Cin, Cout, R, S),), dtype=torch.uint8,
+                                      device=x.device)
+                    torch_ops.fast.conv_igemm_wgrad(x, dy, ctx.dilation, dwk, wws)
+                    dw = dwk.permute(0, 3, 1, 2)                                         # the parameter's layout
         return dx, dw, None, None
 
 
@@ -270,12 +282,12 @@ class FinalConvFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, 64, 1, 1),), dtype=torch.uint8, device=dev)
                 dy = torch.empty_like(y)
-                torch.ops.eeseg.conv_igemm_dgrad(gp, wt, 1, dy, ws)
+                torch_ops.fast.conv_igemm_dgrad(gp, wt, 1, dy, ws)
             if ctx.needs_input_grad[1]:
                 dwk = torch.empty((64, 1, 1, Cin), dtype=torch.float32, device=dev)
                 wws = torch.empty((lib().eeseg_conv_igemm_wgrad_workspace_bytes(N, h, w, Cin, 64, 1, 1),), dtype=torch.uint8,
                                   device=dev)
-                torch.ops.eeseg.conv_igemm_wgrad(y, gp, 1, dwk, wws)
+                torch_ops.fast.conv_igemm_wgrad(y, gp, 1, dwk, wws)
                 dw = dwk[:C].permute(0, 3, 1, 2).reshape(ctx.wshape)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 per_img = (global_avgpool_nhwc(gp) * float(h * w)).contiguous()       # [N,64] channel sums per image

@@ -9,7 +9,7 @@ import torch
 from . import _lib, torch_ops  # noqa: F401  (torch_ops registers torch.ops.eeseg.*)
 from ._lib import BF16, F32, check, lib
 
-_ops = torch.ops.eeseg
+_ops = torch_ops.fast
 
 
 def _dt(t):

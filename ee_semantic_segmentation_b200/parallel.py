@@ -48,9 +48,16 @@ def miou_from_cm(cm):
     return (tp / (tp + fp + fn)).sum(dim=-1) / C
 
 
+# backward kernels may add parameter gradients straight into FlatGradients views (direct_grad); EESEG_DIRECT_GRADS=0: A/B
+DIRECT_GRADS = os.environ.get("EESEG_DIRECT_GRADS", "1") != "0"
+
+
 def wrap_ddp(net, local_rank):
     """Training: torch DDP (bucketed gradient all-reduce over NCCL, overlapped with backward).
-    BatchNorm stays per rank, as in a single-GPU reference run at the per-GPU batch."""
+    BatchNorm stays per rank, as in a single-GPU reference run at the per-GPU batch. DDP's reducer listens to
+    autograd's AccumulateGrad nodes, so the direct-to-.grad kernels are switched off for the process."""
+    global DIRECT_GRADS
+    DIRECT_GRADS = False
     from torch.nn.parallel import DistributedDataParallel as DDP
     return DDP(net, device_ids=[local_rank], gradient_as_bucket_view=True)
 
@@ -88,6 +95,7 @@ class FlatGradients:
                 self.buckets.append((start, o))          # close the bucket before a tensor that would overshoot its share
                 start, cur = o, cur + 1
             p.grad = self.flat[o:o + p.numel()].view_as(p)
+            p._eeseg_flat = self           # kernels may add their gradient straight into p.grad (direct_grad below)
             self._bucket_of[id(p)] = cur
             o += size
         self.buckets.append((start, o))
@@ -95,6 +103,7 @@ class FlatGradients:
         for p in order:
             self._need[self._bucket_of[id(p)]] += 1
         self._left = list(self._need)
+        self._seen = set()
         self._hooks = []
         self._side = None
         self._armed = False
@@ -115,8 +124,9 @@ class FlatGradients:
             t.div_(dist.get_world_size())
 
     def _on_grad(self, p):
-        if not self._armed:
+        if not self._armed or id(p) in self._seen:      # a parameter counts once per backward, however it was notified
             return
+        self._seen.add(id(p))
         b = self._bucket_of[id(p)]
         self._left[b] -= 1
         if self._left[b] == 0 and self._world() > 1:
@@ -132,9 +142,14 @@ class FlatGradients:
                 self._reduce_range(a, e)
             self._left[b] = -1                          # reduced
 
+    def written(self, p):
+        """A kernel has added p's gradient straight into p.grad (no AccumulateGrad node ran, so no hook fired)."""
+        self._on_grad(p)
+
     def begin(self):
         """Call before backward(): arms the per-bucket countdown (overlapped exchange)."""
         self._left = list(self._need)
+        self._seen = set()
         self._armed = bool(self._hooks)
 
     def finish(self):
@@ -154,3 +169,18 @@ class FlatGradients:
         """Everything in one go after the backward (no overlap)."""
         self._armed = False
         self.finish()
+
+
+def direct_grad(p):
+    """p.grad when a backward kernel may ADD its result straight into it (a dense fp32 view of a FlatGradients buffer that
+    the owner zeroes before every backward), else None. The caller then returns None for this gradient from its
+    autograd.Function and calls `p._eeseg_flat.written(p)` — one read-modify-write launch less per parameter than autograd's
+    AccumulateGrad."""
+    fg = getattr(p, '_eeseg_flat', None)
+    g = p.grad
+    if not DIRECT_GRADS or fg is None or g is None or g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda:
+        return None
+    lo, hi = fg.flat.data_ptr(), fg.flat.data_ptr() + fg.flat.numel() * 4
+    if not (lo <= g.data_ptr() < hi):
+        return None                      # someone replaced .grad (zero_grad(set_to_none=True), another optimizer)
+    return g

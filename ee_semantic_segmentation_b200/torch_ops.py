@@ -181,3 +181,16 @@ def _confusion_hist(pred, pred_kind, targets, n_classes, out, accumulate):
 
 
 ops = torch.ops.eeseg
+
+
+class _Handles:
+    """`torch.ops.eeseg.<name>.default` resolved once: calling the OpOverload directly skips the per-call packet lookup and
+    overload resolution of `torch.ops.eeseg.<name>(...)` (the eager, un-graphed host path makes ~100 such calls per step)."""
+
+    def __getattr__(self, name):
+        h = getattr(torch.ops.eeseg, name).default
+        setattr(self, name, h)
+        return h
+
+
+fast = _Handles()

@@ -235,6 +235,14 @@ size_t eeseg_conv_igemm_wgrad_workspace_bytes(int N, int h, int w, int Cin, int 
 int eeseg_conv_igemm_wgrad(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
                            int w, int Cin, int Cout, int R, int S, int dilation, float* dw, void* workspace,
                            void* stream);
+/* The weight gradient written straight into the PARAMETER's gradient tensor: grad fp32 [Cout][Cin][R][S] (the layout of
+ * nn.Conv2d.weight.grad), overwritten or, with accumulate != 0, added to — what autograd's AccumulateGrad does with one
+ * more strided read-modify-write launch per layer (`grad.add_(dW.permute(0, 3, 1, 2))`). The partial sums always go
+ * through `workspace` (eeseg_conv_igemm_wgrad_to_param_workspace_bytes bytes) and are reduced in a fixed order. */
+size_t eeseg_conv_igemm_wgrad_to_param_workspace_bytes(int N, int h, int w, int Cin, int Cout, int R, int S);
+int eeseg_conv_igemm_wgrad_to_param(const void* x, const void* dy, int64_t ldy, int dy_channels, int co_off, int N, int h,
+                                    int w, int Cin, int Cout, int R, int S, int dilation, float* grad, int accumulate,
+                                    void* workspace, void* stream);
 size_t eeseg_conv_igemm_dgrad_workspace_bytes(int Cin, int Cout, int R, int S);
 int eeseg_conv_igemm_dgrad(const void* dy, const void* wt, int N, int h, int w, int Cin, int Cout, int R, int S,
                            int dilation, void* dx, int dx_dtype, int64_t lddx, void* workspace, void* stream);
@@ -289,6 +297,11 @@ int eeseg_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, cons
 int eeseg_bn_train_bwd(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
                        const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres,
                        float* dgamma, float* dbeta, void* workspace, void* stream);
+/* The same with dgamma / dbeta ADDED to gamma_grad / beta_grad, the parameters' own .grad tensors (no separate
+ * accumulation launch per BatchNorm). */
+int eeseg_bn_train_bwd_acc(const void* dy, const void* x, const void* y, int64_t P, int C, const float* gamma,
+                           const float* save_mean, const float* save_invstd, int relu, void* dx, void* dres,
+                           float* gamma_grad, float* beta_grad, void* workspace, void* stream);
 
 /* ResNet stem helpers (base_model[0][0:4], torchvision resnet.py conv1/bn1/relu/maxpool):
  * space-to-depth (2x2) plus horizontal tap unrolling of the fp32 NCHW image, so that the 7x7 / stride-2 /

@@ -177,3 +177,41 @@ def test_graphed_train_step_with_eeseg_sgd_follows_the_scheduler():
     pb = torch.cat([p.detach().flatten() for p in net_b.classifier.parameters()])
     assert torch.allclose(pa, pb, rtol=2e-2, atol=2e-5)
     step.release()
+
+
+def test_direct_parameter_gradients_equal_autograd_accumulation():
+    """Weight gradients of the convolutions and dgamma / dbeta of the BatchNorms written straight into the flat-buffer views
+    of the eeseg SGD (no AccumulateGrad launch) against the same backward through autograd's accumulation (torch SGD, plain
+    .grad tensors): every parameter gradient of a head + a Bottleneck section, and the gradient-hook bucket countdown."""
+    from ee_semantic_segmentation_b200 import parallel
+    from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
+    from ee_semantic_segmentation_b200.my_pixelwise_xentropy import BrXEntropyLoss
+    from ee_semantic_segmentation_b200.train_funcs import SGD
+    torch.manual_seed(0)
+    net_a = branchyDeepv3(None, "deeplabv3_resnet50", 1, 65, sections=[18, 2], pretrained=False).to(dev()).train()
+    for mod in net_a.modules():
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+    net_b = copy.deepcopy(net_a)
+    g = torch.Generator().manual_seed(11)
+    X = torch.randn(2, 3, 65, 65, generator=g).to(dev())
+    y = torch.randint(0, 22, (2, 1, 65, 65), generator=g).to(dev())
+    loss = BrXEntropyLoss(ignore_index=21, b_reduction='sum', n_exits=2)
+    opt = SGD(list(net_a.parameters()), lr=0.0, momentum=0.9, weight_decay=0.0, buckets=3)
+    fg = opt.flat_grads
+    fg._world = lambda: 2                      # pretend two ranks so that the countdown reduces buckets ...
+    reduced = []
+    fg._reduce_range = lambda a, b: reduced.append((a, b))     # ... without a process group
+    opt.zero_grad()
+    fg.begin()
+    loss(net_a(X), y).backward()
+    assert all(v == -1 for v in fg._left), (fg._left, fg._need)   # hooks AND direct writes counted every parameter
+    assert sorted(reduced) == sorted(fg.buckets)
+    fg._armed = False
+    loss(net_b(X), y).backward()                                # plain autograd accumulation into fresh .grad tensors
+    n_direct = 0
+    for (name, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        assert pa.grad.data_ptr() >= fg.flat.data_ptr()
+        assert torch.allclose(pa.grad, pb.grad, rtol=2e-3, atol=1e-6), name
+        n_direct += parallel.direct_grad(pa) is not None
+    assert n_direct == len(list(net_a.parameters()))

@@ -14,6 +14,9 @@ torch.backends.cudnn.allow_tf32 = True
 torch.backends.cuda.matmul.allow_tf32 = True
 fast = "--torch-heads" not in sys.argv
 X, y = bench.synth_batch(0, 4)
+from ee_semantic_segmentation_b200 import parallel
+if "--no-direct" in sys.argv:
+    parallel.DIRECT_GRADS = False
 X, y = X.to(dev), y.to(dev)
 torch.manual_seed(0)
 net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=bench.SECTIONS, pretrained=False).to(dev).train()
