@@ -23,6 +23,9 @@ class img_norm_entropy:
     def scores(self, x, kind='probs', out_hw=None, layout='NCHW', want_amax=False):
         """Batched form: x [N,C,h,w] CUDA (probabilities or logits) -> (scores f32 [N] on device,
         GateResult)."""
+        if layout == 'NCHW' and x.shape[1] != self.C:
+            # the reference normalises by log(self.C) whatever the tensor holds (eval_br_ent.py:29); a mismatch is a caller bug
+            raise ValueError(f'img_norm_entropy(n_classes={self.C}) got a tensor with {x.shape[1]} channels')
         res = ops.exit_gate(x, out_hw, layout=layout, kind=kind, n_classes=self.C,
                             want_ent=self.pool, want_amax=want_amax, want_score=not self.pool)
         if self.pool:
