@@ -74,6 +74,8 @@ PROTOTYPES = {
     "eeseg_sgd_chunk_bytes": (c_sz, []),
     "eeseg_sgd_multi": (c_i, [c_p, c_i, c_p, c_f, c_f, c_p]),
     "eeseg_dense_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "eeseg_weight_prep_tile_bytes": (c_sz, []),
+    "eeseg_weight_prep_multi": (c_i, [c_p, c_i, c_i, c_p]),
     "eeseg_bn_rows_fwd": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p, c_p]),
     "eeseg_bn_rows_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
     "eeseg_broadcast_rows_nhwc": (c_i, [c_p, c_i, c_i64, c_i, c_f, c_p, c_p]),

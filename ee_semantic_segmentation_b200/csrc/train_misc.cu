@@ -199,6 +199,41 @@ __global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const float* __restric
   }
 }
 
+// ---- per-step weight preparation for ALL convolutions in one launch ---------------------------------------------------
+// A training step needs every conv weight twice in bf16: [Cout][R][S][Cin] (forward, weight gradient) and the 180-degree
+// rotated transpose [Cin][R][S][Cout] (input gradient = the forward kernel on it). Doing that per layer costs three small
+// launches per convolution per step (layout/precision copy, rotation, unit scale/shift fill); this kernel walks a table of
+// 32 x 32 (co, ci) tiles over all layers: coalesced fp32 reads of the parameter [Cout][Cin][R][S], both bf16 layouts
+// written as 64-byte runs through one shared-memory tile.
+struct WeightPrepTile {
+  const float* src;          // parameter [Cout][Cin][RS]
+  __nv_bfloat16* krsc;       // [Cout][RS][Cin]
+  __nv_bfloat16* rot;        // [Cin][RS][Cout], taps reversed
+  int32_t Cout, Cin, RS, co0, ci0, pad;
+};
+
+__global__ void __launch_bounds__(256) weight_prep_kernel(const WeightPrepTile* __restrict__ tiles) {
+  extern __shared__ float wp_tile[];                 // [32][32 * RS + 1]
+  const WeightPrepTile t = tiles[blockIdx.x];
+  const int RS = t.RS, row = 32 * RS, pitch = row + 1;
+  for (int j = threadIdx.x >> 5; j < 32; j += 8) {
+    const float* s = t.src + ((int64_t)(t.co0 + j) * t.Cin + t.ci0) * RS;
+    for (int i = threadIdx.x & 31; i < row; i += 32) wp_tile[j * pitch + i] = __ldg(s + i);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  // krsc[(co*RS + rs)*Cin + ci0 + lane] = w[co][ci0 + lane][rs]
+  for (int q = threadIdx.x >> 5; q < 32 * RS; q += 8) {
+    const int j = q / RS, rs = q - j * RS;
+    t.krsc[((int64_t)(t.co0 + j) * RS + rs) * t.Cin + t.ci0 + lane] = __float2bfloat16_rn(wp_tile[j * pitch + lane * RS + rs]);
+  }
+  // rot[(ci*RS + RS-1-rs)*Cout + co0 + lane] = w[co0 + lane][ci][rs]
+  for (int q = threadIdx.x >> 5; q < 32 * RS; q += 8) {
+    const int c = q / RS, rs = q - c * RS;
+    t.rot[((int64_t)(t.ci0 + c) * RS + (RS - 1 - rs)) * t.Cout + t.co0 + lane] = __float2bfloat16_rn(wp_tile[lane * pitch + c * RS + rs]);
+  }
+}
+
 }  // namespace eeseg
 
 using namespace eeseg;
@@ -291,4 +326,16 @@ extern "C" int eeseg_bn_rows_bwd(const float* dy, const float* x, const float* y
   bn_rows_bwd_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(dy, x, y, N, C, gamma, save_mean, save_invstd, relu, dx,
                                                                           dgamma, dbeta);
   return check_launch("bn_rows_bwd_kernel");
+}
+
+extern "C" size_t eeseg_weight_prep_tile_bytes(void) { return sizeof(WeightPrepTile); }
+
+extern "C" int eeseg_weight_prep_multi(const void* tiles, int n_tiles, int max_rs, void* stream_) {
+  EESEG_REQUIRE(tiles, "weight_prep_multi: null pointer");
+  EESEG_REQUIRE(max_rs >= 1 && max_rs <= 32, "weight_prep_multi: at most 32 taps");
+  if (n_tiles <= 0) return EESEG_OK;
+  const size_t smem = (size_t)32 * (32 * max_rs + 1) * sizeof(float);
+  EESEG_CUDA(ensure_max_smem(weight_prep_kernel, 160 * 1024));
+  weight_prep_kernel<<<n_tiles, 256, smem, (cudaStream_t)stream_>>>((const WeightPrepTile*)tiles);
+  return check_launch("weight_prep_kernel");
 }

@@ -159,6 +159,7 @@ class branchyDeepv3(nn.Module):
         st = dict(self.__dict__)
         st['_plans'], st['_section_plans'], st['_lowres_graphs'] = {}, {}, {}
         st['_token_tensors'] = None
+        st.pop('_train_wcache', None)
         return st
 
     def __setstate__(self, st):
@@ -350,14 +351,27 @@ class branchyDeepv3(nn.Module):
     def _forward_torch(self, X):
         """The reference data flow with autograd (training): backbone sections on the PyTorch modules,
         exit heads through _head_autograd."""
+        import contextlib
+        wcache = contextlib.nullcontext()
+        if self.training and X.is_cuda and (self.fast_training_heads or self.fast_training_backbone):
+            # bf16 copies of every conv weight in both layouts the step reads: one launch per step for all layers
+            wc = self.__dict__.get('_train_wcache')
+            if wc is None or not wc.valid():
+                convs = head_train.trainable_convs(self)
+                wc = head_train.TrainWeightCache(convs) if convs else None
+                self.__dict__['_train_wcache'] = wc
+            if wc is not None:
+                wc.refresh()
+                wcache = wc.active()
         outputs = []
         inp_shape = X.shape[-2:]
-        for i in range(self.n_branches):
-            X = self._section_autograd(self.base_model[i], X)
-            br = self._head_autograd(self.branches[i], X)
-            outputs.append(self._upsample_autograd(br, inp_shape).unsqueeze(0))
-        y = self._head_autograd(self.classifier, self._section_autograd(self.base_model[-1], X))
-        outputs.append(self._upsample_autograd(y, inp_shape).unsqueeze(0))
+        with wcache:
+            for i in range(self.n_branches):
+                X = self._section_autograd(self.base_model[i], X)
+                br = self._head_autograd(self.branches[i], X)
+                outputs.append(self._upsample_autograd(br, inp_shape).unsqueeze(0))
+            y = self._head_autograd(self.classifier, self._section_autograd(self.base_model[-1], X))
+            outputs.append(self._upsample_autograd(y, inp_shape).unsqueeze(0))
         return tch.cat(outputs)
 
     def _use_fast(self, X):

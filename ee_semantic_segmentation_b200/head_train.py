@@ -31,6 +31,73 @@ def _unit_scale_shift(dev, n):
     return _UNIT[key]
 
 
+class TrainWeightCache:
+    """bf16 copies of every supported convolution weight of a model in the two layouts a training step reads —
+    [Cout,R,S,Cin] (forward, weight gradient) and the rotated transpose [Cin,R,S,Cout] (input gradient) — refreshed by ONE
+    launch per step (eeseg_weight_prep_multi) instead of three small launches per convolution per step. Only consulted
+    inside `with cache.active():`, which the model's training forward opens right after `refresh()`; anywhere else
+    ConvIgemmFn converts per call, so a stale copy can never be read."""
+
+    def __init__(self, convs):
+        import numpy as np
+        self.weights = [c.weight for c in convs]
+        dev = self.weights[0].device
+        total = sum(w.numel() for w in self.weights)
+        self.krsc = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self.rot = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self.entries, rows, o, self.max_rs = {}, [], 0, 1
+        assert lib().eeseg_weight_prep_tile_bytes() == 48
+        for w in self.weights:
+            Cout, Cin, R, S = w.shape
+            n = w.numel()
+            wt = self.krsc[o:o + n].view(Cout, R, S, Cin)
+            wT = self.rot[o:o + n].view(Cin, R, S, Cout)
+            self.entries[id(w)] = (wt, wT)
+            self.max_rs = max(self.max_rs, R * S)
+            for co0 in range(0, Cout, 32):
+                for ci0 in range(0, Cin, 32):
+                    rows.append((w.data_ptr(), wt.data_ptr(), wT.data_ptr(), Cout, Cin, R * S, co0, ci0, 0))
+            o += n
+        table = np.zeros(len(rows), dtype=np.dtype([('s', '<u8'), ('k', '<u8'), ('r', '<u8'), ('co', '<i4'), ('ci', '<i4'),
+                                                    ('rs', '<i4'), ('co0', '<i4'), ('ci0', '<i4'), ('pad', '<i4')]))
+        for i, r in enumerate(rows):
+            table[i] = r
+        self.table = torch.from_numpy(table.view(np.uint8).copy()).to(dev)
+        self.n_tiles = len(rows)
+        self.ptrs = [w.data_ptr() for w in self.weights]
+
+    def valid(self):
+        return all(w.data_ptr() == p for w, p in zip(self.weights, self.ptrs))
+
+    def refresh(self):
+        dev = self.table.device
+        with torch.cuda.device(dev):
+            check(lib().eeseg_weight_prep_multi(self.table.data_ptr(), self.n_tiles, self.max_rs,
+                                                torch.cuda.current_stream(dev).cuda_stream), "eeseg_weight_prep_multi")
+
+    def active(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            global _CUR_WCACHE
+            prev, _CUR_WCACHE = _CUR_WCACHE, self
+            try:
+                yield
+            finally:
+                _CUR_WCACHE = prev
+        return ctx()
+
+
+_CUR_WCACHE = None
+
+
+def trainable_convs(model):
+    """The convolutions of a model that ConvIgemmFn runs (everything _conv_ok admits with 32-channel multiples)."""
+    return [m for m in model.modules() if isinstance(m, nn.Conv2d) and _conv_ok(m) and m.weight.is_cuda
+            and m.weight.dtype == torch.float32]
+
+
 class ConvIgemmFn(torch.autograd.Function):
     """y = conv2d(x, weight; stride 1 or 2, padding dilation*(R//2), no bias) on NHWC bf16 activations.
     x [N,h,w,Cin] bf16 contiguous (Cin % 64 == 0); weight: the nn.Conv2d parameter [Cout,Cin,R,S]
@@ -46,8 +113,13 @@ class ConvIgemmFn(torch.autograd.Function):
         x = x.contiguous()
         N, h, w, Cin = x.shape
         Cout, _, R, S = weight.shape
-        wt = torch.empty((Cout, R, S, Cin), dtype=torch.bfloat16, device=x.device)    # [Cout,R,S,Cin]
-        wt.copy_(weight.detach().permute(0, 2, 3, 1))                                  # layout + precision in one pass
+        ent = _CUR_WCACHE.entries.get(id(weight)) if _CUR_WCACHE is not None else None
+        if ent is not None:                                                            # prepared once per step for all layers
+            wt, ctx.wT = ent
+        else:
+            ctx.wT = None
+            wt = torch.empty((Cout, R, S, Cin), dtype=torch.bfloat16, device=x.device)    # [Cout,R,S,Cin]
+            wt.copy_(weight.detach().permute(0, 2, 3, 1))                                  # layout + precision in one pass
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         out = torch.empty((N, ho, wo, Cout), dtype=torch.bfloat16, device=x.device)
         one, zero = _unit_scale_shift(x.device, Cout)
@@ -74,10 +146,15 @@ class ConvIgemmFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream(x.device).cuda_stream
             if ctx.needs_input_grad[0]:
-                ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, S),), dtype=torch.uint8,
-                                 device=x.device)
                 dx = torch.empty_like(x)
-                torch_ops.fast.conv_igemm_dgrad(dy, wt, ctx.dilation, dx, ws)
+                if ctx.wT is not None:       # the rotated transpose is in the per-step cache: dgrad = the forward kernel on it
+                    from .head_plan import conv_igemm
+                    one, zero = _unit_scale_shift(x.device, Cin)
+                    conv_igemm(dy, ctx.wT, one, zero, ctx.dilation, False, dx, _lib.BF16, Cin)
+                else:
+                    ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, S),), dtype=torch.uint8,
+                                     device=x.device)
+                    torch_ops.fast.conv_igemm_dgrad(dy, wt, ctx.dilation, dx, ws)
             if ctx.needs_input_grad[1]:
                 from .parallel import direct_grad
                 g = direct_grad(ctx.weight) if ctx.weight is not None else None

@@ -383,6 +383,14 @@ int eeseg_sgd_multi(const void* chunks, int n_chunks, const float* lrs, float mo
  * (either output may be NULL). fp32, fixed summation order. */
 int eeseg_dense_bwd(const float* dy, const float* x, const float* W, int N, int K, int O, float* dW, float* dx, void* stream);
 
+/* Per-step weight preparation of MANY convolutions in one launch: for every table record {const float* src
+ * [Cout][Cin][RS] (the nn.Conv2d parameter); bf16* krsc [Cout][RS][Cin]; bf16* rot [Cin][RS][Cout] with the taps reversed;
+ * int32 Cout, Cin, RS, co0, ci0, pad} (eeseg_weight_prep_tile_bytes() bytes, DEVICE array) one thread block converts the
+ * 32 x 32 (co, ci) tile at (co0, ci0): what the forward / weight-gradient kernels (krsc) and the input-gradient kernel
+ * (rot, see eeseg_conv_weight_rot180_t) read. Cout, Cin multiples of 32; max_rs = the largest RS in the table. */
+size_t eeseg_weight_prep_tile_bytes(void);
+int eeseg_weight_prep_multi(const void* tiles, int n_tiles, int max_rs, void* stream);
+
 /* BatchNorm (batch statistics over the N rows, biased variance for the normalisation, unbiased for the running estimate,
  * as nn.BatchNorm2d on an [N,C,1,1] tensor) + optional ReLU on fp32 row vectors [N][C] — the pooled ASPP branch
  * (deeplabv3.py:70-83); forward saves mean / invstd for the backward, which returns dx, dgamma, dbeta. */

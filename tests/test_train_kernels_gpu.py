@@ -215,3 +215,23 @@ def test_direct_parameter_gradients_equal_autograd_accumulation():
         assert torch.allclose(pa.grad, pb.grad, rtol=2e-3, atol=1e-6), name
         n_direct += parallel.direct_grad(pa) is not None
     assert n_direct == len(list(net_a.parameters()))
+
+
+def test_weight_prep_multi_matches_permute_and_rotation():
+    """eeseg_weight_prep_multi over a mixed set of conv weights (1x1, 3x3, 64..2048 channels): krsc = w.permute(0,2,3,1) in
+    bf16, rot = the 180-degree rotated transpose [Cin,R,S,Cout] (what eeseg_conv_weight_rot180_t produces per layer)."""
+    from ee_semantic_segmentation_b200.head_train import TrainWeightCache
+    torch.manual_seed(2)
+    convs = [nn.Conv2d(64, 64, 3, padding=1, bias=False), nn.Conv2d(256, 64, 1, bias=False),
+             nn.Conv2d(128, 512, 1, bias=False), nn.Conv2d(2048, 256, 3, padding=12, dilation=12, bias=False),
+             nn.Conv2d(512, 512, 3, padding=2, dilation=2, bias=False)]
+    convs = [c.to(dev()) for c in convs]
+    cache = TrainWeightCache(convs)
+    cache.refresh()
+    for c in convs:
+        wt, wT = cache.entries[id(c.weight)]
+        ref = c.weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
+        assert torch.equal(wt, ref)
+        ref_rot = c.weight.detach().flip(2, 3).permute(1, 2, 3, 0).to(torch.bfloat16)
+        assert torch.equal(wT, ref_rot)
+    assert cache.valid()
