@@ -536,3 +536,41 @@ def test_similarity_operator_keys_and_rule(nets):
     with torch.no_grad():
         ref = net(x.unsqueeze(0))[-1, 0].argmax(0).cpu()
     assert (out["last"] == ref).float().mean().item() > 0.999
+
+
+def test_engine_input_formats_bf16_and_uint8(nets):
+    """The streaming engine's input formats: bf16 images + uint8 labels give bit-identical exits, maps and confusion
+    matrices to fp32 images + int64 labels (the stem rounds to bf16 first; labels are widened in the accumulate kernel);
+    uint8 images are normalised inside the stem kernel like ToTensor + Normalize (get_seg_datasets.py:62-70)."""
+    from ee_semantic_segmentation_b200.engine import EarlyExitEngine
+    _, net = nets
+    g = torch.Generator().manual_seed(41)
+    N, H, W = 3, 97, 113
+    X = torch.randn(N, 3, H, W, generator=g)
+    y = torch.randint(0, 22, (N, 1, H, W), generator=g)
+    y[0, 0, :5] = 255                                              # VOC's void value: >= C is void in either dtype
+    y64 = torch.where(y == 255, torch.full_like(y, 21), y)
+    sc = EarlyExitEngine(net, 21, 0.5).evaluate(X.to(dev()), y64.to(dev()))["scores"][0].float().cpu()
+    tau = float(sc.median())
+    for skip_compute in (False, True):
+        a = EarlyExitEngine(net, 21, tau, skip_compute=skip_compute, use_graph=True)
+        b = EarlyExitEngine(net, 21, tau, skip_compute=skip_compute, use_graph=True, input_dtype=torch.bfloat16,
+                            target_dtype=torch.uint8)
+        for _ in range(2):
+            ra = a.evaluate(X.to(dev()), y64.to(dev()))
+            rb = b.evaluate(X.to(torch.bfloat16).to(dev()), y.to(torch.uint8).to(dev()))
+        assert torch.equal(ra["exit"], rb["exit"]) and torch.equal(ra["pred"], rb["pred"])
+        assert torch.equal(a.cm, b.cm) and torch.equal(a.counts, b.counts)
+    # uint8 pixels with the ImageNet normalisation inside the kernel == normalised fp32 images
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    U = torch.randint(0, 256, (N, 3, H, W), generator=g, dtype=torch.uint8)
+    Xn = (U.float() / 255 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    net.input_norm = (mean, std)
+    try:
+        lo_u8 = [t.clone() for t in net._lowres_eager(U.to(dev()))]
+        lo_f = net._lowres_eager(Xn.to(dev()))
+    finally:
+        net.input_norm = None
+    for p, q in zip(lo_u8, lo_f):
+        # the two paths round slightly different fp32 values to bf16 (u * a + b vs (u / 255 - m) / s): one bf16 ulp at the input
+        assert (p - q).abs().max().item() < 2e-2 * q.abs().max().item()

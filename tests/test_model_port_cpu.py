@@ -66,3 +66,27 @@ def test_port_operator_matches_reference_operator(golden):
                 # identical third-party calls on identical weights: the maps agree except where fp32 summation order
                 # inside the conv library flips a near-tie (none observed; bound it instead of assuming it)
                 assert (got != ref).mean() < 1e-4, (k, tag, key, (got != ref).mean())
+
+
+def test_reference_staging_recipe(tmp_path, monkeypatch):
+    """oracle/build_ref.py stages the hot-path reference modules verbatim (sha256 manifest) next to the stub set, and
+    oracle/ref_import.py can import the reference from such a staged copy (what the GPU box's CPU arm does)."""
+    import hashlib
+    import importlib
+    import json
+    import os
+    from oracle import build_ref, ref_import
+    if not os.path.isdir(build_ref.SRC):
+        pytest.skip("reference sources not present")
+    monkeypatch.setattr(build_ref, "DST", str(tmp_path / "_ref"))
+    dst = build_ref.build()
+    man = json.load(open(os.path.join(dst, "MANIFEST.json")))["sha256"]
+    assert set(man) == set(build_ref.FILES)
+    for f, h in man.items():
+        assert hashlib.sha256(open(os.path.join(dst, "reference", f), "rb").read()).hexdigest() == h
+        assert open(os.path.join(dst, "reference", f), "rb").read() == open(os.path.join(build_ref.SRC, f), "rb").read()
+    assert os.path.exists(os.path.join(dst, "stubs", "pthflops.py"))
+    monkeypatch.setattr(ref_import, "REFERENCE_DIR", os.path.join(dst, "reference"))
+    monkeypatch.setattr(ref_import, "STUB_DIR", os.path.join(dst, "stubs"))
+    ebe, cm = ref_import.load("eval_br_ent", "compute_mIoU")
+    assert ebe.__file__.startswith(dst) and hasattr(ebe, "br_evaluator") and hasattr(cm, "mIoU")
