@@ -6,6 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ee_semantic_segmentation_b200 import _lib
 from ee_semantic_segmentation_b200.head_plan import conv_igemm
 
+if not hasattr(_lib.lib(), "eeseg_conv_debug_stats"):
+    raise SystemExit("this tool needs the tuning build: python -m ee_semantic_segmentation_b200.build --tuning, then run with "
+                     "EESEG_LIB=ee_semantic_segmentation_b200/libeeseg_b200_tuning.so (the product library has no EESEG_TUNING hooks)")
 dev = torch.device("cuda:0")
 shapes = [  # name, N, h, w, Cin, Cout, R, dil, stride, residual
     ("l1.c3 64>256+res", 4, 129, 129, 64, 256, 1, 1, 1, True),

@@ -8,6 +8,9 @@ from ee_semantic_segmentation_b200 import _lib, head_plan
 from ee_semantic_segmentation_b200.engine import EarlyExitEngine
 from ee_semantic_segmentation_b200.from_deepv3_new import branchyDeepv3
 
+if not hasattr(_lib.lib(), "eeseg_conv_timing"):
+    raise SystemExit("this tool needs the tuning build: python -m ee_semantic_segmentation_b200.build --tuning, then run with "
+                     "EESEG_LIB=ee_semantic_segmentation_b200/libeeseg_b200_tuning.so (the product library has no EESEG_TUNING hooks)")
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = branchyDeepv3(None, "deeplabv3_resnet50", 2, bench.IMG, sections=bench.SECTIONS, pretrained=False).to(dev).eval()
