@@ -305,8 +305,9 @@ def leg_cityscapes_sweep(dev, rank, world, steps, warmup, barrier):
     net = branchyDeepv3(None, "deeplabv3_resnet50", 2, 513, sections=SECTIONS, pretrained=False, num_classes=C).to(dev).eval()
     net.strict_kernels = True
     Xh, yh = synth_batch(rank, B, img=hw, n_classes=C)
-    Xh, yh = Xh.pin_memory(), yh.pin_memory()
     Xd, yd = Xh.to(dev), yh.to(dev)
+    # what the e2e leg uploads: bf16 images (the stem rounds to bf16 first: identical results) and uint8 labels
+    Xh, yh = Xh.to(torch.bfloat16).pin_memory(), yh.to(torch.uint8).pin_memory()
     probe = ThresholdSweep(net, C, [0.5])
     sc = probe.update(Xd, yd)[:2].float().cpu()
     taus = [round(0.1 * k, 1) for k in range(1, 10)] + [float(sc[0].median()), float(sc[1].median())]
@@ -316,6 +317,8 @@ def leg_cityscapes_sweep(dev, rank, world, steps, warmup, barrier):
     out = {}
     for name, inputs in (("value", lambda: (Xd, yd)),
                          ("e2e", lambda: (Xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)))):
+        for _ in range(3):                       # per input dtype: the forward graph is captured on second sight
+            sweep.update(*inputs())
         sweep.cm.zero_(); sweep.counts.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -334,7 +337,7 @@ def leg_cityscapes_sweep(dev, rank, world, steps, warmup, barrier):
     return {"metric": "tau_sweep_images_per_sec_1024x2048", "value": out["value"][0], "unit": "images/s",
             "ms_per_step": out["value"][1], "steps": steps, "per_gpu_batch": B, "n_taus": len(taus), "n_classes": C,
             "e2e": {"value": out["e2e"][0], "unit": "images/s", "ms_per_step": out["e2e"][1],
-                    "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 8, "mode": "sequential upload + update"},
+                    "h2d_bytes_per_step": Xh.numel() * 2 + yh.numel(), "mode": "sequential upload (bf16 images, uint8 labels) + update"},
             "collective": "one int64 all-reduce(SUM) of cm[T,E+1,C+1,C] + counts inside the timed region (per sweep, not per batch)",
             "exits_at_median_tau": {k: res[-2][k] for k in ("b1_count", "b2_count", "count_out")},
             "l2": "working set of a step (50 MB of inputs, GBs of activations) exceeds the 126 MB L2; no flush"}
