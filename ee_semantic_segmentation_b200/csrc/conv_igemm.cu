@@ -13,7 +13,7 @@
 // * Taps that fall entirely into the zero padding for a tile (common for dilation 24/36 on a 65x65
 //   map) are skipped: they contribute exactly 0.
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-//   warps 2..5 = epilogue (tcgen05.ld 32x32b, each warp its TMEM lane quadrant; thread = output
+//   warps 2..17 = epilogue (tcgen05.ld 32x32b, four warps per TMEM lane quadrant, one column quarter each; thread = output
 //   pixel): scale/shift (+ residual, prefetched by TMA into shared memory at kernel start) (+ ReLU),
 //   packed into a 128B-swizzled shared-memory tile and written with ONE TMA tensor store per
 //   64-channel block — full 128 B lines to L2, image-edge rows clipped by the tensor map.
@@ -29,7 +29,8 @@ namespace eeseg {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quadrant (column halves)
+constexpr int kEpiWarps = 16;                        // four warps per TMEM lane quadrant (column quarters): the epilogue is
+                                                     // issue / latency bound, 4 warps per scheduler instead of 2
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer
 constexpr int kMaxStages = 8;
@@ -384,14 +385,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..9. TMEM lane quadrant = warp % 4 (hardware rule); warps 2-5 take the
-    // lower half of the tile's columns, warps 6-9 the upper half =====
+    // ===== epilogue: warps 2..17. TMEM lane quadrant = warp % 4 (hardware rule); warps 2-5 take the
+    // first quarter of the tile columns, warps 6-9 the second, ... =====
     const int quad = warp & 3;
     const int hsel = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;                    // 0..255
     const int m = quad * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
-    const int col_lo = hsel * (p.BN >> 1) , col_hi = p.BN < 32 ? (hsel ? 0 : p.BN) : col_lo + (p.BN >> 1);
+    // column groups of the kEpiWarps / 4 warps of a lane quadrant: at least 16 columns each (narrow tiles leave groups idle)
+    const int cg_cols = max(16, p.BN / (kEpiWarps / 4));
+    const int col_lo = min(hsel * cg_cols, p.BN), col_hi = min(col_lo + cg_cols, p.BN);
     unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long dbg_t0 = clock64();
     unsigned long long dbg_g0 = 0;
@@ -413,7 +416,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (DBG_ON(p)) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
       // the staging tile is reused every tile: the previous TMA stores must have read it out
       if (et == 0 && !p.direct) DBG_T(2, bulk_wait_read(0));
-      DBG_T(3, asm volatile("bar.sync 1, 256;" ::: "memory"));
+      DBG_T(3, asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"));
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
@@ -505,7 +508,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
       fence_proxy_async();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
       if (DBG_ON(p)) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
       if (et == 0 && !p.direct) {
         for (int blk = 0; blk < p.nblk; ++blk)
