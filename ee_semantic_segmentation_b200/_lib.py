@@ -87,6 +87,7 @@ PROTOTYPES = {
 # present only in the -DEESEG_TUNING build (include/eeseg_tuning.h); bound when the loaded library has them
 TUNING_PROTOTYPES = {
     "eeseg_conv_debug_stats": (c_i, [c_p]),
+    "eeseg_conv_probe": (c_i, [c_i, c_i]),
     "eeseg_conv_timing": (c_i, [c_p, c_i]),
 }
 

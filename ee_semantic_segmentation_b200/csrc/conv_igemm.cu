@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -36,6 +37,26 @@ constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, 
 constexpr int kMaxStages = 8;
 
 constexpr int kMaxGroup = 4;   // convolutions sharing one input that can run as one grouped launch
+
+// Division by a launch constant as multiply-high + shift (exact for n < 2^31): every role of the persistent kernel turns
+// a work-item index into (image, tile row, tile column, channel tile) once per tile, the 512 epilogue threads included
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f = {d, 0u, 0u};
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;   // ceil(log2 d)
+    const int p = 31 + (int)l;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) {
+  return f.d == 1u ? n : (__umulhi(n, f.mul) >> f.shr);
+}
 
 struct ConvProblem {      // what differs between the members of a group (ASPP branches)
   int R, S, dil, pad;     // tap (r,s) reads input (y*stride + r*dil - pad_y, x*stride + s*dil - pad_x) where the
@@ -66,6 +87,7 @@ struct ConvParams {
                                        // 32 KB instead of 48 KB per 128x256x64 MMA block (the L2->SM port, ~64 B/clk,
                                        // is what bounds the single-CTA kernel at ~62 % of the tensor peak)
   int m_tiles;                         // N * tiles_x * tiles_y
+  FastDiv fd_ntiles, fd_tiles_img, fd_tiles_x, fd_bw;   // Cout / BN, tiles_x * tiles_y, tiles_x, BW
   int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
   int direct;                          // deep-K launches: epilogue stores straight from registers (no staging
                                        // tile), so the operand ring gets all the shared memory
@@ -79,6 +101,8 @@ struct ConvParams {
   int64_t shift_sn;
   unsigned long long* dbg;   // optional [gridDim.x][32] cycle counters (eeseg_conv_debug_stats)
   unsigned long long* tslot; // optional {min start, max end} wall-clock ns of this launch (eeseg_conv_timing)
+  int probe;                 // tuning builds: bit 0 = do not load A tiles, bit 1 = no weight tiles, bit 2 = no residual
+                             // tiles, bit 3 = no output stores (timing probes of the operand stream; results are garbage)
 };
 
 // Tuning instrumentation (cycle accounting per role, %globaltimer launch brackets) exists only in builds with
@@ -87,6 +111,7 @@ struct ConvParams {
 #ifdef EESEG_TUNING
 #define DBG_ON(p) ((p).dbg != nullptr)
 #define TS_ON(p) ((p).tslot != nullptr)
+#define PROBE(p, bit) (((p).probe >> (bit)) & 1)
 // DBG_T(slot, stmt) adds the cycles `stmt` takes to counter `slot`
 #define DBG_T(slot, stmt)                                   \
   do {                                                      \
@@ -101,6 +126,7 @@ struct ConvParams {
 #else
 #define DBG_ON(p) false
 #define TS_ON(p) false
+#define PROBE(p, bit) false
 #define DBG_T(slot, stmt) \
   do {                    \
     stmt;                 \
@@ -149,6 +175,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t blk_bytes = (uint32_t)kBlockM * (uint32_t)p.row_bytes;
   const int nblk_res = p.has_res ? p.BN / 64 : 0;             // residual K blocks per tile (64 channels each)
+  const int res_per_stage = (kPair || p.BN < 128) ? 1 : 2;    // residual blocks staged together
   uint8_t* stg_smem = smem + (p.overlay ? 0 : p.main_bytes);   // overlay: <= 1 tile per CTA, ring is idle by then
   // 64x64 bf16 identity (K-major, SW128): the B operand of the residual K blocks
   uint8_t* eye_smem = smem + p.main_bytes + ((p.overlay || p.direct) ? 0 : (size_t)p.nblk * blk_bytes);
@@ -237,19 +264,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (p.schedule) {
       const int item = __ldg(p.schedule + item_idx * cs + rank);
       prob = item >> 24;
-      const int t = item & 0xffffff;
-      nt = t % n_tiles;
-      return t / n_tiles;
+      const uint32_t t = (uint32_t)item & 0xffffffu;
+      const uint32_t mt = fd_div(t, p.fd_ntiles);
+      nt = (int)(t - mt * (uint32_t)n_tiles);
+      return (int)mt;
     }
     prob = 0;
-    nt = item_idx % n_tiles;
-    return min((item_idx / n_tiles) * cs + rank, p.m_tiles - 1);
+    const uint32_t g = fd_div((uint32_t)item_idx, p.fd_ntiles);
+    nt = item_idx - (int)g * n_tiles;
+    return min((int)g * cs + rank, p.m_tiles - 1);
   };
   auto mt_origin = [&](int mt, int& n_img, int& y0, int& x0) {
-    n_img = mt / tiles_img;
-    const int trem = mt % tiles_img;
-    y0 = (trem / p.tiles_x) * p.BH;
-    x0 = (trem % p.tiles_x) * p.BW;
+    n_img = (int)fd_div((uint32_t)mt, p.fd_tiles_img);
+    const int trem = mt - n_img * tiles_img;
+    const int ty = (int)fd_div((uint32_t)trem, p.fd_tiles_x);
+    y0 = ty * p.BH;
+    x0 = (trem - ty * p.tiles_x) * p.BW;
   };
   auto tile_coords = [&](int item_idx, int& prob, int& n_img, int& y0, int& x0, int& n0) {
     int nt;
@@ -283,15 +313,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const ConvProblem& q = p.pr[prob];
         const uint32_t taps = item_taps(t, q, y0, x0);
         const uint32_t a_box = (uint32_t)(p.BW * p.BH * kBlockK * 2);
-        for (int j = 0; j < nblk_res; ++j) {   // residual K blocks: A = 64 residual channels of the tile's pixels
+        // residual K blocks: A = 64 residual channels of the tile's pixels; a single CTA packs two of them into one
+        // ring stage (the second one where the weight tile goes: BN >= 128 there), halving the stage hand-shakes
+        for (int j = 0; j < nblk_res; j += res_per_stage) {
           DBG_T(0, mbar_wait(empty_bar + s, ph ^ 1u));
           if constexpr (pair) {   // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both
             if (crank == 0) mbar_expect_tx(full_bar + s, 2 * a_box);
             tma_load_4d_pair(smem + (size_t)s * stage_bytes, &tmap_res, mapa_u32(smem_u32(full_bar + s), 0),
                              q.ch_off + n0 + j * 64, x0, y0, n_img);
           } else {
-            mbar_expect_tx(full_bar + s, a_box);
-            tma_load_4d(smem + (size_t)s * stage_bytes, &tmap_res, full_bar + s, q.ch_off + n0 + j * 64, x0, y0, n_img);
+            const int nb = min(res_per_stage, nblk_res - j);
+            mbar_expect_tx(full_bar + s, PROBE(p, 2) ? 0u : (uint32_t)nb * a_box);
+            if (!PROBE(p, 2)) {
+              for (int jj = 0; jj < nb; ++jj)
+                tma_load_4d(smem + (size_t)s * stage_bytes + (size_t)jj * a_bytes, &tmap_res, full_bar + s,
+                            q.ch_off + n0 + (j + jj) * 64, x0, y0, n_img);
+            }
           }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -308,9 +345,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               tma_load_4d_pair(sa, &tmap_x, fb, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
               tma_load_2d_pair(sb, &wmaps.m[prob], fb, tp * p.Cin + cb * kBlockK, n0 + (int)crank * (p.BN >> 1));
             } else {
-              mbar_expect_tx(full_bar + s, a_box + b_bytes);
-              tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
-              tma_load_2d(sb, &wmaps.m[prob], full_bar + s, tp * p.Cin + cb * kBlockK, n0);
+              mbar_expect_tx(full_bar + s, (PROBE(p, 0) ? 0u : a_box) + (PROBE(p, 1) ? 0u : b_bytes));
+              if (!PROBE(p, 0))
+                tma_load_4d(sa, &tmap_x, full_bar + s, cb * kBlockK, x0 * p.stride + dx, y0 * p.stride + dy, n_img);
+              if (!PROBE(p, 1)) tma_load_2d(sb, &wmaps.m[prob], full_bar + s, tp * p.Cin + cb * kBlockK, n0);
             }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
@@ -342,17 +380,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue(s) drained this buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * p.BN);
-        for (int j = 0; j < nblk_res; ++j) {   // D[:, 64j..64j+63] = R_j x I64 (overwrites: first MMAs of the tile)
+        for (int j = 0; j < nblk_res; j += res_per_stage) {   // D[:, 64j..64j+63] = R_j x I64 (overwrites: first MMAs of the tile)
           DBG_T(1, mbar_wait(full_bar + s, ph));
           tcgen05_fence_after();
-          const uint64_t adesc = make_sw128_desc(smem_u32(smem + (size_t)s * stage_bytes));
           const uint64_t edesc = make_sw128_desc(smem_u32(eye_smem));
+          const int nb = min(res_per_stage, nblk_res - j);
+          for (int jj = 0; jj < nb; ++jj) {
+            const uint64_t adesc = make_sw128_desc(smem_u32(smem + (size_t)s * stage_bytes + (size_t)jj * a_bytes));
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            if constexpr (pair)
-              umma_bf16_pair(tacc + (uint32_t)(j * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
-            else
-              umma_bf16(tacc + (uint32_t)(j * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              if constexpr (pair)
+                umma_bf16_pair(tacc + (uint32_t)((j + jj) * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
+              else
+                umma_bf16(tacc + (uint32_t)((j + jj) * 64), adesc + (uint64_t)(k * 2), edesc + (uint64_t)(k * 2), idesc64, k > 0 ? 1u : 0u);
+            }
           }
           if constexpr (pair) umma_commit_pair(empty_bar + s, 3); else umma_commit(empty_bar + s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -385,22 +426,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..17. TMEM lane quadrant = warp % 4 (hardware rule); warps 2-5 take the
-    // first quarter of the tile columns, warps 6-9 the second, ... =====
+    // ===== epilogue: warps 2..17. TMEM lane quadrant = warp % 4 (hardware rule); the four warps of a quadrant split
+    // the tile's columns. The tile is converted in passes of 128 columns (32 per warp, one tcgen05.ld.x32; tiles
+    // narrower than 128 columns: one pass of 16 per warp): the output blocks of a finished pass are handed to the TMA
+    // store while the next pass is read out of TMEM. All shared-memory traffic uses shared-space addresses =====
     const int quad = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;                    // 0..255
+    const int et = threadIdx.x - 64;                    // 0..511
     const int m = quad * 32 + lane;                        // tile row = output pixel (y0 + m / BW, x0 + m % BW)
     const uint32_t sw = p.swz ? (uint32_t)(m & 7) : 0u; // SWIZZLE_128B: 16 B chunk index ^= row % 8
-    // column groups of the kEpiWarps / 4 warps of a lane quadrant: at least 16 columns each (narrow tiles leave groups idle)
-    const int cg_cols = max(16, p.BN / (kEpiWarps / 4));
-    const int col_lo = min(hsel * cg_cols, p.BN), col_hi = min(col_lo + cg_cols, p.BN);
+    const int wcols = p.BN >= 128 ? 32 : 16;               // columns of one warp in one pass
+    const int pass_cols = 4 * wcols;
+    const int npass = p.BN > pass_cols ? p.BN / pass_cols : 1;
+    const int blk_shift = 31 - __clz(p.blk_cols);          // blk_cols is a power of two
+    const int blk_per_pass = max(1, pass_cols >> blk_shift);
+    const uint32_t stg_row = smem_u32(stg_smem) + (uint32_t)m * (uint32_t)p.row_bytes;
+    const uint32_t ss_base = smem_u32(s_scale);            // scale[256] | shift[256]
+    // scale / shift of a tile: thread et < BN fetches scale[et], thread BN <= et < 2 BN shift[et - BN] (2 BN <= 512
+    // threads); the value for the NEXT tile is fetched while this one is converted
+    const uint32_t ss_slot = ss_base + (et < p.BN ? (uint32_t)et * 4u : 1024u + (uint32_t)(et - p.BN) * 4u);
+    auto fetch_ss = [&](int item_idx) -> float {
+      if (et >= 2 * p.BN) return 0.f;
+      int prob_, n_img_, y0_, x0_, n0_;
+      tile_coords(item_idx, prob_, n_img_, y0_, x0_, n0_);
+      const ConvProblem& qq = p.pr[prob_];
+      return et < p.BN ? __ldg(qq.scale + n0_ + et) : __ldg(qq.shift + (int64_t)n_img_ * p.shift_sn + n0_ + (et - p.BN));
+    };
     unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long dbg_t0 = clock64();
     unsigned long long dbg_g0 = 0;
     if (DBG_ON(p)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
     long long dbg_t1 = 0;
     int it = 0;
+    float ss_next = first_item < total_tiles ? fetch_ss(first_item) : 0.f;
     for (int t = first_item; t < total_tiles; t += item_step, ++it) {
       int prob, n_img, y0, x0, n0;
       tile_coords(t, prob, n_img, y0, x0, n0);
@@ -409,93 +467,109 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const uint32_t aph = ((uint32_t)it >> 1) & 1u;
       // every epilogue thread passed the last barrier of the previous tile: scale/shift can change
       if (DBG_ON(p)) dbg_t1 = clock64();
-      for (int i = et; i < p.BN; i += kEpiThreads) {
-        s_scale[i] = q.scale[n0 + i];
-        s_shift[i] = q.shift[(int64_t)n_img * p.shift_sn + n0 + i];
-      }
+      if (et < 2 * p.BN) sts_f32(ss_slot, ss_next);
       if (DBG_ON(p)) dbg_acc[4] += (unsigned long long)(clock64() - dbg_t1);
       // the staging tile is reused every tile: the previous TMA stores must have read it out
       if (et == 0 && !p.direct) DBG_T(2, bulk_wait_read(0));
       DBG_T(3, asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"));
+      if (t + item_step < total_tiles) ss_next = fetch_ss(t + item_step);   // in flight during this tile
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
-      if (DBG_ON(p)) dbg_t1 = clock64();
-      for (int col = col_lo; col < col_hi; col += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)col, v);
-        // scale/shift for these 16 columns while the TMEM load is in flight
-        float4 sc4[4], sh4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sc4[j] = *reinterpret_cast<const float4*>(s_scale + col + 4 * j);
-          sh4[j] = *reinterpret_cast<const float4*>(s_shift + col + 4 * j);
-        }
+      // direct epilogue: this thread's pixel
+      const int my = (int)fd_div((uint32_t)m, p.fd_bw);
+      const int yy = y0 + my, xx = x0 + (m - my * p.BW);
+      const bool in_image = m < p.BW * p.BH && yy < p.h && xx < p.w;
+      const int64_t out_off = (((int64_t)n_img * p.h + yy) * p.w + xx) * p.ldo + q.ch_off + n0;
+      const float relu_lo = p.relu ? 0.f : -INFINITY;
+      // kMode: 0 = bf16 staging tile, 1 = fp32 staging tile, 2 = bf16 direct, 3 = fp32 direct (compile-time: the loop
+      // body is straight-line code, the scale/shift loads of all column groups issue up front)
+      auto convert_cols = [&](auto nc_tag, auto mode_tag, int col) {
+        constexpr int NC = decltype(nc_tag)::value;
+        constexpr int kMode = decltype(mode_tag)::value;
+        constexpr bool kF32 = (kMode & 1) != 0, kDirect = (kMode & 2) != 0;
+        uint32_t v[NC];
+        if constexpr (NC == 32) tmem_ld32(trow + (uint32_t)col, v); else tmem_ld16(trow + (uint32_t)col, v);
         tmem_ld_wait();
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc4[j].x, sh4[j].x);
-          f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc4[j].y, sh4[j].y);
-          f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc4[j].z, sh4[j].z);
-          f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc4[j].w, sh4[j].w);
-        }
-        if (p.relu) {
+        for (int g = 0; g < NC / 8; ++g) {   // 8 columns: 16 B of bf16, 32 B of fp32
+          const int c8 = col + 8 * g;
+          const uint32_t sa = ss_base + (uint32_t)c8 * 4u;
+          const float4 sc0 = lds_f4(sa), sc1 = lds_f4(sa + 16u), sh0 = lds_f4(sa + 1024u), sh1 = lds_f4(sa + 1040u);
+          float f[8];
+          f[0] = fmaf(__uint_as_float(v[8 * g + 0]), sc0.x, sh0.x);
+          f[1] = fmaf(__uint_as_float(v[8 * g + 1]), sc0.y, sh0.y);
+          f[2] = fmaf(__uint_as_float(v[8 * g + 2]), sc0.z, sh0.z);
+          f[3] = fmaf(__uint_as_float(v[8 * g + 3]), sc0.w, sh0.w);
+          f[4] = fmaf(__uint_as_float(v[8 * g + 4]), sc1.x, sh1.x);
+          f[5] = fmaf(__uint_as_float(v[8 * g + 5]), sc1.y, sh1.y);
+          f[6] = fmaf(__uint_as_float(v[8 * g + 6]), sc1.z, sh1.z);
+          f[7] = fmaf(__uint_as_float(v[8 * g + 7]), sc1.w, sh1.w);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.direct) {
-          // deep-K launch: the epilogue is a small fraction of the tile and overlaps the next main
-          // loop; store the pixel's 16 channels straight from registers
-          const int yy = y0 + m / p.BW, xx = x0 + m % p.BW;
-          if (m < p.BW * p.BH && yy < p.h && xx < p.w) {
-            const int64_t pix = ((int64_t)n_img * p.h + yy) * p.w + xx;
-            if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + q.ch_off + n0 + col);
+          for (int j = 0; j < 8; ++j) f[j] = fmax_nan(f[j], relu_lo);   // -inf without ReLU: identity, NaN kept
+          uint32_t u[4] = {0u, 0u, 0u, 0u};
+          if constexpr (!kF32) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + q.ch_off + n0 + col);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&b0);
-                u.y = *reinterpret_cast<uint32_t*>(&b1);
-                u.z = *reinterpret_cast<uint32_t*>(&b2);
-                u.w = *reinterpret_cast<uint32_t*>(&b3);
-                o[j] = u;
-              }
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              u[j] = *reinterpret_cast<uint32_t*>(&b);
             }
           }
-          continue;
-        }
-        const int blk = col / p.blk_cols;
-        uint8_t* orow = stg_smem + (size_t)blk * blk_bytes + (size_t)m * p.row_bytes;
-        if (p.out_f32) {
-          const uint32_t k0 = (uint32_t)((col - blk * p.blk_cols) >> 2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(orow + (((k0 + j) ^ sw) << 4)) =
-                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          const uint32_t k0 = (uint32_t)((col - blk * p.blk_cols) >> 3);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&b0);
-            u.y = *reinterpret_cast<uint32_t*>(&b1);
-            u.z = *reinterpret_cast<uint32_t*>(&b2);
-            u.w = *reinterpret_cast<uint32_t*>(&b3);
-            *reinterpret_cast<uint4*>(orow + (((k0 + j) ^ sw) << 4)) = u;
+          if constexpr (kDirect) {
+            // deep-K launch: the epilogue is a small fraction of the tile and overlaps the next main loop; the pixel's
+            // channels go straight from registers to global memory
+            if (in_image) {
+              if constexpr (kF32) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + c8);
+                o[0] = make_float4(f[0], f[1], f[2], f[3]);
+                o[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + c8) =
+                    make_uint4(u[0], u[1], u[2], u[3]);
+              }
+            }
+          } else {
+            const uint32_t orow = stg_row + (uint32_t)(c8 >> blk_shift) * blk_bytes;
+            const uint32_t cb = (uint32_t)(c8 & (p.blk_cols - 1));   // column inside the output block
+            if constexpr (kF32) {
+              const uint32_t k0 = cb >> 2;
+              sts_f4(orow + ((k0 ^ sw) << 4), f[0], f[1], f[2], f[3]);
+              sts_f4(orow + (((k0 + 1u) ^ sw) << 4), f[4], f[5], f[6], f[7]);
+            } else {
+              sts_u4(orow + (((cb >> 3) ^ sw) << 4), u[0], u[1], u[2], u[3]);
+            }
           }
+        }
+      };
+      auto store_blocks = [&](int pass) {   // one thread: TMA-store the output blocks of a converted pass
+        const int b_hi = min((pass + 1) * blk_per_pass, p.nblk);
+        for (int blk = pass * blk_per_pass; blk < b_hi; ++blk)
+          tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, q.ch_off + n0 + blk * p.blk_cols, x0, y0, n_img);
+        bulk_commit();
+      };
+      if (DBG_ON(p)) dbg_t1 = clock64();
+      for (int pass = 0; pass < npass; ++pass) {
+        const int col = pass * pass_cols + hsel * wcols;
+        if (col < p.BN) {
+          using std::integral_constant;
+          const int mode = (p.direct ? 2 : 0) | (p.out_f32 ? 1 : 0);
+          if (wcols == 32) {
+            if (mode == 0) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 0>{}, col);
+            else if (mode == 1) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 1>{}, col);
+            else if (mode == 2) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 2>{}, col);
+            else convert_cols(integral_constant<int, 32>{}, integral_constant<int, 3>{}, col);
+          } else {
+            if (mode == 0) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 0>{}, col);
+            else if (mode == 1) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 1>{}, col);
+            else if (mode == 2) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 2>{}, col);
+            else convert_cols(integral_constant<int, 16>{}, integral_constant<int, 3>{}, col);
+          }
+        }
+        if (pass + 1 < npass && !p.direct) {
+          // generic-proxy writes -> visible to the async proxy, then one thread stores this pass's blocks
+          fence_proxy_async();
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+          if (et == 0 && !PROBE(p, 3)) store_blocks(pass);
         }
       }
       if (DBG_ON(p)) { dbg_acc[5] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
@@ -506,15 +580,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if constexpr (pair) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty_bar + a), 0));   // the leader's MMA warp waits for both
         else mbar_arrive(tmem_empty_bar + a);
       }
-      // generic-proxy writes -> visible to the async proxy, then one thread stores the tile
       fence_proxy_async();
       asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
       if (DBG_ON(p)) { dbg_acc[6] += (unsigned long long)(clock64() - dbg_t1); dbg_t1 = clock64(); }
-      if (et == 0 && !p.direct) {
-        for (int blk = 0; blk < p.nblk; ++blk)
-          tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, q.ch_off + n0 + blk * p.blk_cols, x0, y0, n_img);
-        bulk_commit();
-      }
+      if (et == 0 && !p.direct && !PROBE(p, 3)) store_blocks(npass - 1);
       if (DBG_ON(p)) dbg_acc[7] += (unsigned long long)(clock64() - dbg_t1);
     }
     if (et == 0) bulk_wait_read(0);   // shared memory must outlive the stores' reads
@@ -526,6 +595,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       unsigned long long g1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
       d[7] = g1 - dbg_g0;   // wall nanoseconds of the epilogue role (clock calibration)
+      p.dbg[(size_t)blockIdx.x * 32 + 18] = dbg_acc[6];   // TMEM hand-back, proxy fence, barrier 2
+      p.dbg[(size_t)blockIdx.x * 32 + 19] = dbg_acc[7];   // issue of the last pass's TMA stores
     }
     tcgen05_fence_before();
   }
@@ -602,6 +673,14 @@ using namespace eeseg;
 static unsigned long long* g_conv_dbg = nullptr;
 static unsigned long long* g_conv_tbuf = nullptr;
 static int g_conv_tcap = 0, g_conv_tnext = 0;
+static int g_conv_probe = 0, g_conv_max_ctas = 0;
+// Timing probes of the operand stream (tuning builds only): `skip_mask` bits as ConvParams::probe (the outputs of the
+// following launches are garbage), `max_ctas` > 0 caps the grid. (0, 0) restores the normal launches.
+extern "C" int eeseg_conv_probe(int skip_mask, int max_ctas) {
+  g_conv_probe = skip_mask;
+  g_conv_max_ctas = max_ctas;
+  return EESEG_OK;
+}
 // Measurement hook (tuning builds only): every following conv launch i records {first CTA start, last CTA end} in
 // wall-clock nanoseconds (%globaltimer) at buffer[2*i], buffer[2*i+1] (i < capacity; the caller initialises starts
 // to UINT64_MAX and ends to 0). NULL switches it off. Returns the number of launches recorded so far.
@@ -747,10 +826,12 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.relu = relu; p.out_f32 = out_dtype == EESEG_F32; p.shift_sn = shift_sn;
 #ifdef EESEG_TUNING
   p.dbg = g_conv_dbg;
+  p.probe = g_conv_probe;
   p.tslot = (g_conv_tbuf && g_conv_tnext < g_conv_tcap) ? g_conv_tbuf + 2 * (size_t)(g_conv_tnext++) : nullptr;
 #else
   p.dbg = nullptr;
   p.tslot = nullptr;
+  p.probe = 0;
 #endif
   // epilogue blocks: 128 B of output per pixel row (64 bf16 / 32 fp32 channels), swizzled; narrower
   // tiles use one dense block
@@ -770,6 +851,10 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   EESEG_REQUIRE(schedule || nprob == 1, "conv_igemm: a grouped launch needs a schedule");
   p.schedule = schedule;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
+  p.fd_ntiles = make_fastdiv((uint32_t)(Cout / BN));
+  p.fd_tiles_img = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
+  p.fd_tiles_x = make_fastdiv((uint32_t)p.tiles_x);
+  p.fd_bw = make_fastdiv((uint32_t)p.BW);
   // CTA pairs (cta_group::2): two m-tiles per work item, each CTA stages half of the weight tile's rows
   int cs = 1;
   if (!schedule) {
@@ -781,7 +866,10 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)(BN / cs) * kBlockK * 2;
   const int total_tiles = schedule ? n_items : ((p.m_tiles + cs - 1) / cs) * (Cout / BN);   // work items (clusters' worth)
   p.n_items = total_tiles;
-  const int max_clusters = cs == 1 ? kNumSMs : max_active_clusters(cs);
+  int max_clusters = cs == 1 ? kNumSMs : max_active_clusters(cs);
+#ifdef EESEG_TUNING
+  if (g_conv_max_ctas > 0 && max_clusters > g_conv_max_ctas / cs) max_clusters = g_conv_max_ctas / cs;
+#endif
   EESEG_REQUIRE(max_clusters > 0, "conv_igemm: no cluster of %d CTAs fits", cs);
   // with at most one tile per CTA the ring is idle when the epilogue runs: the staging tile overlays
   // it and the ring gets the shared memory (deep-K ASPP convs: 4 stages instead of 3)

@@ -10,6 +10,8 @@ if not hasattr(_lib.lib(), "eeseg_conv_debug_stats"):
     raise SystemExit("this tool needs the tuning build: python -m ee_semantic_segmentation_b200.build --tuning, then run with "
                      "EESEG_LIB=ee_semantic_segmentation_b200/libeeseg_b200_tuning.so (the product library has no EESEG_TUNING hooks)")
 dev = torch.device("cuda:0")
+if os.environ.get("EESEG_PROBE"):   # operand-stream probe (see tools/conv_stream_probe.py): e.g. 15 = no loads, no stores
+    _lib.lib().eeseg_conv_probe(int(os.environ["EESEG_PROBE"]), 0)
 shapes = [  # name, N, h, w, Cin, Cout, R, dil, stride, residual
     ("l1.c3 64>256+res", 4, 129, 129, 64, 256, 1, 1, 1, True),
     ("l1.c1 256>64", 4, 129, 129, 256, 64, 1, 1, 1, False),
@@ -50,7 +52,7 @@ for name, N, h, w, cin, cout, R, dil, stride, res in shapes:
     pro_us = ((di[act][:, 17] - di[act][:, 16]).double().mean().item() - m[15].item()) / 1e3
     print(f"{name:22s} event {us:6.1f}us KERNEL {kern_us:6.1f}us (outside epilogue role {pro_us:4.1f}us) tiles/CTA {tiles:4.1f} | PROD total {m[2]:8.0f} wait_res_empty {m[0]:7.0f} wait_empty {m[1]:7.0f} | "
           f"MMA total {m[6]:8.0f} wait_tmem_empty {m[4]:7.0f} wait_full {m[5]:7.0f} | "
-          f"EPI total {m[12]:8.0f} wait_tmem_full {m[8]:7.0f} wait_res {m[9]:7.0f} wait_store_read {m[10]:7.0f} bar1 {m[11]:6.0f} ss_load {m[13]:6.0f} colloop {m[14]:7.0f} epi_ns {m[15]:7.0f} => {m[12]/max(m[15],1):.2f} GHz", flush=True)
+          f"EPI total {m[12]:8.0f} wait_tmem_full {m[8]:7.0f} wait_res {m[9]:7.0f} wait_store_read {m[10]:7.0f} bar1 {m[11]:6.0f} ss_load {m[13]:6.0f} colloop {m[14]:7.0f} fence_bar2 {m[18]:6.0f} store_issue {m[19]:6.0f} epi_ns {m[15]:7.0f} => {m[12]/max(m[15],1):.2f} GHz", flush=True)
 
 # ---- grouped ASPP launch vs the four separate launches (kernel wall time from the dbg stamps) ----
 from ee_semantic_segmentation_b200.head_plan import conv_igemm_grouped, group_schedule
