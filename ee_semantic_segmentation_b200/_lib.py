@@ -64,7 +64,8 @@ PROTOTYPES = {
     "eeseg_bn_train_bwd_acc": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "eeseg_conv_group_tiles": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "eeseg_conv_igemm_grouped": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i,
-                                       c_p, c_i64, c_i, c_p, c_i, c_p]),
+                                       c_p, c_i64, c_i, c_p, c_i, c_i, c_p]),
+    "eeseg_conv_pair_clusters": (c_i, []),
     "eeseg_stem_space_to_depth": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_stem_space_to_depth_any": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "eeseg_maxpool3x3s2_nhwc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),

@@ -760,7 +760,7 @@ static int max_active_clusters(int cs) {
 static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t shift_sn, int N, int hin,
                        int win, int Cin, int Cout, int stride, int relu, const void* residual, int64_t ldr,
                        void* out, int out_dtype, int64_t ldo, int out_channels, const int32_t* schedule,
-                       int n_items, cudaStream_t stream) {
+                       int n_items, int sched_pairs, cudaStream_t stream) {
   EESEG_REQUIRE(x && out && nprob >= 1 && nprob <= kMaxGroup, "conv_igemm: null pointer / bad group size");
   EESEG_REQUIRE(N >= 1 && hin >= 1 && win >= 1, "conv_igemm: bad sizes");
   EESEG_REQUIRE(stride == 1 || stride == 2, "conv_igemm: stride %d (1 or 2)", stride);
@@ -807,7 +807,6 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   // less shared-memory bandwidth per FLOP (N=128 runs at the 128 B/clk smem limit)
   int BN = 256;
   while (BN > 16 && (Cout % BN)) BN >>= 1;
-  (void)kb_total;
   if (schedule) {
     // grouped launch: the caller's work list fixes the number of channel tiles (eeseg_conv_group_tiles + the
     // under-filled-grid rule below, applied by the scheduler)
@@ -859,12 +858,22 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   int cs = 1;
   if (!schedule) {
     cs = conv_cluster_override();
-    if (cs == 0) cs = 1;
+    // deep-K launches (layer4's 1x1 reduce: 32 K blocks per tile, its 3x3: 72) run as CTA pairs: per 128x256x64 MMA
+    // block an SM then ingests 32 KB instead of 48 KB and the ring holds 6-7 stages instead of 4 (-5 % / -6 %);
+    // shallow-K launches and the 36-block 3x3 of layer3 lose to the coupling of the two SMs (whole step, rules
+    // compared in profiles/r02_conv_cluster_experiments.md)
+    const bool is1x1 = hp[0].R == 1 && hp[0].S == 1;
+    if (cs == 0) cs = (kb_total >= 64 || (kb_total >= 32 && is1x1)) ? 2 : 1;
     if (cs == 2 && (BN < 32 || p.m_tiles < 2)) cs = 1;
+  } else if (sched_pairs) {
+    // pair work list: entries 2i, 2i+1 are the two m-tiles of item i (same problem and channel tile; the scheduler pairs
+    // the same tile position of two images, so both have the same live taps); every tile appears once
+    EESEG_REQUIRE(BN >= 32 && n_items % 2 == 0, "conv_igemm: a pair work list needs an even number of entries and BN >= 32");
+    cs = 2;
   }
   p.cs = cs;
   stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)(BN / cs) * kBlockK * 2;
-  const int total_tiles = schedule ? n_items : ((p.m_tiles + cs - 1) / cs) * (Cout / BN);   // work items (clusters' worth)
+  const int total_tiles = schedule ? n_items / cs : ((p.m_tiles + cs - 1) / cs) * (Cout / BN);   // work items (clusters' worth)
   p.n_items = total_tiles;
   int max_clusters = cs == 1 ? kNumSMs : max_active_clusters(cs);
 #ifdef EESEG_TUNING
@@ -883,11 +892,17 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
     if (kb < kb_min) kb_min = kb;
   }
   p.direct = (!p.overlay && kb_min >= 16) ? 1 : 0;
+#ifdef EESEG_TUNING
+  if ((g_conv_probe & 16) && !p.overlay) p.direct = 1;   // probe: register -> global epilogue everywhere (deeper ring)
+#endif
   p.out = out; p.ldo = ldo;
   const size_t fixed = 1024 + ((p.overlay || p.direct) ? 0 : staging_bytes) + res_bytes + tail_bytes;
   if (fixed + stage_bytes > 227 * 1024) { set_error("conv_igemm: tile does not fit shared memory"); return EESEG_ERR_UNSUPPORTED; }
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+#ifdef EESEG_TUNING
+  if ((g_conv_probe & 32) && stages > 2) stages = 2;       // probe: sensitivity to the ring depth
+#endif
   p.stages = stages;
   size_t ring = stages * stage_bytes;
   if (p.overlay && ring < staging_bytes) ring = staging_bytes;
@@ -954,7 +969,7 @@ extern "C" int eeseg_conv_igemm_fwd(const void* x, const void* wt, const float* 
                                     int out_dtype, int64_t ldo, void* stream_) {
   HostProblem hp = {wt, scale, shift, R, S, dilation, pad, 0};
   return launch_conv(x, &hp, 1, shift_sn, N, hin, win, Cin, Cout, stride, relu, residual, ldr, out, out_dtype,
-                     ldo, Cout, nullptr, 0, (cudaStream_t)stream_);
+                     ldo, Cout, nullptr, 0, 0, (cudaStream_t)stream_);
 }
 
 extern "C" int eeseg_conv_group_tiles(int hin, int win, int Cout, int* tiles_x, int* tiles_y, int* bw, int* bh,
@@ -973,15 +988,19 @@ extern "C" int eeseg_conv_igemm_grouped(const void* x, int nprob, const void* co
                                         const float* const* scale, const float* const* shift,
                                         const int* ksize, const int* dilation, const int* ch_off, int N,
                                         int hin, int win, int Cin, int Cout, int relu, void* out, int64_t ldo,
-                                        int out_channels, const int32_t* schedule, int n_items, void* stream_) {
+                                        int out_channels, const int32_t* schedule, int n_items, int cta_pairs,
+                                        void* stream_) {
   EESEG_REQUIRE(wt && scale && shift && ksize && dilation && ch_off, "conv_igemm_grouped: null pointer");
   EESEG_REQUIRE(nprob >= 1 && nprob <= kMaxGroup, "conv_igemm_grouped: 1..%d problems", kMaxGroup);
   HostProblem hp[kMaxGroup];
   for (int g = 0; g < nprob; ++g)
     hp[g] = HostProblem{wt[g], scale[g], shift[g], ksize[g], ksize[g], dilation[g], -1, ch_off[g]};
   return launch_conv(x, hp, nprob, 0, N, hin, win, Cin, Cout, 1, relu, nullptr, 0, out, EESEG_BF16, ldo,
-                     out_channels, schedule, n_items, (cudaStream_t)stream_);
+                     out_channels, schedule, n_items, cta_pairs, (cudaStream_t)stream_);
 }
+
+// Clusters of two conv CTAs the device runs at once (the G of a pair work list); 0 if the query fails.
+extern "C" int eeseg_conv_pair_clusters(void) { return max_active_clusters(2); }
 
 extern "C" size_t eeseg_global_avgpool_workspace_bytes(int N, int C) {
   return (size_t)(N > 0 ? N : 0) * kPoolSplits * (size_t)(C > 0 ? C : 0) * sizeof(float) + 256;

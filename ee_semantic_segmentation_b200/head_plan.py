@@ -89,11 +89,15 @@ def conv_igemm(x, wt, scale, shift, dilation, relu, out, out_dtype_code, ldo, sh
             FLOP_LOG.append((nominal, nominal * frac, PROFILE_TAG))
 
 
-def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
+def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148, pairs=False, n_clusters=None):
     """Work list of a grouped conv launch: item = problem << 24 | tile, ordered in passes over IMAGES_PER_PASS images and,
     inside a pass, by decreasing cost (live taps x channel blocks — taps that fall entirely into the zero padding of a tile
     are skipped by the kernel), each round of n_ctas items dealt to the persistent CTAs by their load so far. Returns an
-    int32 CPU tensor."""
+    int32 CPU tensor.
+
+    pairs=True (N even): a PAIR list for clusters of two CTAs (eeseg_conv_igemm_grouped, cta_pairs) — an item is the same
+    tile position of images 2k and 2k+1 (identical live taps, so the joint 256-row MMA skips exactly what each tile would
+    skip alone); entries 2i, 2i+1 are its two tiles, rounds are n_clusters items."""
     import ctypes
     import numpy as np
     tx, ty, bw, bh, bn = (ctypes.c_int() for _ in range(5))
@@ -105,9 +109,12 @@ def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
     while bn > 64 and len(ksizes) * N * tx * ty * (cout // bn) <= n_ctas:
         bn //= 2
     n_tiles = cout // bn
+    if pairs and (N % 2 or bn < 32):
+        raise ValueError("group_schedule(pairs=True) needs an even number of images")
     y0 = np.arange(ty) * bh
     x0 = np.arange(tx) * bw
-    items, costs = [], []
+    step = 2 if pairs else 1                 # images per item
+    items, costs, imgs = [], [], []
     for g, (k, d) in enumerate(zip(ksizes, dils)):
         pad = d * (k // 2)
         off = np.arange(k) * d - pad
@@ -116,12 +123,14 @@ def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
         live_y = ((y_hi[:, None] - 1 + off[None, :] >= 0) & (y0[:, None] + off[None, :] < h)).sum(1)   # [ty]
         live_x = ((x_hi[:, None] - 1 + off[None, :] >= 0) & (x0[:, None] + off[None, :] < w)).sum(1)   # [tx]
         taps = live_y[:, None] * live_x[None, :]                                                      # [ty, tx]
-        cost = np.broadcast_to(taps.reshape(1, ty * tx, 1), (N, ty * tx, n_tiles)).reshape(-1) * (cin // 64)
-        tile = np.arange(N * ty * tx * n_tiles)
-        items.append((g << 24) | tile)
+        n_it = N // step
+        cost = np.broadcast_to(taps.reshape(1, ty * tx, 1), (n_it, ty * tx, n_tiles)).reshape(-1) * (cin // 64)
+        first = np.arange(n_it)[:, None, None] * step                                                  # first image of the item
+        tile = ((first * (ty * tx) + np.arange(ty * tx)[None, :, None]) * n_tiles + np.arange(n_tiles)[None, None, :])
+        items.append((g << 24) | tile.reshape(-1))
         costs.append(cost)
-    items, costs = np.concatenate(items), np.concatenate(costs)
-    img = (items & 0xffffff) // (ty * tx * n_tiles)
+        imgs.append(np.broadcast_to(first, (n_it, ty * tx, n_tiles)).reshape(-1))
+    items, costs, img = np.concatenate(items), np.concatenate(costs), np.concatenate(imgs)
     ipp = IMAGES_PER_PASS if IMAGES_PER_PASS else N
     # Passes over `ipp` images at a time: the CTAs then work on the same few images at any moment, so their activation
     # (17 MB per image at Cin = 2048) plus the weights of all problems (28 MB) stay L2-resident across the 27 taps that
@@ -129,11 +138,11 @@ def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
     # for 98.6 MB of input + weights with the all-images order). Inside a pass: rounds of n_ctas items, longest first,
     # each round dealt to the CTAs in order of their load so far (CTA c walks positions c, c+G, c+2G, ...).
     flat = []
-    for p0 in range(0, N, ipp):
-        idx = np.nonzero((img >= p0) & (img < p0 + ipp))[0]
+    for p0 in range(0, N, max(ipp, step)):
+        idx = np.nonzero((img >= p0) & (img < p0 + max(ipp, step)))[0]
         flat.append(idx[np.argsort(-costs[idx], kind="stable")])
     flat = np.concatenate(flat)
-    G = min(n_ctas, len(items))
+    G = min((n_clusters if n_clusters else n_ctas // 2) if pairs else n_ctas, len(items))
     out = np.zeros(len(items), dtype=np.int64)
     load = np.zeros(G)
     for r in range((len(flat) + G - 1) // G):
@@ -142,11 +151,15 @@ def group_schedule(N, h, w, cin, cout, ksizes, dils, n_ctas=148):
         ctas = np.argsort(load[:len(seg)], kind="stable")          # a short last round uses CTAs 0 .. len-1
         out[r * G + ctas] = items[seg]
         load[ctas] += costs[seg]
+    if pairs:   # entry 2i = the item's tile in image 2k, entry 2i+1 = the same tile of image 2k+1
+        out = np.stack([out, out + ty * tx * n_tiles], axis=1).reshape(-1)
     return torch.from_numpy(out.astype(np.int32))
 
 
-def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out, ldo, out_channels, schedule):
-    """One persistent launch for several 'same' convolutions of x (see eeseg_conv_igemm_grouped)."""
+def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out, ldo, out_channels, schedule,
+                       cta_pairs=False):
+    """One persistent launch for several 'same' convolutions of x (see eeseg_conv_igemm_grouped); cta_pairs: `schedule`
+    is a pair list (group_schedule(pairs=True))."""
     import ctypes
     N, h, w, Cin = x.shape
     n = len(wts)
@@ -158,7 +171,7 @@ def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out,
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
         torch_ops.fast.conv_igemm_grouped(x, list(wts), list(scales), list(shifts), list(ksizes), list(dils),
-                                           list(ch_offs), bool(relu), out, ldo, out_channels, schedule)
+                                           list(ch_offs), bool(relu), out, ldo, out_channels, schedule, bool(cta_pairs))
         if PROFILE is not None:
             b.record()
             PROFILE.append((a, b, sum(2 * N * h * w * Cout * k * k * Cin for k in ksizes), PROFILE_TAG))
@@ -195,6 +208,7 @@ def global_avgpool_nhwc(xh):
 
 GROUPED = True   # run the ASPP branch convolutions as one grouped launch
 IMAGES_PER_PASS = int(os.environ.get("EESEG_GROUP_IMAGES_PER_PASS", "2"))   # grouped work list: images per pass (0 = all)
+GROUP_PAIRS = os.environ.get("EESEG_GROUP_PAIRS", "1") != "0"   # grouped ASPP launch as CTA pairs when the batch is even
 OVERLAP_POOLED = True   # pooled ASPP branch on a side stream, next to the grouped ASPP launch
 
 _SIDE = {}
@@ -282,15 +296,20 @@ class HeadPlan:
                 and any(wt.shape[1] == 3 for wt, _, _, _ in self.branches):
             # the ASPP branches (1x1 + atrous 3x3) as ONE persistent launch over a cost-sorted work list
             key = (N, h, w, str(dev))
+            # an even batch runs as CTA pairs (cta_group::2: the same tile of two images per cluster)
+            pairs = GROUP_PAIRS and N % 2 == 0 and xh.shape[-1] >= 256
             sched = self._schedules.get(key)
             if sched is None:
-                sched = group_schedule(N, h, w, xh.shape[-1], mid, [wt.shape[1] for wt, _, _, _ in self.branches],
-                                       [d for _, _, _, d in self.branches]).to(dev)
+                n_cl = lib().eeseg_conv_pair_clusters() if pairs else None
+                pairs = pairs and bool(n_cl)
+                sched = (group_schedule(N, h, w, xh.shape[-1], mid, [wt.shape[1] for wt, _, _, _ in self.branches],
+                                        [d for _, _, _, d in self.branches], pairs=pairs, n_clusters=n_cl).to(dev), pairs)
                 self._schedules[key] = sched
+            sched, pairs = sched
             conv_igemm_grouped(xh, [b[0] for b in self.branches], [b[1] for b in self.branches],
                                [b[2] for b in self.branches], [b[0].shape[1] for b in self.branches],
                                [b[3] for b in self.branches], [k * mid for k in range(nb)], True, cat,
-                               nb * mid, nb * mid, sched)
+                               nb * mid, nb * mid, sched, cta_pairs=pairs)
         else:
             for k, (wt, s, b, dil) in enumerate(self.branches):
                 conv_igemm(xh, wt, s, b, dil, True, cat[..., k * mid:], BF, nb * mid)

@@ -62,8 +62,8 @@ def _conv_igemm_fwd(x, wt, scale, shift, shift_sn, dilation, stride, pad, relu, 
 
 
 @_op("conv_igemm_grouped(Tensor x, Tensor[] wts, Tensor[] scales, Tensor[] shifts, int[] ksizes, int[] dils, int[] ch_offs, "
-     "bool relu, Tensor(a!) out, int ldo, int out_channels, Tensor schedule) -> ()")
-def _conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out, ldo, out_channels, schedule):
+     "bool relu, Tensor(a!) out, int ldo, int out_channels, Tensor schedule, bool cta_pairs) -> ()")
+def _conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out, ldo, out_channels, schedule, cta_pairs):
     N, h, w, Cin = x.shape
     n = len(wts)
     Cout = wts[0].shape[0]
@@ -74,7 +74,7 @@ def _conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out
             x.data_ptr(), n, PA(*[t.data_ptr() for t in wts]), PA(*[t.data_ptr() for t in scales]),
             PA(*[t.data_ptr() for t in shifts]), IA(*ksizes), IA(*dils), IA(*ch_offs), N, h, w, Cin, Cout,
             1 if relu else 0, out.data_ptr(), ldo, out_channels, schedule.data_ptr(), schedule.numel(),
-            _stream(x)), "eeseg_conv_igemm_grouped")
+            1 if cta_pairs else 0, _stream(x)), "eeseg_conv_igemm_grouped")
 
 
 @_op("conv_igemm_dgrad(Tensor dy, Tensor wt, int dilation, Tensor(a!) dx, Tensor(b!) workspace) -> ()")

@@ -335,13 +335,18 @@ int eeseg_maxpool3x3s2_nhwc_bwd(const void* dout, const void* idx, int N, int h,
  *   problem g writes Cout channels at channel ch_off[g] of `out` (bf16 NHWC, pixel stride ldo,
  *   out_channels channels in total);
  *   schedule: DEVICE int32[n_items], item = g << 24 | tile (tile = m_tile * (Cout/BN) + n_tile in the
- *   geometry eeseg_conv_group_tiles reports), every (g, tile) exactly once, ordered by decreasing cost. */
+ *   geometry eeseg_conv_group_tiles reports), every (g, tile) exactly once, ordered by decreasing cost;
+ *   cta_pairs != 0: the list is a PAIR list — entries 2i and 2i+1 are the two spatial tiles (same g, same channel
+ *   tile) that one cluster of two CTAs runs as a single 256-row tcgen05.mma.cta_group::2 tile, each CTA staging its own
+ *   activation tile and half of the weight tile; n_items counts entries (even). eeseg_conv_pair_clusters() = number of
+ *   such clusters resident at once (the round size of a pair list). */
 int eeseg_conv_group_tiles(int hin, int win, int Cout, int* tiles_x, int* tiles_y, int* bw, int* bh, int* bn);
 int eeseg_conv_igemm_grouped(const void* x, int nprob, const void* const* wt, const float* const* scale,
                              const float* const* shift, const int* ksize, const int* dilation,
                              const int* ch_off, int N, int hin, int win, int Cin, int Cout, int relu,
                              void* out, int64_t ldo, int out_channels, const int32_t* schedule, int n_items,
-                             void* stream);
+                             int cta_pairs, void* stream);
+int eeseg_conv_pair_clusters(void);
 
 /* Programmatic dependent launch (the prologue of conv launch i+1 overlaps the tail of launch i; the kernel executes
  * griddepcontrol.wait before touching its inputs) is on unless the environment holds EESEG_CONV_PDL=0 when the library

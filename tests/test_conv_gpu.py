@@ -52,6 +52,38 @@ def test_conv_igemm_vs_torch(cfg):
     assert err < 1e-2, err
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(N=1, h=13, w=15, Cin=512, Cout=512, R=3, dil=4),      # 72 K blocks: CTA pairs; 4 spatial tiles, 2-4 channel tiles
+    dict(N=3, h=13, w=15, Cin=512, Cout=512, R=3, dil=4),
+    dict(N=3, h=9, w=9, Cin=2048, Cout=512, R=1, dil=1),       # 1x1, 32 K blocks: pairs; 3 spatial tiles (odd: last repeated)
+    dict(N=4, h=65, w=65, Cin=2048, Cout=512, R=1, dil=1),     # layer4 conv1 of the headline shape
+    dict(N=2, h=33, w=33, Cin=512, Cout=512, R=3, dil=4),
+])
+def test_cta_pair_launches_are_deterministic_and_correct(cfg):
+    """Launches the launcher runs as CTA pairs (cta_group::2; >= 64 K blocks per tile, or a 1x1 with >= 32) against the fp32
+    convolution, and twenty repeats against the first result bit for bit (two SMs share the barriers of one tile)."""
+    from ee_semantic_segmentation_b200 import _lib
+    from ee_semantic_segmentation_b200.head_plan import conv_igemm
+    N, h, w, Cin, Cout, R, dil = (cfg[k] for k in ("N", "h", "w", "Cin", "Cout", "R", "dil"))
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, h, w, Cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(Cout, R, R, Cin, generator=g) / np.sqrt(R * R * Cin)).to(torch.bfloat16)
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    xd, wd, sd, bd = x.to(dev()), wt.to(dev()), scale.to(dev()), shift.to(dev())
+    outs = []
+    for _ in range(21):
+        out = torch.empty(N, h, w, Cout, dtype=torch.bfloat16, device=dev())
+        conv_igemm(xd, wd, sd, bd, dil, True, out, _lib.BF16, Cout)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), padding=dil * (R // 2), dilation=dil)
+    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu().permute(0, 2, 3, 1)
+    err = (outs[0].float().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
+
+
 def test_conv_igemm_full_head_shapes():
     """The ASPP shapes at 513x513 (65x65 maps): Cin=2048, d=24, and the K=1280-like projection."""
     assert run_conv(N=1, h=65, w=65, Cin=2048, Cout=256, R=3, dil=24, relu=True, seed=1) < 1e-2
@@ -167,13 +199,15 @@ def test_stem_plan_vs_torch():
         assert err < 1e-2, err
 
 
-def test_grouped_conv_matches_separate_launches():
+@pytest.mark.parametrize("N,pairs", [(2, False), (2, True), (4, True), (3, False)])
+def test_grouped_conv_matches_separate_launches(N, pairs):
     """The grouped ASPP launch (one persistent kernel over a cost-sorted work list) writes exactly
-    what the four separate launches write."""
+    what the four separate launches write — as single CTAs and as CTA pairs (cta_group::2: the same tile position of two
+    images per cluster, pair work list)."""
     from ee_semantic_segmentation_b200 import _lib
     from ee_semantic_segmentation_b200.head_plan import conv_igemm, conv_igemm_grouped, group_schedule
     g = torch.Generator().manual_seed(8)
-    N, h, w, cin, mid = 2, 65, 65, 256, 256
+    h, w, cin, mid = 65, 65, 256, 256
     x = torch.randn(N, h, w, cin, generator=g).to(torch.bfloat16).to(dev())
     ks, dl = [1, 3, 3, 3], [1, 12, 24, 36]
     wts = [(torch.randn(mid, k, k, cin, generator=g) / np.sqrt(k * k * cin)).to(torch.bfloat16).to(dev()) for k in ks]
@@ -183,9 +217,12 @@ def test_grouped_conv_matches_separate_launches():
     for k in range(4):
         conv_igemm(x, wts[k], scs[k], shs[k], dl[k], True, ref[..., k * mid:], _lib.BF16, 4 * mid)
     out = torch.zeros_like(ref)
-    sched = group_schedule(N, h, w, cin, mid, ks, dl).to(dev())
+    n_cl = _lib.lib().eeseg_conv_pair_clusters() if pairs else None
+    assert not pairs or n_cl >= 32, n_cl
+    sched = group_schedule(N, h, w, cin, mid, ks, dl, pairs=pairs, n_clusters=n_cl).to(dev())
     assert sorted(sched.tolist()) == sorted((gi << 24) | t for gi in range(4) for t in range(N * 36))
-    conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, out, 4 * mid, 4 * mid, sched)
+    conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, out, 4 * mid, 4 * mid, sched,
+                       cta_pairs=pairs)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
 

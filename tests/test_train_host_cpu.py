@@ -172,6 +172,15 @@ def test_grouped_conv_work_list_tile_width_rule():
             np.testing.assert_array_equal(tiles, np.arange(n_items))
     # the first round holds the most expensive items: none of the cheap 1x1 tiles (problem 0)
     assert not np.any((s4[:148] >> 24) == 0)
+    # pair list (CTA pairs): the same tiles, entries 2i / 2i+1 = one tile position in images 2k / 2k+1 of one problem
+    p4 = group_schedule(4, 65, 65, 2048, 256, ks, ds, pairs=True, n_clusters=74).numpy()
+    assert sorted(p4.tolist()) == sorted(s4.tolist())
+    a = p4.reshape(-1, 2)
+    assert np.all((a[:, 0] >> 24) == (a[:, 1] >> 24)) and np.all((a[:, 1] & 0xffffff) - (a[:, 0] & 0xffffff) == 36)
+    assert np.all(((a[:, 0] & 0xffffff) // 36) % 2 == 0)
+    assert not np.any((a[:74, 0] >> 24) == 0)
+    with pytest.raises(ValueError):
+        group_schedule(3, 65, 65, 2048, 256, ks, ds, pairs=True, n_clusters=74)
 
 
 def test_old_pickles_and_weights_token():

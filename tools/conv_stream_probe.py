@@ -33,7 +33,8 @@ SHAPES = [  # name, N, h, w, Cin, Cout, R, dil, residual
     ("l4.c3 512>2048+res", 4, 65, 65, 512, 2048, 1, 1, True),
     ("aspp 3x3 d12 2048", 4, 65, 65, 2048, 256, 3, 12, False),
 ]
-MASKS = [("full", 0), ("-A", 1), ("-B", 2), ("-R", 4), ("-S", 8), ("-A-B", 3), ("-A-B-R", 7), ("none", 15)]
+MASKS = [("full", 0), ("-A", 1), ("-B", 2), ("-R", 4), ("-S", 8), ("-A-B", 3), ("-A-B-R", 7), ("none", 15),
+         ("direct", 16), ("2stages", 32)]   # 16: register -> global epilogue (one more ring stage), 32: ring capped at 2
 GRIDS = [148, 111, 74, 37]
 
 
@@ -75,11 +76,11 @@ def main():
             run()
         row = {"shape": name}
         for mname, mask in MASKS:
-            if (mask & 4) and not res and mask != 15 and mname != "-A-B-R":
+            if (mask & 4) and mask < 16 and not res and mask != 15 and mname != "-A-B-R":
                 continue
             L.eeseg_conv_probe(mask, 0)
             row[f"warm {mname}"] = timed(run, False, args.reps)
-            if mname in ("full", "-R", "-A-B-R"):
+            if mname in ("full", "-R", "-A-B-R", "direct"):
                 row[f"cold {mname}"] = timed(run, True, args.reps)
         for g in GRIDS[1:]:
             L.eeseg_conv_probe(0, g)
