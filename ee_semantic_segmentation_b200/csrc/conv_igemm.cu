@@ -36,6 +36,7 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer
 constexpr int kMaxStages = 8;
 
+constexpr int kTileTab = 32;   // work items per CTA whose coordinates are precomputed in the prologue
 constexpr int kMaxGroup = 4;   // convolutions sharing one input that can run as one grouped launch
 
 // Division by a launch constant as multiply-high + shift (exact for n < 2^31): every role of the persistent kernel turns
@@ -187,6 +188,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_scale = reinterpret_cast<float*>(tail + 256);   // 16 B aligned (read as float4)
   float* s_shift = s_scale + 256;
+  const uint32_t tile_tab = smem_u32(tail + 256 + 2 * 256 * 4);   // int4[kTileTab]: {image | problem << 24, y0 | x0 << 16, n0, taps}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((DBG_ON(p) || TS_ON(p)) && threadIdx.x == 0) {   // kernel-entry wall clock (ns) of this CTA
@@ -242,22 +244,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const int cs = p.cs;
-  if constexpr (pair) cluster_sync_all();   // the peer's barriers / TMEM are set up before anything is sent to them
-  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map
-  // prefetch) overlapped the tail of the previous kernel in the stream; from here on we touch its
-  // outputs, so wait for it to complete. Our own dependents may start their prologue right away.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
   // item -> (problem, n-tile) + the m-tile of cluster rank r; tile -> (image, y0, x0, n0); identical in every role.
   // Pair mode: an item is two m-tiles of one (problem, n-tile); without a work list these are the consecutive tiles
   // 2g, 2g+1 (an odd last tile is repeated: same values written twice), with a work list entry 2*item + r names rank r's
   // tile (the host pairs tiles with equal live taps).
+  const int cs = p.cs;
   const int first_item = (int)(blockIdx.x / (unsigned)cs);
   const int item_step = (int)(gridDim.x / (unsigned)cs);
   auto item_tile = [&](int item_idx, int rank, int& prob, int& nt) -> int {
@@ -299,6 +290,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     return m;
   };
 
+  // The first kTileTab work items of this CTA, decoded once by the 32 lanes of one warp (here in the prologue, which under
+  // programmatic dependent launch overlaps the previous kernel's tail; the work list is written at plan time, not by that
+  // kernel): the producer thread, the MMA thread and the 512 epilogue threads then read 16 bytes per tile instead of each
+  // redoing the index arithmetic and the live-tap scan (1.5-4 k cycles per tile of a single thread's time, which is what
+  // bounded the launches with few K blocks per tile)
+  if (warp == 2) {
+    const int t = first_item + lane * item_step;
+    if (lane < kTileTab && t < total_tiles) {
+      int prob, n_img, y0, x0, n0;
+      tile_coords(t, prob, n_img, y0, x0, n0);
+      const uint32_t taps = item_taps(t, p.pr[prob], y0, x0);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_tab + (uint32_t)lane * 16u), "r"(n_img | (prob << 24)),
+                   "r"(y0 | (x0 << 16)), "r"(n0), "r"(taps)
+                   : "memory");
+    }
+  }
+  // tile `it` (work item t) of this CTA: coordinates and live taps
+  auto get_tile = [&](int it, int t, int& prob, int& n_img, int& y0, int& x0, int& n0) -> uint32_t {
+    if (it < kTileTab) {
+      const int4 d = lds_i4(tile_tab + (uint32_t)it * 16u);
+      prob = d.x >> 24;
+      n_img = d.x & 0xffffff;
+      y0 = d.y & 0xffff;
+      x0 = (int)((uint32_t)d.y >> 16);
+      n0 = d.z;
+      return (uint32_t)d.w;
+    }
+    tile_coords(t, prob, n_img, y0, x0, n0);
+    return item_taps(t, p.pr[prob], y0, x0);
+  };
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if constexpr (pair) cluster_sync_all();   // the peer's barriers / TMEM are set up before anything is sent to them
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map
+  // prefetch) overlapped the tail of the previous kernel in the stream; from here on we touch its
+  // outputs, so wait for it to complete. Our own dependents may start their prologue right away.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
@@ -309,9 +341,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       int it = 0;
       for (int t = first_item; t < total_tiles; t += item_step, ++it) {
         int prob, n_img, y0, x0, n0;
-        tile_coords(t, prob, n_img, y0, x0, n0);
+        const uint32_t taps = get_tile(it, t, prob, n_img, y0, x0, n0);
         const ConvProblem& q = p.pr[prob];
-        const uint32_t taps = item_taps(t, q, y0, x0);
         const uint32_t a_box = (uint32_t)(p.BW * p.BH * kBlockK * 2);
         // residual K blocks: A = 64 residual channels of the tile's pixels; a single CTA packs two of them into one
         // ring stage (the second one where the weight tile goes: BN >= 128 there), halving the stage hand-shakes
@@ -332,9 +363,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
+        // taps in (r, s) order without a division per tap: this single thread's issue rate bounds the shallow layers
+        // (one 64-channel block per tap at Cin = 64)
+        const int pad_y = q.R > 1 ? q.pad : 0, pad_x = q.S > 1 ? q.pad : 0;
+        int tr = 0, ts = -1;
         for (int tp = 0; tp < q.R * q.S; ++tp) {
+          if (++ts == q.S) { ts = 0; ++tr; }
           if (!((taps >> tp) & 1u)) continue;
-          const int dy = (tp / q.S) * q.dil - (q.R > 1 ? q.pad : 0), dx = (tp % q.S) * q.dil - (q.S > 1 ? q.pad : 0);
+          const int dy = tr * q.dil - pad_y, dx = ts * q.dil - pad_x;
           for (int cb = 0; cb < cblocks; ++cb) {
             DBG_T(1, mbar_wait(empty_bar + s, ph ^ 1u));
             uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -374,8 +410,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       int it = 0;
       for (int t = first_item; t < total_tiles; t += item_step, ++it) {
         int prob, n_img, y0, x0, n0;
-        tile_coords(t, prob, n_img, y0, x0, n0);
-        const int num_kb = __popc(item_taps(t, p.pr[prob], y0, x0)) * cblocks;
+        const int num_kb = __popc(get_tile(it, t, prob, n_img, y0, x0, n0)) * cblocks;
         const int a = it & 1;
         DBG_T(0, mbar_wait(tmem_empty_bar + a, (((uint32_t)it >> 1) & 1u) ^ 1u));   // epilogue(s) drained this buffer
         tcgen05_fence_after();
@@ -445,10 +480,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // scale / shift of a tile: thread et < BN fetches scale[et], thread BN <= et < 2 BN shift[et - BN] (2 BN <= 512
     // threads); the value for the NEXT tile is fetched while this one is converted
     const uint32_t ss_slot = ss_base + (et < p.BN ? (uint32_t)et * 4u : 1024u + (uint32_t)(et - p.BN) * 4u);
-    auto fetch_ss = [&](int item_idx) -> float {
+    auto fetch_ss = [&](int it_, int item_idx) -> float {
       if (et >= 2 * p.BN) return 0.f;
       int prob_, n_img_, y0_, x0_, n0_;
-      tile_coords(item_idx, prob_, n_img_, y0_, x0_, n0_);
+      get_tile(it_, item_idx, prob_, n_img_, y0_, x0_, n0_);
       const ConvProblem& qq = p.pr[prob_];
       return et < p.BN ? __ldg(qq.scale + n0_ + et) : __ldg(qq.shift + (int64_t)n_img_ * p.shift_sn + n0_ + (et - p.BN));
     };
@@ -458,10 +493,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (DBG_ON(p)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
     long long dbg_t1 = 0;
     int it = 0;
-    float ss_next = first_item < total_tiles ? fetch_ss(first_item) : 0.f;
+    float ss_next = first_item < total_tiles ? fetch_ss(0, first_item) : 0.f;
     for (int t = first_item; t < total_tiles; t += item_step, ++it) {
       int prob, n_img, y0, x0, n0;
-      tile_coords(t, prob, n_img, y0, x0, n0);
+      get_tile(it, t, prob, n_img, y0, x0, n0);
       const ConvProblem& q = p.pr[prob];
       const int a = it & 1;
       const uint32_t aph = ((uint32_t)it >> 1) & 1u;
@@ -472,7 +507,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // the staging tile is reused every tile: the previous TMA stores must have read it out
       if (et == 0 && !p.direct) DBG_T(2, bulk_wait_read(0));
       DBG_T(3, asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"));
-      if (t + item_step < total_tiles) ss_next = fetch_ss(t + item_step);   // in flight during this tile
+      if (t + item_step < total_tiles) ss_next = fetch_ss(it + 1, t + item_step);   // in flight during this tile
       DBG_T(0, mbar_wait(tmem_full_bar + a, aph));
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
@@ -842,7 +877,7 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   const size_t staging_bytes = (size_t)p.nblk * kBlockM * p.row_bytes;
   const size_t res_bytes = residual ? 8192 : 0;   // the 64x64 identity tile
   size_t stage_bytes = (size_t)kBlockM * kBlockK * 2 + (size_t)BN * kBlockK * 2;
-  const size_t tail_bytes = 256 + 2 * 256 * 4;   // barriers + tmem pointer (< 256 B), scale, shift
+  const size_t tail_bytes = 256 + 2 * 256 * 4 + kTileTab * 16;   // barriers + tmem pointer (< 256 B), scale, shift, tile table
   const int tiles_per_problem = N * p.tiles_x * p.tiles_y * (Cout / BN);
   EESEG_REQUIRE(tiles_per_problem < (1 << 24), "conv_igemm: too many tiles");
   EESEG_REQUIRE(!schedule || n_items == tiles_per_problem * nprob, "conv_igemm: schedule has %d items, expected %d", n_items,
