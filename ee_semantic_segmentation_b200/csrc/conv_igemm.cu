@@ -512,10 +512,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.BN);
       // direct epilogue: this thread's pixel
-      const int my = (int)fd_div((uint32_t)m, p.fd_bw);
-      const int yy = y0 + my, xx = x0 + (m - my * p.BW);
-      const bool in_image = m < p.BW * p.BH && yy < p.h && xx < p.w;
-      const int64_t out_off = (((int64_t)n_img * p.h + yy) * p.w + xx) * p.ldo + q.ch_off + n0;
+      bool in_image = false;
+      int64_t out_off = 0;
+      if (p.direct) {
+        const int my = (int)fd_div((uint32_t)m, p.fd_bw);
+        const int yy = y0 + my, xx = x0 + (m - my * p.BW);
+        in_image = m < p.BW * p.BH && yy < p.h && xx < p.w;
+        out_off = (((int64_t)n_img * p.h + yy) * p.w + xx) * p.ldo + q.ch_off + n0;
+      }
       const float relu_lo = p.relu ? 0.f : -INFINITY;
       // kMode: 0 = bf16 staging tile, 1 = fp32 staging tile, 2 = bf16 direct, 3 = fp32 direct (compile-time: the loop
       // body is straight-line code, the scale/shift loads of all column groups issue up front)
