@@ -15,18 +15,22 @@ from . import _lib, head_plan
 from .head_plan import _fold_bn, _krsc, conv_igemm
 
 
+FOLD_SCALE = head_plan.FOLD_SCALE
+
+
 class _Conv:
     def __init__(self, conv, bn, fold_scale=False):
         assert conv.groups == 1 and conv.bias is None
         s, b = _fold_bn(bn)
+        fold_scale = fold_scale or FOLD_SCALE >= 2
         if fold_scale:
             # convs that take a residual: the kernel adds the residual inside the accumulator (identity
             # K blocks on the tensor core), so the BN scale goes into the weights and the epilogue scale is 1
             self.w = (conv.weight.detach().float() * s.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-            s = torch.ones_like(s)
+            s = torch.ones_like(s) if FOLD_SCALE == 0 else None
         else:
             self.w = _krsc(conv)
-        self.s, self.b = s.contiguous(), b.contiguous()
+        self.s, self.b = (None if s is None else s.contiguous()), b.contiguous()
         self.dil = conv.dilation[0]
         self.stride = conv.stride[0]
         self.cout = conv.out_channels

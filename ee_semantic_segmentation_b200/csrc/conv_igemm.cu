@@ -88,6 +88,7 @@ struct ConvParams {
                                        // 32 KB instead of 48 KB per 128x256x64 MMA block (the L2->SM port, ~64 B/clk,
                                        // is what bounds the single-CTA kernel at ~62 % of the tensor peak)
   int m_tiles;                         // N * tiles_x * tiles_y
+  int unit_scale;                      // every problem's scale pointer is NULL: y = act(conv + shift (+ residual))
   FastDiv fd_ntiles, fd_tiles_img, fd_tiles_x, fd_bw;   // Cout / BN, tiles_x * tiles_y, tiles_x, BW
   int overlay;                         // output staging overlays the ring (every CTA runs at most one tile)
   int direct;                          // deep-K launches: epilogue stores straight from registers (no staging
@@ -485,7 +486,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       int prob_, n_img_, y0_, x0_, n0_;
       get_tile(it_, item_idx, prob_, n_img_, y0_, x0_, n0_);
       const ConvProblem& qq = p.pr[prob_];
-      return et < p.BN ? __ldg(qq.scale + n0_ + et) : __ldg(qq.shift + (int64_t)n_img_ * p.shift_sn + n0_ + (et - p.BN));
+      if (et < p.BN) return p.unit_scale ? 1.f : __ldg(qq.scale + n0_ + et);
+      return __ldg(qq.shift + (int64_t)n_img_ * p.shift_sn + n0_ + (et - p.BN));
     };
     unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long dbg_t0 = clock64();
@@ -526,7 +528,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       auto convert_cols = [&](auto nc_tag, auto mode_tag, int col) {
         constexpr int NC = decltype(nc_tag)::value;
         constexpr int kMode = decltype(mode_tag)::value;
-        constexpr bool kF32 = (kMode & 1) != 0, kDirect = (kMode & 2) != 0;
+        constexpr bool kF32 = (kMode & 1) != 0, kDirect = (kMode & 2) != 0, kUnit = (kMode & 4) != 0;
         uint32_t v[NC];
         if constexpr (NC == 32) tmem_ld32(trow + (uint32_t)col, v); else tmem_ld16(trow + (uint32_t)col, v);
         tmem_ld_wait();
@@ -534,16 +536,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int g = 0; g < NC / 8; ++g) {   // 8 columns: 16 B of bf16, 32 B of fp32
           const int c8 = col + 8 * g;
           const uint32_t sa = ss_base + (uint32_t)c8 * 4u;
-          const float4 sc0 = lds_f4(sa), sc1 = lds_f4(sa + 16u), sh0 = lds_f4(sa + 1024u), sh1 = lds_f4(sa + 1040u);
+          const float4 sh0 = lds_f4(sa + 1024u), sh1 = lds_f4(sa + 1040u);
           float f[8];
-          f[0] = fmaf(__uint_as_float(v[8 * g + 0]), sc0.x, sh0.x);
-          f[1] = fmaf(__uint_as_float(v[8 * g + 1]), sc0.y, sh0.y);
-          f[2] = fmaf(__uint_as_float(v[8 * g + 2]), sc0.z, sh0.z);
-          f[3] = fmaf(__uint_as_float(v[8 * g + 3]), sc0.w, sh0.w);
-          f[4] = fmaf(__uint_as_float(v[8 * g + 4]), sc1.x, sh1.x);
-          f[5] = fmaf(__uint_as_float(v[8 * g + 5]), sc1.y, sh1.y);
-          f[6] = fmaf(__uint_as_float(v[8 * g + 6]), sc1.z, sh1.z);
-          f[7] = fmaf(__uint_as_float(v[8 * g + 7]), sc1.w, sh1.w);
+          if constexpr (kUnit) {   // scale folded into the weights: half the shared-memory reads of the column loop
+            f[0] = __uint_as_float(v[8 * g + 0]) + sh0.x;
+            f[1] = __uint_as_float(v[8 * g + 1]) + sh0.y;
+            f[2] = __uint_as_float(v[8 * g + 2]) + sh0.z;
+            f[3] = __uint_as_float(v[8 * g + 3]) + sh0.w;
+            f[4] = __uint_as_float(v[8 * g + 4]) + sh1.x;
+            f[5] = __uint_as_float(v[8 * g + 5]) + sh1.y;
+            f[6] = __uint_as_float(v[8 * g + 6]) + sh1.z;
+            f[7] = __uint_as_float(v[8 * g + 7]) + sh1.w;
+          } else {
+            const float4 sc0 = lds_f4(sa), sc1 = lds_f4(sa + 16u);
+            f[0] = fmaf(__uint_as_float(v[8 * g + 0]), sc0.x, sh0.x);
+            f[1] = fmaf(__uint_as_float(v[8 * g + 1]), sc0.y, sh0.y);
+            f[2] = fmaf(__uint_as_float(v[8 * g + 2]), sc0.z, sh0.z);
+            f[3] = fmaf(__uint_as_float(v[8 * g + 3]), sc0.w, sh0.w);
+            f[4] = fmaf(__uint_as_float(v[8 * g + 4]), sc1.x, sh1.x);
+            f[5] = fmaf(__uint_as_float(v[8 * g + 5]), sc1.y, sh1.y);
+            f[6] = fmaf(__uint_as_float(v[8 * g + 6]), sc1.z, sh1.z);
+            f[7] = fmaf(__uint_as_float(v[8 * g + 7]), sc1.w, sh1.w);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = fmax_nan(f[j], relu_lo);   // -inf without ReLU: identity, NaN kept
           uint32_t u[4] = {0u, 0u, 0u, 0u};
@@ -591,17 +605,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int col = pass * pass_cols + hsel * wcols;
         if (col < p.BN) {
           using std::integral_constant;
-          const int mode = (p.direct ? 2 : 0) | (p.out_f32 ? 1 : 0);
+          // bit 2: unit scale (bf16 outputs only; an fp32 launch with NULL scales reads the 1.0 the fetch wrote)
+          const int mode = (p.direct ? 2 : 0) | (p.out_f32 ? 1 : 0) | ((p.unit_scale && !p.out_f32) ? 4 : 0);
           if (wcols == 32) {
             if (mode == 0) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 0>{}, col);
             else if (mode == 1) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 1>{}, col);
             else if (mode == 2) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 2>{}, col);
-            else convert_cols(integral_constant<int, 32>{}, integral_constant<int, 3>{}, col);
+            else if (mode == 3) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 3>{}, col);
+            else if (mode == 4) convert_cols(integral_constant<int, 32>{}, integral_constant<int, 4>{}, col);
+            else convert_cols(integral_constant<int, 32>{}, integral_constant<int, 6>{}, col);
           } else {
             if (mode == 0) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 0>{}, col);
             else if (mode == 1) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 1>{}, col);
             else if (mode == 2) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 2>{}, col);
-            else convert_cols(integral_constant<int, 16>{}, integral_constant<int, 3>{}, col);
+            else if (mode == 3) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 3>{}, col);
+            else if (mode == 4) convert_cols(integral_constant<int, 16>{}, integral_constant<int, 4>{}, col);
+            else convert_cols(integral_constant<int, 16>{}, integral_constant<int, 6>{}, col);
           }
         }
         if (pass + 1 < npass && !p.direct) {
@@ -822,11 +841,13 @@ static int launch_conv(const void* x, const HostProblem* hp, int nprob, int64_t 
   p.N = N; p.h = h; p.w = w; p.Cin = Cin; p.Cout = Cout;
   p.hin = hin; p.win = win; p.stride = stride;
   p.has_res = residual ? 1 : 0;
+  p.unit_scale = hp[0].scale == nullptr ? 1 : 0;
   p.nprob = nprob;
   int kb_total = 0;
   for (int g = 0; g < kMaxGroup; ++g) {
     const HostProblem& q = hp[g < nprob ? g : 0];
-    EESEG_REQUIRE(q.wt && q.scale && q.shift && ((uintptr_t)q.wt & 15) == 0, "conv_igemm: null / misaligned weights");
+    EESEG_REQUIRE(q.wt && q.shift && ((uintptr_t)q.wt & 15) == 0, "conv_igemm: null / misaligned weights");
+    EESEG_REQUIRE((q.scale == nullptr) == (hp[0].scale == nullptr), "conv_igemm: scale must be NULL for all problems of a group or for none");
     EESEG_REQUIRE(q.R >= 1 && q.S >= 1 && q.R * q.S <= 32, "conv_igemm: at most 32 taps");
     int pad = q.pad;
     if (pad < 0) {  // 'same' padding of an odd square kernel

@@ -170,7 +170,8 @@ def conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out,
         if PROFILE is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        torch_ops.fast.conv_igemm_grouped(x, list(wts), list(scales), list(shifts), list(ksizes), list(dils),
+        torch_ops.fast.conv_igemm_grouped(x, list(wts), None if scales is None or scales[0] is None else list(scales),
+                                           list(shifts), list(ksizes), list(dils),
                                            list(ch_offs), bool(relu), out, ldo, out_channels, schedule, bool(cta_pairs))
         if PROFILE is not None:
             b.record()
@@ -206,6 +207,11 @@ def global_avgpool_nhwc(xh):
     return pooled
 
 
+# BatchNorm scale of the inference convolutions: 2 = folded into the bf16 weights (one rounding of w * s instead of one
+# rounding of w; the kernel's epilogue then only adds the shift: scale pointer NULL, half the shared-memory reads of its
+# column loop; measured -1.1 % on the 513x513 step), 1 = only for the Bottleneck convolutions that take a residual (they
+# need it: the residual is added inside the accumulator), 0 = as 1 but with an explicit tensor of ones (kept for A/B runs)
+FOLD_SCALE = int(os.environ.get("EESEG_FOLD_SCALE", "2"))
 GROUPED = True   # run the ASPP branch convolutions as one grouped launch
 IMAGES_PER_PASS = int(os.environ.get("EESEG_GROUP_IMAGES_PER_PASS", "2"))   # grouped work list: images per pass (0 = all)
 GROUP_PAIRS = os.environ.get("EESEG_GROUP_PAIRS", "1") != "0"   # grouped ASPP launch as CTA pairs when the batch is even
@@ -245,11 +251,19 @@ class HeadPlan:
         self.pool_s, self.pool_b = (t.contiguous() for t in _fold_bn(pool[2]))
         nb = len(self.branches)
         proj = aspp.project[0].weight.detach().float().flatten(1)          # [mid, (nb+1)*mid]
-        self.proj_w = proj[:, :nb * self.mid].contiguous().view(self.mid, 1, 1, nb * self.mid).to(torch.bfloat16)
         self.proj_pool_w = proj[:, nb * self.mid:].contiguous()             # [mid, mid] fp32
         self.proj_s, self.proj_b = (t.contiguous() for t in _fold_bn(aspp.project[1]))
-        self.c3_w = _krsc(conv3)
         self.c3_s, self.c3_b = _fold_bn(bn3)
+        pw = proj[:, :nb * self.mid]
+        if FOLD_SCALE >= 2:   # projection and 3x3: scale into the weights, NULL scale for the kernel (the pooled branch's
+            # per-image shift keeps its own scale: dense_bn_act below)
+            pw = pw * self.proj_s.view(-1, 1)
+            self.c3_w = (conv3.weight.detach().float() * self.c3_s.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+            self.proj_cs = self.c3_s = None
+        else:
+            self.c3_w = _krsc(conv3)
+            self.proj_cs = self.proj_s
+        self.proj_w = pw.contiguous().view(self.mid, 1, 1, nb * self.mid).to(torch.bfloat16)
         # final classifier: pad Cout to a multiple of 16 for the MMA N dimension
         C = self.n_classes
         Cp = (C + 15) // 16 * 16
@@ -316,7 +330,7 @@ class HeadPlan:
         if side is not main:
             main.wait_stream(side)
         y = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
-        conv_igemm(cat, self.proj_w, self.proj_s, pshift, 1, True, y, BF, mid, shift_sn=mid)
+        conv_igemm(cat, self.proj_w, self.proj_cs, pshift, 1, True, y, BF, mid, shift_sn=mid)
         z = torch.empty((N, h, w, mid), dtype=torch.bfloat16, device=dev)
         conv_igemm(y, self.c3_w, self.c3_s, self.c3_b, 1, True, z, BF, mid)
         out = torch.empty((N, h, w, self.Cp), dtype=torch.float32, device=dev)

@@ -49,19 +49,19 @@ def _op(schema):
 
 
 # ---- convolutions ----------------------------------------------------------------------------------------------
-@_op("conv_igemm_fwd(Tensor x, Tensor wt, Tensor scale, Tensor shift, int shift_sn, int dilation, int stride, int pad, "
+@_op("conv_igemm_fwd(Tensor x, Tensor wt, Tensor? scale, Tensor shift, int shift_sn, int dilation, int stride, int pad, "
      "bool relu, Tensor? residual, Tensor(a!) out, int ldo) -> ()")
 def _conv_igemm_fwd(x, wt, scale, shift, shift_sn, dilation, stride, pad, relu, residual, out, ldo):
     N, h, w, Cin = x.shape
     Cout, R, S, _ = wt.shape
     with torch.cuda.device(x.device):
         check(lib().eeseg_conv_igemm_fwd(
-            x.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), shift_sn, N, h, w, Cin, Cout, R, S,
+            x.data_ptr(), wt.data_ptr(), _p(scale), shift.data_ptr(), shift_sn, N, h, w, Cin, Cout, R, S,
             dilation, stride, pad, 1 if relu else 0, _p(residual), 0 if residual is None else residual.stride(2),
             out.data_ptr(), _dt(out), ldo, _stream(x)), "eeseg_conv_igemm_fwd")
 
 
-@_op("conv_igemm_grouped(Tensor x, Tensor[] wts, Tensor[] scales, Tensor[] shifts, int[] ksizes, int[] dils, int[] ch_offs, "
+@_op("conv_igemm_grouped(Tensor x, Tensor[] wts, Tensor[]? scales, Tensor[] shifts, int[] ksizes, int[] dils, int[] ch_offs, "
      "bool relu, Tensor(a!) out, int ldo, int out_channels, Tensor schedule, bool cta_pairs) -> ()")
 def _conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out, ldo, out_channels, schedule, cta_pairs):
     N, h, w, Cin = x.shape
@@ -71,7 +71,8 @@ def _conv_igemm_grouped(x, wts, scales, shifts, ksizes, dils, ch_offs, relu, out
     IA = ctypes.c_int * n
     with torch.cuda.device(x.device):
         check(lib().eeseg_conv_igemm_grouped(
-            x.data_ptr(), n, PA(*[t.data_ptr() for t in wts]), PA(*[t.data_ptr() for t in scales]),
+            x.data_ptr(), n, PA(*[t.data_ptr() for t in wts]),
+            PA(*([t.data_ptr() for t in scales] if scales is not None else [None] * n)),
             PA(*[t.data_ptr() for t in shifts]), IA(*ksizes), IA(*dils), IA(*ch_offs), N, h, w, Cin, Cout,
             1 if relu else 0, out.data_ptr(), ldo, out_channels, schedule.data_ptr(), schedule.numel(),
             1 if cta_pairs else 0, _stream(x)), "eeseg_conv_igemm_grouped")

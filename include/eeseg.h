@@ -200,6 +200,8 @@ int eeseg_lovasz_fwd_bwd(const void* probas, int dtype, int64_t exit_stride, con
  *   residual: optional bf16 NHWC tensor of the OUTPUT shape (pixel stride ldr), or NULL. It is added
  *   inside the accumulator (identity K blocks on the tensor core), i.e. BEFORE the scale: pass
  *   weights with the scale folded in and scale == 1 (Cout %% 64 == 0)
+ *   scale: NULL = 1 for every channel (weights with the scale folded in): the epilogue then only adds the shift and
+ *   reads half as much shared memory per output column (a group passes NULL for all of its problems or for none)
  *   out NHWC with pixel stride ldo elements, written at channel offset already applied to `out`
  *   out_dtype EESEG_BF16 or EESEG_F32; relu != 0 applies max(.,0) last
  * ---------------------------------------------------------------------------------------------- */

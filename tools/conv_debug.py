@@ -83,9 +83,21 @@ for cin in (2048, 1024):
         us, _ = stamp(lambda: conv_igemm(x, wts[k], scs[k], shs[k], dl[k], True, cat[..., k * mid:], _lib.BF16, 4 * mid))
         print(f"  Cin={cin} separate k={ks[k]} d={dl[k]}: {us:.1f} us")
         tot += us
-    us, di = stamp(lambda: conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, cat, 4 * mid, 4 * mid, sched))
-    d = di.double()
-    act = d[:, 3] > 0
-    m = d[act].mean(0)
-    print(f"  Cin={cin} separate total {tot:.1f} us | GROUPED {us:.1f} us  (MMA total {m[6]:.0f} cyc, wait_full {m[5]:.0f}, wait_tmem_empty {m[4]:.0f}; "
-          f"per-CTA MMA total min/max {d[act][:,6].min():.0f}/{d[act][:,6].max():.0f})")
+    n_cl = _lib.lib().eeseg_conv_pair_clusters()
+    psched = group_schedule(N, h, w, cin, mid, ks, dl, pairs=True, n_clusters=n_cl).to(dev)
+    for label, sc_, pr_ in (("GROUPED", sched, False), (f"GROUPED as CTA pairs ({n_cl} clusters)", psched, True)):
+        us, di = stamp(lambda: conv_igemm_grouped(x, wts, scs, shs, ks, dl, [k * mid for k in range(4)], True, cat, 4 * mid,
+                                                  4 * mid, sc_, cta_pairs=pr_))
+        d = di.double()
+        act = d[:, 6] > 0          # CTAs whose MMA thread ran (pair launches: the leaders)
+        m = d[act].mean(0)
+        ep = d[d[:, 12] > 0]
+        print(f"  Cin={cin} separate total {tot:.1f} us | {label} {us:.1f} us  (MMA total {m[6]:.0f} cyc, wait_full {m[5]:.0f}, "
+              f"wait_tmem_empty {m[4]:.0f}; per-CTA MMA total min/max {d[act][:,6].min():.0f}/{d[act][:,6].max():.0f}; "
+              f"EPI total mean {ep[:,12].mean():.0f} wait_tmem_full {ep[:,8].mean():.0f} colloop {ep[:,14].mean():.0f}; "
+              f"PROD total {d[d[:,2]>0][:,2].mean():.0f} wait_empty {d[d[:,2]>0][:,1].mean():.0f})")
+        run = di[di[:, 17] > 0]
+        st, en = run[:, 16], run[:, 17]
+        print(f"      CTA start skew {(st.max() - st.min()).item() / 1e3:.1f} us, end skew {(en.max() - en.min()).item() / 1e3:.1f} us, "
+              f"CTA lifetime min/mean/max {(en - st).min().item() / 1e3:.1f}/{(en - st).double().mean().item() / 1e3:.1f}/{(en - st).max().item() / 1e3:.1f} us, "
+              f"MMA role mean {m[6] / 1e3:.0f} k cycles, epilogue role wall {ep[:, 15].mean() / 1e3:.1f} us (=> {ep[:, 12].mean() / ep[:, 15].mean():.2f} GHz)")
