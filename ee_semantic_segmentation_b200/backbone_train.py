@@ -59,7 +59,7 @@ class StemConvFn(torch.autograd.Function):
         wt = w2.detach().to(torch.bfloat16).contiguous()
         out = torch.empty((N, H2, W2, Cout), dtype=torch.bfloat16, device=s2d.device)
         one, zero = _unit_scale_shift(s2d.device, Cout)
-        conv_igemm(s2d, wt, one, zero, 1, False, out, _lib.BF16, Cout, pad=2)
+        conv_igemm(s2d, wt, None, zero, 1, False, out, _lib.BF16, Cout, pad=2)
         ctx.save_for_backward(s2d)
         ctx.cout = Cout
         return out

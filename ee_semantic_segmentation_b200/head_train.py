@@ -123,7 +123,7 @@ class ConvIgemmFn(torch.autograd.Function):
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         out = torch.empty((N, ho, wo, Cout), dtype=torch.bfloat16, device=x.device)
         one, zero = _unit_scale_shift(x.device, Cout)
-        conv_igemm(x, wt, one, zero, dilation, False, out, _lib.BF16, Cout, stride=stride)
+        conv_igemm(x, wt, None, zero, dilation, False, out, _lib.BF16, Cout, stride=stride)
         ctx.save_for_backward(x, wt)
         ctx.dilation = dilation
         ctx.stride = stride
@@ -150,7 +150,7 @@ class ConvIgemmFn(torch.autograd.Function):
                 if ctx.wT is not None:       # the rotated transpose is in the per-step cache: dgrad = the forward kernel on it
                     from .head_plan import conv_igemm
                     one, zero = _unit_scale_shift(x.device, Cin)
-                    conv_igemm(dy, ctx.wT, one, zero, ctx.dilation, False, dx, _lib.BF16, Cin)
+                    conv_igemm(dy, ctx.wT, None, zero, ctx.dilation, False, dx, _lib.BF16, Cin)
                 else:
                     ws = torch.empty((lib().eeseg_conv_igemm_dgrad_workspace_bytes(Cin, Cout, R, S),), dtype=torch.uint8,
                                      device=x.device)
