@@ -179,7 +179,7 @@ def test_bench_config_logits(bench_nets):
 # DELTA from tau at every gate it reaches must take the oracle's exit. north_star's 1e-4 band applies to the gate
 # arithmetic on IDENTICAL logits (tests/test_kernels_gpu.py checks the gate kernel against the oracle at 1e-4 / mask
 # identical outside 1e-4 of tau); DELTA is that plus the bf16 network's effect on the score.
-SCORE_TOL = 1.5e-3     # measured 8.7e-4 over 32 images x 2 gates
+SCORE_TOL = 1.5e-3     # measured 8.7e-4 .. 1.06e-3 over 32 images x 2 gates (profiles/r02_parity_v1.txt, _v2)
 DELTA = 1.5e-3
 
 
