@@ -59,40 +59,37 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const T* __restrict__ x, 
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int N, int h,
                                                             int w, int C, int ho, int wo,
                                                             __nv_bfloat16* __restrict__ out) {
+  // one thread per 16-byte chunk (8 channels) of an output pixel; grid = (chunks of an output row / 256, Y, n)
   const int cv = C / 8;
-  const int64_t total = (int64_t)N * ho * wo * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    const int X = (int)((i / cv) % wo);
-    const int Y = (int)((i / ((int64_t)cv * wo)) % ho);
-    const int n = (int)(i / ((int64_t)cv * wo * ho));
-    float m[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= wo * cv) return;
+  const int X = i / cv, c8 = i - X * cv;
+  const int Y = blockIdx.y, n = blockIdx.z;
+  float m[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
+  for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int yy = 2 * Y + dy, xx = 2 * X + dx;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * h + yy) * w + xx) * C) + c8);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int yy = 2 * Y + dy, xx = 2 * X + dx;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * h + yy) * w + xx) * C) + c8);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            m[2 * k] = fmaxf(m[2 * k], __uint_as_float(w4[k] << 16));
-            m[2 * k + 1] = fmaxf(m[2 * k + 1], __uint_as_float(w4[k] & 0xffff0000u));
-          }
+        for (int k = 0; k < 4; ++k) {
+          m[2 * k] = fmaxf(m[2 * k], __uint_as_float(w4[k] << 16));
+          m[2 * k + 1] = fmaxf(m[2 * k + 1], __uint_as_float(w4[k] & 0xffff0000u));
         }
       }
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      __nv_bfloat162 b2 = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]);
-      o[k] = *reinterpret_cast<uint32_t*>(&b2);
     }
-    reinterpret_cast<uint4*>(out + (((int64_t)n * ho + Y) * wo + X) * C)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]);
+    o[k] = *reinterpret_cast<uint32_t*>(&b2);
   }
+  reinterpret_cast<uint4*>(out + (((int64_t)n * ho + Y) * wo + X) * C)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // Training max-pool: forward also records which of the 9 window taps won (first maximum in row-major window order,
@@ -254,8 +251,8 @@ extern "C" int eeseg_maxpool3x3s2_nhwc(const void* x, int N, int h, int w, int C
                 "maxpool3x3s2: C %% 8 == 0 and 16-byte aligned pointers required");
   if (N <= 0) return EESEG_OK;
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-  const int64_t total = (int64_t)N * ho * wo * (C / 8);
-  const int blocks = (int)((total + 255) / 256 < kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  EESEG_REQUIRE(ho <= 65535 && N <= 65535, "maxpool3x3s2: map too tall / batch too large for the grid");
+  const dim3 blocks((unsigned)((wo * (C / 8) + 255) / 256), (unsigned)ho, (unsigned)N);
   maxpool3x3s2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, h, w, C, ho, wo,
                                                                   (__nv_bfloat16*)out);
   return check_launch("maxpool3x3s2_kernel");
