@@ -600,8 +600,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           tma_store_4d(&tmap_out, stg_smem + (size_t)blk * blk_bytes, q.ch_off + n0 + blk * p.blk_cols, x0, y0, n_img);
         bulk_commit();
       };
+      // 16 columns of the hot mode (bf16 staging tile, scale folded into the weights): shift, ReLU, pack, one 16-byte
+      // shared-memory store per 8 columns
+      auto convert16_unit = [&](const uint32_t (&v)[16], int col) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int c8 = col + 8 * g;
+          const uint32_t sa = ss_base + 1024u + (uint32_t)c8 * 4u;
+          const float4 sh0 = lds_f4(sa), sh1 = lds_f4(sa + 16u);
+          const float f0 = fmax_nan(__uint_as_float(v[8 * g + 0]) + sh0.x, relu_lo), f1 = fmax_nan(__uint_as_float(v[8 * g + 1]) + sh0.y, relu_lo);
+          const float f2 = fmax_nan(__uint_as_float(v[8 * g + 2]) + sh0.z, relu_lo), f3 = fmax_nan(__uint_as_float(v[8 * g + 3]) + sh0.w, relu_lo);
+          const float f4 = fmax_nan(__uint_as_float(v[8 * g + 4]) + sh1.x, relu_lo), f5 = fmax_nan(__uint_as_float(v[8 * g + 5]) + sh1.y, relu_lo);
+          const float f6 = fmax_nan(__uint_as_float(v[8 * g + 6]) + sh1.z, relu_lo), f7 = fmax_nan(__uint_as_float(v[8 * g + 7]) + sh1.w, relu_lo);
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(f0, f1), b1 = __floats2bfloat162_rn(f2, f3);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(f4, f5), b3 = __floats2bfloat162_rn(f6, f7);
+          const uint32_t orow = stg_row + (uint32_t)(c8 >> blk_shift) * blk_bytes;
+          const uint32_t cb = (uint32_t)(c8 & (p.blk_cols - 1));
+          sts_u4(orow + (((cb >> 3) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
+                 *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
+        }
+      };
       if (DBG_ON(p)) dbg_t1 = clock64();
-      for (int pass = 0; pass < npass; ++pass) {
+      const bool piped = wcols == 32 && p.unit_scale && !p.out_f32 && !p.direct && !PROBE(p, 7);   // probe bit 7: the un-pipelined loop
+      if (piped) {
+        // software pipeline over 16-column chunks and two register sets: the tcgen05.ld of the next chunk is in flight
+        // while the current one is converted (TMEM read-out alone is ~1.4 k cycles per 128x256 tile, conversion and
+        // staging ~1.7 k: back to back they were 3.1 k)
+        uint32_t va[16], vb[16];
+        int col = hsel * 32;
+        tmem_ld16(trow + (uint32_t)col, va);
+        tmem_ld_wait();
+        tmem_ld16(trow + (uint32_t)(col + 16), vb);
+        convert16_unit(va, col);
+        tmem_ld_wait();
+        if (npass == 2) {
+          tmem_ld16(trow + (uint32_t)(col + pass_cols), va);
+          convert16_unit(vb, col + 16);
+          fence_proxy_async();
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+          if (et == 0 && !PROBE(p, 3)) store_blocks(0);
+          col += pass_cols;
+          tmem_ld_wait();
+          tmem_ld16(trow + (uint32_t)(col + 16), vb);
+          convert16_unit(va, col);
+          tmem_ld_wait();
+        }
+        convert16_unit(vb, col + 16);
+      }
+      for (int pass = 0; pass < npass && !piped; ++pass) {
         const int col = pass * pass_cols + hsel * wcols;
         if (col < p.BN) {
           using std::integral_constant;
