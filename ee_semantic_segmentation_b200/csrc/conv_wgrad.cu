@@ -177,15 +177,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       mbar_wait(acc_bar, 0);
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-      for (int col = 0; col < p.BN; col += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)col, v);
-        tmem_ld_wait();
-        if (!store) continue;
+      // 16-column chunks over two register sets: the next tcgen05.ld is in flight while the current chunk is stored
+      // (BN is 64, 128 or 256)
+      auto put = [&](const uint32_t (&v)[16], int col) {
+        if (!store) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           reinterpret_cast<float4*>(row + col)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      };
+      uint32_t va[16], vb[16];
+      tmem_ld16(trow, va);
+      tmem_ld_wait();
+      for (int col = 0; col < p.BN; col += 32) {
+        tmem_ld16(trow + (uint32_t)(col + 16), vb);
+        put(va, col);
+        tmem_ld_wait();
+        if (col + 32 < p.BN) tmem_ld16(trow + (uint32_t)(col + 32), va);
+        put(vb, col + 16);
+        if (col + 32 < p.BN) tmem_ld_wait();
       }
     } else if (store) {
       for (int col = 0; col < p.BN; col += 4) *reinterpret_cast<float4*>(row + col) = make_float4(0.f, 0.f, 0.f, 0.f);

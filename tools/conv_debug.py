@@ -30,7 +30,7 @@ for name, N, h, w, cin, cout, R, dil, stride, res in shapes:
     sc, sh = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
     out = torch.empty(N, h, w, cout, dtype=torch.bfloat16, device=dev)
     r = torch.randn(N, h, w, cout, device=dev).to(torch.bfloat16) if res else None
-    run = lambda: conv_igemm(x, wt, sc, sh, dil, True, out, _lib.BF16, cout, stride=stride, residual=r)
+    run = lambda: conv_igemm(x, wt, None, sh, dil, True, out, _lib.BF16, cout, stride=stride, residual=r)   # scale folded (NULL), as the inference plans launch it
     for _ in range(3):
         run()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
