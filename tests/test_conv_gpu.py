@@ -46,6 +46,8 @@ def run_conv(N, h, w, Cin, Cout, R, dil, relu, out_f32=False, per_image_shift=Fa
     dict(N=1, h=65, w=65, Cin=64, Cout=64, R=3, dil=36, relu=False),                # most taps all-padding
     dict(N=2, h=33, w=47, Cin=192, Cout=32, R=1, dil=1, relu=False, out_f32=True, per_image_shift=True),
     dict(N=1, h=24, w=40, Cin=1024, Cout=512, R=1, dil=1, relu=True),               # two N tiles, deep K
+    # 88 x 57 = 5016 spatial tiles = 34 per CTA: past the 32-entry tile table of the prologue (items 32+ are decoded inline)
+    dict(N=1, h=700, w=900, Cin=64, Cout=64, R=3, dil=1, relu=True),
 ])
 def test_conv_igemm_vs_torch(cfg):
     err = run_conv(**cfg)
