@@ -104,7 +104,8 @@ struct ConvParams {
   unsigned long long* dbg;   // optional [gridDim.x][32] cycle counters (eeseg_conv_debug_stats)
   unsigned long long* tslot; // optional {min start, max end} wall-clock ns of this launch (eeseg_conv_timing)
   int probe;                 // tuning builds: bit 0 = do not load A tiles, bit 1 = no weight tiles, bit 2 = no residual
-                             // tiles, bit 3 = no output stores (timing probes of the operand stream; results are garbage)
+                             // tiles, bit 3 = no output stores (timing probes of the operand stream; results are garbage),
+                             // bit 7 = un-pipelined epilogue (include/eeseg_tuning.h)
 };
 
 // Tuning instrumentation (cycle accounting per role, %globaltimer launch brackets) exists only in builds with

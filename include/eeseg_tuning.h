@@ -18,8 +18,9 @@ int eeseg_conv_timing(void* device_buffer, int capacity);
  * filled by subsequent conv launches; NULL switches it off. */
 int eeseg_conv_debug_stats(void* device_buffer);
 
-/* Timing probes of the conv kernel's operand stream: skip_mask bit 0 = no activation tiles, 1 = no weight tiles,
- * 2 = no residual tiles, 3 = no output stores (the launches' outputs are garbage); max_ctas > 0 caps the grid.
+/* Timing probes of the conv kernel: skip_mask bit 0 = no activation tiles, 1 = no weight tiles, 2 = no residual tiles,
+ * 3 = no output stores (the launches' outputs are then garbage), 4 = register -> global epilogue on every multi-tile
+ * launch, 5 = operand ring capped at two stages, 7 = the un-pipelined epilogue column loop; max_ctas > 0 caps the grid.
  * (0, 0) restores normal launches. */
 int eeseg_conv_probe(int skip_mask, int max_ctas);
 
