@@ -13,10 +13,15 @@
 // * Taps that fall entirely into the zero padding for a tile (common for dilation 24/36 on a 65x65
 //   map) are skipped: they contribute exactly 0.
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-//   warps 2..17 = epilogue (tcgen05.ld 32x32b, four warps per TMEM lane quadrant, one column quarter each; thread = output
-//   pixel): scale/shift (+ residual, prefetched by TMA into shared memory at kernel start) (+ ReLU),
-//   packed into a 128B-swizzled shared-memory tile and written with ONE TMA tensor store per
-//   64-channel block — full 128 B lines to L2, image-edge rows clipped by the tensor map.
+//   warps 2..17 = epilogue (tcgen05.ld 32x32b, four warps per TMEM lane quadrant, one column quarter each; thread =
+//   output pixel): shift (+ scale unless folded into the weights) (+ ReLU), packed into a 128B-swizzled shared-memory
+//   tile and written with ONE TMA tensor store per 64-channel block — full 128 B lines to L2, image-edge rows clipped by
+//   the tensor map. A residual is added by the tensor core: its 64-channel blocks travel through the operand ring and
+//   are multiplied by an identity tile into the accumulator before the main loop.
+// * Persistent: one CTA per SM walks a work list; its first 32 items are decoded once in the prologue (tile table).
+//   conv_igemm_kernel<true> is the CTA-pair variant (tcgen05.mma.cta_group::2: two CTAs of a cluster on one 256-row
+//   tile, each staging its own activation tile and half of the weight tile), used for the grouped ASPP launch of an
+//   even batch and for the deepest layer4 launches.
 #include <cuda.h>
 
 #include <cstdlib>
