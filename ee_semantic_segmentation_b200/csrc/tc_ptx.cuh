@@ -65,6 +65,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, 
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// the same load with an L2 eviction-priority hint (policy from l2_policy_evict_first): data that is read exactly once
+__device__ __forceinline__ void tma_load_4d_hint(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0,
                                             int c1) {
   asm volatile(
