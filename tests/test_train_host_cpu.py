@@ -221,3 +221,27 @@ def test_old_pickles_and_weights_token():
     assert net.weights_token()[0] == t2[0] + 1
     net.float()                                                                  # _apply: storages may have moved
     assert net.weights_token()[0] == t2[0] + 2
+
+
+def test_fastdiv_formula_is_exact_below_2_31():
+    """The multiply-high division the conv kernel uses for its tile coordinates (csrc/conv_igemm.cu: make_fastdiv / fd_div):
+    mul = ceil(2^(31+l) / d), l = ceil(log2 d); q = umulhi(n, mul) >> (l - 1). Restated here and checked against integer
+    division for every divisor up to 4096, a spread of larger ones, and edge / random n below 2^31 (the kernel's n are work-item
+    and tile indices, < 2^24)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    ds = list(range(2, 4097)) + [4097, 5016, 16384, 16385, 65535, 65536, 1 << 20, (1 << 24) - 1, (1 << 24) + 1]
+    n = np.concatenate([np.arange(0, 5000), rng.integers(0, 1 << 31, 20000), np.array([(1 << 31) - 1, (1 << 31) - 2, (1 << 24) - 1])]
+                       ).astype(np.uint64)
+    for d in ds:
+        l = int(np.ceil(np.log2(d)))
+        if (1 << l) < d:
+            l += 1
+        p = 31 + l
+        mul = ((1 << p) + d - 1) // d
+        assert mul < (1 << 32)
+        q = ((n * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(p - 32)
+        extra = np.array([d - 1, d, d + 1, 2 * d - 1, 2 * d, 7 * d - 1, 7 * d], dtype=np.uint64)
+        qe = ((extra * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(p - 32)
+        assert np.array_equal(q, n // np.uint64(d)), d
+        assert np.array_equal(qe, extra // np.uint64(d)), d
