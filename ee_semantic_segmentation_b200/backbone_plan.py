@@ -2,7 +2,8 @@
 implicit-GEMM kernel: every torchvision ResNet `Bottleneck` becomes three (four with a projection
 shortcut) `eeseg_conv_igemm_fwd` launches on bf16 NHWC activations with BatchNorm folded into the
 epilogue scale/shift, ReLU fused, and the residual add fused into the last 1x1 — instead of
-conv + BN + ReLU + add as separate library kernels. Stride-2 convolutions (layer2.0) use TMA element
+conv + BN + ReLU + add as separate library kernels (the BatchNorm scale goes into the bf16 weights, the shift stays in the
+epilogue: head_plan.FOLD_SCALE). Stride-2 convolutions (layer2.0) use TMA element
 strides. The 7x7/stride-2 stem (3 input channels) is a space-to-depth 4x1 implicit GEMM followed by the NHWC
 max-pool kernel (StemPlan). A section with any other unit is not `supported` (the model then warns once, or raises
 under `strict_kernels`).

@@ -1,10 +1,11 @@
 """Inference plan of one DeepLabHead / my_branch exit head on the eeseg kernels.
 
 Takes the torchvision module (parameter container, reference layout `branches.{i}.0.convs.*`),
-folds every BatchNorm into a per-channel scale/shift, converts weights once to bf16 [Cout][R][S][Cin]
-and runs the head as implicit-GEMM launches (csrc/conv_igemm.cu) on NHWC bf16 activations:
+folds every BatchNorm into a per-channel scale/shift (projection and 3x3: scale into the bf16 weights, FOLD_SCALE), converts
+weights once to bf16 [Cout][R][S][Cin] and runs the head as implicit-GEMM launches (csrc/conv_igemm.cu) on NHWC bf16 activations:
 
-    ASPP 1x1 + three atrous 3x3 -> written side by side into one [N,h,w,4*256] buffer (no concat),
+    ASPP 1x1 + three atrous 3x3 -> ONE grouped launch over a cost-sorted work list (CTA pairs for an even batch), written
+    side by side into one [N,h,w,4*256] buffer (no concat),
     pooled branch -> global-avg-pool kernel + tiny matvec, folded into the projection as a
     per-image shift (the broadcast "bilinear" up-sampling of a 1x1 map is a constant),
     projection 1x1 (K = 4*256) -> 3x3 -> final 1x1 (+bias) to fp32 logits [N,h,w,Cp].
